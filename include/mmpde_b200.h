@@ -1,0 +1,154 @@
+/*
+ * mmpde_b200.h -- C ABI of libmmpde_b200.so, the sm_100a kernels behind the MM-PDE hot path.
+ *
+ * The reference (Peiyannn/MM-PDE) has no FFI of its own: its boundary is the Python module surface
+ * (SURVEY.md section 8b).  Each entry point below replaces one third-party operator call that the
+ * reference's Python reaches (file:line relative to the reference tree), and is what the host-side
+ * mirror in mm-pde_b200/*.py binds with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), never allocate or
+ *     free, and keep no global state;
+ *   - return 0 on success, a negative MMPDE_E* code for argument errors, a positive cudaError_t
+ *     for launch failures;
+ *   - fp32 row-major matrices with an explicit leading dimension (elements); int32 indices;
+ *   - hidden width H = 128, time window 1, one "variables" column (gnn_2d.py:76-78,96): the node
+ *     scalars travel as one float4 per node, node4 = (u, pos_x/Lx, pos_y/Ly, t/tmax).
+ */
+#ifndef MMPDE_B200_H
+#define MMPDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMPDE_H 128
+#define MMPDE_OK 0
+#define MMPDE_EINVAL (-1)
+#define MMPDE_EUNSUPPORTED (-2)
+
+/* library / device facts: abi version, SM count the kernels were sized for. */
+int mmpde_abi_version(void);
+int mmpde_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- graph construction --------------------------------------------------------------------
+ * Replaces torch_cluster.knn_graph (data_creator_2d.py:260, mesh/dmm_model.py:228) and sklearn
+ * NearestNeighbors.kneighbors (data_creator_2d.py:66,75-76).
+ * pts [P,2], qry [Q,2] fp32; pts_off/qry_off [S+1] int32 sample offsets (neighbours never cross
+ * samples).  out_idx [Q,k] int32 GLOBAL rows of pts, ascending (d2, index); -1 pads short samples.
+ * rule 0: d2 = fmaf(dy,dy,dx*dx) fp32 (torch_cluster CUDA kernel); rule 1: fp64 dx*dx+dy*dy (sklearn).
+ * exclude_self: skip the point whose within-sample index equals the query's (qry == pts). */
+int mmpde_knn(const float* pts, const int32_t* pts_off, const float* qry, const int32_t* qry_off,
+              int n_samples, int64_t n_queries, int k, int rule, int exclude_self,
+              int32_t* out_idx, void* stream);
+
+/* Same contract for one large sample (P up to 2^31): uniform-cell binned exact search.
+ * cell_start [gx*gy+1] int32 and order [P] int32 (points sorted by cell, original index) are built
+ * by mmpde_knn_grid_build into caller workspace. */
+int mmpde_knn_grid_build(const float* pts, int64_t n_pts, float x0, float y0, float inv_cell,
+                         int gx, int gy, int32_t* cell_of_pt, int32_t* cell_start, int32_t* cursor,
+                         int32_t* order, void* stream);
+int mmpde_knn_grid(const float* pts, int64_t n_pts, const float* qry, int64_t n_queries,
+                   float x0, float y0, float inv_cell, int gx, int gy,
+                   const int32_t* cell_start, const int32_t* order,
+                   int k, int rule, int exclude_self, int32_t* out_idx, void* stream);
+
+/* radius_graph (data_creator_2d.py:258): first <= max_nb points in index order with d2 < r*r. */
+int mmpde_radius(const float* pts, const int32_t* off, int n_samples, int64_t n_pts, float r,
+                 int max_nb, int32_t* out_idx, void* stream);
+
+/* ---- dense node-level contraction -------------------------------------------------------------
+ * Replaces nn.Linear + ReLU on node tensors (gnn_2d.py:44-49,67-68,99-106) and their autograd.
+ * C[M,N] (+)= act( opA(A)[M,K] * opB(B)[K,N] + bias[N] + r1_row[M]*r1_col[N] )
+ *   a_kmajor = 1: A stored [M,K] (lda >= K);  0: A stored [K,M] (lda >= M)   (transposed operand)
+ *   b_kmajor = 1: B stored [N,K] (ldb >= K);  0: B stored [K,N] (ldb >= N)
+ *   bias, r1_row (stride r1_stride), r1_col may be NULL;  relu: 0/1;  accumulate: C += result;
+ *   split_k > 1 splits the K loop over grid.z and adds atomically (C must be pre-zeroed or hold the
+ *   value to accumulate onto; relu/bias then apply only when split_k == 1). */
+int mmpde_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor,
+               float* C, int64_t ldc, int64_t M, int N, int64_t K,
+               const float* bias, const float* r1_row, int64_t r1_stride, const float* r1_col,
+               int relu, int accumulate, int split_k, void* stream);
+
+/* ---- message passing over the target-sorted edge list -------------------------------------------
+ * Replaces PyG propagate + message_net_1/2 + scatter-mean (gnn_2d.py:55,59-63) with the algebraic
+ * split of SURVEY.md appendix A:  z1 = P[i] + Q[j] + W1c*e_ij,  P = x*W1a^T + b1,  Q = x*W1b^T.
+ *   PQ [N_src,256]: cols 0..127 = P, 128..255 = Q;   node4 [N_src] float4;
+ *   edge_src / edge_dst [E] int32, sorted by dst;  inv_deg [N_dst] = 1/max(deg,1);
+ *   w1c [128,4] (ld 4) = W1[:,256:260];  w2 [128,128] row-major ([out,in]);  b2 [128];
+ *   agg [N_dst, ld_agg]: mean message, MUST be zero on entry (partial segments add atomically);
+ *   mask2 [E,4] uint32: bit c of (z2 > 0), saved for the backward. */
+int mmpde_edge_fwd(const float* PQ, const float* node4, const int32_t* edge_src, const int32_t* edge_dst,
+                   const float* inv_deg, int64_t n_edges, const float* w1c, const float* w2, const float* b2,
+                   float* agg, int64_t ld_agg, uint32_t* mask2, void* stream);
+
+/* Backward of the above (autograd of gnn_2d.py:59-63 + scatter-mean), h1 recomputed, z2 mask read.
+ *   g_agg [N_dst, ld_gagg]: dL/d(mean message).
+ *   Outputs (all ACCUMULATED atomically, zero them first):
+ *   dPQ [N_src,256] (dP by target segment, dQ scattered to source), dW2 [128,128], db2 [128],
+ *   dW1c [128,4], g_u [N_src] with stride g_u_stride (NULL to skip). */
+int mmpde_edge_bwd(const float* PQ, const float* node4, const int32_t* edge_src, const int32_t* edge_dst,
+                   const float* inv_deg, int64_t n_edges, const float* w1c, const float* w2,
+                   const uint32_t* mask2, const float* g_agg, int64_t ld_gagg,
+                   float* dPQ, float* dW2, float* db2, float* dW1c, float* g_u, int64_t g_u_stride,
+                   void* stream);
+
+/* ---- BatchNorm over all nodes (PyG BatchNorm / nn.BatchNorm1d, gnn_2d.py:51,56,101,104) ---------
+ * y = A (+ B if non-NULL), [M,128] with leading dims lda/ldb.
+ * stats: sums [2,128] fp64 += (sum_c, sum_c^2)   (zero first; all-reduce across ranks for sync-BN)
+ * finalize: from sums and the GLOBAL row count -> mean_rstd [2,128] fp32, and, if running_* given,
+ *           running stats update with momentum and the unbiased variance.
+ * apply : out = gamma*(y-mean)*rstd + beta, optional ReLU. */
+int mmpde_bn_stats(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, double* sums, void* stream);
+int mmpde_bn_finalize(const double* sums, double count, float eps, float momentum,
+                      float* mean_rstd, float* running_mean, float* running_var, void* stream);
+int mmpde_bn_apply(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
+                   const float* mean_rstd, const float* gamma, const float* beta, int relu,
+                   float* out, int64_t ldo, void* stream);
+/* backward: g [M,128] (ldg) is dL/d(out).  If relu, `out` (the forward output) gates g first.
+ * reduce: bsums [2,128] fp64 += (sum g, sum g*yhat)  -> dbeta, dgamma (all-reduce for sync-BN)
+ * apply : gy = gamma*rstd*( g - sum_g/count - yhat*sum_gyhat/count ); written to gy (ldgy);
+ *         accumulate!=0 adds into gy instead. */
+int mmpde_bn_bwd_reduce(const float* g, int64_t ldg, const float* out, int64_t ldo, int relu,
+                        const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
+                        const float* mean_rstd, double* bsums, void* stream);
+int mmpde_bn_bwd_apply(const float* g, int64_t ldg, const float* out, int64_t ldo, int relu,
+                       const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
+                       const float* mean_rstd, const float* gamma, const double* bsums, double count,
+                       float* gy, int64_t ldgy, int accumulate, void* stream);
+
+/* ---- small elementwise helpers of the node path -------------------------------------------------
+ * relu_bwd: out = g * (act > 0); colsum[128] += column sums of out (NULL to skip).  [M,128] */
+int mmpde_relu_bwd(const float* g, int64_t ldg, const float* act, int64_t lda, int64_t M,
+                   float* out, int64_t ldo, float* colsum, void* stream);
+/* colsum[N] += sum over rows of A[M,N] */
+int mmpde_colsum(const float* A, int64_t lda, int64_t M, int N, float* colsum, void* stream);
+
+/* ---- Conv1d decoder over the feature axis (gnn_2d.py:108-114,136-139) ---------------------------
+ * h [M,128] (ldh) -> out[M] = scale * conv3(relu(conv2(relu(conv1(h)))));  params packed fp32:
+ * w1[4*16] b1[4] w2[8*4*12] b2[8] w3[8*8] b3[1]  (525 floats, torch Conv1d weight order). */
+int mmpde_decoder_fwd(const float* h, int64_t ldh, int64_t M, const float* params, float scale,
+                      float* out, void* stream);
+/* g_out[M] -> g_h [M,128] (ldg, overwritten) and g_params[525] (accumulated). */
+int mmpde_decoder_bwd(const float* h, int64_t ldh, int64_t M, const float* params, float scale,
+                      const float* g_out, float* g_h, int64_t ldg, float* g_params, void* stream);
+
+/* ---- fused k-NN interpolation (data_creator_2d.py:77-83 + interpolate.py:79-93) ----------------
+ * For query q of sample s: p = (x_1,y_1,...,x_30,y_30,x_q,y_q) from idx[q,0..29];
+ * w = Wc*tanh(Wb*tanh(Wa*p+ba)+bb)+bc;  out[q] = sum_k w_k * src_val[idx[q,k]].
+ * params packed fp32: Wa[128*62] ba[128] Wb[64*128] bb[64] Wc[30*64] bc[30]  (18270 floats). */
+int mmpde_itp_fwd(const float* src_xy, const float* src_val, const float* qry_xy, const int32_t* idx,
+                  int64_t n_queries, const float* params, float* out, void* stream);
+/* g_out[Q] -> g_params[18270] (accumulated), g_src_val[P] (accumulated atomically; NULL to skip). */
+int mmpde_itp_bwd(const float* src_xy, const float* src_val, const float* qry_xy, const int32_t* idx,
+                  int64_t n_queries, const float* params, const float* g_out,
+                  float* g_params, float* g_src_val, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMPDE_B200_H */

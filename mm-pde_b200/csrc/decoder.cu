@@ -1,0 +1,183 @@
+// Conv1d decoder over the 128-wide feature axis, one warp per node.
+// Replaces nn.Conv1d(1,4,16,s3) -> ReLU -> Conv1d(4,8,12,s3) -> ReLU -> Conv1d(8,1,8,s2) and the
+// 0.1*dt scaling (/root/reference/gnn_2d.py:108-114,136-139) plus their autograd.
+// Lengths: 128 -> [4][38] -> [8][9] -> [1][1]; the last conv reads positions 0..7 of the 9.
+#include "common.cuh"
+
+namespace mmpde {
+
+constexpr int DEC_NP = 525;
+constexpr int OFF_W1 = 0, OFF_B1 = 64, OFF_W2 = 68, OFF_B2 = 452, OFF_W3 = 460, OFF_B3 = 524;
+constexpr int WARPS = 8;
+
+struct DecScratch {
+    float h[128];
+    float a1[4 * 38];   // post-ReLU
+    float a2[8 * 9];    // post-ReLU
+    float g1[4 * 38];
+    float g2[8 * 9];
+};
+
+__device__ __forceinline__ float dec_forward(const float* sp, DecScratch& s, int lane) {
+    for (int idx = lane; idx < 152; idx += 32) {
+        int c = idx / 38, p = idx - c * 38;
+        float acc = sp[OFF_B1 + c];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc = fmaf(sp[OFF_W1 + c * 16 + t], s.h[3 * p + t], acc);
+        s.a1[idx] = fmaxf(acc, 0.f);
+    }
+    __syncwarp();
+    for (int idx = lane; idx < 72; idx += 32) {
+        int o = idx / 9, p = idx - o * 9;
+        float acc = sp[OFF_B2 + o];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int t = 0; t < 12; ++t) acc = fmaf(sp[OFF_W2 + (o * 4 + c) * 12 + t], s.a1[c * 38 + 3 * p + t], acc);
+        s.a2[idx] = fmaxf(acc, 0.f);
+    }
+    __syncwarp();
+    float part = 0.f;
+    for (int idx = lane; idx < 64; idx += 32) {
+        int c = idx >> 3, t = idx & 7;
+        part = fmaf(sp[OFF_W3 + idx], s.a2[c * 9 + t], part);
+    }
+    return warp_sum(part) + sp[OFF_B3];
+}
+
+__global__ void __launch_bounds__(WARPS * 32) decoder_fwd_kernel(const float* __restrict__ h, int64_t ldh, int64_t M,
+                                                                 const float* __restrict__ params, float scale,
+                                                                 float* __restrict__ out) {
+    __shared__ float sp[DEC_NP];
+    __shared__ DecScratch scr[WARPS];
+    for (int i = threadIdx.x; i < DEC_NP; i += blockDim.x) sp[i] = __ldg(params + i);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DecScratch& s = scr[warp];
+    for (int64_t n = (int64_t)blockIdx.x * WARPS + warp; n < M; n += (int64_t)gridDim.x * WARPS) {
+        __syncwarp();
+        *reinterpret_cast<float4*>(&s.h[lane * 4]) = ldg4(h + n * ldh + lane * 4);
+        __syncwarp();
+        float v = dec_forward(sp, s, lane);
+        if (lane == 0) out[n] = scale * v;
+    }
+}
+
+__global__ void __launch_bounds__(WARPS * 32) decoder_bwd_kernel(const float* __restrict__ h, int64_t ldh, int64_t M,
+                                                                 const float* __restrict__ params, float scale,
+                                                                 const float* __restrict__ g_out, float* __restrict__ g_h,
+                                                                 int64_t ldg, float* __restrict__ g_params) {
+    __shared__ float sp[DEC_NP];
+    __shared__ DecScratch scr[WARPS];
+    for (int i = threadIdx.x; i < DEC_NP; i += blockDim.x) sp[i] = __ldg(params + i);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DecScratch& s = scr[warp];
+    // lane-private accumulators for parameter index lane + 32*i (17 slots cover 525 parameters)
+    float gp[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) gp[i] = 0.f;
+
+    for (int64_t n = (int64_t)blockIdx.x * WARPS + warp; n < M; n += (int64_t)gridDim.x * WARPS) {
+        __syncwarp();
+        *reinterpret_cast<float4*>(&s.h[lane * 4]) = ldg4(h + n * ldh + lane * 4);
+        __syncwarp();
+        (void)dec_forward(sp, s, lane);
+        const float g3 = scale * __ldg(g_out + n);
+        // layer 3: g wrt pre-activation of layer 2
+        for (int idx = lane; idx < 72; idx += 32) {
+            int c = idx / 9, t = idx - c * 9;
+            float g = (t < 8) ? g3 * sp[OFF_W3 + c * 8 + t] : 0.f;
+            s.g2[idx] = s.a2[idx] > 0.f ? g : 0.f;
+        }
+        __syncwarp();
+        // layer 2 -> g wrt pre-activation of layer 1
+        for (int idx = lane; idx < 152; idx += 32) {
+            int c = idx / 38, q = idx - c * 38;
+            float acc = 0.f;
+            for (int t = 0; t < 12; ++t) {
+                int r = q - t;
+                if (r < 0 || r % 3) continue;
+                int p = r / 3;
+                if (p >= 9) continue;
+#pragma unroll
+                for (int o = 0; o < 8; ++o) acc = fmaf(s.g2[o * 9 + p], sp[OFF_W2 + (o * 4 + c) * 12 + t], acc);
+            }
+            s.g1[idx] = s.a1[idx] > 0.f ? acc : 0.f;
+        }
+        __syncwarp();
+        // layer 1 -> g_h
+        float gh[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int q = lane * 4 + i;
+            float acc = 0.f;
+            for (int t = 0; t < 16; ++t) {
+                int r = q - t;
+                if (r < 0 || r % 3) continue;
+                int p = r / 3;
+                if (p >= 38) continue;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc = fmaf(s.g1[c * 38 + p], sp[OFF_W1 + c * 16 + t], acc);
+            }
+            gh[i] = acc;
+        }
+        *reinterpret_cast<float4*>(g_h + n * ldg + lane * 4) = make_float4(gh[0], gh[1], gh[2], gh[3]);
+        // parameter gradients
+#pragma unroll
+        for (int i = 0; i < 17; ++i) {
+            int pi = lane + 32 * i;
+            if (pi >= DEC_NP) break;
+            float acc = 0.f;
+            if (pi < OFF_B1) {                       // w1[c][t]
+                int c = pi >> 4, t = pi & 15;
+                for (int p = 0; p < 38; ++p) acc = fmaf(s.g1[c * 38 + p], s.h[3 * p + t], acc);
+            } else if (pi < OFF_W2) {                // b1[c]
+                int c = pi - OFF_B1;
+                for (int p = 0; p < 38; ++p) acc += s.g1[c * 38 + p];
+            } else if (pi < OFF_B2) {                // w2[o][c][t]
+                int r = pi - OFF_W2;
+                int o = r / 48, c = (r % 48) / 12, t = r % 12;
+                for (int p = 0; p < 9; ++p) acc = fmaf(s.g2[o * 9 + p], s.a1[c * 38 + 3 * p + t], acc);
+            } else if (pi < OFF_W3) {                // b2[o]
+                int o = pi - OFF_B2;
+                for (int p = 0; p < 9; ++p) acc += s.g2[o * 9 + p];
+            } else if (pi < OFF_B3) {                // w3[c][t]
+                int r = pi - OFF_W3;
+                acc = g3 * s.a2[(r >> 3) * 9 + (r & 7)];
+            } else {
+                acc = g3;
+            }
+            gp[i] += acc;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+        int pi = lane + 32 * i;
+        if (pi < DEC_NP) atomicAdd(g_params + pi, gp[i]);
+    }
+}
+
+}  // namespace mmpde
+
+using namespace mmpde;
+
+extern "C" int mmpde_decoder_fwd(const float* h, int64_t ldh, int64_t M, const float* params, float scale, float* out,
+                                 void* stream) {
+    if (M < 0 || ldh % 4) return MMPDE_EINVAL;
+    if (M == 0) return MMPDE_OK;
+    int grid = (int)imin64((M + WARPS - 1) / WARPS, (int64_t)sm_count() * 8);
+    decoder_fwd_kernel<<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(h, ldh, M, params, scale, out);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_decoder_bwd(const float* h, int64_t ldh, int64_t M, const float* params, float scale,
+                                 const float* g_out, float* g_h, int64_t ldg, float* g_params, void* stream) {
+    if (M < 0 || ldh % 4 || ldg % 4) return MMPDE_EINVAL;
+    if (M == 0) return MMPDE_OK;
+    int grid = (int)imin64((M + WARPS - 1) / WARPS, (int64_t)sm_count() * 4);
+    decoder_bwd_kernel<<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(h, ldh, M, params, scale, g_out, g_h, ldg, g_params);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}

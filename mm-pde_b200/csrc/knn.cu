@@ -1,0 +1,258 @@
+// Exact ordered k-nearest-neighbour search (graph construction + interpolation neighbour lists).
+// Replaces torch_cluster.knn_graph (/root/reference/data_creator_2d.py:260) and
+// sklearn NearestNeighbors.kneighbors (/root/reference/data_creator_2d.py:66,75-76).
+// Integer outputs must equal oracle/knn_oracle.c bit for bit: ascending (d2, original index).
+#include "common.cuh"
+
+namespace mmpde {
+
+template <typename D> struct Dist;
+template <> struct Dist<float> {   // rule 0: torch_cluster CUDA kernel arithmetic (fp32, FMA on the 2nd term)
+    static __device__ __forceinline__ float d2(float qx, float qy, float px, float py) {
+        float dx = qx - px, dy = qy - py;
+        return __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+    }
+};
+template <> struct Dist<double> {  // rule 1: sklearn kd-tree arithmetic (fp64, no contraction)
+    static __device__ __forceinline__ double d2(float qx, float qy, float px, float py) {
+        double dx = __dsub_rn((double)qx, (double)px), dy = __dsub_rn((double)qy, (double)py);
+        return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    }
+};
+
+// Sorted list of the K best (d, idx), ascending lexicographically.  Lives in local memory (L1-resident).
+template <typename D, int KMAX>
+struct TopK {
+    D d[KMAX];
+    int i[KMAX];
+    int cnt, k;
+    __device__ __forceinline__ void init(int k_) { cnt = 0; k = k_; }
+    __device__ __forceinline__ bool before(D a, int ai, D b, int bi) const { return a < b || (a == b && ai < bi); }
+    __device__ __forceinline__ void push(D dv, int iv) {
+        if (cnt == k && !before(dv, iv, d[k - 1], i[k - 1])) return;
+        int pos = (cnt < k) ? cnt : k - 1;
+        while (pos > 0 && before(dv, iv, d[pos - 1], i[pos - 1])) { d[pos] = d[pos - 1]; i[pos] = i[pos - 1]; --pos; }
+        d[pos] = dv; i[pos] = iv;
+        if (cnt < k) ++cnt;
+    }
+};
+
+constexpr int KNN_KMAX = 64;
+constexpr int KNN_TILE = 512;
+
+// One thread per query, the sample's points streamed through shared memory in index order.
+template <typename D>
+__global__ void __launch_bounds__(128) knn_brute_kernel(const float2* __restrict__ pts, const int* __restrict__ pts_off,
+                                                        const float2* __restrict__ qry, const int* __restrict__ qry_off,
+                                                        int n_samples, int k, int exclude_self, int* __restrict__ out) {
+    __shared__ float2 tile[KNN_TILE];
+    // blockIdx.y = sample, blockIdx.x = query block inside the sample
+    int s = blockIdx.y;
+    int q0 = qry_off[s], q1 = qry_off[s + 1], p0 = pts_off[s], p1 = pts_off[s + 1];
+    for (int qb = q0 + blockIdx.x * blockDim.x; qb < q1; qb += gridDim.x * blockDim.x) {
+        int q = qb + threadIdx.x;
+        bool live = q < q1;
+        float2 qq = live ? qry[q] : make_float2(0.f, 0.f);
+        int self = (exclude_self && live) ? p0 + (q - q0) : -1;
+        TopK<D, KNN_KMAX> best;
+        best.init(k);
+        for (int t0 = p0; t0 < p1; t0 += KNN_TILE) {
+            int nt = min(KNN_TILE, p1 - t0);
+            __syncthreads();
+            for (int j = threadIdx.x; j < nt; j += blockDim.x) tile[j] = pts[t0 + j];
+            __syncthreads();
+            if (live) {
+                for (int j = 0; j < nt; ++j) {
+                    int p = t0 + j;
+                    if (p == self) continue;
+                    float2 pp = tile[j];
+                    best.push(Dist<D>::d2(qq.x, qq.y, pp.x, pp.y), p);
+                }
+            }
+        }
+        if (live)
+            for (int j = 0; j < k; ++j) out[(int64_t)q * k + j] = (j < best.cnt) ? best.i[j] : -1;
+    }
+}
+
+// ---- cell-binned search for one large sample ----------------------------------------------------
+__device__ __forceinline__ int cell_coord(float v, float v0, float inv_cell, int g) {
+    int c = (int)floorf((v - v0) * inv_cell);
+    return min(max(c, 0), g - 1);
+}
+
+__global__ void grid_count_kernel(const float2* __restrict__ pts, int64_t n, float x0, float y0, float inv_cell,
+                                  int gx, int gy, int* __restrict__ cell_of_pt, int* __restrict__ counts) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float2 p = pts[i];
+        int c = cell_coord(p.y, y0, inv_cell, gy) * gx + cell_coord(p.x, x0, inv_cell, gx);
+        cell_of_pt[i] = c;
+        atomicAdd(&counts[c + 1], 1);
+    }
+}
+
+// single-block exclusive scan over counts[1..ncell] in place (ncell up to a few million: chunked)
+__global__ void grid_scan_kernel(int* __restrict__ cs, int ncell) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 1; base <= ncell; base += blockDim.x) {
+        int idx = base + threadIdx.x;
+        int v = (idx <= ncell) ? cs[idx] : 0;
+        int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warp_tot[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int t = (lane < (blockDim.x >> 5)) ? warp_tot[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        int incl = x + (w > 0 ? warp_tot[w - 1] : 0) + carry;
+        if (idx <= ncell) cs[idx] = incl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = incl;
+        __syncthreads();
+    }
+}
+
+__global__ void grid_fill_kernel(const int* __restrict__ cell_of_pt, int64_t n, const int* __restrict__ cell_start,
+                                 int* __restrict__ cursor, int* __restrict__ order) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = cell_of_pt[i];
+        int slot = cell_start[c] + atomicAdd(&cursor[c], 1);
+        order[slot] = (int)i;   // order inside a cell is arbitrary; the (d2, idx) comparator makes the result unique
+    }
+}
+
+template <typename D>
+__global__ void __launch_bounds__(128) knn_grid_kernel(const float2* __restrict__ pts, const float2* __restrict__ qry, int64_t nq,
+                                                       float x0, float y0, float inv_cell, int gx, int gy,
+                                                       const int* __restrict__ cell_start, const int* __restrict__ order,
+                                                       int k, int exclude_self, int* __restrict__ out) {
+    const float cell = 1.0f / inv_cell;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        float2 qq = qry[q];
+        int cx = cell_coord(qq.x, x0, inv_cell, gx), cy = cell_coord(qq.y, y0, inv_cell, gy);
+        int self = exclude_self ? (int)q : -1;
+        TopK<D, KNN_KMAX> best;
+        best.init(k);
+        int rmax = max(max(cx, gx - 1 - cx), max(cy, gy - 1 - cy));
+        for (int r = 0; r <= rmax; ++r) {
+            if (best.cnt == k && r > 0) {
+                // every unvisited point lies outside the (2r-1)^2 block of cells around (cx,cy):
+                // its distance is at least the gap from the query to that block's border.
+                float lo_x = x0 + (cx - (r - 1)) * cell, hi_x = x0 + (cx + r) * cell;
+                float lo_y = y0 + (cy - (r - 1)) * cell, hi_y = y0 + (cy + r) * cell;
+                // border cells are clamped (they extend to infinity): sides on the domain edge impose no bound
+                float gap = 3.0e38f;
+                if (cx - (r - 1) > 0) gap = fminf(gap, qq.x - lo_x);
+                if (cx + r < gx) gap = fminf(gap, hi_x - qq.x);
+                if (cy - (r - 1) > 0) gap = fminf(gap, qq.y - lo_y);
+                if (cy + r < gy) gap = fminf(gap, hi_y - qq.y);
+                gap = gap * (1.0f - 1e-5f) - 2e-6f * (gx + gy) * cell;   // conservative (cell-assignment rounding): never stop early
+                if (gap > 0.f && (double)best.d[k - 1] < (double)gap * (double)gap) break;
+            }
+            int ylo = cy - r, yhi = cy + r, xlo = cx - r, xhi = cx + r;
+            for (int yy = max(ylo, 0); yy <= min(yhi, gy - 1); ++yy) {
+                bool edge_row = (yy == ylo) || (yy == yhi);
+                int step = edge_row ? 1 : max(xhi - xlo, 1);
+                for (int xx = xlo; xx <= xhi; xx += step) {
+                    if (xx < 0 || xx >= gx) continue;
+                    int c = yy * gx + xx;
+                    for (int s = cell_start[c]; s < cell_start[c + 1]; ++s) {
+                        int p = order[s];
+                        if (p == self) continue;
+                        float2 pp = pts[p];
+                        best.push(Dist<D>::d2(qq.x, qq.y, pp.x, pp.y), p);
+                    }
+                }
+            }
+        }
+        for (int j = 0; j < k; ++j) out[q * k + j] = (j < best.cnt) ? best.i[j] : -1;
+    }
+}
+
+__global__ void radius_kernel(const float2* __restrict__ pts, const int* __restrict__ off, int n_samples, float r2,
+                              int max_nb, int* __restrict__ out) {
+    int s = blockIdx.y;
+    int p0 = off[s], p1 = off[s + 1];
+    for (int q = p0 + blockIdx.x * blockDim.x + threadIdx.x; q < p1; q += gridDim.x * blockDim.x) {
+        float2 qq = pts[q];
+        int cnt = 0;
+        for (int p = p0; p < p1 && cnt < max_nb; ++p) {
+            if (p == q) continue;
+            float2 pp = pts[p];
+            if (Dist<float>::d2(qq.x, qq.y, pp.x, pp.y) < r2) out[(int64_t)q * max_nb + cnt++] = p;
+        }
+        for (int j = cnt; j < max_nb; ++j) out[(int64_t)q * max_nb + j] = -1;
+    }
+}
+
+}  // namespace mmpde
+
+using namespace mmpde;
+
+extern "C" int mmpde_knn(const float* pts, const int32_t* pts_off, const float* qry, const int32_t* qry_off,
+                         int n_samples, int64_t n_queries, int k, int rule, int exclude_self, int32_t* out_idx,
+                         void* stream) {
+    if (k <= 0 || k > KNN_KMAX || n_samples < 0 || (rule != 0 && rule != 1)) return MMPDE_EINVAL;
+    if (n_samples == 0 || n_queries == 0) return MMPDE_OK;
+    int64_t per = (n_queries + n_samples - 1) / n_samples;
+    dim3 grid((unsigned)((per + 127) / 128), (unsigned)n_samples);
+    auto st = (cudaStream_t)stream;
+    if (rule == 0)
+        knn_brute_kernel<float><<<grid, 128, 0, st>>>((const float2*)pts, pts_off, (const float2*)qry, qry_off, n_samples, k, exclude_self, out_idx);
+    else
+        knn_brute_kernel<double><<<grid, 128, 0, st>>>((const float2*)pts, pts_off, (const float2*)qry, qry_off, n_samples, k, exclude_self, out_idx);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_knn_grid_build(const float* pts, int64_t n_pts, float x0, float y0, float inv_cell, int gx, int gy,
+                                    int32_t* cell_of_pt, int32_t* cell_start, int32_t* cursor, int32_t* order, void* stream) {
+    if (n_pts < 0 || gx <= 0 || gy <= 0 || (int64_t)gx * gy > (1 << 28)) return MMPDE_EINVAL;
+    auto st = (cudaStream_t)stream;
+    int ncell = gx * gy;
+    cudaMemsetAsync(cell_start, 0, sizeof(int) * (size_t)(ncell + 1), st);
+    cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)ncell, st);
+    if (n_pts == 0) return MMPDE_OK;
+    int blocks = (int)imin64((n_pts + 255) / 256, (int64_t)sm_count() * 16);
+    grid_count_kernel<<<blocks, 256, 0, st>>>((const float2*)pts, n_pts, x0, y0, inv_cell, gx, gy, cell_of_pt, cell_start);
+    grid_scan_kernel<<<1, 1024, 0, st>>>(cell_start, ncell);
+    grid_fill_kernel<<<blocks, 256, 0, st>>>(cell_of_pt, n_pts, cell_start, cursor, order);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_knn_grid(const float* pts, int64_t n_pts, const float* qry, int64_t n_queries, float x0, float y0,
+                              float inv_cell, int gx, int gy, const int32_t* cell_start, const int32_t* order, int k,
+                              int rule, int exclude_self, int32_t* out_idx, void* stream) {
+    if (k <= 0 || k > KNN_KMAX || (rule != 0 && rule != 1) || gx <= 0 || gy <= 0) return MMPDE_EINVAL;
+    if (n_queries == 0) return MMPDE_OK;
+    (void)n_pts;
+    auto st = (cudaStream_t)stream;
+    int blocks = (int)imin64((n_queries + 127) / 128, (int64_t)sm_count() * 32);
+    if (rule == 0)
+        knn_grid_kernel<float><<<blocks, 128, 0, st>>>((const float2*)pts, (const float2*)qry, n_queries, x0, y0, inv_cell, gx, gy, cell_start, order, k, exclude_self, out_idx);
+    else
+        knn_grid_kernel<double><<<blocks, 128, 0, st>>>((const float2*)pts, (const float2*)qry, n_queries, x0, y0, inv_cell, gx, gy, cell_start, order, k, exclude_self, out_idx);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_radius(const float* pts, const int32_t* off, int n_samples, int64_t n_pts, float r, int max_nb,
+                            int32_t* out_idx, void* stream) {
+    if (max_nb <= 0 || n_samples < 0) return MMPDE_EINVAL;
+    if (n_samples == 0 || n_pts == 0) return MMPDE_OK;
+    int64_t per = (n_pts + n_samples - 1) / n_samples;
+    dim3 grid((unsigned)((per + 127) / 128), (unsigned)n_samples);
+    radius_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)pts, off, n_samples, r * r, max_nb, out_idx);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}

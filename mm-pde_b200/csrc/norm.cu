@@ -1,0 +1,252 @@
+// BatchNorm over all nodes of the batch + the elementwise helpers of the node path (all HBM-bound).
+// Replaces PyG BatchNorm / nn.BatchNorm1d (/root/reference/gnn_2d.py:51,56,101,104) and autograd's ReLU masks.
+// Row-major [M,128] fp32; every thread moves one float4 (4 channels), a warp one 512-byte row.
+#include "common.cuh"
+
+namespace mmpde {
+
+constexpr int ROWS_PER_CTA = 256;   // rows reduced by one CTA before it touches the fp64 accumulators
+
+__device__ __forceinline__ float4 load_y(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t r, int c4) {
+    float4 y = ldg4(A + r * lda + c4 * 4);
+    if (B) {
+        float4 b = ldg4(B + r * ldb + c4 * 4);
+        y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
+    }
+    return y;
+}
+
+// block-level reduction of per-thread float4 partials (8 row groups x 32 lanes) into fp64 atomics on dst[0..127]
+__device__ __forceinline__ void block_reduce_to_double(float4 v, double* dst) {
+    __shared__ float4 red[8][32];
+    const int c4 = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    __syncthreads();
+    red[rg][c4] = v;
+    __syncthreads();
+    if (rg == 0) {
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) { float4 t = red[g][c4]; s0 += t.x; s1 += t.y; s2 += t.z; s3 += t.w; }
+        atomicAdd(dst + c4 * 4 + 0, s0); atomicAdd(dst + c4 * 4 + 1, s1);
+        atomicAdd(dst + c4 * 4 + 2, s2); atomicAdd(dst + c4 * 4 + 3, s3);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                       int64_t ldb, int64_t M, double* __restrict__ sums) {
+    const int c4 = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    for (int64_t base = (int64_t)blockIdx.x * ROWS_PER_CTA; base < M; base += (int64_t)gridDim.x * ROWS_PER_CTA) {
+        float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+        int64_t end = (base + ROWS_PER_CTA < M) ? base + ROWS_PER_CTA : M;
+        for (int64_t r = base + rg; r < end; r += 8) {
+            float4 y = load_y(A, lda, B, ldb, r, c4);
+            s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
+            q.x = fmaf(y.x, y.x, q.x); q.y = fmaf(y.y, y.y, q.y); q.z = fmaf(y.z, y.z, q.z); q.w = fmaf(y.w, y.w, q.w);
+        }
+        block_reduce_to_double(s, sums);
+        block_reduce_to_double(q, sums + 128);
+    }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, float eps, float momentum,
+                                   float* __restrict__ mean_rstd, float* __restrict__ rmean, float* __restrict__ rvar) {
+    int c = threadIdx.x;
+    if (c >= 128) return;
+    double mean = sums[c] / count;
+    double var = sums[128 + c] / count - mean * mean;
+    if (var < 0) var = 0;
+    mean_rstd[c] = (float)mean;
+    mean_rstd[128 + c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (rmean) {
+        double unbiased = count > 1 ? var * count / (count - 1) : var;
+        rmean[c] = (float)((1.0 - momentum) * rmean[c] + momentum * mean);
+        rvar[c] = (float)((1.0 - momentum) * rvar[c] + momentum * unbiased);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                       int64_t ldb, int64_t M, const float* __restrict__ mean_rstd,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int relu, float* __restrict__ out, int64_t ldo) {
+    const int c4 = threadIdx.x & 31;
+    float4 mu = ldg4(mean_rstd + c4 * 4), rs = ldg4(mean_rstd + 128 + c4 * 4);
+    float4 ga = ldg4(gamma + c4 * 4), be = ldg4(beta + c4 * 4);
+    float4 sc = make_float4(ga.x * rs.x, ga.y * rs.y, ga.z * rs.z, ga.w * rs.w);
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < M; r += (int64_t)gridDim.x * 8) {
+        float4 y = load_y(A, lda, B, ldb, r, c4);
+        float4 o = make_float4(fmaf(y.x - mu.x, sc.x, be.x), fmaf(y.y - mu.y, sc.y, be.y),
+                               fmaf(y.z - mu.z, sc.z, be.z), fmaf(y.w - mu.w, sc.w, be.w));
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(out + r * ldo + c4 * 4) = o;
+    }
+}
+
+__device__ __forceinline__ float4 gated_grad(const float* g, int64_t ldg, const float* out, int64_t ldo, int relu,
+                                             int64_t r, int c4) {
+    float4 gv = ldg4(g + r * ldg + c4 * 4);
+    if (relu) {
+        float4 o = ldg4(out + r * ldo + c4 * 4);
+        gv.x = o.x > 0.f ? gv.x : 0.f; gv.y = o.y > 0.f ? gv.y : 0.f;
+        gv.z = o.z > 0.f ? gv.z : 0.f; gv.w = o.w > 0.f ? gv.w : 0.f;
+    }
+    return gv;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ out,
+                                                            int64_t ldo, int relu, const float* __restrict__ A, int64_t lda,
+                                                            const float* __restrict__ B, int64_t ldb, int64_t M,
+                                                            const float* __restrict__ mean_rstd, double* __restrict__ bsums) {
+    const int c4 = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    float4 mu = ldg4(mean_rstd + c4 * 4), rs = ldg4(mean_rstd + 128 + c4 * 4);
+    for (int64_t base = (int64_t)blockIdx.x * ROWS_PER_CTA; base < M; base += (int64_t)gridDim.x * ROWS_PER_CTA) {
+        float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+        int64_t end = (base + ROWS_PER_CTA < M) ? base + ROWS_PER_CTA : M;
+        for (int64_t r = base + rg; r < end; r += 8) {
+            float4 gv = gated_grad(g, ldg, out, ldo, relu, r, c4);
+            float4 y = load_y(A, lda, B, ldb, r, c4);
+            s.x += gv.x; s.y += gv.y; s.z += gv.z; s.w += gv.w;
+            q.x = fmaf(gv.x, (y.x - mu.x) * rs.x, q.x); q.y = fmaf(gv.y, (y.y - mu.y) * rs.y, q.y);
+            q.z = fmaf(gv.z, (y.z - mu.z) * rs.z, q.z); q.w = fmaf(gv.w, (y.w - mu.w) * rs.w, q.w);
+        }
+        block_reduce_to_double(s, bsums);
+        block_reduce_to_double(q, bsums + 128);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ out,
+                                                           int64_t ldo, int relu, const float* __restrict__ A, int64_t lda,
+                                                           const float* __restrict__ B, int64_t ldb, int64_t M,
+                                                           const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                                                           const double* __restrict__ bsums, double count,
+                                                           float* __restrict__ gy, int64_t ldgy, int accumulate) {
+    const int c4 = threadIdx.x & 31;
+    float4 mu = ldg4(mean_rstd + c4 * 4), rs = ldg4(mean_rstd + 128 + c4 * 4), ga = ldg4(gamma + c4 * 4);
+    float mg[4], mgy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        mg[j] = (float)(bsums[c4 * 4 + j] / count);
+        mgy[j] = (float)(bsums[128 + c4 * 4 + j] / count);
+    }
+    float4 sc = make_float4(ga.x * rs.x, ga.y * rs.y, ga.z * rs.z, ga.w * rs.w);
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < M; r += (int64_t)gridDim.x * 8) {
+        float4 gv = gated_grad(g, ldg, out, ldo, relu, r, c4);
+        float4 y = load_y(A, lda, B, ldb, r, c4);
+        float4 o;
+        o.x = sc.x * (gv.x - mg[0] - (y.x - mu.x) * rs.x * mgy[0]);
+        o.y = sc.y * (gv.y - mg[1] - (y.y - mu.y) * rs.y * mgy[1]);
+        o.z = sc.z * (gv.z - mg[2] - (y.z - mu.z) * rs.z * mgy[2]);
+        o.w = sc.w * (gv.w - mg[3] - (y.w - mu.w) * rs.w * mgy[3]);
+        float4* dst = reinterpret_cast<float4*>(gy + r * ldgy + c4 * 4);
+        if (accumulate) { float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+        *dst = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ act,
+                                                       int64_t lda, int64_t M, float* __restrict__ out, int64_t ldo,
+                                                       float* __restrict__ colsum) {
+    __shared__ float4 red[8][32];
+    const int c4 = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    float4 s = make_float4(0, 0, 0, 0);
+    for (int64_t r = (int64_t)blockIdx.x * 8 + rg; r < M; r += (int64_t)gridDim.x * 8) {
+        float4 gv = ldg4(g + r * ldg + c4 * 4), a = ldg4(act + r * lda + c4 * 4);
+        gv.x = a.x > 0.f ? gv.x : 0.f; gv.y = a.y > 0.f ? gv.y : 0.f;
+        gv.z = a.z > 0.f ? gv.z : 0.f; gv.w = a.w > 0.f ? gv.w : 0.f;
+        *reinterpret_cast<float4*>(out + r * ldo + c4 * 4) = gv;
+        s.x += gv.x; s.y += gv.y; s.z += gv.z; s.w += gv.w;
+    }
+    if (colsum) {
+        red[rg][c4] = s;
+        __syncthreads();
+        if (rg == 0) {
+            float4 t = red[0][c4];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) { float4 u = red[k][c4]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+            atomicAdd(colsum + c4 * 4 + 0, t.x); atomicAdd(colsum + c4 * 4 + 1, t.y);
+            atomicAdd(colsum + c4 * 4 + 2, t.z); atomicAdd(colsum + c4 * 4 + 3, t.w);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N,
+                                                     float* __restrict__ colsum) {
+    // thread -> column (coalesced across the row), blockIdx.y strides over row chunks
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    float s = 0.f;
+    for (int64_t r = blockIdx.y; r < M; r += gridDim.y) s += __ldg(A + r * lda + c);
+    atomicAdd(colsum + c, s);
+}
+
+inline int row_grid(int64_t M, int rows_per_cta) {
+    int64_t g = (M + rows_per_cta - 1) / rows_per_cta;
+    return (int)imin64(g > 0 ? g : 1, (int64_t)sm_count() * 8);
+}
+
+}  // namespace mmpde
+
+using namespace mmpde;
+
+extern "C" int mmpde_bn_stats(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, double* sums, void* stream) {
+    if (M < 0 || lda % 4 || (B && ldb % 4)) return MMPDE_EINVAL;
+    if (M == 0) return MMPDE_OK;
+    bn_stats_kernel<<<row_grid(M, ROWS_PER_CTA), 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, M, sums);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_bn_finalize(const double* sums, double count, float eps, float momentum, float* mean_rstd,
+                                 float* running_mean, float* running_var, void* stream) {
+    if (count <= 0 || ((running_mean == nullptr) != (running_var == nullptr))) return MMPDE_EINVAL;
+    bn_finalize_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(sums, count, eps, momentum, mean_rstd, running_mean, running_var);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_bn_apply(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, const float* mean_rstd,
+                              const float* gamma, const float* beta, int relu, float* out, int64_t ldo, void* stream) {
+    if (M < 0 || lda % 4 || (B && ldb % 4) || ldo % 4) return MMPDE_EINVAL;
+    if (M == 0) return MMPDE_OK;
+    bn_apply_kernel<<<row_grid(M, 32), 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, M, mean_rstd, gamma, beta, relu, out, ldo);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_bn_bwd_reduce(const float* g, int64_t ldg, const float* out, int64_t ldo, int relu, const float* A,
+                                   int64_t lda, const float* B, int64_t ldb, int64_t M, const float* mean_rstd,
+                                   double* bsums, void* stream) {
+    if (M < 0 || ldg % 4 || lda % 4 || (B && ldb % 4) || (relu && (!out || ldo % 4))) return MMPDE_EINVAL;
+    if (M == 0) return MMPDE_OK;
+    bn_bwd_reduce_kernel<<<row_grid(M, ROWS_PER_CTA), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, bsums);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_bn_bwd_apply(const float* g, int64_t ldg, const float* out, int64_t ldo, int relu, const float* A,
+                                  int64_t lda, const float* B, int64_t ldb, int64_t M, const float* mean_rstd,
+                                  const float* gamma, const double* bsums, double count, float* gy, int64_t ldgy,
+                                  int accumulate, void* stream) {
+    if (M < 0 || count <= 0 || ldg % 4 || lda % 4 || (B && ldb % 4) || ldgy % 4 || (relu && (!out || ldo % 4))) return MMPDE_EINVAL;
+    if (M == 0) return MMPDE_OK;
+    bn_bwd_apply_kernel<<<row_grid(M, 32), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, gamma, bsums, count, gy, ldgy, accumulate);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_relu_bwd(const float* g, int64_t ldg, const float* act, int64_t lda, int64_t M, float* out,
+                              int64_t ldo, float* colsum, void* stream) {
+    if (M < 0 || ldg % 4 || lda % 4 || ldo % 4) return MMPDE_EINVAL;
+    if (M == 0) return MMPDE_OK;
+    relu_bwd_kernel<<<row_grid(M, 64), 256, 0, (cudaStream_t)stream>>>(g, ldg, act, lda, M, out, ldo, colsum);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_colsum(const float* A, int64_t lda, int64_t M, int N, float* colsum, void* stream) {
+    if (M < 0 || N <= 0) return MMPDE_EINVAL;
+    if (M == 0) return MMPDE_OK;
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)imin64((M + 63) / 64, (int64_t)sm_count() * 4));
+    colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, M, N, colsum);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}

@@ -1,0 +1,217 @@
+"""Graph / data assembly and the interpolation driver -- drop-in for /root/reference/data_creator_2d.py
+(``GraphCreator_FS_2D`` :18-305) with every third-party operator replaced by sm_100a kernels:
+
+  torch_cluster.knn_graph / radius_graph (:258,:260)  -> ops.knn_indices(rule 0) / ops.radius_indices
+  sklearn NearestNeighbors per sample on the CPU (:66,:75-76, two PCIe copies + a sync per sample)
+                                                     -> ops.knn_indices(rule 1), all samples in one launch
+  points[indices] / labels[indices] + ItpNet + sum (:77-83) -> ops.InterpolateFn (fused, no [nu,Q,30,2] tensor)
+  per-sample torch.cat growth loops (:143-152,:236-254) -> batched views
+
+Differences a caller can observe, both deliberate:
+  * the moved mesh is returned detached: its gradient only reaches the frozen mesh mover;
+  * the uniform-grid graph topology is cached (it is identical every step; the reference rebuilds it).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+
+
+class Data:
+    """Graph batch with the attribute surface the reference uses from torch_geometric.data.Data:
+    x, y, pos, batch, edge_index, to().  ``edge_index`` ([2,E] int64, row 0 = source, row 1 = target) is
+    materialised lazily from the int32 edge list the kernels consume."""
+
+    def __init__(self, x=None, edge_index=None, edges=None, **kw):
+        self.x = x
+        self.y = self.pos = self.batch = None
+        self._edges = edges
+        self._edge_index = edge_index
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    @property
+    def edge_index(self):
+        if self._edge_index is None and self._edges is not None:
+            self._edge_index = self._edges.edge_index()
+        return self._edge_index
+
+    @edge_index.setter
+    def edge_index(self, value):
+        self._edge_index, self._edges = value, None
+
+    def to(self, device):
+        for k, v in list(vars(self).items()):
+            if torch.is_tensor(v):
+                setattr(self, k, v.to(device))
+        return self
+
+
+def _offsets(n_samples, per, device):
+    return torch.arange(n_samples + 1, dtype=torch.int32, device=device) * per
+
+
+class GraphCreator_FS_2D(nn.Module):
+    def __init__(self, pde, neighbors=2, connect_edge="knn", time_window=10, t_resolution=100):
+        super().__init__()
+        assert isinstance(neighbors, int)
+        assert isinstance(time_window, int)
+        self.pde = pde
+        self.n = neighbors
+        self.e = connect_edge
+        self.tw = time_window
+        self.t_res = t_resolution
+        self._static_edges = {}
+
+    # ------------------------------------------------------------------ interpolation (:46-85)
+    def interpolate(self, itp_model, u, init_x, init_y, x, y, mode):
+        """u (nu, ...) known at (init_x, init_y) [nu*P,1]; returns values at (x, y) [nu*Q,1], flattened."""
+        nu = u.shape[0]
+        src = torch.cat((init_x, init_y), dim=-1).detach().to(torch.float32).contiguous()
+        qry = torch.cat((x, y), dim=-1).detach().to(torch.float32).contiguous()
+        P, Q = src.shape[0] // nu, qry.shape[0] // nu
+        dev = src.device
+        idx = ops.knn_indices(src, _offsets(nu, P, dev), qry, _offsets(nu, Q, dev), itp_model.n, rule=1,
+                              exclude_self=False)
+        vals = u.reshape(-1).to(torch.float32).contiguous()
+        return ops.InterpolateFn.apply(vals, src, qry, idx, itp_model.flat_params(mode))
+
+    # ------------------------------------------------------------------ mesh movement (:88-137)
+    @staticmethod
+    def _displace(u, mesh_model, xi1, xi2):
+        with torch.enable_grad():
+            xi1 = xi1.detach().requires_grad_(True)
+            xi2 = xi2.detach().requires_grad_(True)
+            phi = mesh_model(u.detach(), torch.cat((xi1, xi2), dim=-1))
+            g1, g2 = torch.autograd.grad(phi, (xi1, xi2), grad_outputs=torch.ones_like(phi), allow_unused=True)
+        return (g1 + xi1).detach(), (g2 + xi2).detach()
+
+    def moving_mesh(self, u, mesh_model, n_grid_x, n_grid_y):
+        gx = np.linspace(0, self.pde.Lx, n_grid_x)
+        gy = np.linspace(0, self.pde.Ly, n_grid_y)
+        # x-fastest node order, as np.meshgrid gives it (:94-96)
+        grid = torch.tensor(np.array(np.meshgrid(gx, gy)), dtype=torch.float).reshape(2, -1).t().to(u.device)
+        nu = u.shape[0]
+        xi1 = grid[:, 0:1].repeat(nu, 1)
+        xi2 = grid[:, 1:2].repeat(nu, 1)
+        mm = self.pde.movingmesh_grid_size
+        if mm[-2] != n_grid_x or mm[-1] != n_grid_y:
+            u = F.interpolate(u.reshape(-1, 1, u.shape[-2], u.shape[-1]), size=(mm[-2], mm[-1]), mode="bilinear",
+                              align_corners=True).squeeze(1)
+        return self._displace(u, mesh_model, xi1, xi2)
+
+    def moving_mesh_tri(self, u, mesh_model, grid_x, grid_y):
+        return self._displace(u, mesh_model, grid_x.reshape(-1, 1), grid_y.reshape(-1, 1))
+
+    # ------------------------------------------------------------------ data slicing (:139-154)
+    def create_data(self, datapoints, steps):
+        pairs = list(zip(datapoints, steps))
+        if len(pairs) == 0:
+            return torch.Tensor(), torch.Tensor()
+        idx = torch.as_tensor([s for _, s in pairs])
+        dp = datapoints[:len(pairs)]
+        win = torch.arange(self.tw)
+        rows = torch.arange(len(pairs))[:, None]
+        return dp[rows, (idx[:, None] - self.tw + win)], dp[rows, (idx[:, None] + win)]
+
+    # ------------------------------------------------------------------ graph assembly (:157-267)
+    def _edges(self, x_new, n_samples, per_sample, static_key=None):
+        if static_key is not None and static_key in self._static_edges:
+            return self._static_edges[static_key]
+        dev = x_new.device
+        off = _offsets(n_samples, per_sample, dev)
+        pts = x_new.detach().to(torch.float32).contiguous()
+        if self.e == "radius":
+            nbr = ops.radius_indices(pts, off, self._radius, 32)
+            edges = ops.EdgeList.from_knn(nbr, has_pad=True)
+        else:
+            nbr = ops.knn_indices(pts, off, pts, off, self.n, rule=0, exclude_self=True)
+            edges = ops.EdgeList.from_knn(nbr, has_pad=per_sample - 1 < self.n)
+        if static_key is not None:
+            self._static_edges[static_key] = edges
+        return edges
+
+    def create_graph(self, itp_model, data, labels, steps, device, mesh_model=None):
+        data, labels = data.to(device), labels.to(device)
+        pde = self.pde
+        B = data.shape[0]
+        if len(pde.grid_size) == 3:
+            onx, ony = data.shape[-2], data.shape[-1]
+            nt, nx, ny = pde.grid_size
+            n = nx * ny
+            xs = torch.linspace(0, pde.Lx, nx, device=device)
+            ys = torch.linspace(0, pde.Ly, ny, device=device)
+            self._radius = float(self.n * torch.sqrt((xs[1] - xs[0]) ** 2 + (ys[1] - ys[0]) ** 2) + 0.0001) \
+                if self.e == "radius" else None
+            grid = torch.stack(torch.meshgrid(xs, ys, indexing="ij"), dim=2).float().reshape(1, n, 2).expand(B, n, 2)
+            static_key = ("grid", B, nx, ny, str(device))
+            if mesh_model is not None:
+                mm_nx, mm_ny = pde.movingmesh_grid_size[-2], pde.movingmesh_grid_size[-1]
+                coarse = data.reshape(-1, onx, ony)[:, ::int(onx / mm_nx), ::int(ony / mm_ny)]
+                mesh_x, mesh_y = self.moving_mesh(coarse, mesh_model, nx, ny)
+                mesh = torch.cat((mesh_x, mesh_y), dim=-1).reshape(-1, n, 2)
+                og = torch.stack(torch.meshgrid(torch.linspace(0, pde.Lx, onx, device=device),
+                                                torch.linspace(0, pde.Ly, ony, device=device), indexing="ij"), dim=2)
+                og = og.reshape(1, -1, 2).expand(B, -1, 2).reshape(-1, 2)
+                data = self.interpolate(itp_model, data.reshape(-1, onx, ony), og[:, 0:1], og[:, 1:2],
+                                        mesh_x, mesh_y, mode="1").reshape(-1, self.tw, nx, ny)
+                labels = self.interpolate(itp_model, labels.reshape(-1, onx, ony), og[:, 0:1], og[:, 1:2],
+                                          mesh_x, mesh_y, mode="1").reshape(-1, self.tw, nx, ny)
+                static_key = None
+            else:
+                mesh = grid
+        else:
+            n = pde.ori_grid_size[1]
+            nt = pde.grid_size[0]
+            grid = pde.ori_grid.to(device)[None].expand(B, n, 2)
+            if self.e == "radius":
+                side = int(np.sqrt(pde.grid_size[1]))
+                hx = pde.Lx / (side - 1)
+                self._radius = float(self.n * np.sqrt(2 * hx * hx) + 0.0001)
+            static_key = ("cloud", B, n, str(device))
+            if mesh_model is not None:
+                mesh_x, mesh_y = self.moving_mesh_tri(data.reshape(-1, n), mesh_model,
+                                                      grid[:, :, 0].contiguous(), grid[:, :, 1].contiguous())
+                mesh = torch.cat((mesh_x, mesh_y), dim=-1).reshape(-1, n, 2)
+                static_key = None
+            else:
+                mesh = grid
+        t = torch.linspace(pde.tmin, pde.tmax, nt, device=device)
+        B = min(B, len(steps))
+        u_new = data[:B].reshape(B, self.tw, n).permute(0, 2, 1).reshape(B * n, self.tw)
+        y_new = labels[:B].reshape(B, self.tw, n).permute(0, 2, 1).reshape(B * n, self.tw)
+        x_new = mesh[:B].reshape(B * n, 2)
+        t_new = t[torch.as_tensor(list(steps[:B]), device=device)].repeat_interleave(n)
+        batch = torch.arange(B, device=device).repeat_interleave(n)
+        if static_key is not None:
+            static_key = static_key + (B,)
+        graph = Data(x=u_new, edges=self._edges(x_new, B, n, static_key))
+        graph.y = y_new
+        graph.pos = torch.cat((t_new[:, None], x_new), dim=1)
+        graph.batch = batch
+        return graph
+
+    # ------------------------------------------------------------------ prediction back on the grid (:270-305)
+    def interpolate_pred(self, itp_model, pred, graph, data, device):
+        data = data.to(device)
+        pde = self.pde
+        if len(pde.grid_size) == 3:
+            onx, ony = pde.ori_grid_size[1], pde.ori_grid_size[2]
+            nx, ny = pde.grid_size[1], pde.grid_size[2]
+            nu = pred.shape[0] // (nx * ny)
+            og = torch.stack(torch.meshgrid(torch.linspace(0, pde.Lx, onx, device=device),
+                                            torch.linspace(0, pde.Ly, ony, device=device), indexing="ij"), dim=2)
+            og = og.reshape(1, -1, 2).expand(nu, -1, 2).reshape(-1, 2)
+            on_grid = self.interpolate(itp_model, pred.reshape(-1, nx, ny), graph.pos[:, 1:2], graph.pos[:, 2:3],
+                                       og[:, 0:1], og[:, 1:2], mode="2").reshape(-1, 1, onx, ony)
+            out = itp_model(None, None, mode="res_cut", data=data).reshape(-1, 1, onx, ony) + on_grid
+        else:
+            n = pde.ori_grid_size[1]
+            nu = pred.shape[0] // n
+            g = pde.ori_grid.to(device)[None].expand(nu, n, 2).reshape(-1, 2)
+            on_grid = self.interpolate(itp_model, pred.reshape(-1, n), graph.pos[:, 1:2], graph.pos[:, 2:3],
+                                       g[:, 0:1], g[:, 1:2], mode="2").reshape(-1, n)
+            out = itp_model(None, None, mode="res_cut", data=data.reshape(-1, n)).reshape(-1, n) + on_grid
+        return out.reshape(-1, 1)

@@ -1,0 +1,95 @@
+"""One-process-per-GPU scaling of the hot path over NCCL / NVLink (the reference has no distributed code;
+SURVEY.md 8e).  Batch (trajectory) sharding: every rank runs mesh move, k-NN, interpolation and both
+solvers on its own samples; the only couplings are
+  (i)  BatchNorm batch statistics -> all-reduce of the fp64 [2,128] column sums per BN application
+       (forward and backward), installed into ops.COMM;
+  (ii) gradients -> ONE flat-bucket all-reduce per step (~1.28 M fp32 = 5 MB, latency-bound), averaged so
+       that the result equals the global-batch mean-MSE gradient (mmpde.py:33-36).
+On CPU (tests) the same code runs over gloo.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class DistComm(ops._Comm):
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+
+    def allreduce_(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def global_rows(self, n):
+        return float(n) * self.world            # equal shards (the sharder below guarantees it)
+
+
+def init_from_env(backend=None):
+    """Reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun).  Returns (rank, world, device)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    use_cuda = torch.cuda.is_available()
+    device = torch.device(f"cuda:{local}") if use_cuda else torch.device("cpu")
+    if use_cuda:
+        torch.cuda.set_device(device)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        kw = {"device_id": device} if use_cuda else {}
+        dist.init_process_group(backend or ("nccl" if use_cuda else "gloo"), rank=rank, world_size=world, **kw)
+    if world > 1:
+        ops.COMM = DistComm()
+    return rank, world, device
+
+
+def shutdown():
+    ops.COMM = ops._Comm()
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+def shard_batch(t, rank, world):
+    """Equal contiguous shard of the leading (trajectory) axis; the global batch must divide evenly."""
+    if t.shape[0] % world:
+        raise ValueError(f"global batch {t.shape[0]} does not divide over {world} ranks")
+    per = t.shape[0] // world
+    return t[rank * per:(rank + 1) * per]
+
+
+class GradBucket:
+    """Flat fp32 bucket over all trainable parameters: one all-reduce per step."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views, off = [], 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.nbytes = n * 4
+
+    def allreduce(self, average=True):
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            else:
+                v.copy_(p.grad)
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            if average:
+                self.flat.div_(world)
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                p.grad = v.clone()
+            else:
+                p.grad.copy_(v)

@@ -1,0 +1,128 @@
+"""Frozen DMM mesh mover -- PyG-free, device-agnostic counterpart of /root/reference/mesh/dmm_model.py.
+
+Adjacent to the hot path: it supplies the moved mesh and runs as plain PyTorch
+(cuDNN/cuBLAS), as the survey prescribes; it is not one of the hand-written kernels.  State-dict keys
+match the reference (including DenseNet's unused ``fc0``, :29) so its checkpoints load unchanged; the
+reference's hard-coded ``device="cuda"`` tensors (:27-28) are dropped because forward never reads them.
+The graph-mode branch reuses this repo's CUDA k-NN for its static 35-NN graph (:222-234).
+"""
+import torch
+from torch import nn
+
+from .. import ops
+
+
+class DenseNet(nn.Module):
+    def __init__(self, layers, width=32, normalize=False):
+        super().__init__()
+        if normalize or len(layers) < 2:
+            raise NotImplementedError
+        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(layers[:-1], layers[1:]))
+        self.width = width
+        self.fc0 = nn.Linear(4, width)
+
+    def forward(self, x):
+        hidden = x
+        for lin in list(self.layers)[:-1]:
+            hidden = torch.tanh(lin(hidden))
+        return self.layers[-1](hidden), hidden
+
+
+class ConvNet(nn.Module):
+    def __init__(self, s, layers):
+        super().__init__()
+        if layers != 7:
+            raise NotImplementedError("only the 7-layer branch of the reference is defined (:53-60)")
+        self.layers = nn.ModuleList([nn.Conv2d(1, 8, 5, stride=2, padding=2), nn.Conv2d(8, 16, 5, padding=2),
+                                     nn.Conv2d(16, 8, 5, padding=2), nn.Conv2d(8, 1, 5, stride=2, padding=2)])
+        self.fc1 = None
+        self.fc2 = nn.Linear(int(((s + 1) / 2 + 1) / 2) ** 2, 1024)
+        self.fc3 = nn.Linear(1024, 512)
+
+    def forward(self, x):
+        stem = torch.tanh(self.layers[0](x))
+        y = torch.tanh(self.layers[1](stem))
+        y = torch.tanh(stem + self.layers[2](y))
+        y = torch.tanh(self.layers[3](y))
+        return self.fc3(torch.tanh(self.fc2(y.flatten(1))))
+
+
+class _Norm(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.module = nn.BatchNorm1d(c)
+
+    def forward(self, x):
+        return self.module(x)
+
+
+class GNN_Layer_FS_2D(nn.Module):
+    """tanh message-passing layer of the graph-mode branch (:94-142); hidden width 4, so plain torch."""
+
+    def __init__(self, in_features, out_features, hidden_features):
+        super().__init__()
+        self.message_net_1 = nn.Sequential(nn.Linear(2 * in_features + 3, hidden_features), nn.Tanh())
+        self.message_net_2 = nn.Sequential(nn.Linear(hidden_features, out_features), nn.Tanh())
+        self.update_net_1 = nn.Sequential(nn.Linear(in_features + hidden_features, hidden_features), nn.Tanh())
+        self.update_net_2 = nn.Sequential(nn.Linear(hidden_features, out_features), nn.Tanh())
+        self.norm = _Norm(hidden_features)
+
+    def forward(self, x, u, pos_x, pos_y, src, dst, inv_deg):
+        feats = torch.cat((x[dst], x[src], u[dst] - u[src], pos_x[dst] - pos_x[src], pos_y[dst] - pos_y[src]), -1)
+        msg = self.message_net_2(self.message_net_1(feats))
+        agg = torch.zeros_like(x).index_add_(0, dst, msg) * inv_deg[:, None]
+        return self.norm(x + self.update_net_2(self.update_net_1(torch.cat((x, agg), -1))))
+
+
+class DMM(nn.Module):
+    def __init__(self, branch_layer, trunk_layer, grid=None, out_layer=None, s=None, mode="array"):
+        super().__init__()
+        self.mode = mode
+        self.ori_grid = grid
+        if mode == "array":
+            self.branch = ConvNet(s, branch_layer)
+        elif mode == "graph":
+            self.hidden_features, self.hidden_layer = branch_layer[0], branch_layer[1]
+            Hd = self.hidden_features
+            self.gnn_layers = nn.ModuleList(GNN_Layer_FS_2D(Hd, Hd, Hd) for _ in range(self.hidden_layer))
+            self.embedding_mlp = nn.Sequential(nn.Linear(3, Hd), nn.BatchNorm1d(Hd), nn.Tanh(), nn.Linear(Hd, Hd),
+                                               nn.BatchNorm1d(Hd))
+            self.decoding_mlp = DenseNet([Hd, 128, 1])
+            self.output_mlp = nn.Sequential(nn.Linear(grid.shape[0], 512), nn.Tanh(), nn.Linear(512, 256), nn.Tanh(),
+                                            nn.Linear(256, trunk_layer[-1]))
+        else:
+            raise ValueError(mode)
+        self.trunk = DenseNet(trunk_layer)
+        self.out_nn = DenseNet(out_layer)
+        self._graph_cache = {}
+
+    def _static_graph(self, n_samples, device):
+        key = (n_samples, str(device))
+        if key not in self._graph_cache:
+            n = self.ori_grid.shape[0]
+            pts = self.ori_grid.to(device=device, dtype=torch.float32)[None].expand(n_samples, n, 2).reshape(-1, 2).contiguous()
+            off = torch.arange(n_samples + 1, dtype=torch.int32, device=device) * n
+            nbr = ops.knn_indices(pts, off, pts, off, 35, rule=0, exclude_self=True)
+            e = ops.EdgeList.from_knn(nbr, has_pad=n - 1 < 35)
+            self._graph_cache[key] = (pts, e.src.long(), e.dst.long(), e.inv_deg)
+        return self._graph_cache[key]
+
+    def _branch_graph(self, u):
+        pts, src, dst, inv_deg = self._static_graph(u.shape[0], u.device)
+        x = u.reshape(-1, 1)
+        px, py = pts[:, 0:1], pts[:, 1:2]
+        h = self.embedding_mlp(torch.cat((x, px, py), -1))
+        for layer in self.gnn_layers:
+            h = layer(h, x, px, py, src, dst, inv_deg)
+        h, _ = self.decoding_mlp(h)
+        return self.output_mlp(h.reshape(u.shape[0], 1, -1))
+
+    def forward(self, u, grid, rf=False):
+        per_sample = grid.shape[0] // u.shape[0]
+        latent = self.branch(u.unsqueeze(1)).unsqueeze(1) if self.mode == "array" else self._branch_graph(u)
+        latent = latent.expand(-1, per_sample, -1).reshape(-1, latent.shape[-1])
+        trunk, _ = self.trunk(grid)
+        out, hidden = self.out_nn(torch.cat((latent, trunk), dim=-1))
+        if rf:
+            return out, hidden, torch.ones_like(hidden).type_as(trunk).reshape(-1, 1)
+        return out

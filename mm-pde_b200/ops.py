@@ -1,0 +1,415 @@
+"""Host-side launch logic for the sm_100a kernels: tensor checks, the edge-list container, and the two
+autograd Functions (whole-solver forward/backward, fused interpolation) that the module mirrors in
+gnn_2d.py / data_creator_2d.py call.  All device work goes through the C ABI (_cabi.call); torch is
+used for memory, streams, tiny O(parameters) reshuffles and autograd bookkeeping only.
+
+Reference behaviour being reproduced: /root/reference/gnn_2d.py:53-69,119-141 (processor),
+/root/reference/data_creator_2d.py:46-85 + /root/reference/interpolate.py:79-93 (interpolation).
+"""
+import torch
+
+from . import _cabi
+
+H = 128
+KN = 30
+ITP_NPARAM = 18270
+DEC_NPARAM = 525
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t, off=0):
+    if t is None:
+        return None
+    return t.data_ptr() + off * t.element_size()
+
+
+def _chk(t, dtype=torch.float32, name="tensor"):
+    if not t.is_cuda:
+        raise _cabi.MMPDEError(f"{name} must be a CUDA tensor: the MM-PDE hot path has no CPU fallback")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+class _Comm:
+    """Cross-rank coupling of the batch-sharded path (sync-BatchNorm statistics).  Single-GPU default:
+    identity.  mmpde_b200.dist installs the torch.distributed (NCCL) version."""
+
+    def allreduce_(self, t):
+        return t
+
+    def global_rows(self, n):
+        return float(n)
+
+
+COMM = _Comm()
+
+
+# ------------------------------------------------------------------------------------------------
+# graph containers + construction
+# ------------------------------------------------------------------------------------------------
+class EdgeList:
+    """Target-sorted edge list: int32 src/dst [E], inv_deg [N] = 1/max(in-degree, 1)."""
+
+    def __init__(self, src, dst, inv_deg, n_nodes):
+        self.src, self.dst, self.inv_deg, self.n_nodes = src, dst, inv_deg, int(n_nodes)
+        self.n_edges = int(src.shape[0])
+
+    _dst_cache = {}
+
+    @classmethod
+    def from_knn(cls, nbr, has_pad):
+        """nbr int32 [N,k] from knn_graph_indices; rows are targets, entries sources (-1 = pad)."""
+        N, k = nbr.shape
+        dev = nbr.device
+        if not has_pad:
+            key = (N, k, dev)
+            if key not in cls._dst_cache:
+                cls._dst_cache[key] = (torch.arange(N, device=dev, dtype=torch.int32).repeat_interleave(k),
+                                       torch.full((N,), 1.0 / k, device=dev, dtype=torch.float32))
+            dst, inv_deg = cls._dst_cache[key]
+            return cls(nbr.reshape(-1), dst, inv_deg, N)
+        valid = nbr >= 0
+        rows = torch.arange(N, device=dev, dtype=torch.int32)[:, None].expand(N, k)
+        deg = valid.sum(1).clamp(min=1).to(torch.float32)
+        return cls(nbr[valid].contiguous(), rows[valid].contiguous(), 1.0 / deg, N)
+
+    @classmethod
+    def from_edge_index(cls, edge_index, n_nodes):
+        """edge_index [2,E] (row 0 = source j, row 1 = target i), any integer dtype; sorted by target if needed."""
+        src, dst = edge_index[0], edge_index[1]
+        if dst.numel() > 1 and not bool((dst[1:] >= dst[:-1]).all()):
+            dst, order = torch.sort(dst, stable=True)
+            src = src[order]
+        deg = torch.bincount(dst, minlength=n_nodes).clamp(min=1).to(torch.float32)
+        return cls(src.to(torch.int32).contiguous(), dst.to(torch.int32).contiguous(), 1.0 / deg, n_nodes)
+
+    def edge_index(self):
+        return torch.stack((self.src.long(), self.dst.long()))
+
+
+def knn_indices(pts, pts_off, qry, qry_off, k, rule, exclude_self):
+    """Ordered k nearest points of each query inside its sample -> int32 [Q,k] global rows of pts (-1 pads).
+    pts/qry fp32 [.,2]; *_off int32 [S+1] on the device.  rule 0 = fp32 graph rule, 1 = fp64 interpolation rule."""
+    _chk(pts, name="pts"); _chk(qry, name="qry")
+    _chk(pts_off, torch.int32, "pts_off"); _chk(qry_off, torch.int32, "qry_off")
+    Q = qry.shape[0]
+    out = torch.empty((Q, k), dtype=torch.int32, device=pts.device)
+    _cabi.call("mmpde_knn", _ptr(pts), _ptr(pts_off), _ptr(qry), _ptr(qry_off), pts_off.numel() - 1, Q, k, rule,
+               int(exclude_self), _ptr(out), _stream())
+    return out
+
+
+def knn_indices_grid(pts, qry, k, rule, exclude_self, pts_per_cell=8.0):
+    """Same contract for ONE large sample, using the uniform-cell binned search (exact)."""
+    _chk(pts, name="pts"); _chk(qry, name="qry")
+    P, Q = pts.shape[0], qry.shape[0]
+    lo = torch.minimum(pts.min(0).values, qry.min(0).values)
+    hi = torch.maximum(pts.max(0).values, qry.max(0).values)
+    x0, y0, x1, y1 = [float(v) for v in torch.cat((lo, hi)).tolist()]          # one host sync per graph build
+    area = max((x1 - x0) * (y1 - y0), 1e-30)
+    cell = max((area * pts_per_cell / max(P, 1)) ** 0.5, 1e-9)
+    gx = max(int((x1 - x0) / cell) + 1, 1)
+    gy = max(int((y1 - y0) / cell) + 1, 1)
+    dev = pts.device
+    cell_of = torch.empty(P, dtype=torch.int32, device=dev)
+    cell_start = torch.empty(gx * gy + 1, dtype=torch.int32, device=dev)
+    cursor = torch.empty(gx * gy, dtype=torch.int32, device=dev)
+    order = torch.empty(P, dtype=torch.int32, device=dev)
+    st = _stream()
+    _cabi.call("mmpde_knn_grid_build", _ptr(pts), P, x0, y0, 1.0 / cell, gx, gy, _ptr(cell_of), _ptr(cell_start),
+               _ptr(cursor), _ptr(order), st)
+    out = torch.empty((Q, k), dtype=torch.int32, device=dev)
+    _cabi.call("mmpde_knn_grid", _ptr(pts), P, _ptr(qry), Q, x0, y0, 1.0 / cell, gx, gy, _ptr(cell_start), _ptr(order),
+               k, rule, int(exclude_self), _ptr(out), st)
+    return out
+
+
+def radius_indices(pts, off, r, max_nb=32):
+    _chk(pts, name="pts"); _chk(off, torch.int32, "off")
+    out = torch.empty((pts.shape[0], max_nb), dtype=torch.int32, device=pts.device)
+    _cabi.call("mmpde_radius", _ptr(pts), _ptr(off), off.numel() - 1, pts.shape[0], float(r), max_nb, _ptr(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# thin kernel wrappers (pointer + leading-dimension style, mirroring the C ABI)
+# ------------------------------------------------------------------------------------------------
+def gemm(A, lda, a_k, B, ldb, b_k, C, ldc, M, N, K, bias=None, r1_row=None, r1_stride=0, r1_col=None,
+         relu=0, acc=0, split_k=1, st=None):
+    _cabi.call("mmpde_gemm", A, lda, a_k, B, ldb, b_k, C, ldc, M, N, K, bias, r1_row, r1_stride, r1_col,
+               relu, acc, split_k, st if st is not None else _stream())
+
+
+def _split_for(rows):
+    return max(1, min(1024, (rows + 2047) // 2048))
+
+
+class _BNState:
+    """mean/rstd [2,128] of one BatchNorm application (saved for the backward)."""
+    __slots__ = ("mean_rstd", "count")
+
+
+def _bn_forward(A, lda, B, ldb, M, gamma, beta, relu, out, ldo, training, rmean, rvar, nbt, st):
+    state = _BNState()
+    dev = gamma.device
+    if training:
+        sums = torch.zeros(2 * H, dtype=torch.float64, device=dev)
+        _cabi.call("mmpde_bn_stats", A, lda, B, ldb, M, _ptr(sums), st)
+        COMM.allreduce_(sums)
+        state.count = COMM.global_rows(M)
+        state.mean_rstd = torch.empty(2 * H, dtype=torch.float32, device=dev)
+        _cabi.call("mmpde_bn_finalize", _ptr(sums), state.count, BN_EPS, BN_MOMENTUM, _ptr(state.mean_rstd),
+                   _ptr(rmean), _ptr(rvar), st)
+        if nbt is not None:
+            nbt += 1
+    else:
+        state.count = float(M)
+        state.mean_rstd = torch.cat((rmean, torch.rsqrt(rvar + BN_EPS)))
+    _cabi.call("mmpde_bn_apply", A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(gamma), _ptr(beta), int(relu), out, ldo, st)
+    return state
+
+
+def _bn_backward(g, ldg, out, ldo, relu, A, lda, B, ldb, M, state, gamma, gy, ldgy, st):
+    """returns this rank's (dgamma, dbeta); writes dL/dy into gy.  With several ranks the two column sums
+    are all-reduced for the normalisation term (sync-BN), while the parameter grads stay per-rank sums
+    (the gradient all-reduce adds them up afterwards)."""
+    local = torch.zeros(2 * H, dtype=torch.float64, device=gamma.device)
+    _cabi.call("mmpde_bn_bwd_reduce", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(local), st)
+    glob = local
+    if COMM.global_rows(M) != float(M):
+        glob = COMM.allreduce_(local.clone())
+    _cabi.call("mmpde_bn_bwd_apply", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(gamma),
+               _ptr(glob), state.count, gy, ldgy, 0, st)
+    return local[H:].to(torch.float32), local[:H].to(torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# the processor: encoder -> L message-passing layers -> Conv1d decoder, as ONE autograd node
+# ------------------------------------------------------------------------------------------------
+N_ENC = 8          # We1 be1 g1 bt1 We2 be2 g2 bt2
+N_LAYER = 10       # W1 b1 W2 b2 W3 b3 W4 b4 gamma beta
+
+
+def _layer_forward(Xl, node4, edges, lp, bnbuf, training, nxt, nxt_ld, st):
+    """One GNN_Layer_FS_2D (gnn_2d.py:53-69).  Xl [N,256]: cols 0..127 hold the layer input h, cols
+    128..255 must be ZERO on entry and receive the mean message.  Output BN(h + update) -> nxt (ld nxt_ld)."""
+    W1, b1, W2, b2, W3, b3, W4, b4, gam, bet = lp
+    N, E = node4.shape[0], edges.n_edges
+    f32 = dict(dtype=torch.float32, device=node4.device)
+    x, n4 = _ptr(Xl), _ptr(node4)
+    # P = h W1a^T + b1, Q = h W1b^T                              (split of message_net_1, gnn_2d.py:61)
+    PQ = torch.empty(N, 2 * H, **f32)
+    gemm(x, 2 * H, 1, _ptr(W1), 260, 1, _ptr(PQ), 2 * H, N, H, H, bias=_ptr(b1), st=st)
+    gemm(x, 2 * H, 1, _ptr(W1, H), 260, 1, _ptr(PQ, H), 2 * H, N, H, H, st=st)
+    w1c = W1[:, 2 * H:2 * H + 4].contiguous()
+    mask2 = torch.empty(max(E, 1), 4, dtype=torch.int32, device=node4.device)
+    _cabi.call("mmpde_edge_fwd", _ptr(PQ), n4, _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
+               _ptr(w1c), _ptr(W2), _ptr(b2), _ptr(Xl, H), 2 * H, _ptr(mask2), st)
+    # update_net_1/2 + residual                                 (gnn_2d.py:65-69)
+    w3v = W3[:, 2 * H].contiguous()
+    h3 = torch.empty(N, H, **f32)
+    gemm(x, 2 * H, 1, _ptr(W3), 257, 1, _ptr(h3), H, N, H, 2 * H, bias=_ptr(b3), r1_row=_ptr(node4, 3),
+         r1_stride=4, r1_col=_ptr(w3v), relu=1, st=st)
+    r4 = torch.empty(N, H, **f32)
+    gemm(_ptr(h3), H, 1, _ptr(W4), H, 1, _ptr(r4), H, N, H, H, bias=_ptr(b4), relu=1, st=st)
+    bn = _bn_forward(x, 2 * H, _ptr(r4), H, N, gam, bet, 0, nxt, nxt_ld, training, *bnbuf, st)
+    return (PQ, mask2, h3, r4, bn)
+
+
+def _layer_backward(Xl, node4, edges, lp, saved, g_h, g_node4, st):
+    """Backward of _layer_forward.  g_h [N,128] = dL/d(output).  Returns (dL/dh_in [N,128], 10 param grads);
+    adds the layer's dL/du into g_node4[:,0] when g_node4 is given."""
+    W1, b1, W2, b2, W3, b3, W4, b4, gam, bet = lp
+    PQ, mask2, h3, r4, bn = saved
+    N, E = node4.shape[0], edges.n_edges
+    f32 = dict(dtype=torch.float32, device=node4.device)
+    x, n4 = _ptr(Xl), _ptr(node4)
+    split = max(_split_for(N), 2)
+    # BatchNorm backward: y = h + r4
+    g_y = torch.empty(N, H, **f32)
+    dgam, dbet = _bn_backward(_ptr(g_h), H, None, 0, 0, x, 2 * H, _ptr(r4), H, N, bn, gam, _ptr(g_y), H, st)
+    # node MLP backward
+    g_z4 = torch.empty(N, H, **f32)
+    db4 = torch.zeros(H, **f32)
+    _cabi.call("mmpde_relu_bwd", _ptr(g_y), H, _ptr(r4), H, N, _ptr(g_z4), H, _ptr(db4), st)
+    dW4 = torch.zeros(H, H, **f32)
+    gemm(_ptr(g_z4), H, 0, _ptr(h3), H, 0, _ptr(dW4), H, H, H, N, split_k=split, st=st)
+    g_h3 = torch.empty(N, H, **f32)
+    gemm(_ptr(g_z4), H, 1, _ptr(W4), H, 0, _ptr(g_h3), H, N, H, H, st=st)
+    g_z3 = g_z4                                               # reuse
+    db3 = torch.zeros(H, **f32)
+    _cabi.call("mmpde_relu_bwd", _ptr(g_h3), H, _ptr(h3), H, N, _ptr(g_z3), H, _ptr(db3), st)
+    dW3 = torch.zeros(H, 2 * H + 1, **f32)
+    gemm(_ptr(g_z3), H, 0, x, 2 * H, 0, _ptr(dW3), 257, H, 2 * H, N, split_k=split, st=st)
+    gemm(_ptr(g_z3), H, 0, _ptr(node4, 3), 4, 0, _ptr(dW3, 2 * H), 257, H, 1, N, split_k=split, st=st)
+    g_X = torch.empty(N, 2 * H, **f32)
+    gemm(_ptr(g_z3), H, 1, _ptr(W3), 257, 0, _ptr(g_X), 2 * H, N, 2 * H, H, st=st)
+    # message passing backward
+    w1c = W1[:, 2 * H:2 * H + 4].contiguous()
+    dPQ = torch.zeros(N, 2 * H, **f32)
+    dW2 = torch.zeros(H, H, **f32)
+    db2 = torch.zeros(H, **f32)
+    dW1c = torch.zeros(H, 4, **f32)
+    _cabi.call("mmpde_edge_bwd", _ptr(PQ), n4, _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
+               _ptr(w1c), _ptr(W2), _ptr(mask2), _ptr(g_X, H), 2 * H, _ptr(dPQ), _ptr(dW2), _ptr(db2),
+               _ptr(dW1c), _ptr(g_node4), 4, st)
+    dW1 = torch.zeros(H, 260, **f32)
+    gemm(_ptr(dPQ), 2 * H, 0, x, 2 * H, 0, _ptr(dW1), 260, H, H, N, split_k=split, st=st)
+    gemm(_ptr(dPQ, H), 2 * H, 0, x, 2 * H, 0, _ptr(dW1, H), 260, H, H, N, split_k=split, st=st)
+    dW1[:, 2 * H:2 * H + 4] = dW1c
+    db1 = torch.zeros(H, **f32)
+    _cabi.call("mmpde_colsum", _ptr(dPQ), 2 * H, N, H, _ptr(db1), st)
+    # dL/dh_in = g_y (residual) + g_X[:, :128] (update_net_1) + dP W1a + dQ W1b
+    g_y.add_(g_X[:, :H])
+    gemm(_ptr(dPQ), 2 * H, 1, _ptr(W1), 260, 0, _ptr(g_y), H, N, H, H, acc=1, st=st)
+    gemm(_ptr(dPQ, H), 2 * H, 1, _ptr(W1, H), 260, 0, _ptr(g_y), H, N, H, H, acc=1, st=st)
+    return g_y, [dW1, db1, dW2, db2, dW3, db3, dW4, db4, dgam, dbet]
+
+
+class LayerFn(torch.autograd.Function):
+    """One stand-alone GNN_Layer_FS_2D.forward (gnn_2d.py:53-57): out[N,128] = BN(x + update(x, mean messages))."""
+
+    @staticmethod
+    def forward(ctx, x, node4, edges, training, bnbuf, *lp):
+        _chk(x, name="x"); _chk(node4, name="node4")
+        st = _stream()
+        N = x.shape[0]
+        Xl = torch.zeros(N, 2 * H, dtype=torch.float32, device=x.device)
+        Xl[:, :H] = x
+        out = torch.empty(N, H, dtype=torch.float32, device=x.device)
+        saved = _layer_forward(Xl, node4, edges, lp, bnbuf, training, _ptr(out), H, st)
+        ctx.stuff = (Xl, node4, edges, lp, saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        Xl, node4, edges, lp, saved = ctx.stuff
+        g_node4 = torch.zeros_like(node4) if ctx.needs_input_grad[1] else None
+        g_x, grads = _layer_backward(Xl, node4, edges, lp, saved, g_out.contiguous(), g_node4, _stream())
+        return (g_x, g_node4, None, None, None, *grads)
+
+
+class SolverFn(torch.autograd.Function):
+    """out[N,1] = MP_PDE_Solver_2D(node4, edges).  params = 8 encoder + 10 per layer + 1 flat decoder tensor.
+    bn_buffers = [(running_mean, running_var, num_batches_tracked)] * (2 + L), updated in place when training."""
+
+    @staticmethod
+    def forward(ctx, node4, edges, n_layers, training, scale, bn_buffers, *params):
+        _chk(node4, name="node4")
+        for i, p in enumerate(params):
+            _chk(p, name=f"param{i}")
+        st = _stream()
+        dev = node4.device
+        N, L = node4.shape[0], n_layers
+        f32 = dict(dtype=torch.float32, device=dev)
+        We1, be1, g1, bt1, We2, be2, g2, bt2 = params[:N_ENC]
+        dec = params[N_ENC + N_LAYER * L]
+        # ---- encoder: Linear(4,128) BN ReLU Linear(128,128) BN        (gnn_2d.py:99-106,130-131)
+        e1 = torch.empty(N, H, **f32)
+        gemm(_ptr(node4), 4, 1, _ptr(We1), 4, 1, _ptr(e1), H, N, H, 4, bias=_ptr(be1), st=st)
+        e1n = torch.empty(N, H, **f32)
+        bn1 = _bn_forward(_ptr(e1), H, None, 0, N, g1, bt1, 1, _ptr(e1n), H, training, *bn_buffers[0], st)
+        e2 = torch.empty(N, H, **f32)
+        gemm(_ptr(e1n), H, 1, _ptr(We2), H, 1, _ptr(e2), H, N, H, H, bias=_ptr(be2), st=st)
+        # X[l] = [h_l | agg_l]  ([N,256]); the last hidden state lives alone in hL
+        X = [torch.zeros(N, 2 * H, **f32) for _ in range(L)]
+        hL = torch.empty(N, H, **f32)
+        nxt = (_ptr(X[0]), 2 * H) if L > 0 else (_ptr(hL), H)
+        bn2 = _bn_forward(_ptr(e2), H, None, 0, N, g2, bt2, 0, nxt[0], nxt[1], training, *bn_buffers[1], st)
+        saved_layers = []
+        for l in range(L):
+            lp = params[N_ENC + N_LAYER * l: N_ENC + N_LAYER * (l + 1)]
+            nxt = (_ptr(X[l + 1]), 2 * H) if l + 1 < L else (_ptr(hL), H)
+            saved_layers.append(_layer_forward(X[l], node4, edges, lp, bn_buffers[2 + l], training, nxt[0], nxt[1], st))
+        out = torch.empty(N, **f32)
+        _cabi.call("mmpde_decoder_fwd", _ptr(hL), H, N, _ptr(dec), float(scale), _ptr(out), st)
+        ctx.node4, ctx.edges, ctx.L, ctx.scale = node4, edges, L, float(scale)
+        ctx.params = params
+        ctx.enc = (e1, e1n, e2, bn1, bn2)
+        ctx.X, ctx.hL, ctx.layers = X, hL, saved_layers
+        return out.view(N, 1)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        st = _stream()
+        node4, edges, L, params = ctx.node4, ctx.edges, ctx.L, ctx.params
+        N = node4.shape[0]
+        f32 = dict(dtype=torch.float32, device=node4.device)
+        split = max(_split_for(N), 2)
+        We1, be1, g1, bt1, We2, be2, g2, bt2 = params[:N_ENC]
+        dec = params[N_ENC + N_LAYER * L]
+        e1, e1n, e2, bn1, bn2 = ctx.enc
+        grads = [None] * len(params)
+        need_u = ctx.needs_input_grad[0]
+        g_node4 = torch.zeros(N, 4, **f32) if need_u else None
+
+        g_out = g_out.contiguous().view(-1)
+        g_h = torch.empty(N, H, **f32)
+        g_dec = torch.zeros(DEC_NPARAM, **f32)
+        _cabi.call("mmpde_decoder_bwd", _ptr(ctx.hL), H, N, _ptr(dec), ctx.scale, _ptr(g_out), _ptr(g_h), H, _ptr(g_dec), st)
+        grads[N_ENC + N_LAYER * L] = g_dec
+        for l in reversed(range(L)):
+            base = N_ENC + N_LAYER * l
+            g_h, lg = _layer_backward(ctx.X[l], node4, edges, params[base:base + N_LAYER], ctx.layers[l], g_h, g_node4, st)
+            grads[base:base + N_LAYER] = lg
+        # ---- encoder backward
+        g_e2 = torch.empty(N, H, **f32)
+        dg2, db2_ = _bn_backward(_ptr(g_h), H, None, 0, 0, _ptr(e2), H, None, 0, N, bn2, g2, _ptr(g_e2), H, st)
+        dWe2 = torch.zeros(H, H, **f32)
+        gemm(_ptr(g_e2), H, 0, _ptr(e1n), H, 0, _ptr(dWe2), H, H, H, N, split_k=split, st=st)
+        dbe2 = torch.zeros(H, **f32)
+        _cabi.call("mmpde_colsum", _ptr(g_e2), H, N, H, _ptr(dbe2), st)
+        g_e1n = torch.empty(N, H, **f32)
+        gemm(_ptr(g_e2), H, 1, _ptr(We2), H, 0, _ptr(g_e1n), H, N, H, H, st=st)
+        g_e1 = g_e2                                                   # reuse
+        dg1, db1_ = _bn_backward(_ptr(g_e1n), H, _ptr(e1n), H, 1, _ptr(e1), H, None, 0, N, bn1, g1, _ptr(g_e1), H, st)
+        dWe1 = torch.zeros(H, 4, **f32)
+        gemm(_ptr(g_e1), H, 0, _ptr(node4), 4, 0, _ptr(dWe1), 4, H, 4, N, split_k=split, st=st)
+        dbe1 = torch.zeros(H, **f32)
+        _cabi.call("mmpde_colsum", _ptr(g_e1), H, N, H, _ptr(dbe1), st)
+        if need_u:      # only the u column: positions/time feed the frozen mesh mover only
+            gemm(_ptr(g_e1), H, 1, _ptr(We1), 4, 0, _ptr(g_node4), 4, N, 1, H, acc=1, st=st)
+        grads[:N_ENC] = [dWe1, dbe1, dg1, db1_, dWe2, dbe2, dg2, db2_]
+        return (g_node4, None, None, None, None, None, *grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused interpolation
+# ------------------------------------------------------------------------------------------------
+class InterpolateFn(torch.autograd.Function):
+    """out[Q] = sum_k ItpNet(p_q)_k * src_val[idx[q,k]]   (data_creator_2d.py:77-83, interpolate.py:79-93).
+    Gradients: flat ItpNet parameters and src_val; coordinates are treated as constants (they only lead to
+    the frozen mesh mover)."""
+
+    @staticmethod
+    def forward(ctx, src_val, src_xy, qry_xy, idx, flat_params):
+        _chk(src_val, name="src_val"); _chk(src_xy, name="src_xy"); _chk(qry_xy, name="qry_xy")
+        _chk(idx, torch.int32, "idx"); _chk(flat_params, name="flat_params")
+        assert flat_params.numel() == ITP_NPARAM and idx.shape[1] == KN
+        Q = qry_xy.shape[0]
+        out = torch.empty(Q, dtype=torch.float32, device=src_val.device)
+        _cabi.call("mmpde_itp_fwd", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), Q, _ptr(flat_params),
+                   _ptr(out), _stream())
+        ctx.save_for_backward(src_val, src_xy, qry_xy, idx, flat_params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        src_val, src_xy, qry_xy, idx, flat_params = ctx.saved_tensors
+        g_out = g_out.contiguous()
+        g_params = torch.zeros_like(flat_params)
+        g_val = torch.zeros_like(src_val) if ctx.needs_input_grad[0] else None
+        _cabi.call("mmpde_itp_bwd", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), qry_xy.shape[0],
+                   _ptr(flat_params), _ptr(g_out), _ptr(g_params), _ptr(g_val), _stream())
+        return g_val, None, None, None, g_params

@@ -1,0 +1,107 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol that
+include/mmpde_b200.h declares, the ctypes table matches the header, host-side logic works on CPU
+tensors, and the product path fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "mmpde_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = re.findall(r"\bint\s+(mmpde_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    out = {}
+    for name, args in decls:
+        args = args.strip()
+        out[name] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def _ensure_built():
+    from mmpde_b200 import _cabi
+    if not os.path.exists(_cabi.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return _cabi
+
+
+def test_library_exports_every_declared_symbol():
+    _cabi = _ensure_built()
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    declared = _header_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in mmpde_b200.h but not exported"
+    assert lib.mmpde_abi_version() == 1
+
+
+def test_ctypes_table_matches_header():
+    _cabi = _ensure_built()
+    declared = _header_functions()
+    assert set(declared) == set(_cabi.SIGNATURES)
+    for name, n_args in declared.items():
+        assert len(_cabi.SIGNATURES[name]) == n_args, name
+
+
+def test_no_cpu_fallback():
+    from mmpde_b200 import ops, _cabi
+    from mmpde_b200.gnn_2d import GNN_Layer_FS_2D
+    layer = GNN_Layer_FS_2D(128, 128, 128, 1, 1)
+    x = torch.randn(10, 128)
+    s = torch.randn(10, 1)
+    ei = torch.stack((torch.arange(1, 10), torch.zeros(9, dtype=torch.long)))
+    with pytest.raises(_cabi.MMPDEError):
+        layer(x, s, s, s, s, ei, None)
+    with pytest.raises(_cabi.MMPDEError):
+        ops.knn_indices(torch.rand(5, 2), torch.tensor([0, 5], dtype=torch.int32), torch.rand(5, 2),
+                        torch.tensor([0, 5], dtype=torch.int32), 3, 0, True)
+
+
+def test_state_dict_keys_match_oracle():
+    from mmpde_b200.gnn_2d import MP_PDE_Solver_2D
+    from mmpde_b200.interpolate import ItpNet
+    from mmpde_b200.PDEs import burgers
+    from mmpde_b200.mesh.dmm_model import DMM
+    from oracle import processor, itp, pdes, dmm
+    a = MP_PDE_Solver_2D(burgers()).state_dict()
+    b = processor.MP_PDE_Solver_2D(pdes.burgers()).state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape for k in a)
+    assert repr(MP_PDE_Solver_2D(burgers(), hidden_layer=1)) == "GNN"
+    for args in ((12, 12), (77, None)):
+        a = ItpNet(*args, [128, 64], [128, 64], [1, 4, 16, 4, 1]).state_dict()
+        b = itp.ItpNet(*args, [128, 64], [128, 64], [1, 4, 16, 4, 1]).state_dict()
+        assert list(a.keys()) == list(b.keys()) and all(a[k].shape == b[k].shape for k in a)
+    kw = dict(s=12, mode="array", branch_layer=7, trunk_layer=[2, 32, 512], out_layer=[1024, 512, 1])
+    assert sorted(DMM(**kw).state_dict().keys()) == sorted(dmm.DMM(**kw).state_dict().keys())
+    assert burgers().dt == pdes.burgers().dt == 1.0
+
+
+def test_edge_list_from_edge_index_sorts_and_counts():
+    from mmpde_b200.ops import EdgeList
+    ei = torch.tensor([[1, 2, 0, 3, 0], [2, 0, 1, 0, 2]])
+    e = EdgeList.from_edge_index(ei, 5)
+    assert e.dst.tolist() == [0, 0, 1, 2, 2] and e.src.tolist() == [2, 3, 0, 1, 0]
+    assert torch.allclose(e.inv_deg, torch.tensor([0.5, 1.0, 0.5, 1.0, 1.0]))
+    assert e.src.dtype == torch.int32 and e.n_edges == 5
+    nbr = torch.tensor([[1, 2], [0, -1], [-1, -1]], dtype=torch.int32)
+    p = EdgeList.from_knn(nbr, has_pad=True)
+    assert p.src.tolist() == [1, 2, 0] and p.dst.tolist() == [0, 0, 1]
+    assert torch.allclose(p.inv_deg, torch.tensor([0.5, 1.0, 1.0]))
+    assert torch.equal(p.edge_index(), torch.tensor([[1, 2, 0], [0, 0, 1]]))
+
+
+def test_create_data_matches_oracle_slicing():
+    from mmpde_b200.data_creator_2d import GraphCreator_FS_2D
+    from mmpde_b200.PDEs import burgers
+    from oracle import creator, pdes
+    u = torch.randn(5, 31, 6, 6)
+    steps = [1, 7, 30, 12]                      # shorter than the batch: zip truncation (appendix C.5)
+    a = GraphCreator_FS_2D(burgers(), 35, "knn", 1, 31).create_data(u, steps)
+    b = creator.GraphCreator_FS_2D(pdes.burgers(), 35, "knn", 1, 31).create_data(u, steps)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[0].shape == (4, 1, 6, 6)

@@ -1,0 +1,299 @@
+"""Parity of each sm_100a kernel (through the C ABI) with the CPU oracle / plain-torch fp32 definitions.
+Integer outputs: bit-exact.  Floating point: relative L2, tolerance written at each assert
+(north-star bound is 1e-3 per step; the fp32 kernels are held far tighter)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import knn as oknn  # noqa: E402
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _rel(a, b, atol=1e-6):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    err = float((a - b).norm())
+    return 0.0 if err < atol else err / float(b.norm().clamp_min(1e-30))
+
+
+def _off(sizes, dev):
+    return torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32, device=dev)
+
+
+def _cloud(n, seed, jitter=0.3):
+    rng = np.random.default_rng(seed)
+    side = int(np.ceil(np.sqrt(n)))
+    g = np.stack(np.meshgrid(np.linspace(0, 1, side), np.linspace(0, 1, side), indexing="ij"), -1).reshape(-1, 2)[:n]
+    return (g + rng.uniform(-jitter, jitter, g.shape) / max(side - 1, 1)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------- k-NN
+@pytest.mark.parametrize("sizes,k", [([300, 300], 35), ([50, 411, 36, 7], 35), ([2304], 35), ([1], 35)])
+def test_knn_graph_rule_bit_exact(sizes, k):
+    from mmpde_b200 import ops
+    dev = _dev()
+    pts = np.concatenate([_cloud(s, 10 + i) for i, s in enumerate(sizes)])
+    batch = np.repeat(np.arange(len(sizes)), sizes)
+    ref, _ = oknn.knn_indices(pts, pts, k, batch, batch, exclude_self=True, rule="f32")
+    off = _off(sizes, dev)
+    t = torch.from_numpy(pts).to(dev)
+    got = ops.knn_indices(t, off, t, off, k, rule=0, exclude_self=True).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+def test_knn_lattice_ties_and_duplicates_bit_exact():
+    from mmpde_b200 import ops
+    dev = _dev()
+    g = np.linspace(0, 1, 48, dtype=np.float32)
+    lat = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)       # 92% of nodes tie at the k-th place
+    dup = np.zeros((40, 2), np.float32)
+    for pts in (lat, dup, np.concatenate([lat[:100], lat[:100]])):
+        ref, _ = oknn.knn_indices(pts, pts, 35, exclude_self=True, rule="f32")
+        t = torch.from_numpy(pts).to(dev)
+        off = _off([len(pts)], dev)
+        got = ops.knn_indices(t, off, t, off, 35, rule=0, exclude_self=True).cpu().numpy()
+        assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("P,Q", [(2304, 2304), (500, 1300), (31, 64)])
+def test_knn_interpolation_rule_bit_exact(P, Q):
+    from mmpde_b200 import ops
+    dev = _dev()
+    nu = 3
+    pts = np.concatenate([_cloud(P, 20 + s) for s in range(nu)])
+    qry = np.concatenate([_cloud(Q, 30 + s, jitter=0.0) for s in range(nu)])
+    pb, qb = np.repeat(np.arange(nu), P), np.repeat(np.arange(nu), Q)
+    ref, _ = oknn.knn_indices(pts, qry, 30, pb, qb, rule="f64")
+    got = ops.knn_indices(torch.from_numpy(pts).to(dev), _off([P] * nu, dev), torch.from_numpy(qry).to(dev),
+                          _off([Q] * nu, dev), 30, rule=1, exclude_self=False).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("n,rule,excl", [(20000, 0, True), (20000, 1, False), (300, 0, True)])
+def test_knn_grid_search_equals_brute_force(n, rule, excl):
+    from mmpde_b200 import ops
+    dev = _dev()
+    pts = _cloud(n, 40)
+    qry = pts if excl else _cloud(n, 41, jitter=0.0)
+    k = 35 if excl else 30
+    ref, _ = oknn.knn_indices(pts, qry, k, exclude_self=excl, rule="f32" if rule == 0 else "f64")
+    got = ops.knn_indices_grid(torch.from_numpy(pts).to(dev), torch.from_numpy(qry).to(dev), k, rule, excl).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+def test_radius_bit_exact():
+    from mmpde_b200 import ops
+    dev = _dev()
+    pts = np.concatenate([_cloud(200, 50), _cloud(333, 51)])
+    batch = np.repeat([0, 1], [200, 333])
+    ref = oknn.radius_graph(torch.from_numpy(pts), 0.21, torch.from_numpy(batch))
+    nbr = ops.radius_indices(torch.from_numpy(pts).to(dev), _off([200, 333], dev), 0.21, 32)
+    e = ops.EdgeList.from_knn(nbr, has_pad=True)
+    assert torch.equal(e.edge_index().cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,ak,bk", [(1000, 128, 128, 1, 1), (777, 256, 130, 1, 0), (128, 257, 3001, 0, 0),
+                                         (128, 4, 2500, 0, 0), (513, 128, 4, 1, 1), (300, 1, 128, 1, 0),
+                                         (129, 131, 77, 0, 1)])
+def test_gemm_all_layouts(M, N, K, ak, bk):
+    from mmpde_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((M, K) if ak else (K, M), generator=g)
+    B = torch.randn((N, K) if bk else (K, N), generator=g)
+    bias, r_row, r_col = torch.randn(N, generator=g), torch.randn(M, generator=g), torch.randn(N, generator=g)
+    ref = (A if ak else A.t()).double() @ (B.t() if bk else B).double()
+    Ad, Bd = A.to(dev), B.to(dev)
+    C = torch.empty(M, N, device=dev)
+    ops.gemm(ops._ptr(Ad), A.shape[1], ak, ops._ptr(Bd), B.shape[1], bk, ops._ptr(C), N, M, N, K)
+    assert _rel(C, ref) < 2e-6
+    # epilogue: bias + rank-1 + relu, then accumulate on top
+    bd, rr, rc = bias.to(dev), r_row.to(dev), r_col.to(dev)
+    ops.gemm(ops._ptr(Ad), A.shape[1], ak, ops._ptr(Bd), B.shape[1], bk, ops._ptr(C), N, M, N, K, bias=ops._ptr(bd),
+             r1_row=ops._ptr(rr), r1_stride=1, r1_col=ops._ptr(rc), relu=1)
+    full = torch.relu(ref + bias.double() + r_row.double()[:, None] * r_col.double()[None])
+    assert _rel(C, full) < 2e-6
+    ops.gemm(ops._ptr(Ad), A.shape[1], ak, ops._ptr(Bd), B.shape[1], bk, ops._ptr(C), N, M, N, K, acc=1)
+    assert _rel(C, full + ref) < 2e-6
+    # split-K adds atomically onto C
+    C.zero_()
+    ops.gemm(ops._ptr(Ad), A.shape[1], ak, ops._ptr(Bd), B.shape[1], bk, ops._ptr(C), N, M, N, K, split_k=5)
+    assert _rel(C, ref) < 5e-6
+
+
+# ------------------------------------------------------------------------------------------- BN / elementwise
+def test_batchnorm_forward_backward_and_running_stats():
+    from mmpde_b200 import ops
+    dev = _dev()
+    torch.manual_seed(0)
+    M = 3001
+    A, B = torch.randn(M, 256) * 2 + 1, torch.randn(M, 128)
+    bn = torch.nn.BatchNorm1d(128)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-1, 1)
+    y = (A[:, :128] + B).clone().requires_grad_(True)
+    ref = torch.relu(bn(y))
+    g = torch.randn(M, 128)
+    ref.backward(g)
+    Ad, Bd = A.to(dev), B.to(dev)
+    gam, bet = bn.weight.detach().to(dev), bn.bias.detach().to(dev)
+    rm, rv = torch.zeros(128, device=dev), torch.ones(128, device=dev)
+    nbt = torch.zeros((), dtype=torch.long, device=dev)
+    out = torch.empty(M, 128, device=dev)
+    st = ops._stream()
+    state = ops._bn_forward(ops._ptr(Ad), 256, ops._ptr(Bd), 128, M, gam, bet, 1, ops._ptr(out), 128, True, rm, rv, nbt, st)
+    assert _rel(out, ref) < 2e-6
+    assert _rel(rm, bn.running_mean) < 1e-6 and _rel(rv, bn.running_var) < 1e-6 and int(nbt) == 1
+    gy = torch.empty(M, 128, device=dev)
+    gd = g.to(dev)
+    dgam, dbet = ops._bn_backward(ops._ptr(gd), 128, ops._ptr(out), 128, 1, ops._ptr(Ad), 256, ops._ptr(Bd), 128, M, state,
+                                  gam, ops._ptr(gy), 128, st)
+    assert _rel(gy, y.grad) < 1e-5 and _rel(dgam, bn.weight.grad) < 1e-5 and _rel(dbet, bn.bias.grad) < 1e-5
+    # eval mode = affine with running statistics
+    bn.eval()
+    state = ops._bn_forward(ops._ptr(Ad), 256, ops._ptr(Bd), 128, M, gam, bet, 0, ops._ptr(out), 128, False, rm, rv, nbt, st)
+    assert _rel(out, bn(y.detach())) < 2e-6
+
+
+def test_relu_bwd_and_colsum():
+    from mmpde_b200 import ops, _cabi
+    dev = _dev()
+    torch.manual_seed(1)
+    M = 2000
+    g, act = torch.randn(M, 128), torch.randn(M, 128)
+    gd, ad = g.to(dev), act.to(dev)
+    out, cs = torch.empty(M, 128, device=dev), torch.zeros(128, device=dev)
+    _cabi.call("mmpde_relu_bwd", ops._ptr(gd), 128, ops._ptr(ad), 128, M, ops._ptr(out), 128, ops._ptr(cs), ops._stream())
+    ref = g * (act > 0)
+    assert torch.equal(out.cpu(), ref) and _rel(cs, ref.sum(0)) < 1e-5
+    cs2 = torch.zeros(200, device=dev)
+    wide = torch.randn(M, 256).to(dev)
+    _cabi.call("mmpde_colsum", ops._ptr(wide, 28), 256, M, 200, ops._ptr(cs2), ops._stream())
+    assert _rel(cs2, wide[:, 28:228].sum(0)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------- decoder
+def test_decoder_forward_backward():
+    from mmpde_b200 import ops, _cabi
+    dev = _dev()
+    torch.manual_seed(2)
+    dec = torch.nn.Sequential(torch.nn.Conv1d(1, 4, 16, stride=3), torch.nn.ReLU(), torch.nn.Conv1d(4, 8, 12, stride=3),
+                              torch.nn.ReLU(), torch.nn.Conv1d(8, 1, 8, stride=2))
+    M = 777
+    h = torch.randn(M, 128, requires_grad=True)
+    ref = 0.1 * dec(h[:, None]).squeeze(1)
+    g = torch.randn(M, 1)
+    ref.backward(g)
+    flat = torch.cat([p.detach().reshape(-1) for p in dec.parameters()]).to(dev)
+    hd = h.detach().to(dev)
+    out = torch.empty(M, device=dev)
+    _cabi.call("mmpde_decoder_fwd", ops._ptr(hd), 128, M, ops._ptr(flat), 0.1, ops._ptr(out), ops._stream())
+    assert _rel(out, ref.view(-1)) < 2e-6
+    gh, gp = torch.empty(M, 128, device=dev), torch.zeros(525, device=dev)
+    gd = g.view(-1).to(dev)
+    _cabi.call("mmpde_decoder_bwd", ops._ptr(hd), 128, M, ops._ptr(flat), 0.1, ops._ptr(gd), ops._ptr(gh), 128, ops._ptr(gp),
+               ops._stream())
+    assert _rel(gh, h.grad) < 1e-5
+    assert _rel(gp, torch.cat([p.grad.reshape(-1) for p in dec.parameters()])) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------- edge kernels
+def _layer_case(sizes, seed, k=35):
+    pts = np.concatenate([_cloud(s, seed + i) for i, s in enumerate(sizes)])
+    batch = torch.from_numpy(np.repeat(np.arange(len(sizes)), sizes))
+    ei = oknn.knn_graph(torch.from_numpy(pts), k, batch)
+    N = len(pts)
+    g = torch.Generator().manual_seed(seed)
+    return dict(N=N, pos=torch.from_numpy(pts), ei=ei, x=torch.randn(N, 128, generator=g), u=torch.randn(N, 1, generator=g),
+                var=torch.rand(len(sizes), 1, generator=g)[batch], r=torch.randn(N, 128, generator=g))
+
+
+@pytest.mark.parametrize("sizes", [[90, 90], [37, 200, 64], [20, 5]])
+def test_layer_matches_oracle(sizes):
+    """GNN_Layer_FS_2D.forward + backward (edge kernels, node GEMMs, BN) vs the oracle layer, incl. ragged
+    samples, samples smaller than k+1 (variable degree) and tiles that cut through target segments."""
+    from mmpde_b200.gnn_2d import GNN_Layer_FS_2D
+    from oracle import processor
+    from tests.golden.common import fill_params
+    dev = _dev()
+    c = _layer_case(sizes, 7)
+    ref_layer = fill_params(processor.GNN_Layer_FS_2D(128, 128, 128, 1, 1), 5)
+    layer = GNN_Layer_FS_2D(128, 128, 128, 1, 1)
+    layer.load_state_dict(ref_layer.state_dict())
+    layer = layer.to(dev)
+    x0 = c["x"].clone().requires_grad_(True); u0 = c["u"].clone().requires_grad_(True)
+    ref = ref_layer(x0, u0, c["pos"][:, 0:1], c["pos"][:, 1:2], c["var"], c["ei"])
+    (ref * c["r"]).sum().backward()
+    x1 = c["x"].to(dev).requires_grad_(True); u1 = c["u"].to(dev).requires_grad_(True)
+    pos = c["pos"].to(dev)
+    out = layer(x1, u1, pos[:, 0:1], pos[:, 1:2], c["var"].to(dev), c["ei"].to(dev), None)
+    (out * c["r"].to(dev)).sum().backward()
+    assert _rel(out, ref) < 1e-5
+    assert _rel(x1.grad, x0.grad) < 1e-4 and _rel(u1.grad, u0.grad) < 1e-4
+    ref_named = dict(ref_layer.named_parameters())
+    for name, p in layer.named_parameters():
+        assert _rel(p.grad, ref_named[name].grad) < 1e-4, name
+    for name, b in layer.named_buffers():
+        assert _rel(b.float(), dict(ref_layer.named_buffers())[name].float()) < 1e-5, name
+
+
+def test_layer_golden_fixture(golden_dir):
+    """The layer against the fixture produced by the reference's own gnn_2d.py."""
+    import os
+    from mmpde_b200.gnn_2d import GNN_Layer_FS_2D
+    from tests.golden.common import fill_params
+    dev = _dev()
+    g = torch.load(os.path.join(golden_dir, "g1_layer.pt"), weights_only=False)
+    layer = fill_params(GNN_Layer_FS_2D(128, 128, 128, 1, 1), g["seed"]).to(dev)
+    x = g["x"].to(dev).requires_grad_(True); u = g["u"].to(dev).requires_grad_(True)
+    pos = g["pos"].to(dev)
+    out = layer(x, u, pos[:, 0:1], pos[:, 1:2], g["var"].to(dev), g["edge_index"].to(dev), None)
+    (out * g["r"].to(dev)).sum().backward()
+    assert _rel(out, g["out"]) < 1e-5                 # tolerance: fp32 reassociation only
+    assert _rel(x.grad, g["gx"]) < 1e-4 and _rel(u.grad, g["gu"]) < 1e-4
+    for name, p in layer.named_parameters():
+        assert _rel(p.grad, g["gparams"][name]) < 1e-4, name
+    for k, v in g["bn_after"].items():
+        assert _rel(layer.state_dict()[k].float(), v.float()) < 1e-5, k
+
+
+# ------------------------------------------------------------------------------------------- interpolation
+@pytest.mark.parametrize("nu,P,Q", [(2, 400, 400), (3, 150, 333), (1, 64, 7)])
+def test_fused_interpolation_matches_oracle(nu, P, Q):
+    from mmpde_b200 import ops
+    from mmpde_b200.interpolate import ItpNet
+    from oracle import itp as oitp
+    from tests.golden.common import fill_params
+    dev = _dev()
+    ref_net = fill_params(oitp.ItpNet(12, 12, [128, 64], [128, 64], [1, 4, 16, 4, 1]), 9)
+    net = ItpNet(12, 12, [128, 64], [128, 64], [1, 4, 16, 4, 1])
+    net.load_state_dict(ref_net.state_dict())
+    net = net.to(dev)
+    pts = np.concatenate([_cloud(P, 60 + s) for s in range(nu)])
+    qry = np.concatenate([_cloud(Q, 70 + s, jitter=0.0) for s in range(nu)])
+    idx, _ = oknn.knn_indices(pts, qry, 30, np.repeat(np.arange(nu), P), np.repeat(np.arange(nu), Q), rule="f64")
+    idx_t = torch.from_numpy(idx)
+    pts_t, qry_t = torch.from_numpy(pts), torch.from_numpy(qry)
+    for mode in ("1", "2"):
+        vals = torch.randn(nu * P, requires_grad=True)
+        nb = pts_t[idx_t].reshape(nu, Q, 30, 2)
+        w = ref_net(nb, qry_t.reshape(nu, Q, 1, 2), mode)
+        ref = (w * vals[idx_t].reshape(nu, Q, 30)).sum(-1).reshape(-1)
+        r = torch.randn(nu * Q)
+        ref_net.zero_grad()
+        (ref * r).sum().backward()
+        vd = vals.detach().to(dev).requires_grad_(True)
+        net.zero_grad()
+        out = ops.InterpolateFn.apply(vd, pts_t.to(dev), qry_t.to(dev), idx_t.to(torch.int32).to(dev), net.flat_params(mode))
+        (out * r.to(dev)).sum().backward()
+        assert _rel(out, ref) < 1e-5
+        assert _rel(vd.grad, vals.grad) < 1e-4
+        stack = "layers" if mode == "1" else "layers2"
+        for (n1, p1), (n2, p2) in zip(getattr(net, stack).named_parameters(), getattr(ref_net, stack).named_parameters()):
+            assert n1 == n2 and _rel(p1.grad, p2.grad) < 1e-4, (mode, n1)

@@ -10,7 +10,7 @@ constexpr int DEC_NP = 525;
 constexpr int OFF_W1 = 0, OFF_B1 = 64, OFF_W2 = 68, OFF_B2 = 452, OFF_W3 = 460, OFF_B3 = 524;
 constexpr int WARPS = 8;
 
-struct DecScratch {
+struct __align__(16) DecScratch {
     float h[128];
     float a1[4 * 38];   // post-ReLU
     float a2[8 * 9];    // post-ReLU
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(WARPS * 32) decoder_fwd_kernel(const float* __
                                                                  const float* __restrict__ params, float scale,
                                                                  float* __restrict__ out) {
     __shared__ float sp[DEC_NP];
-    __shared__ DecScratch scr[WARPS];
+    __shared__ __align__(16) DecScratch scr[WARPS];
     for (int i = threadIdx.x; i < DEC_NP; i += blockDim.x) sp[i] = __ldg(params + i);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(WARPS * 32) decoder_bwd_kernel(const float* __
                                                                  const float* __restrict__ g_out, float* __restrict__ g_h,
                                                                  int64_t ldg, float* __restrict__ g_params) {
     __shared__ float sp[DEC_NP];
-    __shared__ DecScratch scr[WARPS];
+    __shared__ __align__(16) DecScratch scr[WARPS];
     for (int i = threadIdx.x; i < DEC_NP; i += blockDim.x) sp[i] = __ldg(params + i);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -295,7 +295,7 @@ constexpr size_t EDGE_BWD_SMEM = sizeof(float) * (2 * ET * ELD + 128 * 128) + si
 
 using namespace mmpde;
 
-extern "C" int mmpde_edge_fwd(const float* PQ, const float* node4, const int32_t* edge_src, const int32_t* edge_dst,
+extern "C" int mmpde_edge_fwd_simt(const float* PQ, const float* node4, const int32_t* edge_src, const int32_t* edge_dst,
                               const float* inv_deg, int64_t n_edges, const float* w1c, const float* w2, const float* b2,
                               float* agg, int64_t ld_agg, uint32_t* mask2, void* stream) {
     if (n_edges < 0 || ld_agg < 128) return MMPDE_EINVAL;
@@ -318,7 +318,7 @@ extern "C" int mmpde_edge_fwd(const float* PQ, const float* node4, const int32_t
     return MMPDE_OK;
 }
 
-extern "C" int mmpde_edge_bwd(const float* PQ, const float* node4, const int32_t* edge_src, const int32_t* edge_dst,
+extern "C" int mmpde_edge_bwd_simt(const float* PQ, const float* node4, const int32_t* edge_src, const int32_t* edge_dst,
                               const float* inv_deg, int64_t n_edges, const float* w1c, const float* w2,
                               const uint32_t* mask2, const float* g_agg, int64_t ld_gagg, float* dPQ, float* dW2,
                               float* db2, float* dW1c, float* g_u, int64_t g_u_stride, void* stream) {

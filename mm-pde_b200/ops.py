@@ -14,6 +14,7 @@ H = 128
 KN = 30
 ITP_NPARAM = 18270
 DEC_NPARAM = 525
+W2_IMG_BYTES = 65536
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -214,8 +215,10 @@ def _layer_forward(Xl, node4, edges, lp, bnbuf, training, nxt, nxt_ld, st):
     gemm(x, 2 * H, 1, _ptr(W1, H), 260, 1, _ptr(PQ, H), 2 * H, N, H, H, st=st)
     w1c = W1[:, 2 * H:2 * H + 4].contiguous()
     mask2 = torch.empty(max(E, 1), 4, dtype=torch.int32, device=node4.device)
+    w2_img = torch.empty(W2_IMG_BYTES, dtype=torch.uint8, device=node4.device)     # split-bf16 operand image of W2
+    _cabi.call("mmpde_pack_w128", _ptr(W2), _ptr(w2_img), st)
     _cabi.call("mmpde_edge_fwd", _ptr(PQ), n4, _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
-               _ptr(w1c), _ptr(W2), _ptr(b2), _ptr(Xl, H), 2 * H, _ptr(mask2), st)
+               _ptr(w1c), _ptr(w2_img), _ptr(b2), _ptr(Xl, H), 2 * H, _ptr(mask2), st)
     # update_net_1/2 + residual                                 (gnn_2d.py:65-69)
     w3v = W3[:, 2 * H].contiguous()
     h3 = torch.empty(N, H, **f32)
@@ -224,14 +227,14 @@ def _layer_forward(Xl, node4, edges, lp, bnbuf, training, nxt, nxt_ld, st):
     r4 = torch.empty(N, H, **f32)
     gemm(_ptr(h3), H, 1, _ptr(W4), H, 1, _ptr(r4), H, N, H, H, bias=_ptr(b4), relu=1, st=st)
     bn = _bn_forward(x, 2 * H, _ptr(r4), H, N, gam, bet, 0, nxt, nxt_ld, training, *bnbuf, st)
-    return (PQ, mask2, h3, r4, bn)
+    return (PQ, mask2, h3, r4, bn, w2_img)
 
 
 def _layer_backward(Xl, node4, edges, lp, saved, g_h, g_node4, st):
     """Backward of _layer_forward.  g_h [N,128] = dL/d(output).  Returns (dL/dh_in [N,128], 10 param grads);
     adds the layer's dL/du into g_node4[:,0] when g_node4 is given."""
     W1, b1, W2, b2, W3, b3, W4, b4, gam, bet = lp
-    PQ, mask2, h3, r4, bn = saved
+    PQ, mask2, h3, r4, bn, w2_img = saved
     N, E = node4.shape[0], edges.n_edges
     f32 = dict(dtype=torch.float32, device=node4.device)
     x, n4 = _ptr(Xl), _ptr(node4)
@@ -262,7 +265,7 @@ def _layer_backward(Xl, node4, edges, lp, saved, g_h, g_node4, st):
     db2 = torch.zeros(H, **f32)
     dW1c = torch.zeros(H, 4, **f32)
     _cabi.call("mmpde_edge_bwd", _ptr(PQ), n4, _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
-               _ptr(w1c), _ptr(W2), _ptr(mask2), _ptr(g_X, H), 2 * H, _ptr(dPQ), _ptr(dW2), _ptr(db2),
+               _ptr(w1c), _ptr(w2_img), _ptr(mask2), _ptr(g_X, H), 2 * H, _ptr(dPQ), _ptr(dW2), _ptr(db2),
                _ptr(dW1c), _ptr(g_node4), 4, st)
     dW1 = torch.zeros(H, 260, **f32)
     gemm(_ptr(dPQ), 2 * H, 0, x, 2 * H, 0, _ptr(dW1), 260, H, H, N, split_k=split, st=st)

@@ -298,3 +298,58 @@ def test_fused_interpolation_matches_oracle(nu, P, Q):
         stack = "layers" if mode == "1" else "layers2"
         for (n1, p1), (n2, p2) in zip(getattr(net, stack).named_parameters(), getattr(ref_net, stack).named_parameters()):
             assert n1 == n2 and _rel(p1.grad, p2.grad) < 1e-4, (mode, n1)
+
+
+# ------------------------------------------------------------------------------------------- tcgen05 edge kernels
+def _edge_inputs(sizes, seed, dev, k=35):
+    c = _layer_case(sizes, seed, k)
+    g = torch.Generator().manual_seed(seed + 1)
+    N = c["N"]
+    from mmpde_b200 import ops
+    edges = ops.EdgeList.from_edge_index(c["ei"].to(dev), N)
+    PQ = torch.randn(N, 256, generator=g).to(dev)
+    node4 = torch.cat((c["u"], c["pos"], c["var"]), 1).contiguous().to(dev)
+    w1c = (torch.randn(128, 4, generator=g) * 0.3).to(dev)
+    w2 = (torch.randn(128, 128, generator=g) / 11.0).to(dev)
+    b2 = (torch.randn(128, generator=g) * 0.1).to(dev)
+    g_agg = torch.randn(N, 128, generator=g).to(dev)
+    return N, edges, PQ, node4, w1c, w2, b2, g_agg
+
+
+@pytest.mark.parametrize("sizes", [[90, 90], [37, 200, 64], [300], [20, 5]])
+def test_edge_tensor_core_kernels_match_fp32_kernels(sizes):
+    """tcgen05 split-bf16 edge forward / backward against the fp32 CUDA-core kernels on identical inputs.
+    Tolerance 2e-5 relative L2 (three bf16 products leave ~2^-16 relative error per term)."""
+    from mmpde_b200 import ops, _cabi
+    dev = _dev()
+    N, edges, PQ, node4, w1c, w2, b2, g_agg = _edge_inputs(sizes, 3, dev)
+    E = edges.n_edges
+    st = ops._stream()
+    img = torch.empty(65536, dtype=torch.uint8, device=dev)
+    _cabi.call("mmpde_pack_w128", ops._ptr(w2), ops._ptr(img), st)
+    agg_s, agg_t = torch.zeros(N, 256, device=dev), torch.zeros(N, 256, device=dev)
+    m_s = torch.zeros(E, 4, dtype=torch.int32, device=dev)
+    m_t = torch.zeros(E, 4, dtype=torch.int32, device=dev)
+    common = (ops._ptr(PQ), ops._ptr(node4), ops._ptr(edges.src), ops._ptr(edges.dst), ops._ptr(edges.inv_deg), E, ops._ptr(w1c))
+    _cabi.call("mmpde_edge_fwd_simt", *common, ops._ptr(w2), ops._ptr(b2), ops._ptr(agg_s, 128), 256, ops._ptr(m_s), st)
+    _cabi.call("mmpde_edge_fwd", *common, ops._ptr(img), ops._ptr(b2), ops._ptr(agg_t, 128), 256, ops._ptr(m_t), st)
+    torch.cuda.synchronize()
+    assert float(agg_t[:, :128].abs().max()) == 0.0
+    assert _rel(agg_t[:, 128:], agg_s[:, 128:]) < 2e-5
+    diff_bits = (m_s ^ m_t)
+    flipped = sum(bin(int(v) & 0xFFFFFFFF).count("1") for v in diff_bits.flatten().tolist())
+    assert flipped <= max(2, E * 128 // 200000), flipped          # only z2 values within rounding of 0 may flip
+
+    def bwd(name, w2arg, mask):
+        outs = [torch.zeros(N, 256, device=dev), torch.zeros(128, 128, device=dev), torch.zeros(128, device=dev),
+                torch.zeros(128, 4, device=dev), torch.zeros(N, 4, device=dev)]
+        _cabi.call(name, *common, w2arg, ops._ptr(mask), ops._ptr(g_agg), 128, ops._ptr(outs[0]), ops._ptr(outs[1]),
+                   ops._ptr(outs[2]), ops._ptr(outs[3]), ops._ptr(outs[4]), 4, st)
+        torch.cuda.synchronize()
+        return outs
+    ref = bwd("mmpde_edge_bwd_simt", ops._ptr(w2), m_s)
+    got = bwd("mmpde_edge_bwd", ops._ptr(img), m_s)
+    names = ["dPQ", "dW2", "db2", "dW1c", "g_u"]
+    for n_, a, b in zip(names, got, ref):
+        tol = 1e-3 if n_ == "g_u" else 3e-5
+        assert _rel(a, b) < tol, (n_, _rel(a, b))

@@ -46,14 +46,17 @@ int mmpde_knn(const float* pts, const int32_t* pts_off, const float* qry, const 
               int n_samples, int64_t n_queries, int k, int rule, int exclude_self,
               int32_t* out_idx, void* stream);
 
-/* Same contract for one large sample (P up to 2^31): uniform-cell binned exact search.
- * cell_start [gx*gy+1] int32 and order [P] int32 (points sorted by cell, original index) are built
- * by mmpde_knn_grid_build into caller workspace. */
-int mmpde_knn_grid_build(const float* pts, int64_t n_pts, float x0, float y0, float inv_cell,
-                         int gx, int gy, int32_t* cell_of_pt, int32_t* cell_start, int32_t* cursor,
-                         int32_t* order, void* stream);
-int mmpde_knn_grid(const float* pts, int64_t n_pts, const float* qry, int64_t n_queries,
-                   float x0, float y0, float inv_cell, int gx, int gy,
+/* Same contract and bit-identical results through a uniform-cell binned exact search (the path used for
+ * samples of more than a few hundred points; brute force costs O(P) per query, this O(k)).
+ * All samples share one cell grid gx x gy over the box starting at (x0,y0) with cell size 1/inv_cell; points
+ * outside the box are clamped into border cells (still exact).  cell_start [S*gx*gy+1], cursor [S*gx*gy],
+ * cell_of_pt [P] and order [P] (points sorted by (sample, cell), original index) are caller workspace filled
+ * by mmpde_knn_grid_build. */
+int mmpde_knn_grid_build(const float* pts, const int32_t* pts_off, int n_samples, int64_t n_pts,
+                         float x0, float y0, float inv_cell, int gx, int gy,
+                         int32_t* cell_of_pt, int32_t* cell_start, int32_t* cursor, int32_t* order, void* stream);
+int mmpde_knn_grid(const float* pts, const int32_t* pts_off, const float* qry, const int32_t* qry_off,
+                   int n_samples, int64_t n_queries, float x0, float y0, float inv_cell, int gx, int gy,
                    const int32_t* cell_start, const int32_t* order,
                    int k, int rule, int exclude_self, int32_t* out_idx, void* stream);
 

@@ -18,8 +18,8 @@ SIGNATURES = {
     "mmpde_abi_version": [],
     "mmpde_device_info": [_p, _p, _p],
     "mmpde_knn": [_p, _p, _p, _p, _i, _l, _i, _i, _i, _p, _p],
-    "mmpde_knn_grid_build": [_p, _l, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p],
-    "mmpde_knn_grid": [_p, _l, _p, _l, _f, _f, _f, _i, _i, _p, _p, _i, _i, _i, _p, _p],
+    "mmpde_knn_grid_build": [_p, _p, _i, _l, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p],
+    "mmpde_knn_grid": [_p, _p, _p, _p, _i, _l, _f, _f, _f, _i, _i, _p, _p, _i, _i, _i, _p, _p],
     "mmpde_radius": [_p, _p, _i, _l, _f, _i, _p, _p],
     "mmpde_gemm": [_p, _l, _i, _p, _l, _i, _p, _l, _l, _i, _l, _p, _p, _l, _p, _i, _i, _i, _p],
     "mmpde_pack_w128": [_p, _p, _p],

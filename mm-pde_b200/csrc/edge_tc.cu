@@ -49,37 +49,63 @@ struct FwdSmem {
     static constexpr uint32_t TOTAL = BAR + 64;
 };
 
-// h1 rows of one tile -> split-bf16 operand tile `hbase` (hi at +0, lo at +TILE_BYTES); warp w builds rows 16w..16w+15
-__device__ __forceinline__ void build_h1_tile(const EdgeTcArgs& p, int64_t e0, int rows, unsigned char* hbase, int* sDst,
+// Edge indices of the 16 rows a warp builds: lane r (< 16) holds row 16*warp + r.  Loaded one tile AHEAD so the
+// index -> row-gather dependency never sits on the critical path.
+struct RowIdx { int d, s; };
+__device__ __forceinline__ RowIdx load_row_idx(const int* __restrict__ dst, const int* __restrict__ src, int64_t e0,
+                                               int64_t n_edges) {
+    RowIdx r; r.d = -1; r.s = -1;
+    const int lane = threadIdx.x & 31;
+    const int64_t e = e0 + (threadIdx.x >> 5) * 16 + (lane & 15);
+    if (lane < 16 && e0 >= 0 && e < n_edges) { r.d = __ldg(dst + e); r.s = __ldg(src + e); }
+    return r;
+}
+
+__device__ __forceinline__ float4 h1_row(const float4& P, const float4& Q, const float4& ni, const float4& nj,
+                                         const float (&w1c)[4][4], float4& e) {
+    e = make_float4(ni.x - nj.x, ni.y - nj.y, ni.z - nj.z, ni.w);     // (u_i-u_j, px_i-px_j, py_i-py_j, v_i)
+    float z[4] = {P.x + Q.x, P.y + Q.y, P.z + Q.z, P.w + Q.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        z[c] = fmaf(w1c[c][0], e.x, z[c]);
+        z[c] = fmaf(w1c[c][1], e.y, z[c]);
+        z[c] = fmaf(w1c[c][2], e.z, z[c]);
+        z[c] = fmaf(w1c[c][3], e.w, z[c]);
+    }
+    return make_float4(fmaxf(z[0], 0.f), fmaxf(z[1], 0.f), fmaxf(z[2], 0.f), fmaxf(z[3], 0.f));
+}
+
+// h1 rows of one tile -> split-bf16 operand tile `hbase` (hi at +0, lo at +TILE_BYTES); warp w builds rows 16w..16w+15,
+// 8 rows (16 independent 512-byte row gathers) in flight at a time.
+__device__ __forceinline__ void build_h1_tile(const EdgeTcArgs& p, RowIdx idx, unsigned char* hbase, int* sDst,
                                               const float (&w1c)[4][4]) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll 4
-    for (int r = warp * 16; r < warp * 16 + 16; ++r) {
-        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-        int i = -1;
-        if (r < rows) {
-            i = __ldg(p.dst + e0 + r);
-            int j = __ldg(p.src + e0 + r);
-            float4 ni = __ldg(p.node4 + i), nj = __ldg(p.node4 + j);
-            float4 e = make_float4(ni.x - nj.x, ni.y - nj.y, ni.z - nj.z, ni.w);
-            float4 P = ldg4(p.PQ + (int64_t)i * 256 + lane * 4);
-            float4 Q = ldg4(p.PQ + (int64_t)j * 256 + 128 + lane * 4);
-            float z[4] = {P.x + Q.x, P.y + Q.y, P.z + Q.z, P.w + Q.w};
+    if (lane < 16) sDst[warp * 16 + lane] = idx.d;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                z[c] = fmaf(w1c[c][0], e.x, z[c]);
-                z[c] = fmaf(w1c[c][1], e.y, z[c]);
-                z[c] = fmaf(w1c[c][2], e.z, z[c]);
-                z[c] = fmaf(w1c[c][3], e.w, z[c]);
+    for (int b = 0; b < 2; ++b) {
+        float4 P[8], Q[8], ni[8], nj[8];
+        int di[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            di[k] = __shfl_sync(0xffffffffu, idx.d, b * 8 + k);
+            int j = __shfl_sync(0xffffffffu, idx.s, b * 8 + k);
+            if (di[k] >= 0) {
+                P[k] = ldg4(p.PQ + (int64_t)di[k] * 256 + lane * 4);
+                Q[k] = ldg4(p.PQ + (int64_t)j * 256 + 128 + lane * 4);
+                ni[k] = __ldg(p.node4 + di[k]);
+                nj[k] = __ldg(p.node4 + j);
             }
-            h = make_float4(fmaxf(z[0], 0.f), fmaxf(z[1], 0.f), fmaxf(z[2], 0.f), fmaxf(z[3], 0.f));
         }
-        if (lane == 0) sDst[r] = i;
-        uint2 hi, lo;
-        split4(h, hi, lo);
-        uint32_t off = tile_off(r, lane * 4);
-        *reinterpret_cast<uint2*>(hbase + off) = hi;
-        *reinterpret_cast<uint2*>(hbase + TILE_BYTES + off) = lo;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f), e;
+            if (di[k] >= 0) h = h1_row(P[k], Q[k], ni[k], nj[k], w1c, e);
+            uint2 hi, lo;
+            split4(h, hi, lo);
+            uint32_t off = tile_off(warp * 16 + b * 8 + k, lane * 4);
+            *reinterpret_cast<uint2*>(hbase + off) = hi;
+            *reinterpret_cast<uint2*>(hbase + TILE_BYTES + off) = lo;
+        }
     }
 }
 
@@ -170,11 +196,14 @@ __global__ void __launch_bounds__(256, 1) edge_fwd_tc_kernel(EdgeTcArgs p) {
         tc_fence_before();
     };
 
+    RowIdx idx = load_row_idx(p.dst, p.src, (int64_t)blockIdx.x < n_tiles ? (int64_t)blockIdx.x * TE : -1, p.n_edges);
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
         const int buf = it & 1;
         const int64_t e0 = t * TE;
         const int rows = (int)((p.n_edges - e0 < TE) ? (p.n_edges - e0) : TE);
-        build_h1_tile(p, e0, rows, sm + FwdSmem::H0 + buf * W2_IMG_BYTES, sDst + (it % 3) * TE, w1c);
+        const RowIdx nxt = load_row_idx(p.dst, p.src, (t + gridDim.x < n_tiles) ? (t + gridDim.x) * TE : -1, p.n_edges);
+        build_h1_tile(p, idx, sm + FwdSmem::H0 + buf * W2_IMG_BYTES, sDst + (it % 3) * TE, w1c);
+        idx = nxt;
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -258,50 +287,60 @@ __global__ void __launch_bounds__(256, 1) edge_bwd_tc_kernel(EdgeBwdTcArgs p) {
 
     const int64_t n_tiles = (p.n_edges + TE - 1) / TE;
     int it = 0;
+    RowIdx idx = load_row_idx(p.dst, p.src, (int64_t)blockIdx.x < n_tiles ? (int64_t)blockIdx.x * TE : -1, p.n_edges);
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
         const int64_t e0 = t * TE;
         const int rows = (int)((p.n_edges - e0 < TE) ? (p.n_edges - e0) : TE);
-        // ---- build h1 and G operand tiles (warp w: rows 16w .. 16w+15)
-#pragma unroll 2
-        for (int r = warp * 16; r < warp * 16 + 16; ++r) {
-            float4 h = make_float4(0.f, 0.f, 0.f, 0.f), g = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-            int i = -1, j = -1;
-            if (r < rows) {
-                i = __ldg(p.dst + e0 + r);
-                j = __ldg(p.src + e0 + r);
-                float4 ni = __ldg(p.node4 + i), nj = __ldg(p.node4 + j);
-                e = make_float4(ni.x - nj.x, ni.y - nj.y, ni.z - nj.z, ni.w);
-                float4 P = ldg4(p.PQ + (int64_t)i * 256 + lane * 4);
-                float4 Q = ldg4(p.PQ + (int64_t)j * 256 + 128 + lane * 4);
-                float z[4] = {P.x + Q.x, P.y + Q.y, P.z + Q.z, P.w + Q.w};
+        // ---- build h1 and G operand tiles (warp w: rows 16w .. 16w+15), 4 rows of gathers in flight
+        const RowIdx nxt = load_row_idx(p.dst, p.src, (t + gridDim.x < n_tiles) ? (t + gridDim.x) * TE : -1, p.n_edges);
+        if (lane < 16) { sDst[warp * 16 + lane] = idx.d; sSrc[warp * 16 + lane] = idx.s; }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    z[c] = fmaf(w1c[c][0], e.x, z[c]);
-                    z[c] = fmaf(w1c[c][1], e.y, z[c]);
-                    z[c] = fmaf(w1c[c][2], e.z, z[c]);
-                    z[c] = fmaf(w1c[c][3], e.w, z[c]);
+        for (int b = 0; b < 4; ++b) {
+            float4 P[4], Q[4], ni[4], nj[4], ga[4];
+            float sc[4];
+            uint32_t mw[4];
+            int di[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = warp * 16 + b * 4 + k;
+                di[k] = __shfl_sync(0xffffffffu, idx.d, b * 4 + k);
+                int j = __shfl_sync(0xffffffffu, idx.s, b * 4 + k);
+                if (di[k] >= 0) {
+                    P[k] = ldg4(p.PQ + (int64_t)di[k] * 256 + lane * 4);
+                    Q[k] = ldg4(p.PQ + (int64_t)j * 256 + 128 + lane * 4);
+                    ni[k] = __ldg(p.node4 + di[k]);
+                    nj[k] = __ldg(p.node4 + j);
+                    ga[k] = ldg4(p.g_agg + (int64_t)di[k] * p.ld_gagg + lane * 4);
+                    sc[k] = __ldg(p.inv_deg + di[k]);
+                    mw[k] = __ldg(p.mask2 + (e0 + r) * 4 + (lane >> 3));
                 }
-                h = make_float4(fmaxf(z[0], 0.f), fmaxf(z[1], 0.f), fmaxf(z[2], 0.f), fmaxf(z[3], 0.f));
-                float s = __ldg(p.inv_deg + i);
-                float4 ga = ldg4(p.g_agg + (int64_t)i * p.ld_gagg + lane * 4);
-                uint32_t bits = __ldg(p.mask2 + (e0 + r) * 4 + (lane >> 3)) >> ((lane & 7) * 4);
-                g.x = (bits & 1u) ? ga.x * s : 0.f;
-                g.y = (bits & 2u) ? ga.y * s : 0.f;
-                g.z = (bits & 4u) ? ga.z * s : 0.f;
-                g.w = (bits & 8u) ? ga.w * s : 0.f;
-                db2_acc[0] += g.x; db2_acc[1] += g.y; db2_acc[2] += g.z; db2_acc[3] += g.w;
             }
-            if (lane == 0) { sDst[r] = i; sSrc[r] = j; sE[r] = e; }
-            uint2 hi, lo;
-            uint32_t off = tile_off(r, lane * 4);
-            split4(h, hi, lo);
-            *reinterpret_cast<uint2*>(sH + off) = hi;
-            *reinterpret_cast<uint2*>(sH + TILE_BYTES + off) = lo;
-            split4(g, hi, lo);
-            *reinterpret_cast<uint2*>(sG + off) = hi;
-            *reinterpret_cast<uint2*>(sG + TILE_BYTES + off) = lo;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = warp * 16 + b * 4 + k;
+                float4 h = make_float4(0.f, 0.f, 0.f, 0.f), g = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (di[k] >= 0) {
+                    h = h1_row(P[k], Q[k], ni[k], nj[k], w1c, e);
+                    uint32_t bits = mw[k] >> ((lane & 7) * 4);
+                    g.x = (bits & 1u) ? ga[k].x * sc[k] : 0.f;
+                    g.y = (bits & 2u) ? ga[k].y * sc[k] : 0.f;
+                    g.z = (bits & 4u) ? ga[k].z * sc[k] : 0.f;
+                    g.w = (bits & 8u) ? ga[k].w * sc[k] : 0.f;
+                    db2_acc[0] += g.x; db2_acc[1] += g.y; db2_acc[2] += g.z; db2_acc[3] += g.w;
+                }
+                if (lane == 0) sE[r] = e;
+                uint2 hi, lo;
+                uint32_t off = tile_off(r, lane * 4);
+                split4(h, hi, lo);
+                *reinterpret_cast<uint2*>(sH + off) = hi;
+                *reinterpret_cast<uint2*>(sH + TILE_BYTES + off) = lo;
+                split4(g, hi, lo);
+                *reinterpret_cast<uint2*>(sG + off) = hi;
+                *reinterpret_cast<uint2*>(sG + TILE_BYTES + off) = lo;
+            }
         }
+        idx = nxt;
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();

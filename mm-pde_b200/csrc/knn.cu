@@ -81,11 +81,22 @@ __device__ __forceinline__ int cell_coord(float v, float v0, float inv_cell, int
     return min(max(c, 0), g - 1);
 }
 
-__global__ void grid_count_kernel(const float2* __restrict__ pts, int64_t n, float x0, float y0, float inv_cell,
-                                  int gx, int gy, int* __restrict__ cell_of_pt, int* __restrict__ counts) {
+// sample s with off[s] <= i < off[s+1]
+__device__ __forceinline__ int sample_of(const int* __restrict__ off, int n_samples, int64_t i) {
+    int lo = 0, hi = n_samples;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(off + mid) <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void grid_count_kernel(const float2* __restrict__ pts, int64_t n, const int* __restrict__ pts_off, int n_samples,
+                                  float x0, float y0, float inv_cell, int gx, int gy, int* __restrict__ cell_of_pt,
+                                  int* __restrict__ counts) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float2 p = pts[i];
-        int c = cell_coord(p.y, y0, inv_cell, gy) * gx + cell_coord(p.x, x0, inv_cell, gx);
+        int c = sample_of(pts_off, n_samples, i) * gx * gy + cell_coord(p.y, y0, inv_cell, gy) * gx + cell_coord(p.x, x0, inv_cell, gx);
         cell_of_pt[i] = c;
         atomicAdd(&counts[c + 1], 1);
     }
@@ -131,15 +142,19 @@ __global__ void grid_fill_kernel(const int* __restrict__ cell_of_pt, int64_t n, 
 }
 
 template <typename D>
-__global__ void __launch_bounds__(128) knn_grid_kernel(const float2* __restrict__ pts, const float2* __restrict__ qry, int64_t nq,
-                                                       float x0, float y0, float inv_cell, int gx, int gy,
-                                                       const int* __restrict__ cell_start, const int* __restrict__ order,
-                                                       int k, int exclude_self, int* __restrict__ out) {
+__global__ void __launch_bounds__(128) knn_grid_kernel(const float2* __restrict__ pts, const int* __restrict__ pts_off,
+                                                       const float2* __restrict__ qry, const int* __restrict__ qry_off,
+                                                       int n_samples, int64_t nq, float x0, float y0, float inv_cell,
+                                                       int gx, int gy, const int* __restrict__ cell_start,
+                                                       const int* __restrict__ order, int k, int exclude_self,
+                                                       int* __restrict__ out) {
     const float cell = 1.0f / inv_cell;
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
         float2 qq = qry[q];
         int cx = cell_coord(qq.x, x0, inv_cell, gx), cy = cell_coord(qq.y, y0, inv_cell, gy);
-        int self = exclude_self ? (int)q : -1;
+        const int smp = sample_of(qry_off, n_samples, q);
+        const int cell0 = smp * gx * gy;
+        int self = exclude_self ? (int)(__ldg(pts_off + smp) + (q - __ldg(qry_off + smp))) : -1;
         TopK<D, KNN_KMAX> best;
         best.init(k);
         int rmax = max(max(cx, gx - 1 - cx), max(cy, gy - 1 - cy));
@@ -164,7 +179,7 @@ __global__ void __launch_bounds__(128) knn_grid_kernel(const float2* __restrict_
                 int step = edge_row ? 1 : max(xhi - xlo, 1);
                 for (int xx = xlo; xx <= xhi; xx += step) {
                     if (xx < 0 || xx >= gx) continue;
-                    int c = yy * gx + xx;
+                    int c = cell0 + yy * gx + xx;
                     for (int s = cell_start[c]; s < cell_start[c + 1]; ++s) {
                         int p = order[s];
                         if (p == self) continue;
@@ -214,34 +229,35 @@ extern "C" int mmpde_knn(const float* pts, const int32_t* pts_off, const float* 
     return MMPDE_OK;
 }
 
-extern "C" int mmpde_knn_grid_build(const float* pts, int64_t n_pts, float x0, float y0, float inv_cell, int gx, int gy,
-                                    int32_t* cell_of_pt, int32_t* cell_start, int32_t* cursor, int32_t* order, void* stream) {
-    if (n_pts < 0 || gx <= 0 || gy <= 0 || (int64_t)gx * gy > (1 << 28)) return MMPDE_EINVAL;
+extern "C" int mmpde_knn_grid_build(const float* pts, const int32_t* pts_off, int n_samples, int64_t n_pts, float x0,
+                                    float y0, float inv_cell, int gx, int gy, int32_t* cell_of_pt, int32_t* cell_start,
+                                    int32_t* cursor, int32_t* order, void* stream) {
+    if (n_pts < 0 || n_samples <= 0 || gx <= 0 || gy <= 0 || (int64_t)gx * gy * n_samples > (1 << 28)) return MMPDE_EINVAL;
     auto st = (cudaStream_t)stream;
-    int ncell = gx * gy;
+    int ncell = gx * gy * n_samples;
     cudaMemsetAsync(cell_start, 0, sizeof(int) * (size_t)(ncell + 1), st);
     cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)ncell, st);
     if (n_pts == 0) return MMPDE_OK;
     int blocks = (int)imin64((n_pts + 255) / 256, (int64_t)sm_count() * 16);
-    grid_count_kernel<<<blocks, 256, 0, st>>>((const float2*)pts, n_pts, x0, y0, inv_cell, gx, gy, cell_of_pt, cell_start);
+    grid_count_kernel<<<blocks, 256, 0, st>>>((const float2*)pts, n_pts, pts_off, n_samples, x0, y0, inv_cell, gx, gy, cell_of_pt, cell_start);
     grid_scan_kernel<<<1, 1024, 0, st>>>(cell_start, ncell);
     grid_fill_kernel<<<blocks, 256, 0, st>>>(cell_of_pt, n_pts, cell_start, cursor, order);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }
 
-extern "C" int mmpde_knn_grid(const float* pts, int64_t n_pts, const float* qry, int64_t n_queries, float x0, float y0,
-                              float inv_cell, int gx, int gy, const int32_t* cell_start, const int32_t* order, int k,
-                              int rule, int exclude_self, int32_t* out_idx, void* stream) {
-    if (k <= 0 || k > KNN_KMAX || (rule != 0 && rule != 1) || gx <= 0 || gy <= 0) return MMPDE_EINVAL;
+extern "C" int mmpde_knn_grid(const float* pts, const int32_t* pts_off, const float* qry, const int32_t* qry_off,
+                              int n_samples, int64_t n_queries, float x0, float y0, float inv_cell, int gx, int gy,
+                              const int32_t* cell_start, const int32_t* order, int k, int rule, int exclude_self,
+                              int32_t* out_idx, void* stream) {
+    if (k <= 0 || k > KNN_KMAX || (rule != 0 && rule != 1) || gx <= 0 || gy <= 0 || n_samples <= 0) return MMPDE_EINVAL;
     if (n_queries == 0) return MMPDE_OK;
-    (void)n_pts;
     auto st = (cudaStream_t)stream;
     int blocks = (int)imin64((n_queries + 127) / 128, (int64_t)sm_count() * 32);
     if (rule == 0)
-        knn_grid_kernel<float><<<blocks, 128, 0, st>>>((const float2*)pts, (const float2*)qry, n_queries, x0, y0, inv_cell, gx, gy, cell_start, order, k, exclude_self, out_idx);
+        knn_grid_kernel<float><<<blocks, 128, 0, st>>>((const float2*)pts, pts_off, (const float2*)qry, qry_off, n_samples, n_queries, x0, y0, inv_cell, gx, gy, cell_start, order, k, exclude_self, out_idx);
     else
-        knn_grid_kernel<double><<<blocks, 128, 0, st>>>((const float2*)pts, (const float2*)qry, n_queries, x0, y0, inv_cell, gx, gy, cell_start, order, k, exclude_self, out_idx);
+        knn_grid_kernel<double><<<blocks, 128, 0, st>>>((const float2*)pts, pts_off, (const float2*)qry, qry_off, n_samples, n_queries, x0, y0, inv_cell, gx, gy, cell_start, order, k, exclude_self, out_idx);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }

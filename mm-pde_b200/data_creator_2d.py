@@ -65,6 +65,11 @@ class GraphCreator_FS_2D(nn.Module):
         self.t_res = t_resolution
         self._static_edges = {}
 
+    def _bbox(self):
+        """Box handed to the cell-binned k-NN (a hint: points outside are clamped, results stay exact)."""
+        px, py = 0.02 * self.pde.Lx, 0.02 * self.pde.Ly
+        return (-px, -py, self.pde.Lx + px, self.pde.Ly + py)
+
     # ------------------------------------------------------------------ interpolation (:46-85)
     def interpolate(self, itp_model, u, init_x, init_y, x, y, mode):
         """u (nu, ...) known at (init_x, init_y) [nu*P,1]; returns values at (x, y) [nu*Q,1], flattened."""
@@ -74,7 +79,7 @@ class GraphCreator_FS_2D(nn.Module):
         P, Q = src.shape[0] // nu, qry.shape[0] // nu
         dev = src.device
         idx = ops.knn_indices(src, _offsets(nu, P, dev), qry, _offsets(nu, Q, dev), itp_model.n, rule=1,
-                              exclude_self=False)
+                              exclude_self=False, bbox=self._bbox(), per_sample=P)
         vals = u.reshape(-1).to(torch.float32).contiguous()
         return ops.InterpolateFn.apply(vals, src, qry, idx, itp_model.flat_params(mode))
 
@@ -127,7 +132,8 @@ class GraphCreator_FS_2D(nn.Module):
             nbr = ops.radius_indices(pts, off, self._radius, 32)
             edges = ops.EdgeList.from_knn(nbr, has_pad=True)
         else:
-            nbr = ops.knn_indices(pts, off, pts, off, self.n, rule=0, exclude_self=True)
+            nbr = ops.knn_indices(pts, off, pts, off, self.n, rule=0, exclude_self=True, bbox=self._bbox(),
+                                  per_sample=per_sample)
             edges = ops.EdgeList.from_knn(nbr, has_pad=per_sample - 1 < self.n)
         if static_key is not None:
             self._static_edges[static_key] = edges

@@ -99,11 +99,19 @@ class EdgeList:
         return torch.stack((self.src.long(), self.dst.long()))
 
 
-def knn_indices(pts, pts_off, qry, qry_off, k, rule, exclude_self):
+GRID_MIN_POINTS = 384          # samples at least this large use the cell-binned search
+
+
+def knn_indices(pts, pts_off, qry, qry_off, k, rule, exclude_self, bbox=None, per_sample=None):
     """Ordered k nearest points of each query inside its sample -> int32 [Q,k] global rows of pts (-1 pads).
-    pts/qry fp32 [.,2]; *_off int32 [S+1] on the device.  rule 0 = fp32 graph rule, 1 = fp64 interpolation rule."""
+    pts/qry fp32 [.,2]; *_off int32 [S+1] on the device.  rule 0 = fp32 graph rule, 1 = fp64 interpolation rule.
+    ``bbox`` = (x0, y0, x1, y1) enclosing (most of) the points and ``per_sample`` = points per sample (host
+    ints, so no device sync) switch large samples to the cell-binned search; both paths are exact and
+    return identical indices."""
     _chk(pts, name="pts"); _chk(qry, name="qry")
     _chk(pts_off, torch.int32, "pts_off"); _chk(qry_off, torch.int32, "qry_off")
+    if bbox is not None and per_sample is not None and per_sample >= GRID_MIN_POINTS:
+        return _knn_grid(pts, pts_off, qry, qry_off, k, rule, exclude_self, bbox, per_sample)
     Q = qry.shape[0]
     out = torch.empty((Q, k), dtype=torch.int32, device=pts.device)
     _cabi.call("mmpde_knn", _ptr(pts), _ptr(pts_off), _ptr(qry), _ptr(qry_off), pts_off.numel() - 1, Q, k, rule,
@@ -111,29 +119,38 @@ def knn_indices(pts, pts_off, qry, qry_off, k, rule, exclude_self):
     return out
 
 
-def knn_indices_grid(pts, qry, k, rule, exclude_self, pts_per_cell=8.0):
-    """Same contract for ONE large sample, using the uniform-cell binned search (exact)."""
-    _chk(pts, name="pts"); _chk(qry, name="qry")
+def _knn_grid(pts, pts_off, qry, qry_off, k, rule, exclude_self, bbox, per_sample, pts_per_cell=6.0):
+    x0, y0, x1, y1 = [float(v) for v in bbox]
+    S = pts_off.numel() - 1
     P, Q = pts.shape[0], qry.shape[0]
-    lo = torch.minimum(pts.min(0).values, qry.min(0).values)
-    hi = torch.maximum(pts.max(0).values, qry.max(0).values)
-    x0, y0, x1, y1 = [float(v) for v in torch.cat((lo, hi)).tolist()]          # one host sync per graph build
     area = max((x1 - x0) * (y1 - y0), 1e-30)
-    cell = max((area * pts_per_cell / max(P, 1)) ** 0.5, 1e-9)
+    cell = max((area * pts_per_cell / max(per_sample, 1)) ** 0.5, 1e-9)
     gx = max(int((x1 - x0) / cell) + 1, 1)
     gy = max(int((y1 - y0) / cell) + 1, 1)
     dev = pts.device
+    ncell = S * gx * gy
     cell_of = torch.empty(P, dtype=torch.int32, device=dev)
-    cell_start = torch.empty(gx * gy + 1, dtype=torch.int32, device=dev)
-    cursor = torch.empty(gx * gy, dtype=torch.int32, device=dev)
+    cell_start = torch.empty(ncell + 1, dtype=torch.int32, device=dev)
+    cursor = torch.empty(ncell, dtype=torch.int32, device=dev)
     order = torch.empty(P, dtype=torch.int32, device=dev)
     st = _stream()
-    _cabi.call("mmpde_knn_grid_build", _ptr(pts), P, x0, y0, 1.0 / cell, gx, gy, _ptr(cell_of), _ptr(cell_start),
-               _ptr(cursor), _ptr(order), st)
+    _cabi.call("mmpde_knn_grid_build", _ptr(pts), _ptr(pts_off), S, P, x0, y0, 1.0 / cell, gx, gy, _ptr(cell_of),
+               _ptr(cell_start), _ptr(cursor), _ptr(order), st)
     out = torch.empty((Q, k), dtype=torch.int32, device=dev)
-    _cabi.call("mmpde_knn_grid", _ptr(pts), P, _ptr(qry), Q, x0, y0, 1.0 / cell, gx, gy, _ptr(cell_start), _ptr(order),
-               k, rule, int(exclude_self), _ptr(out), st)
+    _cabi.call("mmpde_knn_grid", _ptr(pts), _ptr(pts_off), _ptr(qry), _ptr(qry_off), S, Q, x0, y0, 1.0 / cell, gx, gy,
+               _ptr(cell_start), _ptr(order), k, rule, int(exclude_self), _ptr(out), st)
     return out
+
+
+def knn_indices_grid(pts, qry, k, rule, exclude_self):
+    """Cell-binned search for ONE large sample with the bounding box measured on the device (one host sync)."""
+    lo = torch.minimum(pts.min(0).values, qry.min(0).values)
+    hi = torch.maximum(pts.max(0).values, qry.max(0).values)
+    bbox = torch.cat((lo, hi)).tolist()
+    dev = pts.device
+    po = torch.tensor([0, pts.shape[0]], dtype=torch.int32, device=dev)
+    qo = torch.tensor([0, qry.shape[0]], dtype=torch.int32, device=dev)
+    return _knn_grid(pts, po, qry, qo, k, rule, exclude_self, bbox, pts.shape[0])
 
 
 def radius_indices(pts, off, r, max_nb=32):
@@ -153,7 +170,9 @@ def gemm(A, lda, a_k, B, ldb, b_k, C, ldc, M, N, K, bias=None, r1_row=None, r1_s
 
 
 def _split_for(rows):
-    return max(1, min(1024, (rows + 2047) // 2048))
+    """split-K factor of the weight-gradient contractions (K = node count): ~one 256-row chunk per CTA so the
+    1-2 output tiles still spread over the whole chip."""
+    return max(2, min(512, (rows + 255) // 256))
 
 
 class _BNState:

@@ -44,6 +44,15 @@ def test_knn_graph_rule_bit_exact(sizes, k):
     t = torch.from_numpy(pts).to(dev)
     got = ops.knn_indices(t, off, t, off, k, rule=0, exclude_self=True).cpu().numpy()
     assert np.array_equal(got, ref)
+    # the cell-binned search (ragged batch, box smaller than the cloud -> clamped border cells) is bit-identical
+    old = ops.GRID_MIN_POINTS
+    ops.GRID_MIN_POINTS = 1
+    try:
+        for box in ((-0.1, -0.1, 1.1, 1.1), (0.2, 0.1, 0.7, 0.9)):
+            got = ops.knn_indices(t, off, t, off, k, rule=0, exclude_self=True, bbox=box, per_sample=max(sizes))
+            assert np.array_equal(got.cpu().numpy(), ref)
+    finally:
+        ops.GRID_MIN_POINTS = old
 
 
 def test_knn_lattice_ties_and_duplicates_bit_exact():
@@ -58,6 +67,8 @@ def test_knn_lattice_ties_and_duplicates_bit_exact():
         off = _off([len(pts)], dev)
         got = ops.knn_indices(t, off, t, off, 35, rule=0, exclude_self=True).cpu().numpy()
         assert np.array_equal(got, ref)
+        got = ops._knn_grid(t, off, t, off, 35, 0, True, (0.0, 0.0, 1.0, 1.0), len(pts)).cpu().numpy()
+        assert np.array_equal(got, ref)
 
 
 @pytest.mark.parametrize("P,Q", [(2304, 2304), (500, 1300), (31, 64)])
@@ -71,6 +82,9 @@ def test_knn_interpolation_rule_bit_exact(P, Q):
     ref, _ = oknn.knn_indices(pts, qry, 30, pb, qb, rule="f64")
     got = ops.knn_indices(torch.from_numpy(pts).to(dev), _off([P] * nu, dev), torch.from_numpy(qry).to(dev),
                           _off([Q] * nu, dev), 30, rule=1, exclude_self=False).cpu().numpy()
+    assert np.array_equal(got, ref)
+    got = ops._knn_grid(torch.from_numpy(pts).to(dev), _off([P] * nu, dev), torch.from_numpy(qry).to(dev),
+                        _off([Q] * nu, dev), 30, 1, False, (0.0, 0.0, 1.0, 1.0), P).cpu().numpy()
     assert np.array_equal(got, ref)
 
 
@@ -234,12 +248,14 @@ def test_layer_matches_oracle(sizes):
     pos = c["pos"].to(dev)
     out = layer(x1, u1, pos[:, 0:1], pos[:, 1:2], c["var"].to(dev), c["ei"].to(dev), None)
     (out * c["r"].to(dev)).sum().backward()
-    assert _rel(out, ref) < 1e-5
-    # dL/du sums +g at the target and -g at the source of every edge: heavy cancellation, atomically ordered
-    assert _rel(x1.grad, x0.grad) < 1e-4 and _rel(u1.grad, u0.grad) < 1e-3
+    assert _rel(out, ref) < 2e-5                      # split-bf16 tensor-core products: ~2^-16 per term
+    # gradients: a ReLU whose pre-activation lies within rounding of 0 flips its mask between two correct
+    # implementations (fp32 CPU vs split-bf16 MMA), which moves individual terms by O(1); the sums agree to
+    # ~1e-4.  dL/du additionally cancels +g (target) against -g (source) per edge.  Bound: the 1e-3 north star.
+    assert _rel(x1.grad, x0.grad) < 1e-3 and _rel(u1.grad, u0.grad) < 1e-3
     ref_named = dict(ref_layer.named_parameters())
     for name, p in layer.named_parameters():
-        assert _rel(p.grad, ref_named[name].grad) < 1e-4, name
+        assert _rel(p.grad, ref_named[name].grad) < 1e-3, name
     for name, b in layer.named_buffers():
         assert _rel(b.float(), dict(ref_layer.named_buffers())[name].float()) < 1e-5, name
 
@@ -256,10 +272,10 @@ def test_layer_golden_fixture(golden_dir):
     pos = g["pos"].to(dev)
     out = layer(x, u, pos[:, 0:1], pos[:, 1:2], g["var"].to(dev), g["edge_index"].to(dev), None)
     (out * g["r"].to(dev)).sum().backward()
-    assert _rel(out, g["out"]) < 1e-5                 # tolerance: fp32 reassociation only
-    assert _rel(x.grad, g["gx"]) < 1e-4 and _rel(u.grad, g["gu"]) < 1e-3
+    assert _rel(out, g["out"]) < 2e-5                 # split-bf16 products
+    assert _rel(x.grad, g["gx"]) < 1e-3 and _rel(u.grad, g["gu"]) < 1e-3      # ReLU-mask flips, see above
     for name, p in layer.named_parameters():
-        assert _rel(p.grad, g["gparams"][name]) < 1e-4, name
+        assert _rel(p.grad, g["gparams"][name]) < 1e-3, name
     for k, v in g["bn_after"].items():
         assert _rel(layer.state_dict()[k].float(), v.float()) < 1e-5, k
 

@@ -78,46 +78,31 @@ int mmpde_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_
                int relu, int accumulate, int split_k, void* stream);
 
 /* ---- message passing over the target-sorted edge list -------------------------------------------
- * Replaces PyG propagate + message_net_1/2 + scatter-mean (gnn_2d.py:55,59-63) with the algebraic
- * split of SURVEY.md appendix A:  z1 = P[i] + Q[j] + W1c*e_ij,  P = x*W1a^T + b1,  Q = x*W1b^T.
- * The 128x128 contraction with W2 runs on the tcgen05 tensor cores as three split-bf16 products
- * (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM); the neighbour gather is fused into the operand build.
+ * Replaces PyG propagate + message_net_1/2 + scatter-mean (gnn_2d.py:55,59-63).  message_net_1 is split per
+ * node: with e_ij = (u_i-u_j, px_i-px_j, py_i-py_j, v_i),
+ *   z1_ij = P'[i] + Q'[j],  P' = x*W1a^T + node4*W1c^T + b1,  Q' = x*W1b^T - node4[:, :3]*W1c[:, :3]^T
+ * (two node-level contractions, mmpde_gemm), so an edge costs h1 = relu(P'[dst] + Q'[src]) and the one dense
+ * contraction z2 = W2*h1 + b2, which runs on the tcgen05 tensor cores as three split-bf16 products
+ * (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) with W2 resident in tensor memory; the neighbour
+ * gather is fused into the operand build, the per-target mean into the accumulator read-out.
  *
- * mmpde_pack_w128: W [128,128] fp32 row-major ([out,in]) -> 65 536-byte operand image (bf16 hi + lo tiles in
- *   the SWIZZLE_128B shared-memory layout) that the edge kernels fetch with one TMA bulk copy.  img must be
- *   16-byte aligned; pack once per layer per optimiser step, forward and backward share it.
- *
- *   PQ [N_src,256]: cols 0..127 = P, 128..255 = Q;   node4 [N_src] float4;
+ *   PQ [N_src,256]: cols 0..127 = P', 128..255 = Q';
  *   edge_src / edge_dst [E] int32, sorted by dst;  inv_deg [N_dst] = 1/max(deg,1);
- *   w1c [128,4] (ld 4) = W1[:,256:260];  w2_img from mmpde_pack_w128(W2);  b2 [128];
+ *   w2 [128,128] fp32 row-major ([out,in]);  b2 [128];
  *   agg [N_dst, ld_agg]: mean message, MUST be zero on entry (partial segments add atomically);
- *   mask2 [E,4] uint32: bit c of (z2 > 0), saved for the backward. */
-int mmpde_pack_w128(const float* w, void* img, void* stream);
-int mmpde_edge_fwd(const float* PQ, const float* node4, const int32_t* edge_src, const int32_t* edge_dst,
-                   const float* inv_deg, int64_t n_edges, const float* w1c, const void* w2_img, const float* b2,
-                   float* agg, int64_t ld_agg, uint32_t* mask2, void* stream);
+ *   mask2: uint32 [ceil(E/128)*4, 128]: word [e/32][c] bit (e%32) = (z2[e][c] > 0), saved for the backward. */
+int mmpde_edge_fwd(const float* PQ, const int32_t* edge_src, const int32_t* edge_dst, const float* inv_deg,
+                   int64_t n_edges, const float* w2, const float* b2, float* agg, int64_t ld_agg,
+                   uint32_t* mask2, void* stream);
 
 /* Backward of the above (autograd of gnn_2d.py:59-63 + scatter-mean), h1 recomputed, z2 mask read.
  *   g_agg [N_dst, ld_gagg]: dL/d(mean message).
  *   Outputs (all ACCUMULATED atomically, zero them first):
- *   dPQ [N_src,256] (dP by target segment, dQ scattered to source), dW2 [128,128], db2 [128],
- *   dW1c [128,4], g_u [N_src] with stride g_u_stride (NULL to skip). */
-int mmpde_edge_bwd(const float* PQ, const float* node4, const int32_t* edge_src, const int32_t* edge_dst,
-                   const float* inv_deg, int64_t n_edges, const float* w1c, const void* w2_img,
-                   const uint32_t* mask2, const float* g_agg, int64_t ld_gagg,
-                   float* dPQ, float* dW2, float* db2, float* dW1c, float* g_u, int64_t g_u_stride,
-                   void* stream);
-
-/* fp32 CUDA-core versions of the two kernels above (w2 = the fp32 [128,128] matrix).  Validation aids for
- * the tensor-core kernels (tests cross-check the two); the host path never calls them. */
-int mmpde_edge_fwd_simt(const float* PQ, const float* node4, const int32_t* edge_src, const int32_t* edge_dst,
-                        const float* inv_deg, int64_t n_edges, const float* w1c, const float* w2, const float* b2,
-                        float* agg, int64_t ld_agg, uint32_t* mask2, void* stream);
-int mmpde_edge_bwd_simt(const float* PQ, const float* node4, const int32_t* edge_src, const int32_t* edge_dst,
-                        const float* inv_deg, int64_t n_edges, const float* w1c, const float* w2,
-                        const uint32_t* mask2, const float* g_agg, int64_t ld_gagg,
-                        float* dPQ, float* dW2, float* db2, float* dW1c, float* g_u, int64_t g_u_stride,
-                        void* stream);
+ *   dPQ [N_src,256] (dP' summed per target, dQ' scattered to the source), dW2 [128,128], db2 [128].
+ *   The caller turns dPQ into dW1 (a, b, c blocks), db1, dL/dx and dL/dnode4 with node-level contractions. */
+int mmpde_edge_bwd(const float* PQ, const int32_t* edge_src, const int32_t* edge_dst, const float* inv_deg,
+                   int64_t n_edges, const float* w2, const uint32_t* mask2, const float* g_agg, int64_t ld_gagg,
+                   float* dPQ, float* dW2, float* db2, void* stream);
 
 /* ---- BatchNorm over all nodes (PyG BatchNorm / nn.BatchNorm1d, gnn_2d.py:51,56,101,104) ---------
  * y = A (+ B if non-NULL), [M,128] with leading dims lda/ldb.

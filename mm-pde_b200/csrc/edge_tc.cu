@@ -1,474 +1,523 @@
 // Message passing over the target-sorted edge list on the 5th-gen tensor cores (tcgen05 + TMEM).
-// Replaces PyG propagate + message_net_1/2 + scatter-mean (/root/reference/gnn_2d.py:55,59-63).
+// Replaces PyG propagate + message_net_1/2 + scatter-mean (/root/reference/gnn_2d.py:55,59-63) and its autograd.
 //
-// Per tile of 128 consecutive edges (rows e), with z1 = P[dst] + Q[src] + W1c.e_ij:
-//   build   : all 8 warps gather P/Q rows (128-bit coalesced loads), add the 4 scalar edge features, ReLU and
-//             write h1[e][c] as split-bf16 (hi, lo) into a SWIZZLE_128B operand tile in shared memory
-//             -> the gather is fused into the operand load of the GEMM, no [E,260] / [E,128] tensor exists;
-//   MMA     : D[o][e] = sum_c W2[o][c] * h1[e][c]   (M = 128 out-channels, N = 128 edges, K = 128), three
-//             bf16 products (hi*hi + hi*lo + lo*hi) accumulated in fp32 in TMEM, issued by one thread;
-//             W2 lives in shared memory for the whole kernel (one TMA bulk copy of a pre-swizzled image);
-//   epilogue: thread = out-channel (TMEM lane), registers = 64 consecutive edges: +b2, ReLU, z2>0 bit mask via
-//             ballot, running sum along the edge axis, flushed as mean at every change of target (coalesced
-//             128-byte reductions; a target's segment may continue in the neighbouring tile / column half).
-// Double-buffered operand tiles and TMEM accumulators: MMA(t) overlaps build(t+1) and epilogue(t-1).
+// Formulation.  message_net_1 is split per node: with e_ij = (u_i-u_j, px_i-px_j, py_i-py_j, v_i)
+//   z1_ij = W1a x_i + W1b x_j + W1c e_ij + b1 = P'[i] + Q'[j],
+//   P'[i] = W1a x_i + W1c (u,px,py,v)_i + b1,      Q'[j] = W1b x_j - W1c[:, :3] (u,px,py)_j
+// (both node-level GEMMs, done by the caller), so an edge only costs h1 = relu(P'[dst] + Q'[src]) before the one
+// dense per-edge contraction  z2 = W2 h1 + b2.  That contraction runs on tcgen05 as three bf16 products
+// (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM: ~2^-16 relative error per term).
+//
+// Both kernels are persistent (one CTA per SM) and warp-specialised:
+//   warps 0-3   epilogue : thread = TMEM lane = channel; tcgen05.ld, ReLU / masks / per-target sums
+//   warps 4-11  builders : gather P'/Q' rows with 128-bit loads (next tile prefetched into registers), ReLU, split
+//                          into bf16 hi/lo and write the SWIZZLE_128B operand tile -- the neighbour gather IS the
+//                          operand load of the GEMM, no [E,260] / [E,128] tensor ever exists
+//   warp  12    MMA      : one thread issues tcgen05.mma; W2 (hi, lo) lives in TENSOR MEMORY as the A operand for the
+//                          whole kernel, so only the per-tile operand is read from shared memory
+// connected by mbarrier pipelines (operand tiles and accumulators are double-buffered).
 #include "tc_common.cuh"
 
 namespace mmpde {
 using namespace tc;
 
-constexpr int TE = 128;                        // edges per tile
-constexpr uint32_t TILE_BYTES = 2 * KBLK_BYTES; // one [128][128] bf16 operand image (2 K-blocks)
-constexpr uint32_t W2_IMG_BYTES = 2 * TILE_BYTES;   // hi + lo
+constexpr int EPI_WARPS = 4;
+constexpr int BLD_WARPS = 8;
+constexpr int MMA_WARP = EPI_WARPS + BLD_WARPS;
+constexpr int EDGE_THREADS = (MMA_WARP + 1) * 32;          // 416
+constexpr uint32_t TMEM_COLS = 512;
 
-// ---------------------------------------------------------------------------------------------------
-// weight image: W [128][128] fp32 row-major -> (hi, lo) bf16 SWIZZLE_128B tiles, 65 536 bytes
-__global__ void pack_w128_kernel(const float* __restrict__ w, unsigned char* __restrict__ img) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one thread per 4 consecutive columns
-    if (idx >= 128 * 32) return;
-    int row = idx >> 5, col = (idx & 31) * 4;
-    uint2 hi, lo;
-    split4(ldg4(w + row * 128 + col), hi, lo);
-    uint32_t off = tile_off(row, col);
-    *reinterpret_cast<uint2*>(img + off) = hi;
-    *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = lo;
-}
-
-struct EdgeTcArgs {
-    const float* PQ; const float4* node4; const int* src; const int* dst; const float* inv_deg;
-    int64_t n_edges; const float* w1c; const unsigned char* w2_img; const float* b2;
-    float* agg; int64_t ld_agg; uint32_t* mask2;
-};
-
-struct FwdSmem {
-    // offsets from the 1024-aligned base
-    static constexpr uint32_t W2 = 0;                               // hi, lo
-    static constexpr uint32_t H0 = W2_IMG_BYTES;                    // buffer 0: hi, lo ; buffer 1 follows
-    static constexpr uint32_t DST = H0 + 2 * W2_IMG_BYTES;          // int dst[3][128] (slot = tile iteration % 3)
-    static constexpr uint32_t BAR = DST + 3 * TE * 4;               // 3 mbarriers + tmem slot
-    static constexpr uint32_t TOTAL = BAR + 64;
-};
-
-// Edge indices of the 16 rows a warp builds: lane r (< 16) holds row 16*warp + r.  Loaded one tile AHEAD so the
-// index -> row-gather dependency never sits on the critical path.
+// ---- rows a builder warp owns --------------------------------------------------------------------------------
+// lane r (< ROWS) of a builder warp holds (dst, src) of row  warp_row0 + r  of a tile; -1 beyond the last edge.
 struct RowIdx { int d, s; };
+template <int ROWS>
 __device__ __forceinline__ RowIdx load_row_idx(const int* __restrict__ dst, const int* __restrict__ src, int64_t e0,
-                                               int64_t n_edges) {
+                                               int row0, int64_t n_edges, bool valid_tile) {
     RowIdx r; r.d = -1; r.s = -1;
     const int lane = threadIdx.x & 31;
-    const int64_t e = e0 + (threadIdx.x >> 5) * 16 + (lane & 15);
-    if (lane < 16 && e0 >= 0 && e < n_edges) { r.d = __ldg(dst + e); r.s = __ldg(src + e); }
+    const int64_t e = e0 + row0 + lane;
+    if (valid_tile && lane < ROWS && e < n_edges) { r.d = __ldg(dst + e); r.s = __ldg(src + e); }
     return r;
 }
 
-__device__ __forceinline__ float4 h1_row(const float4& P, const float4& Q, const float4& ni, const float4& nj,
-                                         const float (&w1c)[4][4], float4& e) {
-    e = make_float4(ni.x - nj.x, ni.y - nj.y, ni.z - nj.z, ni.w);     // (u_i-u_j, px_i-px_j, py_i-py_j, v_i)
-    float z[4] = {P.x + Q.x, P.y + Q.y, P.z + Q.z, P.w + Q.w};
+// gathered operands of 8 consecutive rows of one builder warp (lane = 4 channels)
+struct Gather8 {
+    float4 q[8];          // Q'[src] rows
+    float4 pa, pb;        // P'[dst] of the first / last row (a target's rows are consecutive: usually <= 2 targets)
+    int da, db;
+};
+__device__ __forceinline__ void gather8(Gather8& g, const float* __restrict__ PQ, RowIdx idx, int r0, int lane) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        z[c] = fmaf(w1c[c][0], e.x, z[c]);
-        z[c] = fmaf(w1c[c][1], e.y, z[c]);
-        z[c] = fmaf(w1c[c][2], e.z, z[c]);
-        z[c] = fmaf(w1c[c][3], e.w, z[c]);
+    for (int k = 0; k < 8; ++k) {
+        const int s = __shfl_sync(0xffffffffu, idx.s, r0 + k);
+        g.q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s >= 0) g.q[k] = ldg4(PQ + (int64_t)s * 256 + 128 + lane * 4);
     }
-    return make_float4(fmaxf(z[0], 0.f), fmaxf(z[1], 0.f), fmaxf(z[2], 0.f), fmaxf(z[3], 0.f));
+    g.da = __shfl_sync(0xffffffffu, idx.d, r0);
+    g.db = __shfl_sync(0xffffffffu, idx.d, r0 + 7);
+    g.pa = g.pb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.da >= 0) g.pa = ldg4(PQ + (int64_t)g.da * 256 + lane * 4);
+    if (g.db >= 0) g.pb = ldg4(PQ + (int64_t)g.db * 256 + lane * 4);
+}
+__device__ __forceinline__ float4 pick_row(const float* __restrict__ base, int64_t ld, int d, int da, int db, const float4& a,
+                                           const float4& b, int lane) {
+    if (d == da) return a;
+    if (d == db) return b;
+    return ldg4(base + (int64_t)d * ld + lane * 4);           // > 2 targets inside 8 rows (in-degree < 4): rare
+}
+__device__ __forceinline__ float4 relu_add(const float4& a, const float4& b) {
+    return make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
+}
+template <int ROWS>
+__device__ __forceinline__ void store_split(unsigned char* img, int row, int lane, const float4& v) {
+    uint2 hi, lo;
+    split4(v, hi, lo);
+    const uint32_t off = tile_off<ROWS>(row, lane * 4);
+    *reinterpret_cast<uint2*>(img + off) = hi;
+    *reinterpret_cast<uint2*>(img + 2 * ROWS * 128 + off) = lo;            // lo image follows the hi image
 }
 
-// h1 rows of one tile -> split-bf16 operand tile `hbase` (hi at +0, lo at +TILE_BYTES); warp w builds rows 16w..16w+15,
-// 8 rows (16 independent 512-byte row gathers) in flight at a time.
-__device__ __forceinline__ void build_h1_tile(const EdgeTcArgs& p, RowIdx idx, unsigned char* hbase, int* sDst,
-                                              const float (&w1c)[4][4]) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane < 16) sDst[warp * 16 + lane] = idx.d;
+// W (row-major [128][128] fp32, element (r, k) at w[r*rs + k*ks]) -> TMEM A operand: lane r, 64 columns hi, 64 lo
+__device__ __forceinline__ void weight_to_tmem(const float* __restrict__ w, int rs, int ks, int r, uint32_t t_hi, uint32_t t_lo) {
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        float4 P[8], Q[8], ni[8], nj[8];
-        int di[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            di[k] = __shfl_sync(0xffffffffu, idx.d, b * 8 + k);
-            int j = __shfl_sync(0xffffffffu, idx.s, b * 8 + k);
-            if (di[k] >= 0) {
-                P[k] = ldg4(p.PQ + (int64_t)di[k] * 256 + lane * 4);
-                Q[k] = ldg4(p.PQ + (int64_t)j * 256 + 128 + lane * 4);
-                ni[k] = __ldg(p.node4 + di[k]);
-                nj[k] = __ldg(p.node4 + j);
-            }
+        for (int v = 0; v < 8; ++v) {
+            const int k = g * 32 + v * 4;
+            float4 x;
+            if (ks == 1) x = ldg4(w + r * rs + k);
+            else x = make_float4(__ldg(w + r * rs + k * ks), __ldg(w + r * rs + (k + 1) * ks), __ldg(w + r * rs + (k + 2) * ks),
+                                 __ldg(w + r * rs + (k + 3) * ks));
+            uint2 h, l;
+            split4(x, h, l);
+            hi[2 * v] = h.x; hi[2 * v + 1] = h.y; lo[2 * v] = l.x; lo[2 * v + 1] = l.y;
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float4 h = make_float4(0.f, 0.f, 0.f, 0.f), e;
-            if (di[k] >= 0) h = h1_row(P[k], Q[k], ni[k], nj[k], w1c, e);
-            uint2 hi, lo;
-            split4(h, hi, lo);
-            uint32_t off = tile_off(warp * 16 + b * 8 + k, lane * 4);
-            *reinterpret_cast<uint2*>(hbase + off) = hi;
-            *reinterpret_cast<uint2*>(hbase + TILE_BYTES + off) = lo;
-        }
+        tmem_st16(t_hi + g * 16, hi);
+        tmem_st16(t_lo + g * 16, lo);
     }
 }
 
-// 24 MMAs: (W2hi,Hhi) + (W2hi,Hlo) + (W2lo,Hhi), each 2 K-blocks x 4 K-steps of 16
-__device__ __forceinline__ void issue_w2_times_h(uint32_t w2_addr, uint32_t h_addr, uint32_t tmem_d) {
-    constexpr uint32_t idesc = idesc_bf16(128, TE, 0, 0);
-    uint32_t acc = 0;
-#pragma unroll
-    for (int prod = 0; prod < 3; ++prod) {
-        uint32_t a = w2_addr + (prod == 2 ? TILE_BYTES : 0);
-        uint32_t b = h_addr + (prod == 1 ? TILE_BYTES : 0);
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                uint32_t o = kb * KBLK_BYTES + ks * 32;
-                umma_bf16(tmem_d, smem_desc_sw128(a + o, 16, 1024), smem_desc_sw128(b + o, 16, 1024), idesc, acc);
-                acc = 1;
-            }
-    }
-}
+// ================================================================================================================
+// Forward:  agg[i] = mean_{e: dst=i} relu(W2 relu(P'[i] + Q'[src_e]) + b2);  mask2 = sign bits of z2.
+// Tile = 128 edges.  D[o][e] = sum_c W2[o][c] h1[e][c]  (M = 128 channels on TMEM lanes, N = 128 edges).
+// ================================================================================================================
+constexpr int FTE = 128;
+constexpr uint32_t F_IMG = 2 * FTE * 128;                  // one [128][128] bf16 image (2 column blocks) = 32 KB
+struct EdgeFwdArgs {
+    const float* PQ; const int* src; const int* dst; const float* inv_deg; int64_t n_edges;
+    const float* w2; const float* b2; float* agg; int64_t ld_agg; uint32_t* mask2;
+};
+struct FwdSmem {
+    static constexpr uint32_t H = 0;                       // 2 stages x (hi, lo)
+    static constexpr uint32_t DST = 2 * 2 * F_IMG;         // int dst[4][128]  (slot = tile iteration & 3)
+    static constexpr uint32_t BAR = DST + 4 * FTE * 4;     // h_full[2] h_empty[2] tm_full[2] tm_empty[2], tmem slot
+    static constexpr uint32_t TOTAL = BAR + 128;
+};
 
-__global__ void __launch_bounds__(256, 1) edge_fwd_tc_kernel(EdgeTcArgs p) {
+__global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(sm);
     int* sDst = reinterpret_cast<int*>(sm + FwdSmem::DST);
-    const uint32_t bar_w = sbase + FwdSmem::BAR, bar_mma0 = bar_w + 8, bar_mma1 = bar_w + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + FwdSmem::BAR + 24);
+    const uint32_t bar0 = sbase + FwdSmem::BAR;
+    const uint32_t h_full = bar0, h_empty = bar0 + 16, tm_full = bar0 + 32, tm_empty = bar0 + 48;   // [b] at +8*b
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + FwdSmem::BAR + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     if (tid == 32) {
-        mbar_init(bar_w, 1); mbar_init(bar_mma0, 1); mbar_init(bar_mma1, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(h_full + 8 * b, BLD_WARPS); mbar_init(h_empty + 8 * b, 1);
+            mbar_init(tm_full + 8 * b, 1); mbar_init(tm_empty + 8 * b, EPI_WARPS);
+        }
         fence_mbar_init();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar_w, W2_IMG_BYTES);
-        tma_bulk_g2s(sbase + FwdSmem::W2, p.w2_img, W2_IMG_BYTES, bar_w);
-    }
-    float w1c[4][4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int f = 0; f < 4; ++f) w1c[c][f] = __ldg(p.w1c + (lane * 4 + c) * 4 + f);
-    const int q = warp & 3, half = warp >> 2;
-    const int o = q * 32 + lane;                       // this thread's out-channel in the epilogue
-    const float bias = __ldg(p.b2 + o);
+    const uint32_t tmem_d = tmem_base, tmem_w_hi = tmem_base + 256, tmem_w_lo = tmem_base + 320;
+    const int64_t n_tiles = (p.n_edges + FTE - 1) / FTE;
 
-    const int64_t n_tiles = (p.n_edges + TE - 1) / TE;
-    int it = 0;
-    int64_t prev_e0 = 0;
-    int prev_rows = 0;
-
-    auto epilogue = [&](int buf, int slot, int64_t e0, int rows, uint32_t parity) {
-        mbar_wait(buf ? bar_mma1 : bar_mma0, parity);
-        tc_fence_after();
-        const int* dsts = sDst + slot * TE;
-        int cur = -1;
-        float run = 0.f;
+    if (warp < EPI_WARPS) {
+        // ------------------------------------------------------------------ epilogue: thread = out-channel o
+        const int o = warp * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        const uint32_t bias_bits = __float_as_uint(__ldg(p.b2 + o));
+        weight_to_tmem(p.w2, 128, 1, o, tmem_w_hi + lane_addr, tmem_w_lo + lane_addr);
 #pragma unroll
-        for (int chunk = 0; chunk < 2; ++chunk) {
-            const int col0 = half * 64 + chunk * 32;
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TE + col0), v);
-            uint32_t my_word = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int e = col0 + j;
-                float z = __uint_as_float(v[j]) + bias;
-                uint32_t ball = __ballot_sync(0xffffffffu, z > 0.f);
-                if (lane == j) my_word = ball;
-                int d = dsts[e];                       // -1 beyond the last edge
-                if (d != cur) {
-                    if (cur >= 0) atomicAdd(p.agg + (int64_t)cur * p.ld_agg + o, run * __ldg(p.inv_deg + cur));
-                    cur = d; run = 0.f;
-                }
-                run += fmaxf(z, 0.f);
-            }
-            // mask2[e][q] : bit (o & 31) of (z2[e][o] > 0); lane j holds the word of edge col0 + j
-            if (col0 + lane < rows) p.mask2[(e0 + col0 + lane) * 4 + q] = my_word;
-        }
-        if (cur >= 0) atomicAdd(p.agg + (int64_t)cur * p.ld_agg + o, run * __ldg(p.inv_deg + cur));
+        for (int c = 0; c < 8; ++c) tmem_fill32(tmem_d + lane_addr + c * 32, bias_bits);   // accumulators start at b2
+        tmem_wait_st();
         tc_fence_before();
-    };
-
-    RowIdx idx = load_row_idx(p.dst, p.src, (int64_t)blockIdx.x < n_tiles ? (int64_t)blockIdx.x * TE : -1, p.n_edges);
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int64_t e0 = t * TE;
-        const int rows = (int)((p.n_edges - e0 < TE) ? (p.n_edges - e0) : TE);
-        const RowIdx nxt = load_row_idx(p.dst, p.src, (t + gridDim.x < n_tiles) ? (t + gridDim.x) * TE : -1, p.n_edges);
-        build_h1_tile(p, idx, sm + FwdSmem::H0 + buf * W2_IMG_BYTES, sDst + (it % 3) * TE, w1c);
-        idx = nxt;
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            if (it == 0) mbar_wait(bar_w, 0);
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(tm_empty); mbar_arrive(tm_empty + 8); }
+        int i = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            const int* dsts = sDst + (i & 3) * FTE;
+            mbar_wait(tm_full + 8 * b, ph);
             tc_fence_after();
-            issue_w2_times_h(sbase + FwdSmem::W2, sbase + FwdSmem::H0 + buf * W2_IMG_BYTES, tmem_base + buf * TE);
-            umma_commit(buf ? bar_mma1 : bar_mma0);
+            const uint32_t d_addr = tmem_d + lane_addr + b * FTE;
+            int cur = -1;
+            float run = 0.f;
+            uint32_t v[2][32];
+            tmem_ld32_async(d_addr, v[0]);
+#pragma unroll
+            for (int chunk = 0; chunk < 4; ++chunk) {
+                uint32_t (&vc)[32] = v[chunk & 1];
+                tmem_wait_ld(vc);
+                if (chunk < 3) tmem_ld32_async(d_addr + (chunk + 1) * 32, v[(chunk + 1) & 1]);
+                const int e = chunk * 32 + lane;
+                const int d_me = dsts[e];
+                const int d_pv = (e > 0) ? dsts[e - 1] : -2;              // a tile always starts a new run
+                const uint32_t bm = __ballot_sync(0xffffffffu, d_me != d_pv);
+                uint32_t word = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (bm & (1u << j)) {                                  // warp-uniform: first edge of a target
+                        if (cur >= 0) atomicAdd(p.agg + (int64_t)cur * p.ld_agg + o, run * __ldg(p.inv_deg + cur));
+                        cur = dsts[chunk * 32 + j];
+                        run = 0.f;
+                    }
+                    const float z = __uint_as_float(vc[j]);               // = W2 h1 + b2 (bias was in the accumulator)
+                    if (z > 0.f) { word |= (1u << j); run += z; }
+                }
+                // mask2[chunk of 32 edges][channel]: bit j = (z2 > 0) of edge 32*chunk + j
+                p.mask2[((t * 4 + chunk) * 128) + o] = word;
+            }
+            if (cur >= 0) atomicAdd(p.agg + (int64_t)cur * p.ld_agg + o, run * __ldg(p.inv_deg + cur));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_fill32(d_addr + c * 32, bias_bits);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tm_empty + 8 * b);
         }
-        if (it > 0) epilogue(buf ^ 1, (it - 1) % 3, prev_e0, prev_rows, (uint32_t)(((it - 1) >> 1) & 1));
-        prev_e0 = e0; prev_rows = rows;
+    } else if (warp < MMA_WARP) {
+        // ------------------------------------------------------------------ builders: warp w -> rows 16w .. 16w+15
+        const int w = warp - EPI_WARPS;
+        const int row0 = w * 16;
+        Gather8 ga, gb;
+        RowIdx idx = load_row_idx<16>(p.dst, p.src, (int64_t)blockIdx.x * FTE, row0, p.n_edges, (int64_t)blockIdx.x < n_tiles);
+        gather8(ga, p.PQ, idx, 0, lane);
+        int i = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int b = i & 1;
+            const int64_t tn = t + gridDim.x;
+            const RowIdx nxt = load_row_idx<16>(p.dst, p.src, tn * FTE, row0, p.n_edges, tn < n_tiles);
+            gather8(gb, p.PQ, idx, 8, lane);
+            mbar_wait(h_empty + 8 * b, ((uint32_t)(i >> 1) & 1u) ^ 1u);    // MMA of tile i-2 has consumed this stage
+            unsigned char* img = sm + FwdSmem::H + b * (2 * F_IMG);
+            if (lane < 16) sDst[(i & 3) * FTE + row0 + lane] = idx.d;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int d = __shfl_sync(0xffffffffu, idx.d, k);
+                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (d >= 0) h = relu_add(pick_row(p.PQ, 256, d, ga.da, ga.db, ga.pa, ga.pb, lane), ga.q[k]);
+                store_split<FTE>(img, row0 + k, lane, h);
+            }
+            gather8(ga, p.PQ, nxt, 0, lane);                               // first half of the NEXT tile
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int d = __shfl_sync(0xffffffffu, idx.d, 8 + k);
+                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (d >= 0) h = relu_add(pick_row(p.PQ, 256, d, gb.da, gb.db, gb.pa, gb.pb, lane), gb.q[k]);
+                store_split<FTE>(img, row0 + 8 + k, lane, h);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h_full + 8 * b);
+            idx = nxt;
+        }
+    } else if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = idesc_bf16(128, FTE, 0, 0);
+        int i = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            mbar_wait(h_full + 8 * b, ph);
+            mbar_wait(tm_empty + 8 * b, ph);
+            tc_fence_after();
+            const uint32_t h_addr = sbase + FwdSmem::H + b * (2 * F_IMG);
+#pragma unroll
+            for (int prod = 0; prod < 3; ++prod) {                         // hi*hi + hi*lo + lo*hi
+                const uint32_t a = (prod == 2) ? tmem_w_lo : tmem_w_hi;
+                const uint32_t bb = h_addr + (prod == 1 ? F_IMG : 0);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_bf16_ts(tmem_d + b * FTE, a + ks * 8,
+                                 smem_desc_sw128(bb + (ks >> 2) * (FTE * 128) + (ks & 3) * 32, 16, 1024), idesc, 1u);
+            }
+            umma_commit(h_empty + 8 * b);
+            umma_commit(tm_full + 8 * b);
+        }
     }
-    if (it > 0) epilogue((it - 1) & 1, (it - 1) % 3, prev_e0, prev_rows, (uint32_t)(((it - 1) >> 1) & 1));
+    tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 256);
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-
-// ---------------------------------------------------------------------------------------------------
-// Backward.  Per tile (h1 recomputed, z2 mask read back):
-//   G[e][o]  = g_agg[dst][o] * inv_deg[dst] * [z2 > 0]                     (split-bf16 operand tile)
-//   MMA-A    : D1[c][e] = sum_o W2[o][c] * G[e][o]        (A = W2 image read MN-major, B = G K-major)
-//   MMA-B    : D2[o][c] += sum_e G[e][o] * h1[e][c]       (A = G, B = h1 tiles read MN-major; D2 stays in
-//                                                          TMEM for the whole kernel = this CTA's dW2 partial)
-//   epilogue : thread = channel c: g_z1 = D1 * [h1 > 0]; running sums along e -> dP[dst]; dW1c partials;
-//              g_z1 staged as fp32 rows, then one 128-bit vector reduction per 4 channels -> dQ[src], and g_u.
-struct EdgeBwdTcArgs {
-    const float* PQ; const float4* node4; const int* src; const int* dst; const float* inv_deg;
-    int64_t n_edges; const float* w1c; const unsigned char* w2_img; const uint32_t* mask2;
-    const float* g_agg; int64_t ld_gagg;
-    float* dPQ; float* dW2; float* db2; float* dW1c; float* g_u; int64_t g_u_stride;
+// ================================================================================================================
+// Backward (h1 recomputed, z2 mask read back).  Tile = 64 edges.
+//   G[e][o]  = g_agg[dst][o] * inv_deg[dst] * [z2 > 0]
+//   MMA-A    : D1[c][e] = sum_o W2[o][c] G[e][o]      (A = W2^T in TMEM, B = G tile K-major, N = 64)
+//   MMA-B    : D2[o][c] += sum_e G[e][o] h1[e][c]     (A = G, B = h1 tiles read MN-major; D2 stays in TMEM for the
+//                                                      whole kernel = this CTA's dW2 partial)
+//   epilogue : D1 -> fp32 staging tile [e][c] in shared memory (transpose through TMEM lanes)
+//   row phase: the builder warp that built rows r.. re-reads them: g_z1 = D1 * [h1 > 0]; dQ'[src] += g_z1 row
+//              (128-bit vector reductions), dP'[dst] += per-target sums of consecutive rows.
+// ================================================================================================================
+constexpr int BTE = 64;
+constexpr uint32_t B_IMG = 2 * BTE * 128;                  // one [64][128] bf16 image = 16 KB
+struct EdgeBwdArgs {
+    const float* PQ; const int* src; const int* dst; const float* inv_deg; int64_t n_edges;
+    const float* w2; const uint32_t* mask2; const float* g_agg; int64_t ld_gagg;
+    float* dPQ; float* dW2; float* db2;
 };
-
 struct BwdSmem {
-    static constexpr uint32_t W2 = 0;
-    static constexpr uint32_t H = W2_IMG_BYTES;
-    static constexpr uint32_t G = 2 * W2_IMG_BYTES;                 // later: fp32 staging [128][128]
-    static constexpr uint32_t E4 = 3 * W2_IMG_BYTES;                // float4 e_ij[128]
-    static constexpr uint32_t DST = E4 + TE * 16;
-    static constexpr uint32_t SRC = DST + TE * 4;
-    static constexpr uint32_t BAR = SRC + TE * 4;
-    static constexpr uint32_t TOTAL = BAR + 64;
+    static constexpr uint32_t HG = 0;                      // 2 stages x (H hi, H lo, G hi, G lo) = 2 x 64 KB
+    static constexpr uint32_t ST = 2 * 4 * B_IMG;          // 2 x fp32 [64][128] staging = 2 x 32 KB
+    static constexpr uint32_t BAR = ST + 2 * BTE * 128 * 4;
+    static constexpr uint32_t TOTAL = BAR + 128;
 };
 
-__global__ void __launch_bounds__(256, 1) edge_bwd_tc_kernel(EdgeBwdTcArgs p) {
+__global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArgs p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(sm);
-    unsigned char* sH = sm + BwdSmem::H;
-    unsigned char* sG = sm + BwdSmem::G;
-    float* stage = reinterpret_cast<float*>(sG);
-    float4* sE = reinterpret_cast<float4*>(sm + BwdSmem::E4);
-    int* sDst = reinterpret_cast<int*>(sm + BwdSmem::DST);
-    int* sSrc = reinterpret_cast<int*>(sm + BwdSmem::SRC);
-    const uint32_t bar_w = sbase + BwdSmem::BAR, bar_mma = bar_w + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + BwdSmem::BAR + 24);
+    const uint32_t bar0 = sbase + BwdSmem::BAR;
+    // [b] at +8*b
+    const uint32_t hg_full = bar0, hg_empty = bar0 + 16, d1_full = bar0 + 32, d1_empty = bar0 + 48, st_full = bar0 + 64,
+                   st_empty = bar0 + 80, all_done = bar0 + 96;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + BwdSmem::BAR + 104);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     if (tid == 32) {
-        mbar_init(bar_w, 1); mbar_init(bar_mma, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(hg_full + 8 * b, BLD_WARPS); mbar_init(hg_empty + 8 * b, 1);
+            mbar_init(d1_full + 8 * b, 1); mbar_init(d1_empty + 8 * b, EPI_WARPS);
+            mbar_init(st_full + 8 * b, EPI_WARPS); mbar_init(st_empty + 8 * b, BLD_WARPS);
+        }
+        mbar_init(all_done, 1);
         fence_mbar_init();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d1 = *tmem_slot, tmem_d2 = *tmem_slot + 128;
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar_w, W2_IMG_BYTES);
-        tma_bulk_g2s(sbase + BwdSmem::W2, p.w2_img, W2_IMG_BYTES, bar_w);
-    }
-    float w1c[4][4];                                   // rows 4*lane .. 4*lane+3 (build / scatter mapping)
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int f = 0; f < 4; ++f) w1c[c][f] = __ldg(p.w1c + (lane * 4 + c) * 4 + f);
-    const int q = warp & 3, half = warp >> 2;
-    const int ch = q * 32 + lane;                      // epilogue channel of this thread
-    float db2_acc[4] = {0.f, 0.f, 0.f, 0.f};           // channels 4*lane.. of the rows this warp builds
-    float dw1c_acc[4] = {0.f, 0.f, 0.f, 0.f};          // channel ch, e-half `half`
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + 128, tmem_w_hi = tmem_base + 256, tmem_w_lo = tmem_base + 320;
+    const int64_t n_tiles = (p.n_edges + BTE - 1) / BTE;
 
-    const int64_t n_tiles = (p.n_edges + TE - 1) / TE;
-    int it = 0;
-    RowIdx idx = load_row_idx(p.dst, p.src, (int64_t)blockIdx.x < n_tiles ? (int64_t)blockIdx.x * TE : -1, p.n_edges);
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const int64_t e0 = t * TE;
-        const int rows = (int)((p.n_edges - e0 < TE) ? (p.n_edges - e0) : TE);
-        // ---- build h1 and G operand tiles (warp w: rows 16w .. 16w+15), 4 rows of gathers in flight
-        const RowIdx nxt = load_row_idx(p.dst, p.src, (t + gridDim.x < n_tiles) ? (t + gridDim.x) * TE : -1, p.n_edges);
-        if (lane < 16) { sDst[warp * 16 + lane] = idx.d; sSrc[warp * 16 + lane] = idx.s; }
+    if (warp < EPI_WARPS) {
+        // ------------------------------------------------------------------ epilogue: thread = channel c
+        const int c = warp * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        weight_to_tmem(p.w2, 1, 128, c, tmem_w_hi + lane_addr, tmem_w_lo + lane_addr);     // W2^T: row c, k = o
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(d1_empty); mbar_arrive(d1_empty + 8); }               // D1 stages usable, W2^T in place
+        int i = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            float* stage = reinterpret_cast<float*>(sm + BwdSmem::ST + b * (BTE * 128 * 4));
+            mbar_wait(d1_full + 8 * b, ph);
+            tc_fence_after();
+            mbar_wait(st_empty + 8 * b, ph ^ 1u);                          // row phase of tile i-2 has drained the stage
+            uint32_t v[2][32];
+            tmem_ld32_async(tmem_d1 + lane_addr + b * BTE, v[0]);
+            tmem_ld32_async(tmem_d1 + lane_addr + b * BTE + 32, v[1]);
+            tmem_wait_ld(v[0]);
+            tmem_wait_ld(v[1]);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d1_empty + 8 * b);                  // accumulator stage free for tile i+2
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            float4 P[4], Q[4], ni[4], nj[4], ga[4];
-            float sc[4];
-            uint32_t mw[4];
-            int di[4];
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int r = warp * 16 + b * 4 + k;
-                di[k] = __shfl_sync(0xffffffffu, idx.d, b * 4 + k);
-                int j = __shfl_sync(0xffffffffu, idx.s, b * 4 + k);
-                if (di[k] >= 0) {
-                    P[k] = ldg4(p.PQ + (int64_t)di[k] * 256 + lane * 4);
-                    Q[k] = ldg4(p.PQ + (int64_t)j * 256 + 128 + lane * 4);
-                    ni[k] = __ldg(p.node4 + di[k]);
-                    nj[k] = __ldg(p.node4 + j);
-                    ga[k] = ldg4(p.g_agg + (int64_t)di[k] * p.ld_gagg + lane * 4);
-                    sc[k] = __ldg(p.inv_deg + di[k]);
-                    mw[k] = __ldg(p.mask2 + (e0 + r) * 4 + (lane >> 3));
-                }
+                for (int j = 0; j < 32; ++j) stage[(h * 32 + j) * 128 + c] = __uint_as_float(v[h][j]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(st_full + 8 * b);
+        }
+        // ---- this CTA's dW2 partial: D2[o][c], lane = o, registers = 32 consecutive c = one contiguous piece of
+        //      row o of dW2 -> 128-bit vector reductions straight from the registers
+        if (i > 0) {
+            mbar_wait(all_done, 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int chunk = 0; chunk < 4; ++chunk) {
+                uint32_t v[32];
+                tmem_ld32_async(tmem_d2 + lane_addr + chunk * 32, v);
+                tmem_wait_ld(v);
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                    red_add_v4(p.dW2 + c * 128 + chunk * 32 + 4 * m,
+                               make_float4(__uint_as_float(v[4 * m]), __uint_as_float(v[4 * m + 1]),
+                                           __uint_as_float(v[4 * m + 2]), __uint_as_float(v[4 * m + 3])));
             }
+        }
+    } else if (warp < MMA_WARP) {
+        // ------------------------------------------------------------------ builders + row phase: warp w -> rows 8w .. 8w+7
+        const int w = warp - EPI_WARPS;
+        const int row0 = w * 8;
+        float db2_acc[4] = {0.f, 0.f, 0.f, 0.f};
+        struct Tile { Gather8 g; float4 ga, gb; };                        // ga/gb: g_agg[dst]*inv_deg of first / last row
+        Tile cur, nxt;
+        auto gather_tile = [&](Tile& T, RowIdx idx) {
+            gather8(T.g, p.PQ, idx, 0, lane);
+            T.ga = T.gb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (T.g.da >= 0) {
+                const float s = __ldg(p.inv_deg + T.g.da);
+                const float4 x = ldg4(p.g_agg + (int64_t)T.g.da * p.ld_gagg + lane * 4);
+                T.ga = make_float4(x.x * s, x.y * s, x.z * s, x.w * s);
+            }
+            if (T.g.db >= 0) {
+                const float s = __ldg(p.inv_deg + T.g.db);
+                const float4 x = ldg4(p.g_agg + (int64_t)T.g.db * p.ld_gagg + lane * 4);
+                T.gb = make_float4(x.x * s, x.y * s, x.z * s, x.w * s);
+            }
+        };
+        // row phase of a finished tile: rows of this warp from the staging tile
+        auto row_phase = [&](int b, uint32_t ph, RowIdx idx, uint32_t hmask) {
+            const float* stage = reinterpret_cast<const float*>(sm + BwdSmem::ST + b * (BTE * 128 * 4));
+            mbar_wait(st_full + 8 * b, ph);
+            int seg = -1;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int r = warp * 16 + b * 4 + k;
+            for (int k = 0; k < 8; ++k) {
+                const int d = __shfl_sync(0xffffffffu, idx.d, k);
+                const int s = __shfl_sync(0xffffffffu, idx.s, k);
+                if (d < 0) continue;                                       // beyond the last edge (warp-uniform)
+                float4 g = *reinterpret_cast<const float4*>(stage + (row0 + k) * 128 + lane * 4);
+                const uint32_t bits = hmask >> (4 * k);
+                g.x = (bits & 1u) ? g.x : 0.f; g.y = (bits & 2u) ? g.y : 0.f;
+                g.z = (bits & 4u) ? g.z : 0.f; g.w = (bits & 8u) ? g.w : 0.f;
+                red_add_v4(p.dPQ + (int64_t)s * 256 + 128 + lane * 4, g);                  // dQ'[src]
+                if (d != seg) {
+                    if (seg >= 0) red_add_v4(p.dPQ + (int64_t)seg * 256 + lane * 4, acc);  // dP'[dst]
+                    seg = d;
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+            }
+            if (seg >= 0) red_add_v4(p.dPQ + (int64_t)seg * 256 + lane * 4, acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(st_empty + 8 * b);
+        };
+
+        const int64_t t0 = blockIdx.x, t1 = t0 + gridDim.x;
+        RowIdx idx = load_row_idx<8>(p.dst, p.src, t0 * BTE, row0, p.n_edges, t0 < n_tiles);
+        RowIdx idx_n = load_row_idx<8>(p.dst, p.src, t1 * BTE, row0, p.n_edges, t1 < n_tiles);
+        gather_tile(cur, idx);
+        RowIdx idx_prev; idx_prev.d = idx_prev.s = -1;
+        uint32_t hmask_prev = 0;
+        int i = 0;
+        for (int64_t t = t0; t < n_tiles; t += gridDim.x, ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            const int64_t e0 = t * BTE;
+            const int64_t t2 = t + 2 * (int64_t)gridDim.x;
+            const RowIdx idx_nn = load_row_idx<8>(p.dst, p.src, t2 * BTE, row0, p.n_edges, t2 < n_tiles);
+            gather_tile(nxt, idx_n);                                       // next tile's operands -> registers
+            // z2 sign words of this warp's 8 rows (one 32-edge chunk): channels 4*lane .. 4*lane+3
+            const uint4 mw = __ldg(reinterpret_cast<const uint4*>(p.mask2 + ((e0 + row0) >> 5) * 128 + lane * 4));
+            const int bit0 = (int)((e0 + row0) & 31);
+            mbar_wait(hg_empty + 8 * b, ph ^ 1u);
+            unsigned char* imgH = sm + BwdSmem::HG + b * (4 * B_IMG);
+            unsigned char* imgG = imgH + 2 * B_IMG;
+            uint32_t hmask = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int d = __shfl_sync(0xffffffffu, idx.d, k);
                 float4 h = make_float4(0.f, 0.f, 0.f, 0.f), g = make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (di[k] >= 0) {
-                    h = h1_row(P[k], Q[k], ni[k], nj[k], w1c, e);
-                    uint32_t bits = mw[k] >> ((lane & 7) * 4);
-                    g.x = (bits & 1u) ? ga[k].x * sc[k] : 0.f;
-                    g.y = (bits & 2u) ? ga[k].y * sc[k] : 0.f;
-                    g.z = (bits & 4u) ? ga[k].z * sc[k] : 0.f;
-                    g.w = (bits & 8u) ? ga[k].w * sc[k] : 0.f;
+                if (d >= 0) {
+                    h = relu_add(pick_row(p.PQ, 256, d, cur.g.da, cur.g.db, cur.g.pa, cur.g.pb, lane), cur.g.q[k]);
+                    float4 gs;
+                    if (d == cur.g.da) gs = cur.ga;
+                    else if (d == cur.g.db) gs = cur.gb;
+                    else {
+                        const float s = __ldg(p.inv_deg + d);
+                        const float4 x = ldg4(p.g_agg + (int64_t)d * p.ld_gagg + lane * 4);
+                        gs = make_float4(x.x * s, x.y * s, x.z * s, x.w * s);
+                    }
+                    const int bit = bit0 + k;
+                    g.x = ((mw.x >> bit) & 1u) ? gs.x : 0.f; g.y = ((mw.y >> bit) & 1u) ? gs.y : 0.f;
+                    g.z = ((mw.z >> bit) & 1u) ? gs.z : 0.f; g.w = ((mw.w >> bit) & 1u) ? gs.w : 0.f;
                     db2_acc[0] += g.x; db2_acc[1] += g.y; db2_acc[2] += g.z; db2_acc[3] += g.w;
                 }
-                if (lane == 0) sE[r] = e;
-                uint2 hi, lo;
-                uint32_t off = tile_off(r, lane * 4);
-                split4(h, hi, lo);
-                *reinterpret_cast<uint2*>(sH + off) = hi;
-                *reinterpret_cast<uint2*>(sH + TILE_BYTES + off) = lo;
-                split4(g, hi, lo);
-                *reinterpret_cast<uint2*>(sG + off) = hi;
-                *reinterpret_cast<uint2*>(sG + TILE_BYTES + off) = lo;
+                hmask |= ((h.x > 0.f ? 1u : 0u) | (h.y > 0.f ? 2u : 0u) | (h.z > 0.f ? 4u : 0u) | (h.w > 0.f ? 8u : 0u)) << (4 * k);
+                store_split<BTE>(imgH, row0 + k, lane, h);
+                store_split<BTE>(imgG, row0 + k, lane, g);
             }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(hg_full + 8 * b);
+            if (i > 0) row_phase(b ^ 1, (uint32_t)((i - 1) >> 1) & 1u, idx_prev, hmask_prev);
+            idx_prev = idx; hmask_prev = hmask;
+            idx = idx_n; idx_n = idx_nn;
+            cur = nxt;
         }
-        idx = nxt;
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            if (it == 0) mbar_wait(bar_w, 0);
+        if (i > 0) row_phase((i - 1) & 1, (uint32_t)((i - 1) >> 1) & 1u, idx_prev, hmask_prev);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) atomicAdd(p.db2 + lane * 4 + f, db2_acc[f]);
+    } else if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc_a = idesc_bf16(128, BTE, 0, 0);           // D1: A (TMEM) K-major, B = G K-major
+        constexpr uint32_t idesc_b = idesc_bf16(128, 128, 1, 1);           // D2: A = G, B = h1, both MN-major
+        int i = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            mbar_wait(hg_full + 8 * b, ph);
+            mbar_wait(d1_empty + 8 * b, ph);
             tc_fence_after();
-            const uint32_t w2a = sbase + BwdSmem::W2, ha = sbase + BwdSmem::H, ga = sbase + BwdSmem::G;
-            // MMA-A: D1[c][e] = sum_o W2[o][c] G[e][o]
-            {
-                constexpr uint32_t idesc = idesc_bf16(128, TE, /*A MN-major*/ 1, /*B K-major*/ 0);
-                uint32_t acc = 0;
+            const uint32_t h_addr = sbase + BwdSmem::HG + b * (4 * B_IMG), g_addr = h_addr + 2 * B_IMG;
+            uint32_t acc = 0;
 #pragma unroll
-                for (int prod = 0; prod < 3; ++prod) {
-                    uint32_t a = w2a + (prod == 2 ? TILE_BYTES : 0);
-                    uint32_t b = ga + (prod == 1 ? TILE_BYTES : 0);
+            for (int prod = 0; prod < 3; ++prod) {                         // W2^T hi * G hi + hi * G lo + lo * G hi
+                const uint32_t a = (prod == 2) ? tmem_w_lo : tmem_w_hi;
+                const uint32_t bb = g_addr + (prod == 1 ? B_IMG : 0);
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {          // 16 values of o per step
-                        uint64_t ad = smem_desc_sw128(a + ks * 16 * 128, KBLK_BYTES, 1024);
-                        uint64_t bd = smem_desc_sw128(b + (ks >> 2) * KBLK_BYTES + (ks & 3) * 32, 16, 1024);
-                        umma_bf16(tmem_d1, ad, bd, idesc, acc);
-                        acc = 1;
-                    }
+                for (int ks = 0; ks < 8; ++ks) {                           // 16 values of o per step
+                    umma_bf16_ts(tmem_d1 + b * BTE, a + ks * 8,
+                                 smem_desc_sw128(bb + (ks >> 2) * (BTE * 128) + (ks & 3) * 32, 16, 1024), idesc_a, acc);
+                    acc = 1;
                 }
             }
-            // MMA-B: D2[o][c] += sum_e G[e][o] h1[e][c]
-            {
-                constexpr uint32_t idesc = idesc_bf16(128, 128, 1, 1);
+            umma_commit(d1_full + 8 * b);
 #pragma unroll
-                for (int prod = 0; prod < 3; ++prod) {
-                    uint32_t a = ga + (prod == 2 ? TILE_BYTES : 0);
-                    uint32_t b = ha + (prod == 1 ? TILE_BYTES : 0);
+            for (int prod = 0; prod < 3; ++prod) {                         // G hi * h hi + G hi * h lo + G lo * h hi
+                const uint32_t a = g_addr + (prod == 2 ? B_IMG : 0);
+                const uint32_t bb = h_addr + (prod == 1 ? B_IMG : 0);
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {          // 16 edges per step
-                        uint64_t ad = smem_desc_sw128(a + ks * 16 * 128, KBLK_BYTES, 1024);
-                        uint64_t bd = smem_desc_sw128(b + ks * 16 * 128, KBLK_BYTES, 1024);
-                        umma_bf16(tmem_d2, ad, bd, idesc, (it > 0 || prod > 0 || ks > 0) ? 1u : 0u);
-                    }
-                }
+                for (int ks = 0; ks < BTE / 16; ++ks)                      // 16 edges per step
+                    umma_bf16(tmem_d2, smem_desc_sw128(a + ks * 16 * 128, BTE * 128, 1024),
+                              smem_desc_sw128(bb + ks * 16 * 128, BTE * 128, 1024), idesc_b, (i > 0 || prod > 0 || ks > 0) ? 1u : 0u);
             }
-            umma_commit(bar_mma);
+            umma_commit(hg_empty + 8 * b);
         }
-        mbar_wait(bar_mma, (uint32_t)(it & 1));
-        tc_fence_after();
-        // ---- epilogue: thread = channel ch, 64 edges of half `half`
-        {
-            int cur = -1;
-            float run = 0.f;
-#pragma unroll
-            for (int chunk = 0; chunk < 2; ++chunk) {
-                const int col0 = half * 64 + chunk * 32;
-                uint32_t v[32];
-                tmem_ld32(tmem_d1 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
-#pragma unroll
-                for (int jj = 0; jj < 32; ++jj) {
-                    const int e = col0 + jj;
-                    uint16_t hbits = *reinterpret_cast<const uint16_t*>(sH + tile_off(e, ch));
-                    float gz = ((hbits & 0x7FFFu) != 0 && (hbits & 0x8000u) == 0) ? __uint_as_float(v[jj]) : 0.f;
-                    int d = sDst[e];
-                    if (d != cur) {
-                        if (cur >= 0) atomicAdd(p.dPQ + (int64_t)cur * 256 + ch, run);
-                        cur = d; run = 0.f;
-                    }
-                    run += gz;
-                    float4 ef = sE[e];
-                    dw1c_acc[0] = fmaf(gz, ef.x, dw1c_acc[0]);
-                    dw1c_acc[1] = fmaf(gz, ef.y, dw1c_acc[1]);
-                    dw1c_acc[2] = fmaf(gz, ef.z, dw1c_acc[2]);
-                    dw1c_acc[3] = fmaf(gz, ef.w, dw1c_acc[3]);
-                    stage[e * 128 + ch] = gz;          // G tile is dead once the MMAs have completed
-                }
-            }
-            if (cur >= 0) atomicAdd(p.dPQ + (int64_t)cur * 256 + ch, run);
-        }
-        tc_fence_before();
-        __syncthreads();
-        // ---- dQ[src] += g_z1 rows (128-bit vector reductions), g_u[dst] += g_z1.W1c[:,0], g_u[src] -= same
-        for (int r = warp * 16; r < min(warp * 16 + 16, rows); ++r) {
-            float4 g = *reinterpret_cast<const float4*>(stage + r * 128 + lane * 4);
-            int j = sSrc[r];
-            red_add_v4(p.dPQ + (int64_t)j * 256 + 128 + lane * 4, g);
-            if (p.g_u) {
-                float part = g.x * w1c[0][0] + g.y * w1c[1][0] + g.z * w1c[2][0] + g.w * w1c[3][0];
-                part = warp_sum(part);
-                if (lane == 0) {
-                    atomicAdd(p.g_u + (int64_t)sDst[r] * p.g_u_stride, part);
-                    atomicAdd(p.g_u + (int64_t)j * p.g_u_stride, -part);
-                }
-            }
-        }
-        __syncthreads();                               // staging / tiles free for the next build
-    }
-    // ---- flush per-CTA partials
-    if (it > 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int chunk = 0; chunk < 2; ++chunk) {
-            const int col0 = half * 64 + chunk * 32;
-            uint32_t v[32];
-            tmem_ld32(tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) atomicAdd(p.dW2 + ch * 128 + col0 + jj, __uint_as_float(v[jj]));
-        }
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            atomicAdd(p.dW1c + ch * 4 + f, dw1c_acc[f]);
-            atomicAdd(p.db2 + lane * 4 + f, db2_acc[f]);
-        }
+        if (i > 0) umma_commit(all_done);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d1, 256);
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace mmpde
 
 using namespace mmpde;
 
-extern "C" int mmpde_pack_w128(const float* w, void* img, void* stream) {
-    pack_w128_kernel<<<16, 256, 0, (cudaStream_t)stream>>>(w, (unsigned char*)img);
-    MMPDE_CHECK_LAUNCH();
-    return MMPDE_OK;
-}
+static int edge_grid(int64_t n_tiles) { return (int)imin64(n_tiles, sm_count()); }
 
-extern "C" int mmpde_edge_fwd(const float* PQ, const float* node4, const int32_t* edge_src, const int32_t* edge_dst,
-                              const float* inv_deg, int64_t n_edges, const float* w1c, const void* w2_img, const float* b2,
-                              float* agg, int64_t ld_agg, uint32_t* mask2, void* stream) {
+extern "C" int mmpde_edge_fwd(const float* PQ, const int32_t* edge_src, const int32_t* edge_dst, const float* inv_deg,
+                              int64_t n_edges, const float* w2, const float* b2, float* agg, int64_t ld_agg,
+                              uint32_t* mask2, void* stream) {
     if (n_edges < 0 || ld_agg < 128) return MMPDE_EINVAL;
-    if ((reinterpret_cast<uintptr_t>(w2_img) & 15) != 0) return MMPDE_EINVAL;
     if (n_edges == 0) return MMPDE_OK;
     constexpr size_t smem = FwdSmem::TOTAL + 1024;
     static bool attr = false;
@@ -477,23 +526,18 @@ extern "C" int mmpde_edge_fwd(const float* PQ, const float* node4, const int32_t
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    EdgeTcArgs p;
-    p.PQ = PQ; p.node4 = (const float4*)node4; p.src = edge_src; p.dst = edge_dst; p.inv_deg = inv_deg;
-    p.n_edges = n_edges; p.w1c = w1c; p.w2_img = (const unsigned char*)w2_img; p.b2 = b2;
+    EdgeFwdArgs p;
+    p.PQ = PQ; p.src = edge_src; p.dst = edge_dst; p.inv_deg = inv_deg; p.n_edges = n_edges; p.w2 = w2; p.b2 = b2;
     p.agg = agg; p.ld_agg = ld_agg; p.mask2 = mask2;
-    int64_t n_tiles = (n_edges + TE - 1) / TE;
-    int grid = (int)imin64(n_tiles, sm_count());
-    edge_fwd_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    edge_fwd_tc_kernel<<<edge_grid((n_edges + FTE - 1) / FTE), EDGE_THREADS, smem, (cudaStream_t)stream>>>(p);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }
 
-extern "C" int mmpde_edge_bwd(const float* PQ, const float* node4, const int32_t* edge_src, const int32_t* edge_dst,
-                              const float* inv_deg, int64_t n_edges, const float* w1c, const void* w2_img,
-                              const uint32_t* mask2, const float* g_agg, int64_t ld_gagg, float* dPQ, float* dW2,
-                              float* db2, float* dW1c, float* g_u, int64_t g_u_stride, void* stream) {
+extern "C" int mmpde_edge_bwd(const float* PQ, const int32_t* edge_src, const int32_t* edge_dst, const float* inv_deg,
+                              int64_t n_edges, const float* w2, const uint32_t* mask2, const float* g_agg,
+                              int64_t ld_gagg, float* dPQ, float* dW2, float* db2, void* stream) {
     if (n_edges < 0 || ld_gagg < 128) return MMPDE_EINVAL;
-    if ((reinterpret_cast<uintptr_t>(w2_img) & 15) != 0) return MMPDE_EINVAL;
     if (n_edges == 0) return MMPDE_OK;
     constexpr size_t smem = BwdSmem::TOTAL + 1024;
     static bool attr = false;
@@ -502,14 +546,10 @@ extern "C" int mmpde_edge_bwd(const float* PQ, const float* node4, const int32_t
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    EdgeBwdTcArgs p;
-    p.PQ = PQ; p.node4 = (const float4*)node4; p.src = edge_src; p.dst = edge_dst; p.inv_deg = inv_deg;
-    p.n_edges = n_edges; p.w1c = w1c; p.w2_img = (const unsigned char*)w2_img; p.mask2 = mask2;
-    p.g_agg = g_agg; p.ld_gagg = ld_gagg; p.dPQ = dPQ; p.dW2 = dW2; p.db2 = db2; p.dW1c = dW1c; p.g_u = g_u;
-    p.g_u_stride = g_u_stride;
-    int64_t n_tiles = (n_edges + TE - 1) / TE;
-    int grid = (int)imin64(n_tiles, sm_count());
-    edge_bwd_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    EdgeBwdArgs p;
+    p.PQ = PQ; p.src = edge_src; p.dst = edge_dst; p.inv_deg = inv_deg; p.n_edges = n_edges; p.w2 = w2; p.mask2 = mask2;
+    p.g_agg = g_agg; p.ld_gagg = ld_gagg; p.dPQ = dPQ; p.dW2 = dW2; p.db2 = db2;
+    edge_bwd_tc_kernel<<<edge_grid((n_edges + BTE - 1) / BTE), EDGE_THREADS, smem, (cudaStream_t)stream>>>(p);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }

@@ -72,6 +72,54 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// ---- TMEM <-> registers, asynchronous forms ---------------------------------------------------------
+// tcgen05.ld without the wait: the destination registers are only valid after tmem_wait_ld(), which takes them
+// as in/out operands so that no use can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns <- 16 registers per thread
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+// the same 32-bit value into 32 consecutive columns of this thread's lane
+__device__ __forceinline__ void tmem_fill32(uint32_t taddr, uint32_t v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+        "r"(v)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- UMMA descriptors -------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B (layout_type 2), descriptor version 1 (sm_100).
 //   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
@@ -103,21 +151,33 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same with the A operand in TENSOR MEMORY (lane = row of A, one 32-bit column = two consecutive K elements);
+// A from TMEM is always K-major.  Halves the shared-memory operand traffic of the MMA.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // All MMAs issued so far by this thread -> arrive (count 1) on the mbarrier when they have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 // ---- operand tiles ----------------------------------------------------------------------------------
-// A [rows][128] bf16 operand tile is stored as two K-blocks of 64 columns; inside a K-block row r owns 128
+// A [ROWS][128] bf16 operand tile is stored as two column blocks of 64 columns; inside a block row r owns 128
 // contiguous bytes whose 16-byte chunks are XOR-swizzled with (r & 7)  (the TMA / UMMA SWIZZLE_128B pattern).
 // The same image is a K-major operand (rows = M or N, columns = K) and an MN-major operand (columns = M or N,
 // rows = K).  Tiles must start on a 1024-byte boundary.
 constexpr uint32_t KBLK_BYTES = 128 * 128;   // 128 rows x 128 B
 
-__device__ __forceinline__ uint32_t tile_off(int row, int col) {   // byte offset of bf16 element (row, col), col < 128
-    return (uint32_t)(col >> 6) * KBLK_BYTES + (uint32_t)row * 128u + ((((uint32_t)(col & 63) >> 3) ^ ((uint32_t)row & 7u)) << 4) +
-           ((uint32_t)(col & 7) << 1);
+// byte offset of bf16 element (row, col), col < 128, in an operand image of ROWS rows
+template <int ROWS = 128>
+__device__ __forceinline__ uint32_t tile_off(int row, int col) {
+    return (uint32_t)(col >> 6) * (uint32_t)(ROWS * 128) + (uint32_t)row * 128u +
+           ((((uint32_t)(col & 63) >> 3) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)(col & 7) << 1);
 }
 
 // split-bf16: x = hi + lo (+ O(2^-17 |x|));  products hi*hi + hi*lo + lo*hi give ~fp32-grade GEMMs on the bf16 pipe

@@ -14,7 +14,6 @@ H = 128
 KN = 30
 ITP_NPARAM = 18270
 DEC_NPARAM = 525
-W2_IMG_BYTES = 65536
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -221,6 +220,20 @@ N_ENC = 8          # We1 be1 g1 bt1 We2 be2 g2 bt2
 N_LAYER = 10       # W1 b1 W2 b2 W3 b3 W4 b4 gamma beta
 
 
+def mask_words(n_edges):
+    """uint32 words of the z2 sign mask the edge kernels exchange: [ceil(E/128)*4, 128]."""
+    return max((n_edges + 127) // 128, 1) * 512
+
+
+def _edge_feature_weights(W1):
+    """W1c = W1[:, 256:260] acting on e_ij = (u_i-u_j, px_i-px_j, py_i-py_j, v_i) (gnn_2d.py:61), as the two
+    per-node matrices of the split: target side W1c, source side -W1c with the v column removed."""
+    w1c = W1[:, 2 * H:2 * H + 4].contiguous()
+    w1cq = -w1c
+    w1cq[:, 3] = 0.0
+    return w1c, w1cq
+
+
 def _layer_forward(Xl, node4, edges, lp, bnbuf, training, nxt, nxt_ld, st):
     """One GNN_Layer_FS_2D (gnn_2d.py:53-69).  Xl [N,256]: cols 0..127 hold the layer input h, cols
     128..255 must be ZERO on entry and receive the mean message.  Output BN(h + update) -> nxt (ld nxt_ld)."""
@@ -228,16 +241,17 @@ def _layer_forward(Xl, node4, edges, lp, bnbuf, training, nxt, nxt_ld, st):
     N, E = node4.shape[0], edges.n_edges
     f32 = dict(dtype=torch.float32, device=node4.device)
     x, n4 = _ptr(Xl), _ptr(node4)
-    # P = h W1a^T + b1, Q = h W1b^T                              (split of message_net_1, gnn_2d.py:61)
+    # message_net_1 split per node (gnn_2d.py:61): z1_ij = P'[i] + Q'[j] with
+    #   P' = h W1a^T + b1 + node4 W1c^T,   Q' = h W1b^T - node4[:, :3] W1c[:, :3]^T
     PQ = torch.empty(N, 2 * H, **f32)
     gemm(x, 2 * H, 1, _ptr(W1), 260, 1, _ptr(PQ), 2 * H, N, H, H, bias=_ptr(b1), st=st)
     gemm(x, 2 * H, 1, _ptr(W1, H), 260, 1, _ptr(PQ, H), 2 * H, N, H, H, st=st)
-    w1c = W1[:, 2 * H:2 * H + 4].contiguous()
-    mask2 = torch.empty(max(E, 1), 4, dtype=torch.int32, device=node4.device)
-    w2_img = torch.empty(W2_IMG_BYTES, dtype=torch.uint8, device=node4.device)     # split-bf16 operand image of W2
-    _cabi.call("mmpde_pack_w128", _ptr(W2), _ptr(w2_img), st)
-    _cabi.call("mmpde_edge_fwd", _ptr(PQ), n4, _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
-               _ptr(w1c), _ptr(w2_img), _ptr(b2), _ptr(Xl, H), 2 * H, _ptr(mask2), st)
+    w1c, w1cq = _edge_feature_weights(W1)
+    gemm(n4, 4, 1, _ptr(w1c), 4, 1, _ptr(PQ), 2 * H, N, H, 4, acc=1, st=st)
+    gemm(n4, 4, 1, _ptr(w1cq), 4, 1, _ptr(PQ, H), 2 * H, N, H, 4, acc=1, st=st)
+    mask2 = torch.empty(mask_words(E), dtype=torch.int32, device=node4.device)
+    _cabi.call("mmpde_edge_fwd", _ptr(PQ), _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
+               _ptr(W2), _ptr(b2), _ptr(Xl, H), 2 * H, _ptr(mask2), st)
     # update_net_1/2 + residual                                 (gnn_2d.py:65-69)
     w3v = W3[:, 2 * H].contiguous()
     h3 = torch.empty(N, H, **f32)
@@ -246,14 +260,14 @@ def _layer_forward(Xl, node4, edges, lp, bnbuf, training, nxt, nxt_ld, st):
     r4 = torch.empty(N, H, **f32)
     gemm(_ptr(h3), H, 1, _ptr(W4), H, 1, _ptr(r4), H, N, H, H, bias=_ptr(b4), relu=1, st=st)
     bn = _bn_forward(x, 2 * H, _ptr(r4), H, N, gam, bet, 0, nxt, nxt_ld, training, *bnbuf, st)
-    return (PQ, mask2, h3, r4, bn, w2_img)
+    return (PQ, mask2, h3, r4, bn)
 
 
 def _layer_backward(Xl, node4, edges, lp, saved, g_h, g_node4, st):
     """Backward of _layer_forward.  g_h [N,128] = dL/d(output).  Returns (dL/dh_in [N,128], 10 param grads);
     adds the layer's dL/du into g_node4[:,0] when g_node4 is given."""
     W1, b1, W2, b2, W3, b3, W4, b4, gam, bet = lp
-    PQ, mask2, h3, r4, bn, w2_img = saved
+    PQ, mask2, h3, r4, bn = saved
     N, E = node4.shape[0], edges.n_edges
     f32 = dict(dtype=torch.float32, device=node4.device)
     x, n4 = _ptr(Xl), _ptr(node4)
@@ -278,20 +292,26 @@ def _layer_backward(Xl, node4, edges, lp, saved, g_h, g_node4, st):
     g_X = torch.empty(N, 2 * H, **f32)
     gemm(_ptr(g_z3), H, 1, _ptr(W3), 257, 0, _ptr(g_X), 2 * H, N, 2 * H, H, st=st)
     # message passing backward
-    w1c = W1[:, 2 * H:2 * H + 4].contiguous()
     dPQ = torch.zeros(N, 2 * H, **f32)
     dW2 = torch.zeros(H, H, **f32)
     db2 = torch.zeros(H, **f32)
-    dW1c = torch.zeros(H, 4, **f32)
-    _cabi.call("mmpde_edge_bwd", _ptr(PQ), n4, _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
-               _ptr(w1c), _ptr(w2_img), _ptr(mask2), _ptr(g_X, H), 2 * H, _ptr(dPQ), _ptr(dW2), _ptr(db2),
-               _ptr(dW1c), _ptr(g_node4), 4, st)
+    _cabi.call("mmpde_edge_bwd", _ptr(PQ), _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
+               _ptr(W2), _ptr(mask2), _ptr(g_X, H), 2 * H, _ptr(dPQ), _ptr(dW2), _ptr(db2), st)
+    # message_net_1 parameters from dP', dQ':  dW1a = dP'^T h, dW1b = dQ'^T h, dW1c = dP'^T node4 - dQ'^T node4[:, :3]
     dW1 = torch.zeros(H, 260, **f32)
     gemm(_ptr(dPQ), 2 * H, 0, x, 2 * H, 0, _ptr(dW1), 260, H, H, N, split_k=split, st=st)
     gemm(_ptr(dPQ, H), 2 * H, 0, x, 2 * H, 0, _ptr(dW1, H), 260, H, H, N, split_k=split, st=st)
-    dW1[:, 2 * H:2 * H + 4] = dW1c
+    dW1c = torch.zeros(2, H, 4, **f32)
+    gemm(_ptr(dPQ), 2 * H, 0, n4, 4, 0, _ptr(dW1c), 4, H, 4, N, split_k=split, st=st)
+    gemm(_ptr(dPQ, H), 2 * H, 0, n4, 4, 0, _ptr(dW1c, 4 * H), 4, H, 4, N, split_k=split, st=st)
+    dW1[:, 2 * H:2 * H + 4] = dW1c[0]
+    dW1[:, 2 * H:2 * H + 3] -= dW1c[1, :, :3]
     db1 = torch.zeros(H, **f32)
     _cabi.call("mmpde_colsum", _ptr(dPQ), 2 * H, N, H, _ptr(db1), st)
+    if g_node4 is not None:      # dL/du (column 0 of node4): dP' W1c[:,0] - dQ' W1c[:,0]
+        w1c, w1cq = _edge_feature_weights(W1)
+        gemm(_ptr(dPQ), 2 * H, 1, _ptr(w1c), 4, 0, _ptr(g_node4), 4, N, 1, H, acc=1, st=st)
+        gemm(_ptr(dPQ, H), 2 * H, 1, _ptr(w1cq), 4, 0, _ptr(g_node4), 4, N, 1, H, acc=1, st=st)
     # dL/dh_in = g_y (residual) + g_X[:, :128] (update_net_1) + dP W1a + dQ W1b
     g_y.add_(g_X[:, :H])
     gemm(_ptr(dPQ), 2 * H, 1, _ptr(W1), 260, 0, _ptr(g_y), H, N, H, H, acc=1, st=st)

@@ -36,20 +36,16 @@ def main():
     E = edges.n_edges
     torch.manual_seed(0)
     PQ = torch.randn(N, 256, device=dev)
-    node4 = torch.cat((torch.randn(N, 1, device=dev), pts, torch.rand(N, 1, device=dev)), 1).contiguous()
-    w1c, w2, b2 = torch.randn(128, 4, device=dev) * .3, torch.randn(128, 128, device=dev) / 11, torch.randn(128, device=dev) * .1
+    w2, b2 = torch.randn(128, 128, device=dev) / 11, torch.randn(128, device=dev) * .1
     g_agg = torch.randn(N, 128, device=dev)
-    img = torch.empty(65536, dtype=torch.uint8, device=dev)
     st = ops._stream()
-    _cabi.call("mmpde_pack_w128", ops._ptr(w2), ops._ptr(img), st)
     agg = torch.zeros(N, 256, device=dev)
-    mask = torch.zeros(E, 4, dtype=torch.int32, device=dev)
-    common = (ops._ptr(PQ), ops._ptr(node4), ops._ptr(edges.src), ops._ptr(edges.dst), ops._ptr(edges.inv_deg), E, ops._ptr(w1c))
-    fwd = lambda: _cabi.call("mmpde_edge_fwd", *common, ops._ptr(img), ops._ptr(b2), ops._ptr(agg, 128), 256, ops._ptr(mask), st)
-    outs = [torch.zeros(N, 256, device=dev), torch.zeros(128, 128, device=dev), torch.zeros(128, device=dev),
-            torch.zeros(128, 4, device=dev), torch.zeros(N, 4, device=dev)]
-    bwd = lambda: _cabi.call("mmpde_edge_bwd", *common, ops._ptr(img), ops._ptr(mask), ops._ptr(g_agg), 128, ops._ptr(outs[0]),
-                             ops._ptr(outs[1]), ops._ptr(outs[2]), ops._ptr(outs[3]), ops._ptr(outs[4]), 4, st)
+    mask = torch.zeros(ops.mask_words(E), dtype=torch.int32, device=dev)
+    common = (ops._ptr(PQ), ops._ptr(edges.src), ops._ptr(edges.dst), ops._ptr(edges.inv_deg), E, ops._ptr(w2))
+    fwd = lambda: _cabi.call("mmpde_edge_fwd", *common, ops._ptr(b2), ops._ptr(agg, 128), 256, ops._ptr(mask), st)
+    outs = [torch.zeros(N, 256, device=dev), torch.zeros(128, 128, device=dev), torch.zeros(128, device=dev)]
+    bwd = lambda: _cabi.call("mmpde_edge_bwd", *common, ops._ptr(mask), ops._ptr(g_agg), 128, ops._ptr(outs[0]),
+                             ops._ptr(outs[1]), ops._ptr(outs[2]), st)
     X = torch.randn(N, 256, device=dev)
     W = torch.randn(128, 260, device=dev)
     C = torch.empty(N, 128, device=dev)

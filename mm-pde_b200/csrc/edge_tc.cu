@@ -24,7 +24,12 @@ using namespace tc;
 constexpr int EPI_WARPS = 4;
 constexpr int BLD_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS + BLD_WARPS;
-constexpr int EDGE_THREADS = (MMA_WARP + 1) * 32;          // 416
+constexpr int EDGE_THREADS = 512;                          // 4 warpgroups: epilogue | builders | builders | MMA + 3 idle
+// Register budget moved between the warpgroups with setmaxnreg (launch value 65536 / 512 = 128 per thread):
+// 4*32*104 + 8*32*184 + 4*32*40 = 65536.
+constexpr int EPI_REGS = 104, BLD_REGS = 184, MMA_REGS = 40;
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr uint32_t TMEM_COLS = 512;
 
 // ---- rows a builder warp owns --------------------------------------------------------------------------------
@@ -98,6 +103,16 @@ __device__ __forceinline__ void weight_to_tmem(const float* __restrict__ w, int 
     }
 }
 
+// mean message of one finished target: agg[cur][o] += run / deg (partial runs of a target add up atomically)
+__device__ __noinline__ void flush_mean(float* agg, int64_t ld, const float* __restrict__ inv_deg, int cur, int o, float run) {
+    if (cur >= 0) atomicAdd(agg + (int64_t)cur * ld + o, run * __ldg(inv_deg + cur));
+}
+__device__ __forceinline__ int lds_i32(uint32_t saddr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 // ================================================================================================================
 // Forward:  agg[i] = mean_{e: dst=i} relu(W2 relu(P'[i] + Q'[src_e]) + b2);  mask2 = sign bits of z2.
 // Tile = 128 edges.  D[o][e] = sum_c W2[o][c] h1[e][c]  (M = 128 channels on TMEM lanes, N = 128 edges).
@@ -142,6 +157,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
 
     if (warp < EPI_WARPS) {
         // ------------------------------------------------------------------ epilogue: thread = out-channel o
+        reg_dec<EPI_REGS>();
         const int o = warp * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
         const uint32_t bias_bits = __float_as_uint(__ldg(p.b2 + o));
@@ -156,38 +172,58 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int b = i & 1;
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-            const int* dsts = sDst + (i & 3) * FTE;
+            const uint32_t dsts = sbase + FwdSmem::DST + (uint32_t)(i & 3) * (FTE * 4);
             mbar_wait(tm_full + 8 * b, ph);
             tc_fence_after();
             const uint32_t d_addr = tmem_d + lane_addr + b * FTE;
             int cur = -1;
             float run = 0.f;
-            uint32_t v[2][32];
-            tmem_ld32_async(d_addr, v[0]);
-#pragma unroll
-            for (int chunk = 0; chunk < 4; ++chunk) {
-                uint32_t (&vc)[32] = v[chunk & 1];
-                tmem_wait_ld(vc);
-                if (chunk < 3) tmem_ld32_async(d_addr + (chunk + 1) * 32, v[(chunk + 1) & 1]);
+            // 32 edges of this thread's channel: ReLU, sign mask, running per-target sum.  Targets are contiguous
+            // runs of edges; `bm` marks the first edge of each run (warp-uniform), so groups of 4 edges without a
+            // boundary take the short path.
+            auto process = [&](uint32_t (&vc)[32], int chunk) {
                 const int e = chunk * 32 + lane;
-                const int d_me = dsts[e];
-                const int d_pv = (e > 0) ? dsts[e - 1] : -2;              // a tile always starts a new run
+                const int d_me = lds_i32(dsts + 4 * e);
+                const int d_pv = (e > 0) ? lds_i32(dsts + 4 * e - 4) : -2;                 // a tile always starts a run
                 const uint32_t bm = __ballot_sync(0xffffffffu, d_me != d_pv);
                 uint32_t word = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (bm & (1u << j)) {                                  // warp-uniform: first edge of a target
-                        if (cur >= 0) atomicAdd(p.agg + (int64_t)cur * p.ld_agg + o, run * __ldg(p.inv_deg + cur));
-                        cur = dsts[chunk * 32 + j];
-                        run = 0.f;
+                for (int g = 0; g < 8; ++g) {
+                    const float z0 = __uint_as_float(vc[4 * g]), z1 = __uint_as_float(vc[4 * g + 1]),
+                                z2 = __uint_as_float(vc[4 * g + 2]), z3 = __uint_as_float(vc[4 * g + 3]);
+                    const float r0 = fmaxf(z0, 0.f), r1 = fmaxf(z1, 0.f), r2 = fmaxf(z2, 0.f), r3 = fmaxf(z3, 0.f);
+                    const uint32_t nib = (bm >> (4 * g)) & 15u;
+                    if (nib == 0u) {
+                        run += (r0 + r1) + (r2 + r3);
+                    } else {
+                        const float r[4] = {r0, r1, r2, r3};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (nib & (1u << k)) {
+                                flush_mean(p.agg, p.ld_agg, p.inv_deg, cur, o, run);
+                                cur = lds_i32(dsts + 4 * (chunk * 32 + 4 * g + k));
+                                run = 0.f;
+                            }
+                            run += r[k];
+                        }
                     }
-                    const float z = __uint_as_float(vc[j]);               // = W2 h1 + b2 (bias was in the accumulator)
-                    if (z > 0.f) { word |= (1u << j); run += z; }
+                    word |= ((z0 > 0.f ? 1u : 0u) | (z1 > 0.f ? 2u : 0u) | (z2 > 0.f ? 4u : 0u) | (z3 > 0.f ? 8u : 0u)) << (4 * g);
                 }
                 // mask2[chunk of 32 edges][channel]: bit j = (z2 > 0) of edge 32*chunk + j
                 p.mask2[((t * 4 + chunk) * 128) + o] = word;
+            };
+            uint32_t v0[32], v1[32];
+            tmem_ld32_async(d_addr, v0);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                tmem_wait_ld(v0);
+                tmem_ld32_async(d_addr + half * 64 + 32, v1);
+                process(v0, 2 * half);
+                tmem_wait_ld(v1);
+                if (half == 0) tmem_ld32_async(d_addr + 64, v0);
+                process(v1, 2 * half + 1);
             }
-            if (cur >= 0) atomicAdd(p.agg + (int64_t)cur * p.ld_agg + o, run * __ldg(p.inv_deg + cur));
+            flush_mean(p.agg, p.ld_agg, p.inv_deg, cur, o, run);
 #pragma unroll
             for (int c = 0; c < 4; ++c) tmem_fill32(d_addr + c * 32, bias_bits);
             tmem_wait_st();
@@ -197,6 +233,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
         }
     } else if (warp < MMA_WARP) {
         // ------------------------------------------------------------------ builders: warp w -> rows 16w .. 16w+15
+        reg_inc<BLD_REGS>();
         const int w = warp - EPI_WARPS;
         const int row0 = w * 16;
         Gather8 ga, gb;
@@ -231,10 +268,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
             if (lane == 0) mbar_arrive(h_full + 8 * b);
             idx = nxt;
         }
-    } else if (lane == 0) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (one thread of warp 12)
+        reg_dec<MMA_REGS>();
         constexpr uint32_t idesc = idesc_bf16(128, FTE, 0, 0);
         int i = 0;
+        if (warp == MMA_WARP && lane == 0)
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int b = i & 1;
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
@@ -314,6 +353,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
 
     if (warp < EPI_WARPS) {
         // ------------------------------------------------------------------ epilogue: thread = channel c
+        reg_dec<EPI_REGS>();
         const int c = warp * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
         weight_to_tmem(p.w2, 1, 128, c, tmem_w_hi + lane_addr, tmem_w_lo + lane_addr);     // W2^T: row c, k = o
@@ -363,28 +403,30 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
         }
     } else if (warp < MMA_WARP) {
         // ------------------------------------------------------------------ builders + row phase: warp w -> rows 8w .. 8w+7
+        reg_inc<BLD_REGS>();
         const int w = warp - EPI_WARPS;
         const int row0 = w * 8;
         float db2_acc[4] = {0.f, 0.f, 0.f, 0.f};
-        struct Tile { Gather8 g; float4 ga, gb; };                        // ga/gb: g_agg[dst]*inv_deg of first / last row
-        Tile cur, nxt;
-        auto gather_tile = [&](Tile& T, RowIdx idx) {
+        // gathered operands of one tile's 8 rows; ga/gb = g_agg[dst] of the first / last row with sa/sb = inv_deg,
+        // mw = z2 sign words of the rows' 32-edge chunk for channels 4*lane..4*lane+3.  Everything is kept raw:
+        // nothing may depend on a load inside the prefetch, or the prefetch turns into a stall.
+        struct Tile { Gather8 g; float4 ga, gb; float sa, sb; uint4 mw; };
+        Tile T0, T1;
+        auto gather_tile = [&](Tile& T, RowIdx idx, int64_t t) {
             gather8(T.g, p.PQ, idx, 0, lane);
             T.ga = T.gb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (T.g.da >= 0) {
-                const float s = __ldg(p.inv_deg + T.g.da);
-                const float4 x = ldg4(p.g_agg + (int64_t)T.g.da * p.ld_gagg + lane * 4);
-                T.ga = make_float4(x.x * s, x.y * s, x.z * s, x.w * s);
-            }
-            if (T.g.db >= 0) {
-                const float s = __ldg(p.inv_deg + T.g.db);
-                const float4 x = ldg4(p.g_agg + (int64_t)T.g.db * p.ld_gagg + lane * 4);
-                T.gb = make_float4(x.x * s, x.y * s, x.z * s, x.w * s);
-            }
+            T.sa = T.sb = 0.f;
+            T.mw = make_uint4(0u, 0u, 0u, 0u);
+            if (T.g.da >= 0) { T.sa = __ldg(p.inv_deg + T.g.da); T.ga = ldg4(p.g_agg + (int64_t)T.g.da * p.ld_gagg + lane * 4); }
+            if (T.g.db >= 0) { T.sb = __ldg(p.inv_deg + T.g.db); T.gb = ldg4(p.g_agg + (int64_t)T.g.db * p.ld_gagg + lane * 4); }
+            if (t < n_tiles) T.mw = __ldg(reinterpret_cast<const uint4*>(p.mask2 + ((t * BTE + row0) >> 5) * 128 + lane * 4));
         };
-        // row phase of a finished tile: rows of this warp from the staging tile
-        auto row_phase = [&](int b, uint32_t ph, RowIdx idx, uint32_t hmask) {
+        // row phase of a finished tile: this warp's rows of D1 from the staging tile, g_z1 = D1 * [h1 > 0] with the
+        // sign taken from the bf16 hi image of h1 this warp wrote itself (still intact: stage b is rebuilt only by
+        // this warp, one step later)
+        auto row_phase = [&](int b, uint32_t ph, RowIdx idx) {
             const float* stage = reinterpret_cast<const float*>(sm + BwdSmem::ST + b * (BTE * 128 * 4));
+            const unsigned char* imgH = sm + BwdSmem::HG + b * (4 * B_IMG);
             mbar_wait(st_full + 8 * b, ph);
             int seg = -1;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -394,9 +436,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
                 const int s = __shfl_sync(0xffffffffu, idx.s, k);
                 if (d < 0) continue;                                       // beyond the last edge (warp-uniform)
                 float4 g = *reinterpret_cast<const float4*>(stage + (row0 + k) * 128 + lane * 4);
-                const uint32_t bits = hmask >> (4 * k);
-                g.x = (bits & 1u) ? g.x : 0.f; g.y = (bits & 2u) ? g.y : 0.f;
-                g.z = (bits & 4u) ? g.z : 0.f; g.w = (bits & 8u) ? g.w : 0.f;
+                const uint2 hh = *reinterpret_cast<const uint2*>(imgH + tile_off<BTE>(row0 + k, lane * 4));
+                g.x = (hh.x & 0xFFFFu) ? g.x : 0.f; g.y = (hh.x >> 16) ? g.y : 0.f;
+                g.z = (hh.y & 0xFFFFu) ? g.z : 0.f; g.w = (hh.y >> 16) ? g.w : 0.f;
                 red_add_v4(p.dPQ + (int64_t)s * 256 + 128 + lane * 4, g);                  // dQ'[src]
                 if (d != seg) {
                     if (seg >= 0) red_add_v4(p.dPQ + (int64_t)seg * 256 + lane * 4, acc);  // dP'[dst]
@@ -410,66 +452,86 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
             if (lane == 0) mbar_arrive(st_empty + 8 * b);
         };
 
-        const int64_t t0 = blockIdx.x, t1 = t0 + gridDim.x;
-        RowIdx idx = load_row_idx<8>(p.dst, p.src, t0 * BTE, row0, p.n_edges, t0 < n_tiles);
-        RowIdx idx_n = load_row_idx<8>(p.dst, p.src, t1 * BTE, row0, p.n_edges, t1 < n_tiles);
-        gather_tile(cur, idx);
+        const int64_t G = gridDim.x;
+        RowIdx idx = load_row_idx<8>(p.dst, p.src, (int64_t)blockIdx.x * BTE, row0, p.n_edges, (int64_t)blockIdx.x < n_tiles);
+        RowIdx idx_n = load_row_idx<8>(p.dst, p.src, (blockIdx.x + G) * BTE, row0, p.n_edges, blockIdx.x + G < n_tiles);
         RowIdx idx_prev; idx_prev.d = idx_prev.s = -1;
-        uint32_t hmask_prev = 0;
         int i = 0;
-        for (int64_t t = t0; t < n_tiles; t += gridDim.x, ++i) {
+        // one tile: `cur` was gathered one step ago; gather `nxt` (tile t + G) now, build tile t, then finish tile t - G
+        auto step = [&](int64_t t, Tile& cur, Tile& nxt) {
             const int b = i & 1;
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-            const int64_t e0 = t * BTE;
-            const int64_t t2 = t + 2 * (int64_t)gridDim.x;
-            const RowIdx idx_nn = load_row_idx<8>(p.dst, p.src, t2 * BTE, row0, p.n_edges, t2 < n_tiles);
-            gather_tile(nxt, idx_n);                                       // next tile's operands -> registers
-            // z2 sign words of this warp's 8 rows (one 32-edge chunk): channels 4*lane .. 4*lane+3
-            const uint4 mw = __ldg(reinterpret_cast<const uint4*>(p.mask2 + ((e0 + row0) >> 5) * 128 + lane * 4));
-            const int bit0 = (int)((e0 + row0) & 31);
+            const RowIdx idx_nn = load_row_idx<8>(p.dst, p.src, (t + 2 * G) * BTE, row0, p.n_edges, t + 2 * G < n_tiles);
+            gather_tile(nxt, idx_n, t + G);
+            // G rows are the per-target vector g_agg[dst]/deg gated by the z2 sign bits: split it to bf16 hi/lo once per
+            // target (first / last row's target), per row only select
+            const float4 gsa = make_float4(cur.ga.x * cur.sa, cur.ga.y * cur.sa, cur.ga.z * cur.sa, cur.ga.w * cur.sa);
+            const float4 gsb = make_float4(cur.gb.x * cur.sb, cur.gb.y * cur.sb, cur.gb.z * cur.sb, cur.gb.w * cur.sb);
+            uint2 ahi, alo, bhi, blo;
+            split4(gsa, ahi, alo);
+            split4(gsb, bhi, blo);
+            const int sh = (int)((t * BTE + row0) & 31);
+            const uint32_t mx = cur.mw.x >> sh, my = cur.mw.y >> sh, mz = cur.mw.z >> sh, mw = cur.mw.w >> sh;  // bit k = row k
+            // db2[o] = sum_e G[e][o] = sum over targets of (g/deg)[o] * #(rows of that target with z2 > 0)
+            uint32_t rows_a = __ballot_sync(0xffffffffu, idx.d == cur.g.da && idx.d >= 0) & 0xFFu;
+            uint32_t rows_b = __ballot_sync(0xffffffffu, idx.d == cur.g.db && idx.d >= 0) & 0xFFu & ~rows_a;
+            db2_acc[0] += gsa.x * (float)__popc(mx & rows_a) + gsb.x * (float)__popc(mx & rows_b);
+            db2_acc[1] += gsa.y * (float)__popc(my & rows_a) + gsb.y * (float)__popc(my & rows_b);
+            db2_acc[2] += gsa.z * (float)__popc(mz & rows_a) + gsb.z * (float)__popc(mz & rows_b);
+            db2_acc[3] += gsa.w * (float)__popc(mw & rows_a) + gsb.w * (float)__popc(mw & rows_b);
             mbar_wait(hg_empty + 8 * b, ph ^ 1u);
             unsigned char* imgH = sm + BwdSmem::HG + b * (4 * B_IMG);
             unsigned char* imgG = imgH + 2 * B_IMG;
-            uint32_t hmask = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int d = __shfl_sync(0xffffffffu, idx.d, k);
-                float4 h = make_float4(0.f, 0.f, 0.f, 0.f), g = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint2 ghi = make_uint2(0u, 0u), glo = make_uint2(0u, 0u);
                 if (d >= 0) {
                     h = relu_add(pick_row(p.PQ, 256, d, cur.g.da, cur.g.db, cur.g.pa, cur.g.pb, lane), cur.g.q[k]);
-                    float4 gs;
-                    if (d == cur.g.da) gs = cur.ga;
-                    else if (d == cur.g.db) gs = cur.gb;
-                    else {
-                        const float s = __ldg(p.inv_deg + d);
+                    if (d == cur.g.da) { ghi = ahi; glo = alo; }
+                    else if (d == cur.g.db) { ghi = bhi; glo = blo; }
+                    else {                                                 // a third target inside 8 rows: rare
+                        const float sc = __ldg(p.inv_deg + d);
                         const float4 x = ldg4(p.g_agg + (int64_t)d * p.ld_gagg + lane * 4);
-                        gs = make_float4(x.x * s, x.y * s, x.z * s, x.w * s);
+                        const float4 gs = make_float4(x.x * sc, x.y * sc, x.z * sc, x.w * sc);
+                        split4(gs, ghi, glo);
+                        db2_acc[0] += ((mx >> k) & 1u) ? gs.x : 0.f; db2_acc[1] += ((my >> k) & 1u) ? gs.y : 0.f;
+                        db2_acc[2] += ((mz >> k) & 1u) ? gs.z : 0.f; db2_acc[3] += ((mw >> k) & 1u) ? gs.w : 0.f;
                     }
-                    const int bit = bit0 + k;
-                    g.x = ((mw.x >> bit) & 1u) ? gs.x : 0.f; g.y = ((mw.y >> bit) & 1u) ? gs.y : 0.f;
-                    g.z = ((mw.z >> bit) & 1u) ? gs.z : 0.f; g.w = ((mw.w >> bit) & 1u) ? gs.w : 0.f;
-                    db2_acc[0] += g.x; db2_acc[1] += g.y; db2_acc[2] += g.z; db2_acc[3] += g.w;
+                    // keep the halves whose z2 sign bit is set
+                    const uint32_t k01 = (((mx >> k) & 1u) ? 0x0000FFFFu : 0u) | (((my >> k) & 1u) ? 0xFFFF0000u : 0u);
+                    const uint32_t k23 = (((mz >> k) & 1u) ? 0x0000FFFFu : 0u) | (((mw >> k) & 1u) ? 0xFFFF0000u : 0u);
+                    ghi.x &= k01; glo.x &= k01; ghi.y &= k23; glo.y &= k23;
                 }
-                hmask |= ((h.x > 0.f ? 1u : 0u) | (h.y > 0.f ? 2u : 0u) | (h.z > 0.f ? 4u : 0u) | (h.w > 0.f ? 8u : 0u)) << (4 * k);
                 store_split<BTE>(imgH, row0 + k, lane, h);
-                store_split<BTE>(imgG, row0 + k, lane, g);
+                const uint32_t off = tile_off<BTE>(row0 + k, lane * 4);
+                *reinterpret_cast<uint2*>(imgG + off) = ghi;
+                *reinterpret_cast<uint2*>(imgG + B_IMG + off) = glo;
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(hg_full + 8 * b);
-            if (i > 0) row_phase(b ^ 1, (uint32_t)((i - 1) >> 1) & 1u, idx_prev, hmask_prev);
-            idx_prev = idx; hmask_prev = hmask;
+            if (i > 0) row_phase(b ^ 1, (uint32_t)((i - 1) >> 1) & 1u, idx_prev);
+            idx_prev = idx;
             idx = idx_n; idx_n = idx_nn;
-            cur = nxt;
+            ++i;
+        };
+        gather_tile(T0, idx, blockIdx.x);
+        for (int64_t t = blockIdx.x; t < n_tiles; t += 2 * G) {           // two tiles per trip: T0 / T1 swap roles
+            step(t, T0, T1);
+            if (t + G < n_tiles) step(t + G, T1, T0);
         }
-        if (i > 0) row_phase((i - 1) & 1, (uint32_t)((i - 1) >> 1) & 1u, idx_prev, hmask_prev);
+        if (i > 0) row_phase((i - 1) & 1, (uint32_t)((i - 1) >> 1) & 1u, idx_prev);
 #pragma unroll
         for (int f = 0; f < 4; ++f) atomicAdd(p.db2 + lane * 4 + f, db2_acc[f]);
-    } else if (lane == 0) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (one thread of warp 12)
+        reg_dec<MMA_REGS>();
         constexpr uint32_t idesc_a = idesc_bf16(128, BTE, 0, 0);           // D1: A (TMEM) K-major, B = G K-major
         constexpr uint32_t idesc_b = idesc_bf16(128, 128, 1, 1);           // D2: A = G, B = h1, both MN-major
         int i = 0;
+        if (warp == MMA_WARP && lane == 0)
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int b = i & 1;
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
@@ -501,7 +563,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
             }
             umma_commit(hg_empty + 8 * b);
         }
-        if (i > 0) umma_commit(all_done);
+        if (warp == MMA_WARP && lane == 0 && i > 0) umma_commit(all_done);
     }
     tc_fence_before();
     __syncthreads();

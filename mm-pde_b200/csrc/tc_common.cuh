@@ -18,20 +18,27 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Spin on a phase parity.  A wait that outlives ~4 s of SM clocks can only be a protocol bug: trap
-// (the launch fails with an error) instead of hanging the GPU.
+// Wait on a phase parity.  try_wait suspends the thread in hardware for a bounded time, so the loop rarely
+// iterates; the clock is only read every 256 failed polls.  A wait that outlives ~4 s of SM clocks can only be a
+// protocol bug: trap (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    long long t0 = clock64();
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
+#pragma unroll 1
+        for (int k = 0; k < 256; ++k)
+            if (mbar_try_wait(bar, parity)) return;
         if (clock64() - t0 > 8000000000LL) __trap();
     }
 }

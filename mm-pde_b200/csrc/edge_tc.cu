@@ -21,6 +21,21 @@
 namespace mmpde {
 using namespace tc;
 
+// Optional per-phase timestamps (debug build only: make timeline -> libmmpde_b200_tl.so, read by profiles/timeline.py).
+// Slot layout: [role][tile iteration < TL_ITERS][8 stamps]; roles: 0 first builder warp, 1 last builder warp, 2 MMA
+// thread, 3 epilogue warp 0.  CTA 0 only.
+#ifdef MMPDE_TIMELINE
+__device__ long long* g_timeline = nullptr;
+constexpr int TL_ITERS = 48;
+#define TL(role, it, slot)                                                                                   \
+    do {                                                                                                     \
+        if (g_timeline != nullptr && blockIdx.x == 0 && (it) < TL_ITERS && (threadIdx.x & 31) == 0)          \
+            g_timeline[((role) * TL_ITERS + (it)) * 8 + (slot)] = clock64();                                 \
+    } while (0)
+#else
+#define TL(role, it, slot) do { } while (0)
+#endif
+
 constexpr int EPI_WARPS = 4;
 constexpr int BLD_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS + BLD_WARPS;
@@ -48,8 +63,9 @@ __device__ __forceinline__ RowIdx load_row_idx(const int* __restrict__ dst, cons
 // gathered operands of 8 consecutive rows of one builder warp (lane = 4 channels)
 struct Gather8 {
     float4 q[8];          // Q'[src] rows
-    float4 pa, pb;        // P'[dst] of the first / last row (a target's rows are consecutive: usually <= 2 targets)
-    int da, db;
+    float4 pa, pb;        // P'[dst] of the first / last row: a target's rows are consecutive, so 8 rows span <= 2 targets
+    int da, db;           //   unless some in-degree is < 4; such rows are listed in `odd` and patched afterwards
+    uint32_t odd;         // bit k: row k belongs to a third target
 };
 __device__ __forceinline__ void gather8(Gather8& g, const float* __restrict__ PQ, RowIdx idx, int r0, int lane) {
 #pragma unroll
@@ -63,23 +79,39 @@ __device__ __forceinline__ void gather8(Gather8& g, const float* __restrict__ PQ
     g.pa = g.pb = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g.da >= 0) g.pa = ldg4(PQ + (int64_t)g.da * 256 + lane * 4);
     if (g.db >= 0) g.pb = ldg4(PQ + (int64_t)g.db * 256 + lane * 4);
+    g.odd = (__ballot_sync(0xffffffffu, idx.d >= 0 && idx.d != g.da && idx.d != g.db) >> r0) & 0xFFu;
 }
-__device__ __forceinline__ float4 pick_row(const float* __restrict__ base, int64_t ld, int d, int da, int db, const float4& a,
-                                           const float4& b, int lane) {
-    if (d == da) return a;
-    if (d == db) return b;
-    return ldg4(base + (int64_t)d * ld + lane * 4);           // > 2 targets inside 8 rows (in-degree < 4): rare
+__device__ __forceinline__ float4 sel4(bool c, const float4& a, const float4& b) {
+    return make_float4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
 }
 __device__ __forceinline__ float4 relu_add(const float4& a, const float4& b) {
     return make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
 }
+// fp32 row fragment (4 channels of this lane) -> bf16 hi / lo operand images at shared address `img`
 template <int ROWS>
-__device__ __forceinline__ void store_split(unsigned char* img, int row, int lane, const float4& v) {
+__device__ __forceinline__ void store_split(uint32_t img, int row, int lane, const float4& v) {
     uint2 hi, lo;
     split4(v, hi, lo);
-    const uint32_t off = tile_off<ROWS>(row, lane * 4);
-    *reinterpret_cast<uint2*>(img + off) = hi;
-    *reinterpret_cast<uint2*>(img + 2 * ROWS * 128 + off) = lo;            // lo image follows the hi image
+    const uint32_t a = img + tile_off<ROWS>(row, lane * 4);
+    sts_v2(a, hi);
+    sts_v2(a + 2 * ROWS * 128, lo);                                        // lo image follows the hi image
+}
+// h1 = relu(P'[dst] + Q'[src]) of 8 gathered rows -> operand image rows rowbase .. rowbase+7.  Straight-line code
+// (rows beyond the last edge come out as zero: their Q' and the last row's P' are zero), then the rare patch loop.
+template <int ROWS>
+__device__ __forceinline__ void build_h8(uint32_t img, int rowbase, const Gather8& g, RowIdx idx, int r0,
+                                         const float* __restrict__ PQ, int lane) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int d = __shfl_sync(0xffffffffu, idx.d, r0 + k);
+        store_split<ROWS>(img, rowbase + k, lane, relu_add(sel4(d == g.da, g.pa, g.pb), g.q[k]));
+    }
+    for (uint32_t odd = g.odd; odd != 0u; odd &= odd - 1u) {
+        const int k = __ffs(odd) - 1;
+        const int d = __shfl_sync(0xffffffffu, idx.d, r0 + k), sr = __shfl_sync(0xffffffffu, idx.s, r0 + k);
+        store_split<ROWS>(img, rowbase + k, lane,
+                          relu_add(ldg4(PQ + (int64_t)d * 256 + lane * 4), ldg4(PQ + (int64_t)sr * 256 + 128 + lane * 4)));
+    }
 }
 
 // W (row-major [128][128] fp32, element (r, k) at w[r*rs + k*ks]) -> TMEM A operand: lane r, 64 columns hi, 64 lo
@@ -104,14 +136,10 @@ __device__ __forceinline__ void weight_to_tmem(const float* __restrict__ w, int 
 }
 
 // mean message of one finished target: agg[cur][o] += run / deg (partial runs of a target add up atomically)
-__device__ __noinline__ void flush_mean(float* agg, int64_t ld, const float* __restrict__ inv_deg, int cur, int o, float run) {
-    if (cur >= 0) atomicAdd(agg + (int64_t)cur * ld + o, run * __ldg(inv_deg + cur));
+__device__ __noinline__ void flush_mean(float* agg, int64_t ld, int cur, float inv, int o, float run) {
+    if (cur >= 0) atomicAdd(agg + (int64_t)cur * ld + o, run * inv);
 }
-__device__ __forceinline__ int lds_i32(uint32_t saddr) {
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
-}
+__device__ __forceinline__ int lds_i32(uint32_t saddr) { return (int)lds_b32(saddr); }
 
 // ================================================================================================================
 // Forward:  agg[i] = mean_{e: dst=i} relu(W2 relu(P'[i] + Q'[src_e]) + b2);  mask2 = sign bits of z2.
@@ -126,7 +154,8 @@ struct EdgeFwdArgs {
 struct FwdSmem {
     static constexpr uint32_t H = 0;                       // 2 stages x (hi, lo)
     static constexpr uint32_t DST = 2 * 2 * F_IMG;         // int dst[4][128]  (slot = tile iteration & 3)
-    static constexpr uint32_t BAR = DST + 4 * FTE * 4;     // h_full[2] h_empty[2] tm_full[2] tm_empty[2], tmem slot
+    static constexpr uint32_t INV = DST + 4 * FTE * 4;     // float inv_deg[dst][4][128]
+    static constexpr uint32_t BAR = INV + 4 * FTE * 4;     // h_full[2] h_empty[2] tm_full[2] tm_empty[2], tmem slot
     static constexpr uint32_t TOTAL = BAR + 128;
 };
 
@@ -134,7 +163,6 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(sm);
-    int* sDst = reinterpret_cast<int*>(sm + FwdSmem::DST);
     const uint32_t bar0 = sbase + FwdSmem::BAR;
     const uint32_t h_full = bar0, h_empty = bar0 + 16, tm_full = bar0 + 32, tm_empty = bar0 + 48;   // [b] at +8*b
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + FwdSmem::BAR + 64);
@@ -174,10 +202,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
             const uint32_t dsts = sbase + FwdSmem::DST + (uint32_t)(i & 3) * (FTE * 4);
             mbar_wait(tm_full + 8 * b, ph);
+            if (warp == 0) TL(3, i, 0);
             tc_fence_after();
             const uint32_t d_addr = tmem_d + lane_addr + b * FTE;
             int cur = -1;
-            float run = 0.f;
+            float run = 0.f, cur_inv = 0.f;
             // 32 edges of this thread's channel: ReLU, sign mask, running per-target sum.  Targets are contiguous
             // runs of edges; `bm` marks the first edge of each run (warp-uniform), so groups of 4 edges without a
             // boundary take the short path.
@@ -200,9 +229,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if (nib & (1u << k)) {
-                                flush_mean(p.agg, p.ld_agg, p.inv_deg, cur, o, run);
-                                cur = lds_i32(dsts + 4 * (chunk * 32 + 4 * g + k));
-                                run = 0.f;
+                                flush_mean(p.agg, p.ld_agg, cur, cur_inv, o, run);
+                                cur = lds_i32(dsts + 4 * (chunk * 32 + 4 * g + k));           // used at the NEXT flush:
+                                cur_inv = __uint_as_float(lds_b32(dsts + 4 * FTE * 4 + 4 * (chunk * 32 + 4 * g + k)));
+                                run = 0.f;                                                    // latency stays hidden
                             }
                             run += r[k];
                         }
@@ -223,13 +253,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
                 if (half == 0) tmem_ld32_async(d_addr + 64, v0);
                 process(v1, 2 * half + 1);
             }
-            flush_mean(p.agg, p.ld_agg, p.inv_deg, cur, o, run);
+            flush_mean(p.agg, p.ld_agg, cur, cur_inv, o, run);
 #pragma unroll
             for (int c = 0; c < 4; ++c) tmem_fill32(d_addr + c * 32, bias_bits);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tm_empty + 8 * b);
+            if (warp == 0) TL(3, i, 2);
         }
     } else if (warp < MMA_WARP) {
         // ------------------------------------------------------------------ builders: warp w -> rows 16w .. 16w+15
@@ -237,36 +268,35 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
         const int w = warp - EPI_WARPS;
         const int row0 = w * 16;
         Gather8 ga, gb;
+        const int64_t G = gridDim.x;
+        // row indices run two tiles ahead of the build, the gathers one half tile / one tile ahead
         RowIdx idx = load_row_idx<16>(p.dst, p.src, (int64_t)blockIdx.x * FTE, row0, p.n_edges, (int64_t)blockIdx.x < n_tiles);
+        RowIdx idx_n = load_row_idx<16>(p.dst, p.src, (blockIdx.x + G) * FTE, row0, p.n_edges, blockIdx.x + G < n_tiles);
+        float inv = (idx.d >= 0) ? __ldg(p.inv_deg + idx.d) : 0.f;
         gather8(ga, p.PQ, idx, 0, lane);
         int i = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        for (int64_t t = blockIdx.x; t < n_tiles; t += G, ++i) {
             const int b = i & 1;
-            const int64_t tn = t + gridDim.x;
-            const RowIdx nxt = load_row_idx<16>(p.dst, p.src, tn * FTE, row0, p.n_edges, tn < n_tiles);
+            if (w == 0 || w == BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 0);
+            const RowIdx idx_nn = load_row_idx<16>(p.dst, p.src, (t + 2 * G) * FTE, row0, p.n_edges, t + 2 * G < n_tiles);
+            const float inv_n = (idx_n.d >= 0) ? __ldg(p.inv_deg + idx_n.d) : 0.f;
             gather8(gb, p.PQ, idx, 8, lane);
             mbar_wait(h_empty + 8 * b, ((uint32_t)(i >> 1) & 1u) ^ 1u);    // MMA of tile i-2 has consumed this stage
-            unsigned char* img = sm + FwdSmem::H + b * (2 * F_IMG);
-            if (lane < 16) sDst[(i & 3) * FTE + row0 + lane] = idx.d;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int d = __shfl_sync(0xffffffffu, idx.d, k);
-                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (d >= 0) h = relu_add(pick_row(p.PQ, 256, d, ga.da, ga.db, ga.pa, ga.pb, lane), ga.q[k]);
-                store_split<FTE>(img, row0 + k, lane, h);
+            if (w == 0 || w == BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 1);
+            const uint32_t img = sbase + FwdSmem::H + b * (2 * F_IMG);
+            if (lane < 16) {
+                const uint32_t slot = sbase + FwdSmem::DST + (uint32_t)((i & 3) * FTE + row0 + lane) * 4;
+                sts_b32(slot, (uint32_t)idx.d);
+                sts_b32(slot + 4 * FTE * 4, __float_as_uint(inv));
             }
-            gather8(ga, p.PQ, nxt, 0, lane);                               // first half of the NEXT tile
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int d = __shfl_sync(0xffffffffu, idx.d, 8 + k);
-                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (d >= 0) h = relu_add(pick_row(p.PQ, 256, d, gb.da, gb.db, gb.pa, gb.pb, lane), gb.q[k]);
-                store_split<FTE>(img, row0 + 8 + k, lane, h);
-            }
+            build_h8<FTE>(img, row0, ga, idx, 0, p.PQ, lane);
+            gather8(ga, p.PQ, idx_n, 0, lane);                             // first half of the NEXT tile
+            build_h8<FTE>(img, row0 + 8, gb, idx, 8, p.PQ, lane);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(h_full + 8 * b);
-            idx = nxt;
+            if (w == 0 || w == BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 2);
+            idx = idx_n; idx_n = idx_nn; inv = inv_n;
         }
     } else {
         // ------------------------------------------------------------------ MMA issuer (one thread of warp 12)
@@ -278,7 +308,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
             const int b = i & 1;
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
             mbar_wait(h_full + 8 * b, ph);
+            TL(2, i, 0);
             mbar_wait(tm_empty + 8 * b, ph);
+            TL(2, i, 1);
             tc_fence_after();
             const uint32_t h_addr = sbase + FwdSmem::H + b * (2 * F_IMG);
 #pragma unroll
@@ -292,6 +324,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
             }
             umma_commit(h_empty + 8 * b);
             umma_commit(tm_full + 8 * b);
+            TL(2, i, 2);
         }
     }
     tc_fence_before();
@@ -365,10 +398,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int b = i & 1;
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-            float* stage = reinterpret_cast<float*>(sm + BwdSmem::ST + b * (BTE * 128 * 4));
+            const uint32_t stage = sbase + BwdSmem::ST + b * (BTE * 128 * 4) + c * 4;
             mbar_wait(d1_full + 8 * b, ph);
+            if (warp == 0) TL(3, i, 0);
             tc_fence_after();
             mbar_wait(st_empty + 8 * b, ph ^ 1u);                          // row phase of tile i-2 has drained the stage
+            if (warp == 0) TL(3, i, 1);
             uint32_t v[2][32];
             tmem_ld32_async(tmem_d1 + lane_addr + b * BTE, v[0]);
             tmem_ld32_async(tmem_d1 + lane_addr + b * BTE + 32, v[1]);
@@ -377,12 +412,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(d1_empty + 8 * b);                  // accumulator stage free for tile i+2
+            if (warp == 0) TL(3, i, 2);
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stage[(h * 32 + j) * 128 + c] = __uint_as_float(v[h][j]);
+                for (int j = 0; j < 32; ++j) sts_b32(stage + (h * 32 + j) * 512, v[h][j]);
             __syncwarp();
             if (lane == 0) mbar_arrive(st_full + 8 * b);
+            if (warp == 0) TL(3, i, 3);
         }
         // ---- this CTA's dW2 partial: D2[o][c], lane = o, registers = 32 consecutive c = one contiguous piece of
         //      row o of dW2 -> 128-bit vector reductions straight from the registers
@@ -411,7 +448,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
         // mw = z2 sign words of the rows' 32-edge chunk for channels 4*lane..4*lane+3.  Everything is kept raw:
         // nothing may depend on a load inside the prefetch, or the prefetch turns into a stall.
         struct Tile { Gather8 g; float4 ga, gb; float sa, sb; uint4 mw; };
-        Tile T0, T1;
+        Tile cur, nxt;
+        int i = 0;
         auto gather_tile = [&](Tile& T, RowIdx idx, int64_t t) {
             gather8(T.g, p.PQ, idx, 0, lane);
             T.ga = T.gb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -423,44 +461,57 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
         };
         // row phase of a finished tile: this warp's rows of D1 from the staging tile, g_z1 = D1 * [h1 > 0] with the
         // sign taken from the bf16 hi image of h1 this warp wrote itself (still intact: stage b is rebuilt only by
-        // this warp, one step later)
-        auto row_phase = [&](int b, uint32_t ph, RowIdx idx) {
-            const float* stage = reinterpret_cast<const float*>(sm + BwdSmem::ST + b * (BTE * 128 * 4));
-            const unsigned char* imgH = sm + BwdSmem::HG + b * (4 * B_IMG);
+        // this warp, one step later).  dQ'[src] += row; dP'[dst] += sum of the rows of each target (first / last row's
+        // target in straight-line code, rows of a third target patched one by one).
+        auto masked_row = [&](uint32_t stage, uint32_t imgH, int k) {
+            float4 g = lds_v4f(stage + k * 512);
+            const uint2 hh = lds_v2(imgH + tile_off<BTE>(row0 + k, lane * 4));
+            g.x = (hh.x & 0xFFFFu) ? g.x : 0.f; g.y = (hh.x >> 16) ? g.y : 0.f;
+            g.z = (hh.y & 0xFFFFu) ? g.z : 0.f; g.w = (hh.y >> 16) ? g.w : 0.f;
+            return g;
+        };
+        auto row_phase = [&](int b, uint32_t ph, RowIdx idx, int da, int db, uint32_t odd) {
+            const uint32_t stage = sbase + BwdSmem::ST + b * (BTE * 128 * 4) + row0 * 512 + lane * 16;
+            const uint32_t imgH = sbase + BwdSmem::HG + b * (4 * B_IMG);
             mbar_wait(st_full + 8 * b, ph);
-            int seg = -1;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (w == 0 || w == BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i - 1, 3);
+            float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int d = __shfl_sync(0xffffffffu, idx.d, k);
-                const int s = __shfl_sync(0xffffffffu, idx.s, k);
-                if (d < 0) continue;                                       // beyond the last edge (warp-uniform)
-                float4 g = *reinterpret_cast<const float4*>(stage + (row0 + k) * 128 + lane * 4);
-                const uint2 hh = *reinterpret_cast<const uint2*>(imgH + tile_off<BTE>(row0 + k, lane * 4));
-                g.x = (hh.x & 0xFFFFu) ? g.x : 0.f; g.y = (hh.x >> 16) ? g.y : 0.f;
-                g.z = (hh.y & 0xFFFFu) ? g.z : 0.f; g.w = (hh.y >> 16) ? g.w : 0.f;
-                red_add_v4(p.dPQ + (int64_t)s * 256 + 128 + lane * 4, g);                  // dQ'[src]
-                if (d != seg) {
-                    if (seg >= 0) red_add_v4(p.dPQ + (int64_t)seg * 256 + lane * 4, acc);  // dP'[dst]
-                    seg = d;
-                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+                const int sr = __shfl_sync(0xffffffffu, idx.s, k);
+                const float4 g = masked_row(stage, imgH, k);               // rows beyond the last edge are exactly zero
+                if (sr >= 0) red_add_v4(p.dPQ + (int64_t)sr * 256 + 128 + lane * 4, g);    // dQ'[src]
+                const float fa = (d == da) ? 1.f : 0.f, fb = (d == db && d != da) ? 1.f : 0.f;
+                acc_a.x = fmaf(fa, g.x, acc_a.x); acc_a.y = fmaf(fa, g.y, acc_a.y);
+                acc_a.z = fmaf(fa, g.z, acc_a.z); acc_a.w = fmaf(fa, g.w, acc_a.w);
+                acc_b.x = fmaf(fb, g.x, acc_b.x); acc_b.y = fmaf(fb, g.y, acc_b.y);
+                acc_b.z = fmaf(fb, g.z, acc_b.z); acc_b.w = fmaf(fb, g.w, acc_b.w);
             }
-            if (seg >= 0) red_add_v4(p.dPQ + (int64_t)seg * 256 + lane * 4, acc);
+            if (da >= 0) red_add_v4(p.dPQ + (int64_t)da * 256 + lane * 4, acc_a);          // dP'[dst]
+            if (db >= 0 && db != da) red_add_v4(p.dPQ + (int64_t)db * 256 + lane * 4, acc_b);
+            for (; odd != 0u; odd &= odd - 1u) {
+                const int k = __ffs(odd) - 1;
+                const int d = __shfl_sync(0xffffffffu, idx.d, k);
+                red_add_v4(p.dPQ + (int64_t)d * 256 + lane * 4, masked_row(stage, imgH, k));
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(st_empty + 8 * b);
+            if (w == 0 || w == BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i - 1, 4);
         };
 
         const int64_t G = gridDim.x;
         RowIdx idx = load_row_idx<8>(p.dst, p.src, (int64_t)blockIdx.x * BTE, row0, p.n_edges, (int64_t)blockIdx.x < n_tiles);
         RowIdx idx_n = load_row_idx<8>(p.dst, p.src, (blockIdx.x + G) * BTE, row0, p.n_edges, blockIdx.x + G < n_tiles);
         RowIdx idx_prev; idx_prev.d = idx_prev.s = -1;
-        int i = 0;
-        // one tile: `cur` was gathered one step ago; gather `nxt` (tile t + G) now, build tile t, then finish tile t - G
-        auto step = [&](int64_t t, Tile& cur, Tile& nxt) {
+        int da_prev = -1, db_prev = -1;
+        uint32_t odd_prev = 0u;
+        // per tile: `cur` was gathered one step ago; gather `nxt` (tile t + G) now, build tile t, then finish tile t - G
+        gather_tile(cur, idx, blockIdx.x);
+        for (int64_t t = blockIdx.x; t < n_tiles; t += G) {
             const int b = i & 1;
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            if (w == 0 || w == BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 0);
             const RowIdx idx_nn = load_row_idx<8>(p.dst, p.src, (t + 2 * G) * BTE, row0, p.n_edges, t + 2 * G < n_tiles);
             gather_tile(nxt, idx_n, t + G);
             // G rows are the per-target vector g_agg[dst]/deg gated by the z2 sign bits: split it to bf16 hi/lo once per
@@ -473,56 +524,52 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
             const int sh = (int)((t * BTE + row0) & 31);
             const uint32_t mx = cur.mw.x >> sh, my = cur.mw.y >> sh, mz = cur.mw.z >> sh, mw = cur.mw.w >> sh;  // bit k = row k
             // db2[o] = sum_e G[e][o] = sum over targets of (g/deg)[o] * #(rows of that target with z2 > 0)
-            uint32_t rows_a = __ballot_sync(0xffffffffu, idx.d == cur.g.da && idx.d >= 0) & 0xFFu;
-            uint32_t rows_b = __ballot_sync(0xffffffffu, idx.d == cur.g.db && idx.d >= 0) & 0xFFu & ~rows_a;
+            const uint32_t rows_a = __ballot_sync(0xffffffffu, idx.d == cur.g.da && idx.d >= 0) & 0xFFu;
+            const uint32_t rows_b = __ballot_sync(0xffffffffu, idx.d == cur.g.db && idx.d >= 0) & 0xFFu & ~rows_a;
             db2_acc[0] += gsa.x * (float)__popc(mx & rows_a) + gsb.x * (float)__popc(mx & rows_b);
             db2_acc[1] += gsa.y * (float)__popc(my & rows_a) + gsb.y * (float)__popc(my & rows_b);
             db2_acc[2] += gsa.z * (float)__popc(mz & rows_a) + gsb.z * (float)__popc(mz & rows_b);
             db2_acc[3] += gsa.w * (float)__popc(mw & rows_a) + gsb.w * (float)__popc(mw & rows_b);
             mbar_wait(hg_empty + 8 * b, ph ^ 1u);
-            unsigned char* imgH = sm + BwdSmem::HG + b * (4 * B_IMG);
-            unsigned char* imgG = imgH + 2 * B_IMG;
+            if (w == 0 || w == BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 1);
+            const uint32_t imgH = sbase + BwdSmem::HG + b * (4 * B_IMG);
+            const uint32_t imgG = imgH + 2 * B_IMG;
+            build_h8<BTE>(imgH, row0, cur.g, idx, 0, p.PQ, lane);
+            auto store_g = [&](int k, uint2 ghi, uint2 glo) {              // keep the halves whose z2 sign bit is set
+                const uint32_t k01 = (((mx >> k) & 1u) ? 0x0000FFFFu : 0u) | (((my >> k) & 1u) ? 0xFFFF0000u : 0u);
+                const uint32_t k23 = (((mz >> k) & 1u) ? 0x0000FFFFu : 0u) | (((mw >> k) & 1u) ? 0xFFFF0000u : 0u);
+                const uint32_t off = tile_off<BTE>(row0 + k, lane * 4);
+                sts_v2(imgG + off, make_uint2(ghi.x & k01, ghi.y & k23));
+                sts_v2(imgG + B_IMG + off, make_uint2(glo.x & k01, glo.y & k23));
+            };
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
+                const bool is_a = (__shfl_sync(0xffffffffu, idx.d, k) == cur.g.da);        // rows past the end: gsb = 0
+                store_g(k, make_uint2(is_a ? ahi.x : bhi.x, is_a ? ahi.y : bhi.y), make_uint2(is_a ? alo.x : blo.x, is_a ? alo.y : blo.y));
+            }
+            for (uint32_t odd = cur.g.odd; odd != 0u; odd &= odd - 1u) {   // rows of a third target (in-degree < 4): rare
+                const int k = __ffs(odd) - 1;
                 const int d = __shfl_sync(0xffffffffu, idx.d, k);
-                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-                uint2 ghi = make_uint2(0u, 0u), glo = make_uint2(0u, 0u);
-                if (d >= 0) {
-                    h = relu_add(pick_row(p.PQ, 256, d, cur.g.da, cur.g.db, cur.g.pa, cur.g.pb, lane), cur.g.q[k]);
-                    if (d == cur.g.da) { ghi = ahi; glo = alo; }
-                    else if (d == cur.g.db) { ghi = bhi; glo = blo; }
-                    else {                                                 // a third target inside 8 rows: rare
-                        const float sc = __ldg(p.inv_deg + d);
-                        const float4 x = ldg4(p.g_agg + (int64_t)d * p.ld_gagg + lane * 4);
-                        const float4 gs = make_float4(x.x * sc, x.y * sc, x.z * sc, x.w * sc);
-                        split4(gs, ghi, glo);
-                        db2_acc[0] += ((mx >> k) & 1u) ? gs.x : 0.f; db2_acc[1] += ((my >> k) & 1u) ? gs.y : 0.f;
-                        db2_acc[2] += ((mz >> k) & 1u) ? gs.z : 0.f; db2_acc[3] += ((mw >> k) & 1u) ? gs.w : 0.f;
-                    }
-                    // keep the halves whose z2 sign bit is set
-                    const uint32_t k01 = (((mx >> k) & 1u) ? 0x0000FFFFu : 0u) | (((my >> k) & 1u) ? 0xFFFF0000u : 0u);
-                    const uint32_t k23 = (((mz >> k) & 1u) ? 0x0000FFFFu : 0u) | (((mw >> k) & 1u) ? 0xFFFF0000u : 0u);
-                    ghi.x &= k01; glo.x &= k01; ghi.y &= k23; glo.y &= k23;
-                }
-                store_split<BTE>(imgH, row0 + k, lane, h);
-                const uint32_t off = tile_off<BTE>(row0 + k, lane * 4);
-                *reinterpret_cast<uint2*>(imgG + off) = ghi;
-                *reinterpret_cast<uint2*>(imgG + B_IMG + off) = glo;
+                const float sc = __ldg(p.inv_deg + d);
+                const float4 x = ldg4(p.g_agg + (int64_t)d * p.ld_gagg + lane * 4);
+                const float4 gs = make_float4(x.x * sc, x.y * sc, x.z * sc, x.w * sc);
+                uint2 ghi, glo;
+                split4(gs, ghi, glo);
+                store_g(k, ghi, glo);
+                db2_acc[0] += ((mx >> k) & 1u) ? gs.x : 0.f; db2_acc[1] += ((my >> k) & 1u) ? gs.y : 0.f;
+                db2_acc[2] += ((mz >> k) & 1u) ? gs.z : 0.f; db2_acc[3] += ((mw >> k) & 1u) ? gs.w : 0.f;
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(hg_full + 8 * b);
-            if (i > 0) row_phase(b ^ 1, (uint32_t)((i - 1) >> 1) & 1u, idx_prev);
-            idx_prev = idx;
+            if (w == 0 || w == BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 2);
+            if (i > 0) row_phase(b ^ 1, (uint32_t)((i - 1) >> 1) & 1u, idx_prev, da_prev, db_prev, odd_prev);
+            idx_prev = idx; da_prev = cur.g.da; db_prev = cur.g.db; odd_prev = cur.g.odd;
             idx = idx_n; idx_n = idx_nn;
+            cur = nxt;                                                     // loads issued a whole step ago: no stall
             ++i;
-        };
-        gather_tile(T0, idx, blockIdx.x);
-        for (int64_t t = blockIdx.x; t < n_tiles; t += 2 * G) {           // two tiles per trip: T0 / T1 swap roles
-            step(t, T0, T1);
-            if (t + G < n_tiles) step(t + G, T1, T0);
         }
-        if (i > 0) row_phase((i - 1) & 1, (uint32_t)((i - 1) >> 1) & 1u, idx_prev);
+        if (i > 0) row_phase((i - 1) & 1, (uint32_t)((i - 1) >> 1) & 1u, idx_prev, da_prev, db_prev, odd_prev);
 #pragma unroll
         for (int f = 0; f < 4; ++f) atomicAdd(p.db2 + lane * 4 + f, db2_acc[f]);
     } else {
@@ -536,7 +583,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
             const int b = i & 1;
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
             mbar_wait(hg_full + 8 * b, ph);
+            TL(2, i, 0);
             mbar_wait(d1_empty + 8 * b, ph);
+            TL(2, i, 1);
             tc_fence_after();
             const uint32_t h_addr = sbase + BwdSmem::HG + b * (4 * B_IMG), g_addr = h_addr + 2 * B_IMG;
             uint32_t acc = 0;
@@ -552,6 +601,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
                 }
             }
             umma_commit(d1_full + 8 * b);
+            TL(2, i, 2);
 #pragma unroll
             for (int prod = 0; prod < 3; ++prod) {                         // G hi * h hi + G hi * h lo + G lo * h hi
                 const uint32_t a = g_addr + (prod == 2 ? B_IMG : 0);
@@ -562,6 +612,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
                               smem_desc_sw128(bb + ks * 16 * 128, BTE * 128, 1024), idesc_b, (i > 0 || prod > 0 || ks > 0) ? 1u : 0u);
             }
             umma_commit(hg_empty + 8 * b);
+            TL(2, i, 3);
         }
         if (warp == MMA_WARP && lane == 0 && i > 0) umma_commit(all_done);
     }
@@ -573,6 +624,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
 }  // namespace mmpde
 
 using namespace mmpde;
+
+#ifdef MMPDE_TIMELINE
+extern "C" int mmpde_debug_timeline(long long* buf) {
+    return (int)cudaMemcpyToSymbol(g_timeline, &buf, sizeof(buf));
+}
+#endif
 
 static int edge_grid(int64_t n_tiles) { return (int)imin64(n_tiles, sm_count()); }
 

@@ -188,12 +188,38 @@ __device__ __forceinline__ uint32_t tile_off(int row, int col) {
 }
 
 // split-bf16: x = hi + lo (+ O(2^-17 |x|));  products hi*hi + hi*lo + lo*hi give ~fp32-grade GEMMs on the bf16 pipe
+__device__ __forceinline__ uint32_t cvt_bf16x2(float first, float second) {      // first -> low half
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
+    return d;
+}
 __device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
-    __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
-    float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-    __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
-    hi.x = *reinterpret_cast<uint32_t*>(&h01); hi.y = *reinterpret_cast<uint32_t*>(&h23);
-    lo.x = *reinterpret_cast<uint32_t*>(&l01); lo.y = *reinterpret_cast<uint32_t*>(&l23);
+    hi.x = cvt_bf16x2(v.x, v.y);
+    hi.y = cvt_bf16x2(v.z, v.w);
+    lo.x = cvt_bf16x2(v.x - __uint_as_float(hi.x << 16), v.y - __uint_as_float(hi.x & 0xFFFF0000u));
+    lo.y = cvt_bf16x2(v.z - __uint_as_float(hi.y << 16), v.w - __uint_as_float(hi.y & 0xFFFF0000u));
+}
+
+// ---- explicit shared-space accesses (32-bit shared addresses: STS/LDS instead of generic ST/LD) --------------
+// volatile without a memory clobber: they stay ordered among themselves and against the fence / mbarrier asm.
+__device__ __forceinline__ void sts_v2(uint32_t saddr, uint2 v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(v.x), "r"(v.y));
+}
+__device__ __forceinline__ void sts_b32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v)); }
+__device__ __forceinline__ uint32_t lds_b32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_v4f(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
 }
 
 }  // namespace tc

@@ -142,6 +142,14 @@ __device__ __noinline__ void flush_mean(float* agg, int64_t ld, int cur, float i
 __device__ __forceinline__ int lds_i32(uint32_t saddr) { return (int)lds_b32(saddr); }
 
 // ================================================================================================================
+// Forward warp roles (640 threads): 8 epilogue warps (TMEM lane quadrant = warp & 3, column half = warp >> 2),
+// 8 builder warps, 1 MMA warp (+ 3 idle to fill the warpgroup).  Register budget per thread moved with setmaxnreg
+// from the launch value 96 (the CTA's pool is what it was launched with: 640*96 = 61440):
+// 8*32*72 + 8*32*144 + 4*32*40 = 60416 <= 61440.
+constexpr int F_EPI_WARPS = 8, F_BLD_WARPS = 8, F_MMA_WARP = F_EPI_WARPS + F_BLD_WARPS, F_THREADS = 640;
+constexpr int F_EPI_REGS = 72, F_BLD_REGS = 144, F_MMA_REGS = 40;
+
+// ================================================================================================================
 // Forward:  agg[i] = mean_{e: dst=i} relu(W2 relu(P'[i] + Q'[src_e]) + b2);  mask2 = sign bits of z2.
 // Tile = 128 edges.  D[o][e] = sum_c W2[o][c] h1[e][c]  (M = 128 channels on TMEM lanes, N = 128 edges).
 // ================================================================================================================
@@ -159,7 +167,7 @@ struct FwdSmem {
     static constexpr uint32_t TOTAL = BAR + 128;
 };
 
-__global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p) {
+__global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(sm);
@@ -171,8 +179,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     if (tid == 32) {
         for (int b = 0; b < 2; ++b) {
-            mbar_init(h_full + 8 * b, BLD_WARPS); mbar_init(h_empty + 8 * b, 1);
-            mbar_init(tm_full + 8 * b, 1); mbar_init(tm_empty + 8 * b, EPI_WARPS);
+            mbar_init(h_full + 8 * b, F_BLD_WARPS); mbar_init(h_empty + 8 * b, 1);
+            mbar_init(tm_full + 8 * b, 1); mbar_init(tm_empty + 8 * b, F_EPI_WARPS);
         }
         fence_mbar_init();
     }
@@ -183,16 +191,17 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
     const uint32_t tmem_d = tmem_base, tmem_w_hi = tmem_base + 256, tmem_w_lo = tmem_base + 320;
     const int64_t n_tiles = (p.n_edges + FTE - 1) / FTE;
 
-    if (warp < EPI_WARPS) {
+    if (warp < F_EPI_WARPS) {
         // ------------------------------------------------------------------ epilogue: thread = out-channel o
-        reg_dec<EPI_REGS>();
-        const int o = warp * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        reg_dec<F_EPI_REGS>();
+        const int q = warp & 3, half = warp >> 2;                          // TMEM lane quadrant, column half
+        const int o = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const uint32_t bias_bits = __float_as_uint(__ldg(p.b2 + o));
-        weight_to_tmem(p.w2, 128, 1, o, tmem_w_hi + lane_addr, tmem_w_lo + lane_addr);
+        if (half == 0) weight_to_tmem(p.w2, 128, 1, o, tmem_w_hi + lane_addr, tmem_w_lo + lane_addr);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) tmem_fill32(tmem_d + lane_addr + c * 32, bias_bits);   // accumulators start at b2
-        tmem_wait_st();
+        for (int c = 0; c < 4; ++c) tmem_fill32(tmem_d + lane_addr + (c >> 1) * FTE + half * 64 + (c & 1) * 32, bias_bits);
+        tmem_wait_st();                                                    // accumulators start at b2
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { mbar_arrive(tm_empty); mbar_arrive(tm_empty + 8); }
@@ -204,16 +213,16 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
             mbar_wait(tm_full + 8 * b, ph);
             if (warp == 0) TL(3, i, 0);
             tc_fence_after();
-            const uint32_t d_addr = tmem_d + lane_addr + b * FTE;
+            const uint32_t d_addr = tmem_d + lane_addr + b * FTE + half * 64;
             int cur = -1;
             float run = 0.f, cur_inv = 0.f;
             // 32 edges of this thread's channel: ReLU, sign mask, running per-target sum.  Targets are contiguous
             // runs of edges; `bm` marks the first edge of each run (warp-uniform), so groups of 4 edges without a
-            // boundary take the short path.
+            // boundary take the short path.  A warp's 64 columns always start a new run (partial runs add atomically).
             auto process = [&](uint32_t (&vc)[32], int chunk) {
                 const int e = chunk * 32 + lane;
                 const int d_me = lds_i32(dsts + 4 * e);
-                const int d_pv = (e > 0) ? lds_i32(dsts + 4 * e - 4) : -2;                 // a tile always starts a run
+                const int d_pv = (e > half * 64) ? lds_i32(dsts + 4 * e - 4) : -2;
                 const uint32_t bm = __ballot_sync(0xffffffffu, d_me != d_pv);
                 uint32_t word = 0;
 #pragma unroll
@@ -242,30 +251,26 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
                 // mask2[chunk of 32 edges][channel]: bit j = (z2 > 0) of edge 32*chunk + j
                 p.mask2[((t * 4 + chunk) * 128) + o] = word;
             };
-            uint32_t v0[32], v1[32];
-            tmem_ld32_async(d_addr, v0);
+            uint32_t v[32];
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                tmem_wait_ld(v0);
-                tmem_ld32_async(d_addr + half * 64 + 32, v1);
-                process(v0, 2 * half);
-                tmem_wait_ld(v1);
-                if (half == 0) tmem_ld32_async(d_addr + 64, v0);
-                process(v1, 2 * half + 1);
+            for (int c = 0; c < 2; ++c) {
+                tmem_ld32_async(d_addr + c * 32, v);
+                tmem_wait_ld(v);
+                process(v, 2 * half + c);
             }
             flush_mean(p.agg, p.ld_agg, cur, cur_inv, o, run);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_fill32(d_addr + c * 32, bias_bits);
+            tmem_fill32(d_addr, bias_bits);
+            tmem_fill32(d_addr + 32, bias_bits);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tm_empty + 8 * b);
             if (warp == 0) TL(3, i, 2);
         }
-    } else if (warp < MMA_WARP) {
+    } else if (warp < F_MMA_WARP) {
         // ------------------------------------------------------------------ builders: warp w -> rows 16w .. 16w+15
-        reg_inc<BLD_REGS>();
-        const int w = warp - EPI_WARPS;
+        reg_inc<F_BLD_REGS>();
+        const int w = warp - F_EPI_WARPS;
         const int row0 = w * 16;
         Gather8 ga, gb;
         const int64_t G = gridDim.x;
@@ -277,12 +282,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
         int i = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += G, ++i) {
             const int b = i & 1;
-            if (w == 0 || w == BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 0);
+            if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 0);
             const RowIdx idx_nn = load_row_idx<16>(p.dst, p.src, (t + 2 * G) * FTE, row0, p.n_edges, t + 2 * G < n_tiles);
             const float inv_n = (idx_n.d >= 0) ? __ldg(p.inv_deg + idx_n.d) : 0.f;
             gather8(gb, p.PQ, idx, 8, lane);
             mbar_wait(h_empty + 8 * b, ((uint32_t)(i >> 1) & 1u) ^ 1u);    // MMA of tile i-2 has consumed this stage
-            if (w == 0 || w == BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 1);
+            if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 1);
             const uint32_t img = sbase + FwdSmem::H + b * (2 * F_IMG);
             if (lane < 16) {
                 const uint32_t slot = sbase + FwdSmem::DST + (uint32_t)((i & 3) * FTE + row0 + lane) * 4;
@@ -295,15 +300,15 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArg
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(h_full + 8 * b);
-            if (w == 0 || w == BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 2);
+            if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 2);
             idx = idx_n; idx_n = idx_nn; inv = inv_n;
         }
     } else {
         // ------------------------------------------------------------------ MMA issuer (one thread of warp 12)
-        reg_dec<MMA_REGS>();
+        reg_dec<F_MMA_REGS>();
         constexpr uint32_t idesc = idesc_bf16(128, FTE, 0, 0);
         int i = 0;
-        if (warp == MMA_WARP && lane == 0)
+        if (warp == F_MMA_WARP && lane == 0)
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int b = i & 1;
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
@@ -648,7 +653,7 @@ extern "C" int mmpde_edge_fwd(const float* PQ, const int32_t* edge_src, const in
     EdgeFwdArgs p;
     p.PQ = PQ; p.src = edge_src; p.dst = edge_dst; p.inv_deg = inv_deg; p.n_edges = n_edges; p.w2 = w2; p.b2 = b2;
     p.agg = agg; p.ld_agg = ld_agg; p.mask2 = mask2;
-    edge_fwd_tc_kernel<<<edge_grid((n_edges + FTE - 1) / FTE), EDGE_THREADS, smem, (cudaStream_t)stream>>>(p);
+    edge_fwd_tc_kernel<<<edge_grid((n_edges + FTE - 1) / FTE), F_THREADS, smem, (cudaStream_t)stream>>>(p);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }

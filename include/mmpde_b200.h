@@ -155,6 +155,16 @@ int mmpde_itp_bwd(const float* src_xy, const float* src_val, const float* qry_xy
                   int64_t n_queries, const float* params, const float* g_out,
                   float* g_params, float* g_src_val, void* stream);
 
+/* ---- halo exchange of the graph-partitioned processor (no reference counterpart) ----
+ * Rows of a strided fp32 matrix <-> a contiguous buffer; ncols and the leading dimension are multiples of 4,
+ * pointers 16-byte aligned.
+ * gather:      out[i, 0:ncols]               = src[idx[i]*ld_src + 0:ncols]     (pack what a peer needs)
+ * scatter_add: dst[idx[i]*ld_dst + 0:ncols] += in[i, 0:ncols]                   (atomic: idx may repeat) */
+int mmpde_rows_gather(const float* src, int64_t ld_src, const int32_t* idx, int64_t n_rows, int ncols,
+                      float* out, void* stream);
+int mmpde_rows_scatter_add(const float* in, const int32_t* idx, int64_t n_rows, int ncols,
+                           float* dst, int64_t ld_dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,8 @@ SIGNATURES = {
     "mmpde_decoder_bwd": [_p, _l, _l, _p, _f, _p, _p, _l, _p, _p],
     "mmpde_itp_fwd": [_p, _p, _p, _p, _l, _p, _p, _p],
     "mmpde_itp_bwd": [_p, _p, _p, _p, _l, _p, _p, _p, _p, _p],
+    "mmpde_rows_gather": [_p, _l, _p, _l, _i, _p, _p],
+    "mmpde_rows_scatter_add": [_p, _p, _l, _i, _p, _l, _p],
 }
 
 launches = 0          # number of kernel-launching C-ABI calls made so far (bench.py reports the delta)

@@ -26,6 +26,8 @@ class DistComm(ops._Comm):
         return t
 
     def global_rows(self, n):
+        if self.total_rows is not None:         # partitioned mesh: rows of the whole mesh
+            return float(self.total_rows)
         return float(n) * self.world            # equal shards (the sharder below guarantees it)
 
 
@@ -93,3 +95,40 @@ class GradBucket:
                 p.grad = v.clone()
             else:
                 p.grad.copy_(v)
+
+
+class HaloExchange:
+    """Per-layer halo exchange of a graph-partitioned mesh, one part per rank (partition.py): the Q' half
+    (columns 128..255) of the rows a peer needs is packed (mmpde_rows_gather), moved with ONE all-to-all-v over
+    NCCL / NVLink, and lands in the contiguous halo rows of the receiver; the backward sends dL/dQ' of the halo
+    rows home and adds it there (mmpde_rows_scatter_add)."""
+
+    def __init__(self, plan, group=None):
+        self.plan, self.group = plan, group
+        self.send_idx = plan.send_idx.to(torch.int32).contiguous()
+        self.n_send, self.n_halo, self.n_own = int(plan.send_idx.numel()), plan.n_halo, plan.n_own
+        self.bytes_forward = self.n_halo * ops.H * 4
+
+    def _pack(self, buf):                    # rows the peers need, Q' half -> contiguous [n_send,128]
+        out = torch.empty(self.n_send, ops.H, dtype=torch.float32, device=buf.device)
+        ops._cabi.call("mmpde_rows_gather", ops._ptr(buf, ops.H), 2 * ops.H, ops._ptr(self.send_idx), self.n_send, ops.H,
+                       ops._ptr(out), ops._stream())
+        return out
+
+    def _unpack_add(self, recv, buf):        # rows that came home: add onto the owners' rows
+        ops._cabi.call("mmpde_rows_scatter_add", ops._ptr(recv), ops._ptr(self.send_idx), self.n_send, ops.H,
+                       ops._ptr(buf, ops.H), 2 * ops.H, ops._stream())
+
+    def forward(self, bufs):
+        (buf,) = bufs
+        send = self._pack(buf)
+        recv = torch.empty(self.n_halo, ops.H, dtype=torch.float32, device=buf.device)
+        dist.all_to_all_single(recv, send, self.plan.recv_splits, self.plan.send_splits, group=self.group)
+        buf[self.n_own:, ops.H:].copy_(recv)
+
+    def backward(self, bufs):
+        (buf,) = bufs
+        send = buf[self.n_own:, ops.H:].contiguous()
+        recv = torch.empty(self.n_send, ops.H, dtype=torch.float32, device=buf.device)
+        dist.all_to_all_single(recv, send, self.plan.send_splits, self.plan.recv_splits, group=self.group)
+        self._unpack_add(recv, buf)

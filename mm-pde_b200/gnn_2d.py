@@ -115,3 +115,15 @@ class MP_PDE_Solver_2D(nn.Module):
         params, bufs = self._kernel_inputs()
         scale = 0.1 * self.pde.dt          # cumsum(ones(1,tw) * dt * 0.1) with tw = 1 (gnn_2d.py:137-139)
         return ops.SolverFn.apply(node4, edges, self.hidden_layer, self.training, scale, bufs, *params)
+
+    def forward_partitioned(self, parts, exch):
+        """The same forward on a partitioned mesh (partition.split_graph): ``parts`` = the MeshParts living in
+        this process (one per rank in a multi-GPU run, all of them in the single-process emulation), ``exch`` the
+        halo exchange (dist.HaloExchange / partition.LocalExchange).  Returns one [n_own,1] tensor per part;
+        concatenated in owner order they equal ``forward`` on the whole graph."""
+        node4s = [_node4(p.x, p.pos[:, 1:2] / self.pde.Lx, p.pos[:, 2:3] / self.pde.Ly, p.pos[:, 0:1] / self.pde.tmax)
+                  for p in parts]
+        params, bufs = self._kernel_inputs()
+        scale = 0.1 * self.pde.dt
+        meta = [(p.edges, p.plan) for p in parts]
+        return list(ops.PartitionedSolverFn.apply(meta, exch, self.hidden_layer, self.training, scale, bufs, *node4s, *params))

@@ -43,13 +43,15 @@ def _chk(t, dtype=torch.float32, name="tensor"):
 
 class _Comm:
     """Cross-rank coupling of the batch-sharded path (sync-BatchNorm statistics).  Single-GPU default:
-    identity.  mmpde_b200.dist installs the torch.distributed (NCCL) version."""
+    identity.  mmpde_b200.dist installs the torch.distributed (NCCL) version.  ``total_rows`` (set while a
+    partitioned mesh is being processed) is the node count of the whole mesh = the BatchNorm row count."""
+    total_rows = None
 
     def allreduce_(self, t):
         return t
 
     def global_rows(self, n):
-        return float(n)
+        return float(n) if self.total_rows is None else float(self.total_rows)
 
 
 COMM = _Comm()
@@ -176,48 +178,69 @@ def _split_for(rows):
 
 class _BNState:
     """mean/rstd [2,128] of one BatchNorm application (saved for the backward)."""
-    __slots__ = ("mean_rstd", "count")
+    __slots__ = ("mean_rstd", "count", "rows")
 
 
-def _bn_forward(A, lda, B, ldb, M, gamma, beta, relu, out, ldo, training, rmean, rvar, nbt, st):
+def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st):
+    """BatchNorm over the rows of ALL local parts (and all ranks, through COMM).
+    items: one (A, lda, B, ldb, M, out, ldo) per local part, y = A (+ B)."""
     state = _BNState()
     dev = gamma.device
+    state.rows = sum(it[4] for it in items)
     if training:
         sums = torch.zeros(2 * H, dtype=torch.float64, device=dev)
-        _cabi.call("mmpde_bn_stats", A, lda, B, ldb, M, _ptr(sums), st)
+        for A, lda, B, ldb, M, _, _ in items:
+            _cabi.call("mmpde_bn_stats", A, lda, B, ldb, M, _ptr(sums), st)
         COMM.allreduce_(sums)
-        state.count = COMM.global_rows(M)
+        state.count = COMM.global_rows(state.rows)
         state.mean_rstd = torch.empty(2 * H, dtype=torch.float32, device=dev)
         _cabi.call("mmpde_bn_finalize", _ptr(sums), state.count, BN_EPS, BN_MOMENTUM, _ptr(state.mean_rstd),
                    _ptr(rmean), _ptr(rvar), st)
         if nbt is not None:
             nbt += 1
     else:
-        state.count = float(M)
+        state.count = float(state.rows)
         state.mean_rstd = torch.cat((rmean, torch.rsqrt(rvar + BN_EPS)))
-    _cabi.call("mmpde_bn_apply", A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(gamma), _ptr(beta), int(relu), out, ldo, st)
+    for A, lda, B, ldb, M, out, ldo in items:
+        _cabi.call("mmpde_bn_apply", A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(gamma), _ptr(beta), int(relu), out, ldo, st)
     return state
 
 
-def _bn_backward(g, ldg, out, ldo, relu, A, lda, B, ldb, M, state, gamma, gy, ldgy, st):
-    """returns this rank's (dgamma, dbeta); writes dL/dy into gy.  With several ranks the two column sums
-    are all-reduced for the normalisation term (sync-BN), while the parameter grads stay per-rank sums
-    (the gradient all-reduce adds them up afterwards)."""
+def _bn_backward(items, relu, state, gamma, st):
+    """items: one (g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy) per local part.  Returns this rank's
+    (dgamma, dbeta); writes dL/dy into gy.  With several ranks the two column sums are all-reduced for the
+    normalisation term (sync-BN), while the parameter grads stay per-rank sums (the gradient all-reduce adds
+    them up afterwards)."""
     local = torch.zeros(2 * H, dtype=torch.float64, device=gamma.device)
-    _cabi.call("mmpde_bn_bwd_reduce", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(local), st)
+    for g, ldg, out, ldo, A, lda, B, ldb, M, _, _ in items:
+        _cabi.call("mmpde_bn_bwd_reduce", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(local), st)
     glob = local
-    if COMM.global_rows(M) != float(M):
+    if COMM.global_rows(state.rows) != float(state.rows):
         glob = COMM.allreduce_(local.clone())
-    _cabi.call("mmpde_bn_bwd_apply", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(gamma),
-               _ptr(glob), state.count, gy, ldgy, 0, st)
+    for g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy in items:
+        _cabi.call("mmpde_bn_bwd_apply", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(gamma),
+                   _ptr(glob), state.count, gy, ldgy, 0, st)
     return local[H:].to(torch.float32), local[:H].to(torch.float32)
 
 
 # ------------------------------------------------------------------------------------------------
-# the processor: encoder -> L message-passing layers -> Conv1d decoder, as ONE autograd node
+# the processor: encoder -> L message-passing layers -> Conv1d decoder, as ONE autograd node.
+# Written over a LIST of graph parts that advance in lock step: one part = the whole (batched) graph in the
+# ordinary case; several parts = a partitioned mesh whose halo rows are exchanged once per layer
+# (partition.py).  Parts of other ranks are reached through the exchange object.
 # ------------------------------------------------------------------------------------------------
 N_ENC = 8          # We1 be1 g1 bt1 We2 be2 g2 bt2
 N_LAYER = 10       # W1 b1 W2 b2 W3 b3 W4 b4 gamma beta
+
+
+class GraphPart:
+    """node4 [n_own,4] of the owned nodes, target-sorted edges in local numbering (sources may point into the
+    halo rows n_own .. n_own+n_halo), and the partition plan (None = no halo)."""
+
+    def __init__(self, node4, edges, plan=None):
+        self.node4, self.edges, self.plan = node4, edges, plan
+        self.n_own = int(node4.shape[0])
+        self.n_src = self.n_own + (plan.n_halo if plan is not None else 0)
 
 
 def mask_words(n_edges):
@@ -234,89 +257,112 @@ def _edge_feature_weights(W1):
     return w1c, w1cq
 
 
-def _layer_forward(Xl, node4, edges, lp, bnbuf, training, nxt, nxt_ld, st):
-    """One GNN_Layer_FS_2D (gnn_2d.py:53-69).  Xl [N,256]: cols 0..127 hold the layer input h, cols
-    128..255 must be ZERO on entry and receive the mean message.  Output BN(h + update) -> nxt (ld nxt_ld)."""
+def _layer_forward(parts, Xs, lp, bnbuf, training, nxts, exch, st):
+    """One GNN_Layer_FS_2D (gnn_2d.py:53-69) on every part.  Xs[p] [n_own,256]: cols 0..127 hold the layer input
+    h, cols 128..255 must be ZERO on entry and receive the mean message.  Output BN(h + update) -> nxts[p] =
+    (pointer, leading dimension)."""
     W1, b1, W2, b2, W3, b3, W4, b4, gam, bet = lp
-    N, E = node4.shape[0], edges.n_edges
-    f32 = dict(dtype=torch.float32, device=node4.device)
-    x, n4 = _ptr(Xl), _ptr(node4)
+    w1c, w1cq = _edge_feature_weights(W1)
+    w3v = W3[:, 2 * H].contiguous()
     # message_net_1 split per node (gnn_2d.py:61): z1_ij = P'[i] + Q'[j] with
     #   P' = h W1a^T + b1 + node4 W1c^T,   Q' = h W1b^T - node4[:, :3] W1c[:, :3]^T
-    PQ = torch.empty(N, 2 * H, **f32)
-    gemm(x, 2 * H, 1, _ptr(W1), 260, 1, _ptr(PQ), 2 * H, N, H, H, bias=_ptr(b1), st=st)
-    gemm(x, 2 * H, 1, _ptr(W1, H), 260, 1, _ptr(PQ, H), 2 * H, N, H, H, st=st)
-    w1c, w1cq = _edge_feature_weights(W1)
-    gemm(n4, 4, 1, _ptr(w1c), 4, 1, _ptr(PQ), 2 * H, N, H, 4, acc=1, st=st)
-    gemm(n4, 4, 1, _ptr(w1cq), 4, 1, _ptr(PQ, H), 2 * H, N, H, 4, acc=1, st=st)
-    mask2 = torch.empty(mask_words(E), dtype=torch.int32, device=node4.device)
-    _cabi.call("mmpde_edge_fwd", _ptr(PQ), _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
-               _ptr(W2), _ptr(b2), _ptr(Xl, H), 2 * H, _ptr(mask2), st)
-    # update_net_1/2 + residual                                 (gnn_2d.py:65-69)
-    w3v = W3[:, 2 * H].contiguous()
-    h3 = torch.empty(N, H, **f32)
-    gemm(x, 2 * H, 1, _ptr(W3), 257, 1, _ptr(h3), H, N, H, 2 * H, bias=_ptr(b3), r1_row=_ptr(node4, 3),
-         r1_stride=4, r1_col=_ptr(w3v), relu=1, st=st)
-    r4 = torch.empty(N, H, **f32)
-    gemm(_ptr(h3), H, 1, _ptr(W4), H, 1, _ptr(r4), H, N, H, H, bias=_ptr(b4), relu=1, st=st)
-    bn = _bn_forward(x, 2 * H, _ptr(r4), H, N, gam, bet, 0, nxt, nxt_ld, training, *bnbuf, st)
-    return (PQ, mask2, h3, r4, bn)
+    PQs = []
+    for part, Xl in zip(parts, Xs):
+        N = part.n_own
+        f32 = dict(dtype=torch.float32, device=Xl.device)
+        x, n4 = _ptr(Xl), _ptr(part.node4)
+        PQ = torch.empty(part.n_src, 2 * H, **f32)
+        gemm(x, 2 * H, 1, _ptr(W1), 260, 1, _ptr(PQ), 2 * H, N, H, H, bias=_ptr(b1), st=st)
+        gemm(x, 2 * H, 1, _ptr(W1, H), 260, 1, _ptr(PQ, H), 2 * H, N, H, H, st=st)
+        gemm(n4, 4, 1, _ptr(w1c), 4, 1, _ptr(PQ), 2 * H, N, H, 4, acc=1, st=st)
+        gemm(n4, 4, 1, _ptr(w1cq), 4, 1, _ptr(PQ, H), 2 * H, N, H, 4, acc=1, st=st)
+        PQs.append(PQ)
+    if exch is not None:
+        exch.forward(PQs)                                         # Q' rows of the halo nodes
+    saved, bn_items = [], []
+    for part, Xl, PQ, nxt in zip(parts, Xs, PQs, nxts):
+        N, E, edges = part.n_own, part.edges.n_edges, part.edges
+        f32 = dict(dtype=torch.float32, device=Xl.device)
+        x = _ptr(Xl)
+        mask2 = torch.empty(mask_words(E), dtype=torch.int32, device=Xl.device)
+        _cabi.call("mmpde_edge_fwd", _ptr(PQ), _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
+                   _ptr(W2), _ptr(b2), _ptr(Xl, H), 2 * H, _ptr(mask2), st)
+        # update_net_1/2 + residual                                 (gnn_2d.py:65-69)
+        h3 = torch.empty(N, H, **f32)
+        gemm(x, 2 * H, 1, _ptr(W3), 257, 1, _ptr(h3), H, N, H, 2 * H, bias=_ptr(b3), r1_row=_ptr(part.node4, 3),
+             r1_stride=4, r1_col=_ptr(w3v), relu=1, st=st)
+        r4 = torch.empty(N, H, **f32)
+        gemm(_ptr(h3), H, 1, _ptr(W4), H, 1, _ptr(r4), H, N, H, H, bias=_ptr(b4), relu=1, st=st)
+        saved.append((PQ, mask2, h3, r4))
+        bn_items.append((x, 2 * H, _ptr(r4), H, N, nxt[0], nxt[1]))
+    bn = _bn_forward(bn_items, gam, bet, 0, training, *bnbuf, st)
+    return saved, bn
 
 
-def _layer_backward(Xl, node4, edges, lp, saved, g_h, g_node4, st):
-    """Backward of _layer_forward.  g_h [N,128] = dL/d(output).  Returns (dL/dh_in [N,128], 10 param grads);
-    adds the layer's dL/du into g_node4[:,0] when g_node4 is given."""
+def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st):
+    """Backward of _layer_forward.  g_hs[p] [n_own,128] = dL/d(output).  Returns ([dL/dh_in per part], 10 param
+    grads summed over the local parts); adds the layer's dL/du into g_node4s[p][:,0] when given."""
     W1, b1, W2, b2, W3, b3, W4, b4, gam, bet = lp
-    PQ, mask2, h3, r4, bn = saved
-    N, E = node4.shape[0], edges.n_edges
-    f32 = dict(dtype=torch.float32, device=node4.device)
-    x, n4 = _ptr(Xl), _ptr(node4)
-    split = max(_split_for(N), 2)
+    dev = W1.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    w1c, w1cq = _edge_feature_weights(W1)
     # BatchNorm backward: y = h + r4
-    g_y = torch.empty(N, H, **f32)
-    dgam, dbet = _bn_backward(_ptr(g_h), H, None, 0, 0, x, 2 * H, _ptr(r4), H, N, bn, gam, _ptr(g_y), H, st)
-    # node MLP backward
-    g_z4 = torch.empty(N, H, **f32)
-    db4 = torch.zeros(H, **f32)
-    _cabi.call("mmpde_relu_bwd", _ptr(g_y), H, _ptr(r4), H, N, _ptr(g_z4), H, _ptr(db4), st)
-    dW4 = torch.zeros(H, H, **f32)
-    gemm(_ptr(g_z4), H, 0, _ptr(h3), H, 0, _ptr(dW4), H, H, H, N, split_k=split, st=st)
-    g_h3 = torch.empty(N, H, **f32)
-    gemm(_ptr(g_z4), H, 1, _ptr(W4), H, 0, _ptr(g_h3), H, N, H, H, st=st)
-    g_z3 = g_z4                                               # reuse
-    db3 = torch.zeros(H, **f32)
-    _cabi.call("mmpde_relu_bwd", _ptr(g_h3), H, _ptr(h3), H, N, _ptr(g_z3), H, _ptr(db3), st)
-    dW3 = torch.zeros(H, 2 * H + 1, **f32)
-    gemm(_ptr(g_z3), H, 0, x, 2 * H, 0, _ptr(dW3), 257, H, 2 * H, N, split_k=split, st=st)
-    gemm(_ptr(g_z3), H, 0, _ptr(node4, 3), 4, 0, _ptr(dW3, 2 * H), 257, H, 1, N, split_k=split, st=st)
-    g_X = torch.empty(N, 2 * H, **f32)
-    gemm(_ptr(g_z3), H, 1, _ptr(W3), 257, 0, _ptr(g_X), 2 * H, N, 2 * H, H, st=st)
-    # message passing backward
-    dPQ = torch.zeros(N, 2 * H, **f32)
-    dW2 = torch.zeros(H, H, **f32)
-    db2 = torch.zeros(H, **f32)
-    _cabi.call("mmpde_edge_bwd", _ptr(PQ), _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
-               _ptr(W2), _ptr(mask2), _ptr(g_X, H), 2 * H, _ptr(dPQ), _ptr(dW2), _ptr(db2), st)
-    # message_net_1 parameters from dP', dQ':  dW1a = dP'^T h, dW1b = dQ'^T h, dW1c = dP'^T node4 - dQ'^T node4[:, :3]
-    dW1 = torch.zeros(H, 260, **f32)
-    gemm(_ptr(dPQ), 2 * H, 0, x, 2 * H, 0, _ptr(dW1), 260, H, H, N, split_k=split, st=st)
-    gemm(_ptr(dPQ, H), 2 * H, 0, x, 2 * H, 0, _ptr(dW1, H), 260, H, H, N, split_k=split, st=st)
+    g_ys = [torch.empty(part.n_own, H, **f32) for part in parts]
+    items = [(_ptr(g_h), H, None, 0, _ptr(Xl), 2 * H, _ptr(sv[3]), H, part.n_own, _ptr(g_y), H)
+             for part, Xl, sv, g_h, g_y in zip(parts, Xs, saved, g_hs, g_ys)]
+    dgam, dbet = _bn_backward(items, 0, bn, gam, st)
+    dW1, db1 = torch.zeros(H, 260, **f32), torch.zeros(H, **f32)
+    dW2, db2 = torch.zeros(H, H, **f32), torch.zeros(H, **f32)
+    dW3, db3 = torch.zeros(H, 2 * H + 1, **f32), torch.zeros(H, **f32)
+    dW4, db4 = torch.zeros(H, H, **f32), torch.zeros(H, **f32)
     dW1c = torch.zeros(2, H, 4, **f32)
-    gemm(_ptr(dPQ), 2 * H, 0, n4, 4, 0, _ptr(dW1c), 4, H, 4, N, split_k=split, st=st)
-    gemm(_ptr(dPQ, H), 2 * H, 0, n4, 4, 0, _ptr(dW1c, 4 * H), 4, H, 4, N, split_k=split, st=st)
+    dPQs, g_Xs = [], []
+    for part, Xl, sv, g_y in zip(parts, Xs, saved, g_ys):
+        PQ, mask2, h3, r4 = sv
+        N, E, edges = part.n_own, part.edges.n_edges, part.edges
+        x = _ptr(Xl)
+        split = max(_split_for(N), 2)
+        # node MLP backward
+        g_z4 = torch.empty(N, H, **f32)
+        _cabi.call("mmpde_relu_bwd", _ptr(g_y), H, _ptr(r4), H, N, _ptr(g_z4), H, _ptr(db4), st)
+        gemm(_ptr(g_z4), H, 0, _ptr(h3), H, 0, _ptr(dW4), H, H, H, N, split_k=split, st=st)
+        g_h3 = torch.empty(N, H, **f32)
+        gemm(_ptr(g_z4), H, 1, _ptr(W4), H, 0, _ptr(g_h3), H, N, H, H, st=st)
+        g_z3 = g_z4                                               # reuse
+        _cabi.call("mmpde_relu_bwd", _ptr(g_h3), H, _ptr(h3), H, N, _ptr(g_z3), H, _ptr(db3), st)
+        gemm(_ptr(g_z3), H, 0, x, 2 * H, 0, _ptr(dW3), 257, H, 2 * H, N, split_k=split, st=st)
+        gemm(_ptr(g_z3), H, 0, _ptr(part.node4, 3), 4, 0, _ptr(dW3, 2 * H), 257, H, 1, N, split_k=split, st=st)
+        g_X = torch.empty(N, 2 * H, **f32)
+        gemm(_ptr(g_z3), H, 1, _ptr(W3), 257, 0, _ptr(g_X), 2 * H, N, 2 * H, H, st=st)
+        # message passing backward
+        dPQ = torch.zeros(part.n_src, 2 * H, **f32)
+        _cabi.call("mmpde_edge_bwd", _ptr(PQ), _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
+                   _ptr(W2), _ptr(mask2), _ptr(g_X, H), 2 * H, _ptr(dPQ), _ptr(dW2), _ptr(db2), st)
+        dPQs.append(dPQ)
+        g_Xs.append(g_X)
+    if exch is not None:
+        exch.backward(dPQs)                                       # dL/dQ' of halo rows -> added at their owners
+    for idx, (part, Xl, dPQ, g_X, g_y) in enumerate(zip(parts, Xs, dPQs, g_Xs, g_ys)):
+        N = part.n_own
+        x, n4 = _ptr(Xl), _ptr(part.node4)
+        split = max(_split_for(N), 2)
+        # message_net_1 parameters from dP', dQ':  dW1a = dP'^T h, dW1b = dQ'^T h, dW1c = dP'^T node4 - dQ'^T node4[:, :3]
+        gemm(_ptr(dPQ), 2 * H, 0, x, 2 * H, 0, _ptr(dW1), 260, H, H, N, split_k=split, st=st)
+        gemm(_ptr(dPQ, H), 2 * H, 0, x, 2 * H, 0, _ptr(dW1, H), 260, H, H, N, split_k=split, st=st)
+        gemm(_ptr(dPQ), 2 * H, 0, n4, 4, 0, _ptr(dW1c), 4, H, 4, N, split_k=split, st=st)
+        gemm(_ptr(dPQ, H), 2 * H, 0, n4, 4, 0, _ptr(dW1c, 4 * H), 4, H, 4, N, split_k=split, st=st)
+        _cabi.call("mmpde_colsum", _ptr(dPQ), 2 * H, N, H, _ptr(db1), st)
+        g_node4 = g_node4s[idx] if g_node4s is not None else None
+        if g_node4 is not None:      # dL/du (column 0 of node4): dP' W1c[:,0] - dQ' W1c[:,0]
+            gemm(_ptr(dPQ), 2 * H, 1, _ptr(w1c), 4, 0, _ptr(g_node4), 4, N, 1, H, acc=1, st=st)
+            gemm(_ptr(dPQ, H), 2 * H, 1, _ptr(w1cq), 4, 0, _ptr(g_node4), 4, N, 1, H, acc=1, st=st)
+        # dL/dh_in = g_y (residual) + g_X[:, :128] (update_net_1) + dP' W1a + dQ' W1b
+        g_y.add_(g_X[:, :H])
+        gemm(_ptr(dPQ), 2 * H, 1, _ptr(W1), 260, 0, _ptr(g_y), H, N, H, H, acc=1, st=st)
+        gemm(_ptr(dPQ, H), 2 * H, 1, _ptr(W1, H), 260, 0, _ptr(g_y), H, N, H, H, acc=1, st=st)
     dW1[:, 2 * H:2 * H + 4] = dW1c[0]
     dW1[:, 2 * H:2 * H + 3] -= dW1c[1, :, :3]
-    db1 = torch.zeros(H, **f32)
-    _cabi.call("mmpde_colsum", _ptr(dPQ), 2 * H, N, H, _ptr(db1), st)
-    if g_node4 is not None:      # dL/du (column 0 of node4): dP' W1c[:,0] - dQ' W1c[:,0]
-        w1c, w1cq = _edge_feature_weights(W1)
-        gemm(_ptr(dPQ), 2 * H, 1, _ptr(w1c), 4, 0, _ptr(g_node4), 4, N, 1, H, acc=1, st=st)
-        gemm(_ptr(dPQ, H), 2 * H, 1, _ptr(w1cq), 4, 0, _ptr(g_node4), 4, N, 1, H, acc=1, st=st)
-    # dL/dh_in = g_y (residual) + g_X[:, :128] (update_net_1) + dP W1a + dQ W1b
-    g_y.add_(g_X[:, :H])
-    gemm(_ptr(dPQ), 2 * H, 1, _ptr(W1), 260, 0, _ptr(g_y), H, N, H, H, acc=1, st=st)
-    gemm(_ptr(dPQ, H), 2 * H, 1, _ptr(W1, H), 260, 0, _ptr(g_y), H, N, H, H, acc=1, st=st)
-    return g_y, [dW1, db1, dW2, db2, dW3, db3, dW4, db4, dgam, dbet]
+    return g_ys, [dW1, db1, dW2, db2, dW3, db3, dW4, db4, dgam, dbet]
 
 
 class LayerFn(torch.autograd.Function):
@@ -330,16 +376,109 @@ class LayerFn(torch.autograd.Function):
         Xl = torch.zeros(N, 2 * H, dtype=torch.float32, device=x.device)
         Xl[:, :H] = x
         out = torch.empty(N, H, dtype=torch.float32, device=x.device)
-        saved = _layer_forward(Xl, node4, edges, lp, bnbuf, training, _ptr(out), H, st)
-        ctx.stuff = (Xl, node4, edges, lp, saved)
+        parts = [GraphPart(node4, edges)]
+        saved, bn = _layer_forward(parts, [Xl], lp, bnbuf, training, [(_ptr(out), H)], None, st)
+        ctx.stuff = (parts, Xl, lp, saved, bn)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        Xl, node4, edges, lp, saved = ctx.stuff
-        g_node4 = torch.zeros_like(node4) if ctx.needs_input_grad[1] else None
-        g_x, grads = _layer_backward(Xl, node4, edges, lp, saved, g_out.contiguous(), g_node4, _stream())
-        return (g_x, g_node4, None, None, None, *grads)
+        parts, Xl, lp, saved, bn = ctx.stuff
+        g_node4 = torch.zeros_like(parts[0].node4) if ctx.needs_input_grad[1] else None
+        g_xs, grads = _layer_backward(parts, [Xl], lp, saved, bn, [g_out.contiguous()],
+                                      [g_node4] if g_node4 is not None else None, None, _stream())
+        return (g_xs[0], g_node4, None, None, None, *grads)
+
+
+def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st):
+    """Encoder, L layers and decoder on every part.  Returns ([out [n_own] per part], saved state)."""
+    dev = parts[0].node4.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    We1, be1, g1, bt1, We2, be2, g2, bt2 = params[:N_ENC]
+    dec = params[N_ENC + N_LAYER * L]
+    # ---- encoder: Linear(4,128) BN ReLU Linear(128,128) BN        (gnn_2d.py:99-106,130-131)
+    e1s, e1ns, e2s = [], [], []
+    for part in parts:
+        e1 = torch.empty(part.n_own, H, **f32)
+        gemm(_ptr(part.node4), 4, 1, _ptr(We1), 4, 1, _ptr(e1), H, part.n_own, H, 4, bias=_ptr(be1), st=st)
+        e1s.append(e1)
+        e1ns.append(torch.empty(part.n_own, H, **f32))
+    bn1 = _bn_forward([(_ptr(e1), H, None, 0, part.n_own, _ptr(e1n), H) for part, e1, e1n in zip(parts, e1s, e1ns)],
+                      g1, bt1, 1, training, *bn_buffers[0], st)
+    for part, e1n in zip(parts, e1ns):
+        e2 = torch.empty(part.n_own, H, **f32)
+        gemm(_ptr(e1n), H, 1, _ptr(We2), H, 1, _ptr(e2), H, part.n_own, H, H, bias=_ptr(be2), st=st)
+        e2s.append(e2)
+    # X[l][p] = [h_l | agg_l]  ([n_own,256]); the last hidden state lives alone in hL
+    X = [[torch.zeros(part.n_own, 2 * H, **f32) for part in parts] for _ in range(L)]
+    hL = [torch.empty(part.n_own, H, **f32) for part in parts]
+
+    def dest(l):
+        return [(_ptr(t), 2 * H) for t in X[l]] if l < L else [(_ptr(t), H) for t in hL]
+
+    bn2 = _bn_forward([(_ptr(e2), H, None, 0, part.n_own, d[0], d[1]) for part, e2, d in zip(parts, e2s, dest(0))],
+                      g2, bt2, 0, training, *bn_buffers[1], st)
+    layers = []
+    for l in range(L):
+        lp = params[N_ENC + N_LAYER * l: N_ENC + N_LAYER * (l + 1)]
+        layers.append(_layer_forward(parts, X[l], lp, bn_buffers[2 + l], training, dest(l + 1), exch, st))
+    outs = []
+    for part, h in zip(parts, hL):
+        out = torch.empty(part.n_own, **f32)
+        _cabi.call("mmpde_decoder_fwd", _ptr(h), H, part.n_own, _ptr(dec), float(scale), _ptr(out), st)
+        outs.append(out)
+    return outs, dict(parts=parts, L=L, scale=float(scale), params=params, enc=(e1s, e1ns, e2s, bn1, bn2), X=X, hL=hL,
+                      layers=layers, exch=exch)
+
+
+def _solver_backward(sv, g_outs, need_u, st):
+    """Returns ([dL/dnode4 per part] or None, parameter grads summed over the local parts)."""
+    parts, L, params, exch = sv["parts"], sv["L"], sv["params"], sv["exch"]
+    dev = parts[0].node4.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    We1, be1, g1, bt1, We2, be2, g2, bt2 = params[:N_ENC]
+    dec = params[N_ENC + N_LAYER * L]
+    e1s, e1ns, e2s, bn1, bn2 = sv["enc"]
+    grads = [None] * len(params)
+    g_node4s = [torch.zeros(part.n_own, 4, **f32) for part in parts] if need_u else None
+    g_dec = torch.zeros(DEC_NPARAM, **f32)
+    g_hs = []
+    for part, h, g_out in zip(parts, sv["hL"], g_outs):
+        g_h = torch.empty(part.n_own, H, **f32)
+        _cabi.call("mmpde_decoder_bwd", _ptr(h), H, part.n_own, _ptr(dec), sv["scale"], _ptr(g_out.contiguous().view(-1)),
+                   _ptr(g_h), H, _ptr(g_dec), st)
+        g_hs.append(g_h)
+    grads[N_ENC + N_LAYER * L] = g_dec
+    for l in reversed(range(L)):
+        base = N_ENC + N_LAYER * l
+        saved, bn = sv["layers"][l]
+        g_hs, lg = _layer_backward(parts, sv["X"][l], params[base:base + N_LAYER], saved, bn, g_hs, g_node4s, exch, st)
+        grads[base:base + N_LAYER] = lg
+    # ---- encoder backward
+    g_e2s = [torch.empty(part.n_own, H, **f32) for part in parts]
+    dg2, db2_ = _bn_backward([(_ptr(g_h), H, None, 0, _ptr(e2), H, None, 0, part.n_own, _ptr(g_e2), H)
+                              for part, g_h, e2, g_e2 in zip(parts, g_hs, e2s, g_e2s)], 0, bn2, g2, st)
+    dWe2, dbe2 = torch.zeros(H, H, **f32), torch.zeros(H, **f32)
+    dWe1, dbe1 = torch.zeros(H, 4, **f32), torch.zeros(H, **f32)
+    g_e1ns = []
+    for part, g_e2, e1n in zip(parts, g_e2s, e1ns):
+        split = max(_split_for(part.n_own), 2)
+        gemm(_ptr(g_e2), H, 0, _ptr(e1n), H, 0, _ptr(dWe2), H, H, H, part.n_own, split_k=split, st=st)
+        _cabi.call("mmpde_colsum", _ptr(g_e2), H, part.n_own, H, _ptr(dbe2), st)
+        g_e1n = torch.empty(part.n_own, H, **f32)
+        gemm(_ptr(g_e2), H, 1, _ptr(We2), H, 0, _ptr(g_e1n), H, part.n_own, H, H, st=st)
+        g_e1ns.append(g_e1n)
+    g_e1s = g_e2s                                                     # reuse
+    dg1, db1_ = _bn_backward([(_ptr(g_e1n), H, _ptr(e1n), H, _ptr(e1), H, None, 0, part.n_own, _ptr(g_e1), H)
+                              for part, g_e1n, e1n, e1, g_e1 in zip(parts, g_e1ns, e1ns, e1s, g_e1s)], 1, bn1, g1, st)
+    for idx, (part, g_e1) in enumerate(zip(parts, g_e1s)):
+        split = max(_split_for(part.n_own), 2)
+        gemm(_ptr(g_e1), H, 0, _ptr(part.node4), 4, 0, _ptr(dWe1), 4, H, 4, part.n_own, split_k=split, st=st)
+        _cabi.call("mmpde_colsum", _ptr(g_e1), H, part.n_own, H, _ptr(dbe1), st)
+        if need_u:      # only the u column: positions/time feed the frozen mesh mover only (SURVEY.md 8a-5)
+            gemm(_ptr(g_e1), H, 1, _ptr(We1), 4, 0, _ptr(g_node4s[idx]), 4, part.n_own, 1, H, acc=1, st=st)
+    grads[:N_ENC] = [dWe1, dbe1, dg1, db1_, dWe2, dbe2, dg2, db2_]
+    return g_node4s, grads
 
 
 class SolverFn(torch.autograd.Function):
@@ -351,79 +490,46 @@ class SolverFn(torch.autograd.Function):
         _chk(node4, name="node4")
         for i, p in enumerate(params):
             _chk(p, name=f"param{i}")
-        st = _stream()
-        dev = node4.device
-        N, L = node4.shape[0], n_layers
-        f32 = dict(dtype=torch.float32, device=dev)
-        We1, be1, g1, bt1, We2, be2, g2, bt2 = params[:N_ENC]
-        dec = params[N_ENC + N_LAYER * L]
-        # ---- encoder: Linear(4,128) BN ReLU Linear(128,128) BN        (gnn_2d.py:99-106,130-131)
-        e1 = torch.empty(N, H, **f32)
-        gemm(_ptr(node4), 4, 1, _ptr(We1), 4, 1, _ptr(e1), H, N, H, 4, bias=_ptr(be1), st=st)
-        e1n = torch.empty(N, H, **f32)
-        bn1 = _bn_forward(_ptr(e1), H, None, 0, N, g1, bt1, 1, _ptr(e1n), H, training, *bn_buffers[0], st)
-        e2 = torch.empty(N, H, **f32)
-        gemm(_ptr(e1n), H, 1, _ptr(We2), H, 1, _ptr(e2), H, N, H, H, bias=_ptr(be2), st=st)
-        # X[l] = [h_l | agg_l]  ([N,256]); the last hidden state lives alone in hL
-        X = [torch.zeros(N, 2 * H, **f32) for _ in range(L)]
-        hL = torch.empty(N, H, **f32)
-        nxt = (_ptr(X[0]), 2 * H) if L > 0 else (_ptr(hL), H)
-        bn2 = _bn_forward(_ptr(e2), H, None, 0, N, g2, bt2, 0, nxt[0], nxt[1], training, *bn_buffers[1], st)
-        saved_layers = []
-        for l in range(L):
-            lp = params[N_ENC + N_LAYER * l: N_ENC + N_LAYER * (l + 1)]
-            nxt = (_ptr(X[l + 1]), 2 * H) if l + 1 < L else (_ptr(hL), H)
-            saved_layers.append(_layer_forward(X[l], node4, edges, lp, bn_buffers[2 + l], training, nxt[0], nxt[1], st))
-        out = torch.empty(N, **f32)
-        _cabi.call("mmpde_decoder_fwd", _ptr(hL), H, N, _ptr(dec), float(scale), _ptr(out), st)
-        ctx.node4, ctx.edges, ctx.L, ctx.scale = node4, edges, L, float(scale)
-        ctx.params = params
-        ctx.enc = (e1, e1n, e2, bn1, bn2)
-        ctx.X, ctx.hL, ctx.layers = X, hL, saved_layers
-        return out.view(N, 1)
+        outs, ctx.sv = _solver_forward([GraphPart(node4, edges)], n_layers, training, scale, bn_buffers, params, None, _stream())
+        return outs[0].view(-1, 1)
 
     @staticmethod
     def backward(ctx, g_out):
-        st = _stream()
-        node4, edges, L, params = ctx.node4, ctx.edges, ctx.L, ctx.params
-        N = node4.shape[0]
-        f32 = dict(dtype=torch.float32, device=node4.device)
-        split = max(_split_for(N), 2)
-        We1, be1, g1, bt1, We2, be2, g2, bt2 = params[:N_ENC]
-        dec = params[N_ENC + N_LAYER * L]
-        e1, e1n, e2, bn1, bn2 = ctx.enc
-        grads = [None] * len(params)
-        need_u = ctx.needs_input_grad[0]
-        g_node4 = torch.zeros(N, 4, **f32) if need_u else None
+        g_node4s, grads = _solver_backward(ctx.sv, [g_out], ctx.needs_input_grad[0], _stream())
+        return (g_node4s[0] if g_node4s is not None else None, None, None, None, None, None, *grads)
 
-        g_out = g_out.contiguous().view(-1)
-        g_h = torch.empty(N, H, **f32)
-        g_dec = torch.zeros(DEC_NPARAM, **f32)
-        _cabi.call("mmpde_decoder_bwd", _ptr(ctx.hL), H, N, _ptr(dec), ctx.scale, _ptr(g_out), _ptr(g_h), H, _ptr(g_dec), st)
-        grads[N_ENC + N_LAYER * L] = g_dec
-        for l in reversed(range(L)):
-            base = N_ENC + N_LAYER * l
-            g_h, lg = _layer_backward(ctx.X[l], node4, edges, params[base:base + N_LAYER], ctx.layers[l], g_h, g_node4, st)
-            grads[base:base + N_LAYER] = lg
-        # ---- encoder backward
-        g_e2 = torch.empty(N, H, **f32)
-        dg2, db2_ = _bn_backward(_ptr(g_h), H, None, 0, 0, _ptr(e2), H, None, 0, N, bn2, g2, _ptr(g_e2), H, st)
-        dWe2 = torch.zeros(H, H, **f32)
-        gemm(_ptr(g_e2), H, 0, _ptr(e1n), H, 0, _ptr(dWe2), H, H, H, N, split_k=split, st=st)
-        dbe2 = torch.zeros(H, **f32)
-        _cabi.call("mmpde_colsum", _ptr(g_e2), H, N, H, _ptr(dbe2), st)
-        g_e1n = torch.empty(N, H, **f32)
-        gemm(_ptr(g_e2), H, 1, _ptr(We2), H, 0, _ptr(g_e1n), H, N, H, H, st=st)
-        g_e1 = g_e2                                                   # reuse
-        dg1, db1_ = _bn_backward(_ptr(g_e1n), H, _ptr(e1n), H, 1, _ptr(e1), H, None, 0, N, bn1, g1, _ptr(g_e1), H, st)
-        dWe1 = torch.zeros(H, 4, **f32)
-        gemm(_ptr(g_e1), H, 0, _ptr(node4), 4, 0, _ptr(dWe1), 4, H, 4, N, split_k=split, st=st)
-        dbe1 = torch.zeros(H, **f32)
-        _cabi.call("mmpde_colsum", _ptr(g_e1), H, N, H, _ptr(dbe1), st)
-        if need_u:      # only the u column: positions/time feed the frozen mesh mover only
-            gemm(_ptr(g_e1), H, 1, _ptr(We1), 4, 0, _ptr(g_node4), 4, N, 1, H, acc=1, st=st)
-        grads[:N_ENC] = [dWe1, dbe1, dg1, db1_, dWe2, dbe2, dg2, db2_]
-        return (g_node4, None, None, None, None, None, *grads)
+
+class PartitionedSolverFn(torch.autograd.Function):
+    """The same processor on a partitioned mesh: ``parts`` = [(edges, plan)] of the parts living in THIS process
+    (one per rank in a multi-GPU run; all of them in the single-process emulation), ``exch`` moves the halo rows
+    (partition.LocalExchange / dist.HaloExchange).  Tensor inputs: n_parts node4 tensors, then the parameters.
+    Returns one [n_own,1] tensor per part."""
+
+    @staticmethod
+    def forward(ctx, parts, exch, n_layers, training, scale, bn_buffers, *tensors):
+        n = len(parts)
+        node4s, params = tensors[:n], tensors[n:]
+        for t in node4s:
+            _chk(t, name="node4")
+        gps = [GraphPart(n4, edges, plan) for n4, (edges, plan) in zip(node4s, parts)]
+        COMM.total_rows = float(parts[0][1].n_total)
+        try:
+            outs, ctx.sv = _solver_forward(gps, n_layers, training, scale, bn_buffers, params, exch, _stream())
+        finally:
+            COMM.total_rows = None
+        ctx.n = n
+        return tuple(o.view(-1, 1) for o in outs)
+
+    @staticmethod
+    def backward(ctx, *g_outs):
+        need_u = any(ctx.needs_input_grad[6:6 + ctx.n])
+        COMM.total_rows = float(ctx.sv["parts"][0].plan.n_total)
+        try:
+            g_node4s, grads = _solver_backward(ctx.sv, list(g_outs), need_u, _stream())
+        finally:
+            COMM.total_rows = None
+        g4 = g_node4s if g_node4s is not None else [None] * ctx.n
+        return (None, None, None, None, None, None, *g4, *grads)
 
 
 # ------------------------------------------------------------------------------------------------

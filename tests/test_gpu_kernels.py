@@ -161,17 +161,17 @@ def test_batchnorm_forward_backward_and_running_stats():
     nbt = torch.zeros((), dtype=torch.long, device=dev)
     out = torch.empty(M, 128, device=dev)
     st = ops._stream()
-    state = ops._bn_forward(ops._ptr(Ad), 256, ops._ptr(Bd), 128, M, gam, bet, 1, ops._ptr(out), 128, True, rm, rv, nbt, st)
+    state = ops._bn_forward([(ops._ptr(Ad), 256, ops._ptr(Bd), 128, M, ops._ptr(out), 128)], gam, bet, 1, True, rm, rv, nbt, st)
     assert _rel(out, ref) < 2e-6
     assert _rel(rm, bn.running_mean) < 1e-6 and _rel(rv, bn.running_var) < 1e-6 and int(nbt) == 1
     gy = torch.empty(M, 128, device=dev)
     gd = g.to(dev)
-    dgam, dbet = ops._bn_backward(ops._ptr(gd), 128, ops._ptr(out), 128, 1, ops._ptr(Ad), 256, ops._ptr(Bd), 128, M, state,
-                                  gam, ops._ptr(gy), 128, st)
+    dgam, dbet = ops._bn_backward([(ops._ptr(gd), 128, ops._ptr(out), 128, ops._ptr(Ad), 256, ops._ptr(Bd), 128, M,
+                                    ops._ptr(gy), 128)], 1, state, gam, st)
     assert _rel(gy, y.grad) < 1e-5 and _rel(dgam, bn.weight.grad) < 1e-5 and _rel(dbet, bn.bias.grad) < 1e-5
     # eval mode = affine with running statistics
     bn.eval()
-    state = ops._bn_forward(ops._ptr(Ad), 256, ops._ptr(Bd), 128, M, gam, bet, 0, ops._ptr(out), 128, False, rm, rv, nbt, st)
+    state = ops._bn_forward([(ops._ptr(Ad), 256, ops._ptr(Bd), 128, M, ops._ptr(out), 128)], gam, bet, 0, False, rm, rv, nbt, st)
     assert _rel(out, bn(y.detach())) < 2e-6
 
 

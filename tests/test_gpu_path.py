@@ -218,3 +218,59 @@ def test_config1_full_size_properties():
     on = dict(omodel.named_parameters())
     for k, p in model.named_parameters():
         assert _rel(p.grad, on[k].grad, atol=1e-7) < 5e-3, k
+
+
+# ------------------------------------------------------------------------------------------- partitioned mesh
+@pytest.mark.parametrize("n,n_parts", [(1500, 2), (2600, 3), (900, 8)])
+def test_partitioned_solver_equals_whole_graph(n, n_parts):
+    """Graph-partitioned processor with one halo exchange per layer (all parts emulated in this process, same
+    pack / unpack kernels as the multi-GPU path) == the processor on the whole graph: outputs, dL/du and every
+    parameter gradient, train-mode BatchNorm (statistics over all parts) included."""
+    import numpy as np
+    from mmpde_b200 import ops, partition as pt
+    from mmpde_b200.gnn_2d import MP_PDE_Solver_2D
+    from mmpde_b200.PDEs import burgers
+    dev = _dev()
+    rng = np.random.default_rng(n)
+    side = int(np.ceil(np.sqrt(n)))
+    g = np.stack(np.meshgrid(np.linspace(0, 1, side), np.linspace(0, 1, side), indexing="ij"), -1).reshape(-1, 2)[:n]
+    xy = torch.from_numpy((g + rng.uniform(-0.3, 0.3, g.shape) / (side - 1)).astype(np.float32)).to(dev)
+    off = torch.tensor([0, n], dtype=torch.int32, device=dev)
+    edges = ops.EdgeList.from_knn(ops.knn_indices(xy, off, xy, off, 35, 0, True), has_pad=False)
+    torch.manual_seed(1)
+    u = torch.randn(n, 1, device=dev)
+    pos = torch.cat((torch.full((n, 1), 7.0, device=dev), xy), 1)
+    r = torch.randn(n, 1, device=dev)
+    pde = burgers()
+    model = fill_params(MP_PDE_Solver_2D(pde, hidden_layer=3), 4).to(dev)
+    model.train()
+
+    class G:
+        pass
+    whole = G()
+    whole.x, whole.pos, whole.edge_index, whole.batch = u.clone().requires_grad_(True), pos, edges.edge_index(), None
+    state0 = {k: v.clone() for k, v in model.state_dict().items()}
+    out = model(whole)
+    (out * r).sum().backward()
+    ref_grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+    ref_bn = {k: v.clone() for k, v in model.state_dict().items() if "running" in k}
+    model.zero_grad()
+    model.load_state_dict(state0)
+
+    parts, plans = pt.split_graph(u, pos, edges.src, edges.dst, n_parts)
+    assert sum(p.n_halo for p in plans) > 0
+    for p in parts:
+        p.x = p.x.clone().requires_grad_(True)
+    outs = model.forward_partitioned(parts, pt.LocalExchange(plans))
+    sum((o * r[pl.owned]).sum() for o, pl in zip(outs, plans)).backward()
+    got = torch.empty_like(out)
+    gu = torch.empty_like(u)
+    for o, p, pl in zip(outs, parts, plans):
+        got[pl.owned] = o.detach()
+        gu[pl.owned] = p.x.grad
+    assert _rel(got, out) < 2e-5
+    assert _rel(gu, whole.x.grad) < TOL
+    for k, p in model.named_parameters():       # biases in front of a BatchNorm have a zero gradient: pure rounding noise
+        assert _rel(p.grad, ref_grads[k], atol=1e-5) < TOL, k
+    for k, v in ref_bn.items():
+        assert _rel(model.state_dict()[k].float(), v.float()) < 1e-5, k

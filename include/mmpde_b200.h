@@ -77,6 +77,27 @@ int mmpde_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_
                const float* bias, const float* r1_row, int64_t r1_stride, const float* r1_col,
                int relu, int accumulate, int split_k, void* stream);
 
+/* The same node-level contractions on the tcgen05 tensor cores (three split-bf16 products, fp32 accumulation in
+ * TMEM: ~2^-16 relative error per term), for the shapes the processor uses: 128 outputs per call, K = 128 per
+ * segment.  mmpde_gemm above stays for the odd shapes (K = 4, N = 1).
+ *
+ * mmpde_node_gemm:   C[m][n] = act( sum_k A0[m][k] W0(n,k) (+ sum_k A1[m][k] W1(n,k)) + node4[m] . Wext[n] + bias[n] )
+ *                              + R1[m][n] + R2[m][n],      m < M, n < 128, k < 128
+ *   A0 / A1 [M, >=128] fp32 row-major (ld multiple of 4, 16-byte aligned); A1 / W1 NULL for K = 128;
+ *   W element (n,k) at W[n*w_ns + k*w_ks]  (nn.Linear weight [out,in]: w_ns = ld, w_ks = 1; its transpose for the
+ *   data gradient: w_ns = 1, w_ks = ld);  Aext [M,4] / Wext [128,4] (ld 4) optional extra K columns (the node scalars);
+ *   bias [128], R1, R2 (residuals, may alias C) optional;  relu applies before the residuals.
+ * mmpde_node_wgrad:  dW[i][j] += sum_m A[m][i] B[m][j]   (i, j < 128);   dWext[i][f] += sum_m A[m][i] Bext[m][f] (f < 4);
+ *                    dbias[i] += sum_m A[m][i].   Any of (B, dW), (Bext, dWext), dbias may be NULL.  Accumulates
+ *   atomically: zero the outputs first (or let several calls add up). */
+int mmpde_node_gemm(const float* A0, int64_t lda0, const float* A1, int64_t lda1,
+                    const float* W0, int64_t w0_ns, int64_t w0_ks, const float* W1, int64_t w1_ns, int64_t w1_ks,
+                    const float* Aext, const float* Wext, const float* bias, int relu,
+                    const float* R1, int64_t ldr1, const float* R2, int64_t ldr2,
+                    float* C, int64_t ldc, int64_t M, void* stream);
+int mmpde_node_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, const float* Bext,
+                     float* dW, int64_t ldw, float* dWext, int64_t ldwext, float* dbias, int64_t M, void* stream);
+
 /* ---- message passing over the target-sorted edge list -------------------------------------------
  * Replaces PyG propagate + message_net_1/2 + scatter-mean (gnn_2d.py:55,59-63).  message_net_1 is split per
  * node: with e_ij = (u_i-u_j, px_i-px_j, py_i-py_j, v_i),

@@ -22,6 +22,8 @@ SIGNATURES = {
     "mmpde_knn_grid": [_p, _p, _p, _p, _i, _l, _f, _f, _f, _i, _i, _p, _p, _i, _i, _i, _p, _p],
     "mmpde_radius": [_p, _p, _i, _l, _f, _i, _p, _p],
     "mmpde_gemm": [_p, _l, _i, _p, _l, _i, _p, _l, _l, _i, _l, _p, _p, _l, _p, _i, _i, _i, _p],
+    "mmpde_node_gemm": [_p, _l, _p, _l, _p, _l, _l, _p, _l, _l, _p, _p, _p, _i, _p, _l, _p, _l, _p, _l, _l, _p],
+    "mmpde_node_wgrad": [_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _l, _p],
     "mmpde_edge_fwd": [_p, _p, _p, _p, _l, _p, _p, _p, _l, _p, _p],
     "mmpde_edge_bwd": [_p, _p, _p, _p, _l, _p, _p, _p, _l, _p, _p, _p, _p],
     "mmpde_bn_stats": [_p, _l, _p, _l, _l, _p, _p],

@@ -21,21 +21,6 @@
 namespace mmpde {
 using namespace tc;
 
-// Optional per-phase timestamps (debug build only: make timeline -> libmmpde_b200_tl.so, read by profiles/timeline.py).
-// Slot layout: [role][tile iteration < TL_ITERS][8 stamps]; roles: 0 first builder warp, 1 last builder warp, 2 MMA
-// thread, 3 epilogue warp 0.  CTA 0 only.
-#ifdef MMPDE_TIMELINE
-__device__ long long* g_timeline = nullptr;
-constexpr int TL_ITERS = 48;
-#define TL(role, it, slot)                                                                                   \
-    do {                                                                                                     \
-        if (g_timeline != nullptr && blockIdx.x == 0 && (it) < TL_ITERS && (threadIdx.x & 31) == 0)          \
-            g_timeline[((role) * TL_ITERS + (it)) * 8 + (slot)] = clock64();                                 \
-    } while (0)
-#else
-#define TL(role, it, slot) do { } while (0)
-#endif
-
 constexpr int EPI_WARPS = 4;
 constexpr int BLD_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS + BLD_WARPS;
@@ -43,8 +28,6 @@ constexpr int EDGE_THREADS = 512;                          // 4 warpgroups: epil
 // Register budget moved between the warpgroups with setmaxnreg (launch value 65536 / 512 = 128 per thread):
 // 4*32*104 + 8*32*184 + 4*32*40 = 65536.
 constexpr int EPI_REGS = 104, BLD_REGS = 184, MMA_REGS = 40;
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr uint32_t TMEM_COLS = 512;
 
 // ---- rows a builder warp owns --------------------------------------------------------------------------------
@@ -87,15 +70,6 @@ __device__ __forceinline__ float4 sel4(bool c, const float4& a, const float4& b)
 __device__ __forceinline__ float4 relu_add(const float4& a, const float4& b) {
     return make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
 }
-// fp32 row fragment (4 channels of this lane) -> bf16 hi / lo operand images at shared address `img`
-template <int ROWS>
-__device__ __forceinline__ void store_split(uint32_t img, int row, int lane, const float4& v) {
-    uint2 hi, lo;
-    split4(v, hi, lo);
-    const uint32_t a = img + tile_off<ROWS>(row, lane * 4);
-    sts_v2(a, hi);
-    sts_v2(a + 2 * ROWS * 128, lo);                                        // lo image follows the hi image
-}
 // h1 = relu(P'[dst] + Q'[src]) of 8 gathered rows -> operand image rows rowbase .. rowbase+7.  Straight-line code
 // (rows beyond the last edge come out as zero: their Q' and the last row's P' are zero), then the rare patch loop.
 template <int ROWS>
@@ -111,27 +85,6 @@ __device__ __forceinline__ void build_h8(uint32_t img, int rowbase, const Gather
         const int d = __shfl_sync(0xffffffffu, idx.d, r0 + k), sr = __shfl_sync(0xffffffffu, idx.s, r0 + k);
         store_split<ROWS>(img, rowbase + k, lane,
                           relu_add(ldg4(PQ + (int64_t)d * 256 + lane * 4), ldg4(PQ + (int64_t)sr * 256 + 128 + lane * 4)));
-    }
-}
-
-// W (row-major [128][128] fp32, element (r, k) at w[r*rs + k*ks]) -> TMEM A operand: lane r, 64 columns hi, 64 lo
-__device__ __forceinline__ void weight_to_tmem(const float* __restrict__ w, int rs, int ks, int r, uint32_t t_hi, uint32_t t_lo) {
-#pragma unroll 1
-    for (int g = 0; g < 4; ++g) {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            const int k = g * 32 + v * 4;
-            float4 x;
-            if (ks == 1) x = ldg4(w + r * rs + k);
-            else x = make_float4(__ldg(w + r * rs + k * ks), __ldg(w + r * rs + (k + 1) * ks), __ldg(w + r * rs + (k + 2) * ks),
-                                 __ldg(w + r * rs + (k + 3) * ks));
-            uint2 h, l;
-            split4(x, h, l);
-            hi[2 * v] = h.x; hi[2 * v + 1] = h.y; lo[2 * v] = l.x; lo[2 * v + 1] = l.y;
-        }
-        tmem_st16(t_hi + g * 16, hi);
-        tmem_st16(t_lo + g * 16, lo);
     }
 }
 

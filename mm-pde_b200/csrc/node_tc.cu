@@ -1,0 +1,472 @@
+// Node-level dense contractions of the processor on the 5th-gen tensor cores (tcgen05 + TMEM): nn.Linear forward /
+// dgrad (mmpde_node_gemm) and wgrad (mmpde_node_wgrad) of /root/reference/gnn_2d.py:44-49,61,67-68,99-106 and their
+// autograd.  Same numerics as the edge kernels: every product runs as three bf16 MMAs (hi*hi + hi*lo + lo*hi) with fp32
+// accumulation in TMEM; operands are fp32 in HBM and are split to bf16 hi/lo while they are staged into the
+// SWIZZLE_128B shared-memory tiles (so no TMA: the staging IS the conversion).
+//
+// mmpde_node_gemm  : C[m][n] = act(sum_k A[m][k] W(n,k) + node4[m] . Wext[n] + bias[n]) + R1[m][n] + R2[m][n]
+//   computed TRANSPOSED, D[n][m] = W A^T: the 128 outputs n sit on the TMEM lanes, a tile of 128 rows m on the columns, so
+//   an epilogue warp stores 32 consecutive n of one row per instruction (coalesced) and W (hi, lo) is loaded ONCE per CTA
+//   into tensor memory as the A operand of the TS-form MMA.  K = 128 per segment, 1 or 2 segments (K = 256) with their
+//   own base pointers, plus an optional 4-column extension (the node scalars u, x, y, t) as one more K step.
+// mmpde_node_wgrad : dW[i][j] += sum_m A[m][i] B[m][j]  (+ dWext[i][f] += sum_m A[m][i] node4[m][f], dbias[i] += sum_m A[m][i])
+//   K = the node axis, streamed in tiles of 64 rows; both operand tiles are read MN-major (no transposition in memory);
+//   the accumulator stays in TMEM for the whole CTA and is reduced into HBM once (128-bit vector reductions).
+// Both kernels are persistent and warp-specialised like the edge kernels (epilogue | builders | one MMA thread).
+#include "tc_common.cuh"
+
+namespace mmpde {
+using namespace tc;
+
+constexpr uint32_t N_TMEM_COLS = 512;
+
+// ================================================================================================================
+// forward / dgrad
+// ================================================================================================================
+constexpr int G_EPI_WARPS = 8, G_BLD_WARPS = 8, G_MMA_WARP = 16, G_THREADS = 640;
+constexpr int G_EPI_REGS = 72, G_BLD_REGS = 144, G_MMA_REGS = 40;          // 8*32*72 + 8*32*144 + 4*32*40 <= 640*96
+constexpr int GT = 128;                                                    // rows per tile
+constexpr uint32_t G_IMG = 2 * GT * 128;                                   // one [128][128] bf16 image = 32 KB
+constexpr uint32_t G_XIMG = GT * 128;                                      // extension image [128 rows][128 B] = 16 KB
+
+struct NodeGemmArgs {
+    const float* A[2]; int64_t lda[2]; int nseg;
+    const float* W[2]; int64_t w_ns[2], w_ks[2];
+    const float* Aext; const float* Wext;
+    const float* bias; int relu;
+    const float* R1; int64_t ldr1; const float* R2; int64_t ldr2;
+    float* C; int64_t ldc; int64_t M;
+};
+struct GemmSmem {
+    static constexpr uint32_t SEG = 0;                                     // 2 stages x (hi, lo)
+    static constexpr uint32_t EXT = 2 * 2 * G_IMG;                         // 2 x (hi, lo) extension tiles
+    static constexpr uint32_t BAR = EXT + 2 * 2 * G_XIMG;
+    static constexpr uint32_t TOTAL = BAR + 128;
+};
+
+__global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(sm);
+    const uint32_t bar0 = sbase + GemmSmem::BAR;
+    const uint32_t h_full = bar0, h_empty = bar0 + 16, tm_full = bar0 + 32, tm_empty = bar0 + 48;   // [b] at +8*b
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + GemmSmem::BAR + 64);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), N_TMEM_COLS);
+    if (tid == 32) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(h_full + 8 * b, G_BLD_WARPS); mbar_init(h_empty + 8 * b, 1);
+            mbar_init(tm_full + 8 * b, 1); mbar_init(tm_empty + 8 * b, G_EPI_WARPS);
+        }
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nseg = p.nseg;
+    const bool has_ext = p.Aext != nullptr;
+    const int d_stages = (nseg == 1) ? 2 : 1;                              // TMEM: D stages | W0 hi lo | ext hi lo | W1 hi lo
+    const uint32_t tmem_d = tmem_base, tmem_w = tmem_base + d_stages * GT;
+    const uint32_t tmem_x_hi = tmem_w + 128, tmem_x_lo = tmem_w + 136;
+    const int64_t n_tiles = (p.M + GT - 1) / GT;
+
+    if (warp < G_EPI_WARPS) {
+        // ------------------------------------------------------------------ epilogue: thread = output n, columns = rows m
+        reg_dec<G_EPI_REGS>();
+        const int q = warp & 3, half = warp >> 2;
+        const int n = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t bias_bits = p.bias ? __float_as_uint(__ldg(p.bias + n)) : 0u;
+        if (half == 0) {
+            weight_to_tmem(p.W[0], p.w_ns[0], p.w_ks[0], n, tmem_w + lane_addr, tmem_w + 64 + lane_addr);
+            if (nseg == 2) weight_to_tmem(p.W[1], p.w_ns[1], p.w_ks[1], n, tmem_w + 144 + lane_addr, tmem_w + 208 + lane_addr);
+        } else if (has_ext) {
+            // extension weights: K step of 16 = (w0 w1)(w2 w3) then zeros; hi in columns +0..7, lo in +8..15
+            uint2 h, l;
+            split4(ldg4(p.Wext + n * 4), h, l);
+            uint32_t xw[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) xw[c] = 0u;
+            xw[0] = h.x; xw[1] = h.y; xw[8] = l.x; xw[9] = l.y;
+            tmem_st16(tmem_x_hi + lane_addr, xw);
+        }
+        for (int b = 0; b < d_stages; ++b) {
+            tmem_fill32(tmem_d + lane_addr + b * GT + half * 64, bias_bits);
+            tmem_fill32(tmem_d + lane_addr + b * GT + half * 64 + 32, bias_bits);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(tm_empty); if (d_stages == 2) mbar_arrive(tm_empty + 8); }
+        int i = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int b = (d_stages == 2) ? (i & 1) : 0;
+            const uint32_t ph = (uint32_t)((d_stages == 2) ? (i >> 1) : i) & 1u;
+            mbar_wait(tm_full + 8 * b, ph);
+            tc_fence_after();
+            const uint32_t d_addr = tmem_d + lane_addr + b * GT + half * 64;
+            uint32_t v[32];
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                tmem_ld32_async(d_addr + c * 32, v);
+                tmem_wait_ld(v);
+                const int64_t m0 = t * GT + half * 64 + c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int64_t m = m0 + j;
+                    if (m < p.M) {                                         // warp-uniform
+                        float z = __uint_as_float(v[j]);
+                        if (p.relu) z = fmaxf(z, 0.f);
+                        if (p.R1) z += p.R1[m * p.ldr1 + n];               // plain loads: a residual may alias C
+                        if (p.R2) z += p.R2[m * p.ldr2 + n];
+                        p.C[m * p.ldc + n] = z;
+                    }
+                }
+            }
+            tmem_fill32(d_addr, bias_bits);
+            tmem_fill32(d_addr + 32, bias_bits);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tm_empty + 8 * b);
+        }
+    } else if (warp < G_MMA_WARP) {
+        // ------------------------------------------------------------------ builders: warp w -> rows 16w .. 16w+15 of a tile
+        reg_inc<G_BLD_REGS>();
+        const int w = warp - G_EPI_WARPS;
+        const int row0 = w * 16;
+        // stream of half-stages u = 0, 1, ...: stage j = u >> 1 (tile j / nseg, segment j % nseg), rows row0 + 8*(u&1) ..
+        auto load8 = [&](float4 (&r)[8], int64_t u) {
+            const int64_t j = u >> 1;
+            const int64_t t = (int64_t)blockIdx.x + (j / nseg) * gridDim.x;
+            const int seg = (int)(j % nseg);
+            const float* base = p.A[seg];
+            const int64_t ld = p.lda[seg];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int64_t m = t * GT + row0 + 8 * (int)(u & 1) + k;
+                r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t < n_tiles && m < p.M) r[k] = ldg4(base + m * ld + lane * 4);
+            }
+        };
+        const int64_t my_tiles = ((int64_t)blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t n_half = my_tiles * nseg * 2;
+        float4 ra[8], rb[8];
+        if (n_half > 0) load8(ra, 0);
+        for (int64_t u = 0; u < n_half; u += 2) {
+            const int64_t j = u >> 1;
+            const int sb = (int)(j & 1);
+            const int64_t ti = j / nseg;
+            const int seg = (int)(j % nseg);
+            load8(rb, u + 1);
+            mbar_wait(h_empty + 8 * sb, ((uint32_t)(j >> 1) & 1u) ^ 1u);
+            const uint32_t img = sbase + GemmSmem::SEG + sb * (2 * G_IMG);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) store_split<GT>(img, row0 + k, lane, ra[k]);
+            if (u + 2 < n_half) load8(ra, u + 2);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) store_split<GT>(img, row0 + 8 + k, lane, rb[k]);
+            if (has_ext && seg == nseg - 1) {
+                // extension K step: columns 0..3 = node4[m], 4..15 = 0.  16 rows x 4 pieces of 8 bytes (hi image; lo follows)
+                const int64_t t = (int64_t)blockIdx.x + ti * gridDim.x;
+                const uint32_t ximg = sbase + GemmSmem::EXT + (uint32_t)(ti & 1) * (2 * G_XIMG);
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int id = it * 32 + lane, r = row0 + (id >> 2), pc = id & 3;
+                    uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
+                    const int64_t m = t * GT + r;
+                    if (pc == 0 && m < p.M) split4(ldg4(p.Aext + m * 4), hi, lo);
+                    const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)pc >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)pc & 1u) * 8u;
+                    sts_v2(ximg + off, hi);
+                    sts_v2(ximg + G_XIMG + off, lo);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h_full + 8 * sb);
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        reg_dec<G_MMA_REGS>();
+        constexpr uint32_t idesc = idesc_bf16(128, GT, 0, 0);
+        if (warp == G_MMA_WARP && lane == 0) {
+            int i = 0;
+            int64_t j = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+                const int b = (d_stages == 2) ? (i & 1) : 0;
+                const uint32_t ph = (uint32_t)((d_stages == 2) ? (i >> 1) : i) & 1u;
+                mbar_wait(tm_empty + 8 * b, ph);
+                for (int seg = 0; seg < nseg; ++seg, ++j) {
+                    const int sb = (int)(j & 1);
+                    mbar_wait(h_full + 8 * sb, (uint32_t)(j >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t h_addr = sbase + GemmSmem::SEG + sb * (2 * G_IMG);
+                    const uint32_t w_hi = tmem_w + (seg == 0 ? 0 : 144), w_lo = w_hi + 64;
+#pragma unroll
+                    for (int prod = 0; prod < 3; ++prod) {                 // hi*hi + hi*lo + lo*hi
+                        const uint32_t a = (prod == 2) ? w_lo : w_hi;
+                        const uint32_t bb = h_addr + (prod == 1 ? G_IMG : 0);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            umma_bf16_ts(tmem_d + b * GT, a + ks * 8,
+                                         smem_desc_sw128(bb + (ks >> 2) * (GT * 128) + (ks & 3) * 32, 16, 1024), idesc, 1u);
+                    }
+                    if (has_ext && seg == nseg - 1) {
+                        const uint32_t x_addr = sbase + GemmSmem::EXT + (uint32_t)(i & 1) * (2 * G_XIMG);
+#pragma unroll
+                        for (int prod = 0; prod < 3; ++prod)
+                            umma_bf16_ts(tmem_d + b * GT, (prod == 2) ? tmem_x_lo : tmem_x_hi,
+                                         smem_desc_sw128(x_addr + (prod == 1 ? G_XIMG : 0), 16, 1024), idesc, 1u);
+                    }
+                    umma_commit(h_empty + 8 * sb);
+                }
+                umma_commit(tm_full + 8 * b);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, N_TMEM_COLS);
+}
+
+// ================================================================================================================
+// wgrad
+// ================================================================================================================
+constexpr int W_EPI_WARPS = 4, W_BLD_WARPS = 8, W_MMA_WARP = 12, W_THREADS = 512;
+constexpr int W_EPI_REGS = 104, W_BLD_REGS = 184, W_MMA_REGS = 40;         // 4*32*104 + 8*32*184 + 4*32*40 = 65536 = 512*128
+constexpr int WT = 64;                                                     // node rows per K tile
+constexpr uint32_t W_IMG = 2 * WT * 128;                                   // one [64][128] bf16 image = 16 KB
+constexpr uint32_t W_XIMG = 16 * 128;                                      // extension tile, TRANSPOSED: [16 features][64 rows] = 2 KB
+
+struct NodeWgradArgs {
+    const float* A; int64_t lda; const float* B; int64_t ldb; const float* Bext; int want_bias;
+    float* dW; int64_t ldw; float* dWext; int64_t ldwext; float* dbias; int64_t M;
+};
+struct WgradSmem {
+    static constexpr uint32_t STAGE = 4 * W_IMG + 2 * W_XIMG;             // A hi lo | B hi lo | ext hi lo  = 68 KB
+    static constexpr uint32_t BAR = 2 * STAGE;
+    static constexpr uint32_t TOTAL = BAR + 128;
+};
+
+__global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradArgs p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(sm);
+    const uint32_t bar0 = sbase + WgradSmem::BAR;
+    const uint32_t s_full = bar0, s_empty = bar0 + 16, all_done = bar0 + 32;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + WgradSmem::BAR + 64);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool has_b = p.B != nullptr, has_ext = (p.Bext != nullptr) || p.want_bias;
+
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+    if (tid == 32) {
+        for (int b = 0; b < 2; ++b) { mbar_init(s_full + 8 * b, W_BLD_WARPS); mbar_init(s_empty + 8 * b, 1); }
+        mbar_init(all_done, 1);
+        fence_mbar_init();
+    }
+    // the extension tiles only ever receive features 0..4: zero the rest (and everything else) once
+    for (uint32_t o = tid * 16; o < 2 * WgradSmem::STAGE; o += W_THREADS * 16)
+        *reinterpret_cast<uint4*>(sm + o) = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_d = tmem_base, tmem_dx = tmem_base + 128;
+    const int64_t n_tiles = (p.M + WT - 1) / WT;
+    const int64_t my_tiles = ((int64_t)blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp < W_EPI_WARPS) {
+        // ------------------------------------------------------------------ epilogue (once): lane = row i of dW
+        reg_dec<W_EPI_REGS>();
+        const int i_row = warp * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        if (my_tiles > 0) {
+            mbar_wait(all_done, 0);
+            tc_fence_after();
+            if (has_b) {
+                const bool vec = (p.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0;
+#pragma unroll 1
+                for (int chunk = 0; chunk < 4; ++chunk) {
+                    uint32_t v[32];
+                    tmem_ld32_async(tmem_d + lane_addr + chunk * 32, v);
+                    tmem_wait_ld(v);
+                    float* row = p.dW + (int64_t)i_row * p.ldw + chunk * 32;
+                    if (vec) {
+#pragma unroll
+                        for (int m = 0; m < 8; ++m)
+                            red_add_v4(row + 4 * m, make_float4(__uint_as_float(v[4 * m]), __uint_as_float(v[4 * m + 1]),
+                                                                 __uint_as_float(v[4 * m + 2]), __uint_as_float(v[4 * m + 3])));
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < 32; ++m) atomicAdd(row + m, __uint_as_float(v[m]));
+                    }
+                }
+            }
+            if (has_ext) {
+                uint32_t v[32];                                            // only the first 16 columns are the extension
+                tmem_ld32_async(tmem_dx + lane_addr, v);
+                tmem_wait_ld(v);
+                if (p.dWext) {
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) atomicAdd(p.dWext + (int64_t)i_row * p.ldwext + f, __uint_as_float(v[f]));
+                }
+                if (p.dbias) atomicAdd(p.dbias + i_row, __uint_as_float(v[4]));
+            }
+        }
+    } else if (warp < W_MMA_WARP) {
+        // ------------------------------------------------------------------ builders: warp w -> rows 8w .. 8w+7 of the A and B tiles
+        reg_inc<W_BLD_REGS>();
+        const int w = warp - W_EPI_WARPS;
+        const int row0 = w * 8;
+        const int per_tile = has_b ? 2 : 1;                                // half-steps per tile: A rows, then B rows
+        auto load8 = [&](float4 (&r)[8], int64_t u) {
+            const int64_t ti = u / per_tile;
+            const bool is_b = (u % per_tile) == 1;
+            const int64_t t = (int64_t)blockIdx.x + ti * gridDim.x;
+            const float* base = is_b ? p.B : p.A;
+            const int64_t ld = is_b ? p.ldb : p.lda;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int64_t m = t * WT + row0 + k;
+                r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ti < my_tiles && m < p.M) r[k] = ldg4(base + m * ld + lane * 4);
+            }
+        };
+        const int64_t n_steps = my_tiles * per_tile;
+        float4 ra[8], rb[8];
+        if (n_steps > 0) load8(ra, 0);
+        for (int64_t ti = 0; ti < my_tiles; ++ti) {
+            const int sb = (int)(ti & 1);
+            const int64_t u = ti * per_tile;
+            const int64_t t = (int64_t)blockIdx.x + ti * gridDim.x;
+            if (u + 1 < n_steps) load8(rb, u + 1);
+            mbar_wait(s_empty + 8 * sb, ((uint32_t)(ti >> 1) & 1u) ^ 1u);
+            const uint32_t stage = sbase + sb * WgradSmem::STAGE;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) store_split<WT>(stage, row0 + k, lane, ra[k]);
+            if (has_b) {
+                if (u + 2 < n_steps) load8(ra, u + 2);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) store_split<WT>(stage + 2 * W_IMG, row0 + k, lane, rb[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) ra[k] = rb[k];
+            }
+            if (has_ext && lane < 8) {
+                // extension tile, K-major and transposed: feature f (row of the tile), node r (column): f 0..3 = node4, 4 = 1
+                const int r = row0 + lane;
+                const int64_t m = t * WT + r;
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                float one = 0.f;
+                if (m < p.M) { one = 1.f; if (p.Bext) x = ldg4(p.Bext + m * 4); }
+                const float f5[5] = {x.x, x.y, x.z, x.w, one};
+                const uint32_t ximg = stage + 4 * W_IMG;
+#pragma unroll
+                for (int f = 0; f < 5; ++f) {
+                    const __nv_bfloat16 h = __float2bfloat16_rn(f5[f]);
+                    const __nv_bfloat16 l = __float2bfloat16_rn(f5[f] - __bfloat162float(h));
+                    const uint32_t off = (uint32_t)f * 128u + ((((uint32_t)r >> 3) ^ (uint32_t)f) << 4) + ((uint32_t)r & 7u) * 2u;
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(ximg + off), "h"(*reinterpret_cast<const unsigned short*>(&h)));
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(ximg + W_XIMG + off), "h"(*reinterpret_cast<const unsigned short*>(&l)));
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_full + 8 * sb);
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        reg_dec<W_MMA_REGS>();
+        constexpr uint32_t idesc_main = idesc_bf16(128, 128, 1, 1);        // A^T B: both tiles MN-major
+        constexpr uint32_t idesc_ext = idesc_bf16(128, 16, 1, 0);          // A^T ext: ext tile K-major (transposed storage)
+        if (warp == W_MMA_WARP && lane == 0) {
+            for (int64_t ti = 0; ti < my_tiles; ++ti) {
+                const int sb = (int)(ti & 1);
+                mbar_wait(s_full + 8 * sb, (uint32_t)(ti >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t a_addr = sbase + sb * WgradSmem::STAGE, b_addr = a_addr + 2 * W_IMG, x_addr = a_addr + 4 * W_IMG;
+#pragma unroll
+                for (int prod = 0; prod < 3; ++prod) {
+                    const uint32_t a = a_addr + (prod == 2 ? W_IMG : 0);
+                    if (has_b) {
+                        const uint32_t bb = b_addr + (prod == 1 ? W_IMG : 0);
+#pragma unroll
+                        for (int ks = 0; ks < WT / 16; ++ks)               // 16 node rows per step
+                            umma_bf16(tmem_d, smem_desc_sw128(a + ks * 16 * 128, WT * 128, 1024),
+                                      smem_desc_sw128(bb + ks * 16 * 128, WT * 128, 1024), idesc_main, (ti > 0 || prod > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    if (has_ext) {
+                        const uint32_t xx = x_addr + (prod == 1 ? W_XIMG : 0);
+#pragma unroll
+                        for (int ks = 0; ks < WT / 16; ++ks)
+                            umma_bf16(tmem_dx, smem_desc_sw128(a + ks * 16 * 128, WT * 128, 1024),
+                                      smem_desc_sw128(xx + ks * 32, 16, 1024), idesc_ext, (ti > 0 || prod > 0 || ks > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(s_empty + 8 * sb);
+            }
+            if (my_tiles > 0) umma_commit(all_done);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace mmpde
+
+using namespace mmpde;
+
+extern "C" int mmpde_node_gemm(const float* A0, int64_t lda0, const float* A1, int64_t lda1,
+                               const float* W0, int64_t w0_ns, int64_t w0_ks, const float* W1, int64_t w1_ns, int64_t w1_ks,
+                               const float* Aext, const float* Wext, const float* bias, int relu,
+                               const float* R1, int64_t ldr1, const float* R2, int64_t ldr2,
+                               float* C, int64_t ldc, int64_t M, void* stream) {
+    if (M < 0 || A0 == nullptr || W0 == nullptr || C == nullptr) return MMPDE_EINVAL;
+    if ((A1 == nullptr) != (W1 == nullptr) || (Aext == nullptr) != (Wext == nullptr)) return MMPDE_EINVAL;
+    if ((lda0 & 3) || (A1 && (lda1 & 3))) return MMPDE_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(A0) | reinterpret_cast<uintptr_t>(A1) | reinterpret_cast<uintptr_t>(Aext) |
+         reinterpret_cast<uintptr_t>(Wext)) & 15) return MMPDE_EINVAL;
+    if (M == 0) return MMPDE_OK;
+    constexpr size_t smem = GemmSmem::TOTAL + 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(node_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    NodeGemmArgs p;
+    p.A[0] = A0; p.A[1] = A1; p.lda[0] = lda0; p.lda[1] = lda1; p.nseg = A1 ? 2 : 1;
+    p.W[0] = W0; p.W[1] = W1; p.w_ns[0] = w0_ns; p.w_ks[0] = w0_ks; p.w_ns[1] = w1_ns; p.w_ks[1] = w1_ks;
+    p.Aext = Aext; p.Wext = Wext; p.bias = bias; p.relu = relu; p.R1 = R1; p.ldr1 = ldr1; p.R2 = R2; p.ldr2 = ldr2;
+    p.C = C; p.ldc = ldc; p.M = M;
+    const int64_t n_tiles = (M + GT - 1) / GT;
+    node_gemm_tc_kernel<<<(int)imin64(n_tiles, sm_count()), G_THREADS, smem, (cudaStream_t)stream>>>(p);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_node_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, const float* Bext,
+                                float* dW, int64_t ldw, float* dWext, int64_t ldwext, float* dbias, int64_t M, void* stream) {
+    if (M < 0 || A == nullptr || (lda & 3) || (B && (ldb & 3))) return MMPDE_EINVAL;
+    if ((B == nullptr) != (dW == nullptr) || (Bext == nullptr) != (dWext == nullptr)) return MMPDE_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(Bext)) & 15) return MMPDE_EINVAL;
+    if (M == 0 || (B == nullptr && Bext == nullptr && dbias == nullptr)) return MMPDE_OK;
+    constexpr size_t smem = WgradSmem::TOTAL + 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(node_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    NodeWgradArgs p;
+    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.Bext = Bext; p.want_bias = dbias != nullptr;
+    p.dW = dW; p.ldw = ldw; p.dWext = dWext; p.ldwext = ldwext; p.dbias = dbias; p.M = M;
+    const int64_t n_tiles = (M + WT - 1) / WT;
+    node_wgrad_tc_kernel<<<(int)imin64(n_tiles, sm_count()), W_THREADS, smem, (cudaStream_t)stream>>>(p);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}

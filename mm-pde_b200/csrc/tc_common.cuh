@@ -222,5 +222,60 @@ __device__ __forceinline__ float4 lds_v4f(uint32_t saddr) {
     return v;
 }
 
+// fp32 row fragment (4 consecutive columns owned by this lane) -> bf16 hi / lo operand images (ROWS rows each, the lo
+// image follows the hi image) at shared address `img`
+template <int ROWS>
+__device__ __forceinline__ void store_split(uint32_t img, int row, int lane, const float4& v) {
+    uint2 hi, lo;
+    split4(v, hi, lo);
+    const uint32_t a = img + tile_off<ROWS>(row, lane * 4);
+    sts_v2(a, hi);
+    sts_v2(a + 2 * ROWS * 128, lo);
+}
+
+// W (fp32, element (r, k) at w[r*rs + k*ks], 128 x 128) -> TMEM A operand of the TS-form MMA: lane r, 64 columns hi at
+// t_hi, 64 columns lo at t_lo (one 32-bit column = two consecutive k).  Called by the 4 warps owning the 128 lanes.
+__device__ __forceinline__ void weight_to_tmem(const float* __restrict__ w, int64_t rs, int64_t ks, int r, uint32_t t_hi, uint32_t t_lo) {
+    const bool vec = (ks == 1) && ((rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);   // 128-bit loads need alignment
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const int k = g * 32 + v * 4;
+            float4 x;
+            if (vec) x = ldg4(w + r * rs + k);
+            else x = make_float4(__ldg(w + r * rs + k * ks), __ldg(w + r * rs + (k + 1) * ks), __ldg(w + r * rs + (k + 2) * ks),
+                                 __ldg(w + r * rs + (k + 3) * ks));
+            uint2 h, l;
+            split4(x, h, l);
+            hi[2 * v] = h.x; hi[2 * v + 1] = h.y; lo[2 * v] = l.x; lo[2 * v + 1] = l.y;
+        }
+        tmem_st16(t_hi + g * 16, hi);
+        tmem_st16(t_lo + g * 16, lo);
+    }
+}
+
+// ---- warp-role plumbing -----------------------------------------------------------------------------------
+// Register budget moved between warpgroups (4 consecutive warps each); the CTA's pool is what it was launched with.
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 }  // namespace tc
+
+// Optional per-phase timestamps (debug build only: make timeline -> libmmpde_b200_tl.so, read by profiles/timeline.py).
+// Slot layout: [role][tile iteration < TL_ITERS][8 stamps]; roles: 0 first builder warp, 1 last builder warp, 2 MMA
+// thread, 3 epilogue warp 0.  CTA 0 only.
+#ifdef MMPDE_TIMELINE
+static __device__ long long* g_timeline = nullptr;     // per translation unit (no -rdc): set via mmpde_debug_timeline
+constexpr int TL_ITERS = 48;
+#define TL(role, it, slot)                                                                                   \
+    do {                                                                                                     \
+        if (g_timeline != nullptr && blockIdx.x == 0 && (it) < TL_ITERS && (threadIdx.x & 31) == 0)          \
+            g_timeline[((role) * TL_ITERS + (it)) * 8 + (slot)] = clock64();                                 \
+    } while (0)
+#else
+#define TL(role, it, slot) do { } while (0)
+#endif
+
 }  // namespace mmpde

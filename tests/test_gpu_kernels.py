@@ -403,3 +403,71 @@ def test_edge_kernels_empty_and_single_edge():
                ops._ptr(agg), 128, ops._ptr(mask), st)
     ref = torch.relu(torch.relu(PQ[1, :128] + PQ[2, 128:]).double() @ w2.double().t() + b2.double())
     assert _rel(agg[1], ref) < 2e-5 and float(agg[0].abs().max()) == 0.0 and float(agg[2].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------- tcgen05 node GEMMs
+@pytest.mark.parametrize("M", [1, 127, 128, 300, 5000, 40000])
+@pytest.mark.parametrize("variant", ["linear", "k256_ext_relu", "dgrad_residuals"])
+def test_node_gemm_tensor_core(M, variant):
+    """mmpde_node_gemm against the fp64 definition: 2e-5 relative L2 (three bf16 products)."""
+    from mmpde_b200 import ops, _cabi
+    dev = _dev()
+    g = torch.Generator().manual_seed(M)
+    st = ops._stream()
+    X = torch.randn(M, 256, generator=g).to(dev)
+    n4 = torch.randn(M, 4, generator=g).to(dev)
+    if variant == "linear":          # r4 = h3 W4^T + b4
+        W, b = (torch.randn(128, 128, generator=g) / 11).to(dev), torch.randn(128, generator=g).to(dev)
+        C = torch.full((M, 128), float("nan"), device=dev)
+        _cabi.call("mmpde_node_gemm", ops._ptr(X), 256, None, 0, ops._ptr(W), 128, 1, None, 0, 0, None, None, ops._ptr(b), 0,
+                   None, 0, None, 0, ops._ptr(C), 128, M, st)
+        ref = X[:, :128].double() @ W.double().t() + b.double()
+    elif variant == "k256_ext_relu":  # update_net_1: relu([x | agg | v] W3^T + b3), W3 [128,257]
+        W3 = (torch.randn(128, 257, generator=g) / 16).to(dev)
+        b = torch.randn(128, generator=g).to(dev)
+        wext = torch.zeros(128, 4, device=dev)
+        wext[:, 3] = W3[:, 256]
+        wext[:, 1] = 0.5
+        C = torch.full((M, 200), float("nan"), device=dev)
+        _cabi.call("mmpde_node_gemm", ops._ptr(X), 256, ops._ptr(X, 128), 256, ops._ptr(W3), 257, 1, ops._ptr(W3, 128), 257, 1,
+                   ops._ptr(n4), ops._ptr(wext), ops._ptr(b), 1, None, 0, None, 0, ops._ptr(C, 8), 200, M, st)
+        ref = torch.relu(X.double() @ W3[:, :256].double().t() + n4.double() @ wext.double().t() + b.double())
+        assert bool(torch.isnan(C[:, :8]).all()) and bool(torch.isnan(C[:, 136:]).all())
+        C = C[:, 8:136]
+    else:                             # g_y = g_y + g_X[:, :128] + dP' W1a + dQ' W1b   (W transposed access, residuals alias C)
+        W1 = (torch.randn(128, 260, generator=g) / 16).to(dev)
+        C = torch.randn(M, 128, generator=g).to(dev)
+        R2 = torch.randn(M, 256, generator=g).to(dev)
+        ref = C.double() + R2[:, :128].double() + X[:, :128].double() @ W1[:, :128].double() + X[:, 128:].double() @ W1[:, 128:256].double()
+        _cabi.call("mmpde_node_gemm", ops._ptr(X), 256, ops._ptr(X, 128), 256, ops._ptr(W1), 1, 260, ops._ptr(W1, 128), 1, 260,
+                   None, None, None, 0, ops._ptr(C), 128, ops._ptr(R2), 256, ops._ptr(C), 128, M, st)
+    torch.cuda.synchronize()
+    assert _rel(C, ref) < 2e-5, _rel(C, ref)
+
+
+@pytest.mark.parametrize("M", [1, 63, 64, 1000, 36864])
+def test_node_wgrad_tensor_core(M):
+    """mmpde_node_wgrad against the fp64 definition, incl. the node-scalar extension columns and the bias gradient."""
+    from mmpde_b200 import ops, _cabi
+    dev = _dev()
+    g = torch.Generator().manual_seed(M + 7)
+    st = ops._stream()
+    A = torch.randn(M, 256, generator=g).to(dev)
+    B = torch.randn(M, 256, generator=g).to(dev)
+    n4 = torch.randn(M, 4, generator=g).to(dev)
+    dW = torch.zeros(128, 260, device=dev)          # ld 260: rows stay 16-byte aligned -> vector reductions
+    dW3 = torch.zeros(128, 257, device=dev)         # ld 257: scalar atomics
+    dWe, db = torch.zeros(128, 4, device=dev), torch.zeros(128, device=dev)
+    _cabi.call("mmpde_node_wgrad", ops._ptr(A, 128), 256, ops._ptr(B), 256, ops._ptr(n4), ops._ptr(dW, 128), 260,
+               ops._ptr(dWe), 4, ops._ptr(db), M, st)
+    _cabi.call("mmpde_node_wgrad", ops._ptr(A), 256, ops._ptr(B, 128), 256, None, ops._ptr(dW3, 128), 257, None, 0, None, M, st)
+    db_only = torch.zeros(128, device=dev)
+    _cabi.call("mmpde_node_wgrad", ops._ptr(A), 256, None, 0, None, None, 0, None, 0, ops._ptr(db_only), M, st)
+    torch.cuda.synchronize()
+    Ad, Bd = A.double(), B.double()
+    assert _rel(dW[:, 128:256], Ad[:, 128:].t() @ Bd[:, :128]) < 2e-5
+    assert float(dW[:, :128].abs().max()) == 0.0 and float(dW[:, 256:].abs().max()) == 0.0
+    assert _rel(dWe, Ad[:, 128:].t() @ n4.double()) < 2e-5
+    assert _rel(db, Ad[:, 128:].sum(0)) < 2e-5
+    assert _rel(dW3[:, 128:256], Ad[:, :128].t() @ Bd[:, 128:]) < 2e-5 and float(dW3[:, 256].abs().max()) == 0.0
+    assert _rel(db_only, Ad[:, :128].sum(0)) < 2e-5

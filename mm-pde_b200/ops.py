@@ -170,6 +170,20 @@ def gemm(A, lda, a_k, B, ldb, b_k, C, ldc, M, N, K, bias=None, r1_row=None, r1_s
                relu, acc, split_k, st if st is not None else _stream())
 
 
+def node_gemm(A0, lda0, W0, w0_ns, w0_ks, C, ldc, M, A1=None, lda1=0, W1=None, w1_ns=0, w1_ks=0, ext=None, bias=None, relu=0,
+              R1=None, ldr1=0, R2=None, ldr2=0, st=None):
+    """tcgen05 node contraction (include/mmpde_b200.h: mmpde_node_gemm); ext = (node4 pointer, Wext pointer)."""
+    aext, wext = ext if ext is not None else (None, None)
+    _cabi.call("mmpde_node_gemm", A0, lda0, A1, lda1, W0, w0_ns, w0_ks, W1, w1_ns, w1_ks, aext, wext, bias, relu,
+               R1, ldr1, R2, ldr2, C, ldc, M, st if st is not None else _stream())
+
+
+def node_wgrad(A, lda, M, B=None, ldb=0, dW=None, ldw=0, Bext=None, dWext=None, dbias=None, st=None):
+    """tcgen05 weight gradient (mmpde_node_wgrad): dW += A^T B, dWext += A^T node4, dbias += colsum(A)."""
+    _cabi.call("mmpde_node_wgrad", A, lda, B, ldb, Bext, dW, ldw, dWext, 4 if dWext is not None else 0, dbias, M,
+               st if st is not None else _stream())
+
+
 def _split_for(rows):
     """split-K factor of the weight-gradient contractions (K = node count): ~one 256-row chunk per CTA so the
     1-2 output tiles still spread over the whole chip."""
@@ -263,7 +277,8 @@ def _layer_forward(parts, Xs, lp, bnbuf, training, nxts, exch, st):
     (pointer, leading dimension)."""
     W1, b1, W2, b2, W3, b3, W4, b4, gam, bet = lp
     w1c, w1cq = _edge_feature_weights(W1)
-    w3v = W3[:, 2 * H].contiguous()
+    w3x = torch.zeros(H, 4, dtype=torch.float32, device=W3.device)       # update_net_1 sees [x, agg, v]: v = node4[:, 3]
+    w3x[:, 3] = W3[:, 2 * H]
     # message_net_1 split per node (gnn_2d.py:61): z1_ij = P'[i] + Q'[j] with
     #   P' = h W1a^T + b1 + node4 W1c^T,   Q' = h W1b^T - node4[:, :3] W1c[:, :3]^T
     PQs = []
@@ -272,10 +287,8 @@ def _layer_forward(parts, Xs, lp, bnbuf, training, nxts, exch, st):
         f32 = dict(dtype=torch.float32, device=Xl.device)
         x, n4 = _ptr(Xl), _ptr(part.node4)
         PQ = torch.empty(part.n_src, 2 * H, **f32)
-        gemm(x, 2 * H, 1, _ptr(W1), 260, 1, _ptr(PQ), 2 * H, N, H, H, bias=_ptr(b1), st=st)
-        gemm(x, 2 * H, 1, _ptr(W1, H), 260, 1, _ptr(PQ, H), 2 * H, N, H, H, st=st)
-        gemm(n4, 4, 1, _ptr(w1c), 4, 1, _ptr(PQ), 2 * H, N, H, 4, acc=1, st=st)
-        gemm(n4, 4, 1, _ptr(w1cq), 4, 1, _ptr(PQ, H), 2 * H, N, H, 4, acc=1, st=st)
+        node_gemm(x, 2 * H, _ptr(W1), 260, 1, _ptr(PQ), 2 * H, N, ext=(n4, _ptr(w1c)), bias=_ptr(b1), st=st)
+        node_gemm(x, 2 * H, _ptr(W1, H), 260, 1, _ptr(PQ, H), 2 * H, N, ext=(n4, _ptr(w1cq)), st=st)
         PQs.append(PQ)
     if exch is not None:
         exch.forward(PQs)                                         # Q' rows of the halo nodes
@@ -289,10 +302,10 @@ def _layer_forward(parts, Xs, lp, bnbuf, training, nxts, exch, st):
                    _ptr(W2), _ptr(b2), _ptr(Xl, H), 2 * H, _ptr(mask2), st)
         # update_net_1/2 + residual                                 (gnn_2d.py:65-69)
         h3 = torch.empty(N, H, **f32)
-        gemm(x, 2 * H, 1, _ptr(W3), 257, 1, _ptr(h3), H, N, H, 2 * H, bias=_ptr(b3), r1_row=_ptr(part.node4, 3),
-             r1_stride=4, r1_col=_ptr(w3v), relu=1, st=st)
+        node_gemm(x, 2 * H, _ptr(W3), 257, 1, _ptr(h3), H, N, A1=_ptr(Xl, H), lda1=2 * H, W1=_ptr(W3, H), w1_ns=257, w1_ks=1,
+                  ext=(_ptr(part.node4), _ptr(w3x)), bias=_ptr(b3), relu=1, st=st)
         r4 = torch.empty(N, H, **f32)
-        gemm(_ptr(h3), H, 1, _ptr(W4), H, 1, _ptr(r4), H, N, H, H, bias=_ptr(b4), relu=1, st=st)
+        node_gemm(_ptr(h3), H, _ptr(W4), H, 1, _ptr(r4), H, N, bias=_ptr(b4), relu=1, st=st)
         saved.append((PQ, mask2, h3, r4))
         bn_items.append((x, 2 * H, _ptr(r4), H, N, nxt[0], nxt[1]))
     bn = _bn_forward(bn_items, gam, bet, 0, training, *bnbuf, st)
@@ -316,50 +329,47 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st):
     dW3, db3 = torch.zeros(H, 2 * H + 1, **f32), torch.zeros(H, **f32)
     dW4, db4 = torch.zeros(H, H, **f32), torch.zeros(H, **f32)
     dW1c = torch.zeros(2, H, 4, **f32)
-    dPQs, g_Xs = [], []
+    dW3x = torch.zeros(H, 4, **f32)
+    dPQs = []
     for part, Xl, sv, g_y in zip(parts, Xs, saved, g_ys):
         PQ, mask2, h3, r4 = sv
         N, E, edges = part.n_own, part.edges.n_edges, part.edges
-        x = _ptr(Xl)
-        split = max(_split_for(N), 2)
-        # node MLP backward
+        x, n4 = _ptr(Xl), _ptr(part.node4)
+        # node MLP backward (update_net_2, update_net_1)
         g_z4 = torch.empty(N, H, **f32)
         _cabi.call("mmpde_relu_bwd", _ptr(g_y), H, _ptr(r4), H, N, _ptr(g_z4), H, _ptr(db4), st)
-        gemm(_ptr(g_z4), H, 0, _ptr(h3), H, 0, _ptr(dW4), H, H, H, N, split_k=split, st=st)
+        node_wgrad(_ptr(g_z4), H, N, B=_ptr(h3), ldb=H, dW=_ptr(dW4), ldw=H, st=st)
         g_h3 = torch.empty(N, H, **f32)
-        gemm(_ptr(g_z4), H, 1, _ptr(W4), H, 0, _ptr(g_h3), H, N, H, H, st=st)
+        node_gemm(_ptr(g_z4), H, _ptr(W4), 1, H, _ptr(g_h3), H, N, st=st)
         g_z3 = g_z4                                               # reuse
         _cabi.call("mmpde_relu_bwd", _ptr(g_h3), H, _ptr(h3), H, N, _ptr(g_z3), H, _ptr(db3), st)
-        gemm(_ptr(g_z3), H, 0, x, 2 * H, 0, _ptr(dW3), 257, H, 2 * H, N, split_k=split, st=st)
-        gemm(_ptr(g_z3), H, 0, _ptr(part.node4, 3), 4, 0, _ptr(dW3, 2 * H), 257, H, 1, N, split_k=split, st=st)
-        g_X = torch.empty(N, 2 * H, **f32)
-        gemm(_ptr(g_z3), H, 1, _ptr(W3), 257, 0, _ptr(g_X), 2 * H, N, 2 * H, H, st=st)
+        node_wgrad(_ptr(g_z3), H, N, B=x, ldb=2 * H, dW=_ptr(dW3), ldw=257, Bext=n4, dWext=_ptr(dW3x), st=st)
+        node_wgrad(_ptr(g_z3), H, N, B=_ptr(Xl, H), ldb=2 * H, dW=_ptr(dW3, H), ldw=257, st=st)
+        # dL/dh_in so far: g_y (residual) + g_z3 W3[:, :128];  dL/d(mean message) = g_z3 W3[:, 128:256]
+        node_gemm(_ptr(g_z3), H, _ptr(W3), 1, 257, _ptr(g_y), H, N, R1=_ptr(g_y), ldr1=H, st=st)
+        g_agg = g_h3                                              # reuse
+        node_gemm(_ptr(g_z3), H, _ptr(W3, H), 1, 257, _ptr(g_agg), H, N, st=st)
         # message passing backward
         dPQ = torch.zeros(part.n_src, 2 * H, **f32)
         _cabi.call("mmpde_edge_bwd", _ptr(PQ), _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
-                   _ptr(W2), _ptr(mask2), _ptr(g_X, H), 2 * H, _ptr(dPQ), _ptr(dW2), _ptr(db2), st)
+                   _ptr(W2), _ptr(mask2), _ptr(g_agg), H, _ptr(dPQ), _ptr(dW2), _ptr(db2), st)
         dPQs.append(dPQ)
-        g_Xs.append(g_X)
     if exch is not None:
         exch.backward(dPQs)                                       # dL/dQ' of halo rows -> added at their owners
-    for idx, (part, Xl, dPQ, g_X, g_y) in enumerate(zip(parts, Xs, dPQs, g_Xs, g_ys)):
+    for idx, (part, Xl, dPQ, g_y) in enumerate(zip(parts, Xs, dPQs, g_ys)):
         N = part.n_own
         x, n4 = _ptr(Xl), _ptr(part.node4)
-        split = max(_split_for(N), 2)
         # message_net_1 parameters from dP', dQ':  dW1a = dP'^T h, dW1b = dQ'^T h, dW1c = dP'^T node4 - dQ'^T node4[:, :3]
-        gemm(_ptr(dPQ), 2 * H, 0, x, 2 * H, 0, _ptr(dW1), 260, H, H, N, split_k=split, st=st)
-        gemm(_ptr(dPQ, H), 2 * H, 0, x, 2 * H, 0, _ptr(dW1, H), 260, H, H, N, split_k=split, st=st)
-        gemm(_ptr(dPQ), 2 * H, 0, n4, 4, 0, _ptr(dW1c), 4, H, 4, N, split_k=split, st=st)
-        gemm(_ptr(dPQ, H), 2 * H, 0, n4, 4, 0, _ptr(dW1c, 4 * H), 4, H, 4, N, split_k=split, st=st)
-        _cabi.call("mmpde_colsum", _ptr(dPQ), 2 * H, N, H, _ptr(db1), st)
+        node_wgrad(_ptr(dPQ), 2 * H, N, B=x, ldb=2 * H, dW=_ptr(dW1), ldw=260, Bext=n4, dWext=_ptr(dW1c), dbias=_ptr(db1), st=st)
+        node_wgrad(_ptr(dPQ, H), 2 * H, N, B=x, ldb=2 * H, dW=_ptr(dW1, H), ldw=260, Bext=n4, dWext=_ptr(dW1c, 4 * H), st=st)
         g_node4 = g_node4s[idx] if g_node4s is not None else None
         if g_node4 is not None:      # dL/du (column 0 of node4): dP' W1c[:,0] - dQ' W1c[:,0]
             gemm(_ptr(dPQ), 2 * H, 1, _ptr(w1c), 4, 0, _ptr(g_node4), 4, N, 1, H, acc=1, st=st)
             gemm(_ptr(dPQ, H), 2 * H, 1, _ptr(w1cq), 4, 0, _ptr(g_node4), 4, N, 1, H, acc=1, st=st)
-        # dL/dh_in = g_y (residual) + g_X[:, :128] (update_net_1) + dP' W1a + dQ' W1b
-        g_y.add_(g_X[:, :H])
-        gemm(_ptr(dPQ), 2 * H, 1, _ptr(W1), 260, 0, _ptr(g_y), H, N, H, H, acc=1, st=st)
-        gemm(_ptr(dPQ, H), 2 * H, 1, _ptr(W1, H), 260, 0, _ptr(g_y), H, N, H, H, acc=1, st=st)
+        # dL/dh_in += dP' W1a + dQ' W1b
+        node_gemm(_ptr(dPQ), 2 * H, _ptr(W1), 1, 260, _ptr(g_y), H, N, A1=_ptr(dPQ, H), lda1=2 * H, W1=_ptr(W1, H), w1_ns=1,
+                  w1_ks=260, R1=_ptr(g_y), ldr1=H, st=st)
+    dW3[:, 2 * H] = dW3x[:, 3]
     dW1[:, 2 * H:2 * H + 4] = dW1c[0]
     dW1[:, 2 * H:2 * H + 3] -= dW1c[1, :, :3]
     return g_ys, [dW1, db1, dW2, db2, dW3, db3, dW4, db4, dgam, dbet]
@@ -407,7 +417,7 @@ def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st):
                       g1, bt1, 1, training, *bn_buffers[0], st)
     for part, e1n in zip(parts, e1ns):
         e2 = torch.empty(part.n_own, H, **f32)
-        gemm(_ptr(e1n), H, 1, _ptr(We2), H, 1, _ptr(e2), H, part.n_own, H, H, bias=_ptr(be2), st=st)
+        node_gemm(_ptr(e1n), H, _ptr(We2), H, 1, _ptr(e2), H, part.n_own, bias=_ptr(be2), st=st)
         e2s.append(e2)
     # X[l][p] = [h_l | agg_l]  ([n_own,256]); the last hidden state lives alone in hL
     X = [[torch.zeros(part.n_own, 2 * H, **f32) for part in parts] for _ in range(L)]
@@ -462,19 +472,15 @@ def _solver_backward(sv, g_outs, need_u, st):
     dWe1, dbe1 = torch.zeros(H, 4, **f32), torch.zeros(H, **f32)
     g_e1ns = []
     for part, g_e2, e1n in zip(parts, g_e2s, e1ns):
-        split = max(_split_for(part.n_own), 2)
-        gemm(_ptr(g_e2), H, 0, _ptr(e1n), H, 0, _ptr(dWe2), H, H, H, part.n_own, split_k=split, st=st)
-        _cabi.call("mmpde_colsum", _ptr(g_e2), H, part.n_own, H, _ptr(dbe2), st)
+        node_wgrad(_ptr(g_e2), H, part.n_own, B=_ptr(e1n), ldb=H, dW=_ptr(dWe2), ldw=H, dbias=_ptr(dbe2), st=st)
         g_e1n = torch.empty(part.n_own, H, **f32)
-        gemm(_ptr(g_e2), H, 1, _ptr(We2), H, 0, _ptr(g_e1n), H, part.n_own, H, H, st=st)
+        node_gemm(_ptr(g_e2), H, _ptr(We2), 1, H, _ptr(g_e1n), H, part.n_own, st=st)
         g_e1ns.append(g_e1n)
     g_e1s = g_e2s                                                     # reuse
     dg1, db1_ = _bn_backward([(_ptr(g_e1n), H, _ptr(e1n), H, _ptr(e1), H, None, 0, part.n_own, _ptr(g_e1), H)
                               for part, g_e1n, e1n, e1, g_e1 in zip(parts, g_e1ns, e1ns, e1s, g_e1s)], 1, bn1, g1, st)
     for idx, (part, g_e1) in enumerate(zip(parts, g_e1s)):
-        split = max(_split_for(part.n_own), 2)
-        gemm(_ptr(g_e1), H, 0, _ptr(part.node4), 4, 0, _ptr(dWe1), 4, H, 4, part.n_own, split_k=split, st=st)
-        _cabi.call("mmpde_colsum", _ptr(g_e1), H, part.n_own, H, _ptr(dbe1), st)
+        node_wgrad(_ptr(g_e1), H, part.n_own, Bext=_ptr(part.node4), dWext=_ptr(dWe1), dbias=_ptr(dbe1), st=st)
         if need_u:      # only the u column: positions/time feed the frozen mesh mover only
             gemm(_ptr(g_e1), H, 1, _ptr(We1), 4, 0, _ptr(g_node4s[idx]), 4, part.n_own, 1, H, acc=1, st=st)
     grads[:N_ENC] = [dWe1, dbe1, dg1, db1_, dWe2, dbe2, dg2, db2_]

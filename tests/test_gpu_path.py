@@ -271,6 +271,6 @@ def test_partitioned_solver_equals_whole_graph(n, n_parts):
     assert _rel(got, out) < 2e-5
     assert _rel(gu, whole.x.grad) < TOL
     for k, p in model.named_parameters():       # biases in front of a BatchNorm have a zero gradient: pure rounding noise
-        assert _rel(p.grad, ref_grads[k], atol=1e-5) < TOL, k
+        assert _rel(p.grad, ref_grads[k], atol=1e-4) < TOL, k
     for k, v in ref_bn.items():
         assert _rel(model.state_dict()[k].float(), v.float()) < 1e-5, k

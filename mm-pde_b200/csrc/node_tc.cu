@@ -24,7 +24,7 @@ constexpr uint32_t N_TMEM_COLS = 512;
 // forward / dgrad
 // ================================================================================================================
 constexpr int G_EPI_WARPS = 8, G_BLD_WARPS = 8, G_MMA_WARP = 16, G_THREADS = 640;
-constexpr int G_EPI_REGS = 72, G_BLD_REGS = 144, G_MMA_REGS = 40;          // 8*32*72 + 8*32*144 + 4*32*40 <= 640*96
+constexpr int G_EPI_REGS = 104, G_BLD_REGS = 112, G_MMA_REGS = 40;         // 8*32*104 + 8*32*112 + 4*32*40 <= 640*96
 constexpr int GT = 128;                                                    // rows per tile
 constexpr uint32_t G_IMG = 2 * GT * 128;                                   // one [128][128] bf16 image = 32 KB
 constexpr uint32_t G_XIMG = GT * 128;                                      // extension image [128 rows][128 B] = 16 KB
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + GemmSmem::BAR + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), N_TMEM_COLS);
+    if (warp == 0) { TL(3, 0, 6); tmem_alloc(smem_u32(tmem_slot), N_TMEM_COLS); }
     if (tid == 32) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(h_full + 8 * b, G_BLD_WARPS); mbar_init(h_empty + 8 * b, 1);
@@ -74,15 +74,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
 
     if (warp < G_EPI_WARPS) {
         // ------------------------------------------------------------------ epilogue: thread = output n, columns = rows m
-        reg_dec<G_EPI_REGS>();
+        if (warp == 0) TL(3, 0, 4);
+        reg_inc<G_EPI_REGS>();                                             // 104 > the launch value 96
+        if (warp == 0) TL(3, 0, 5);
         const int q = warp & 3, half = warp >> 2;
         const int n = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const uint32_t bias_bits = p.bias ? __float_as_uint(__ldg(p.bias + n)) : 0u;
-        if (half == 0) {
-            weight_to_tmem(p.W[0], p.w_ns[0], p.w_ks[0], n, tmem_w + lane_addr, tmem_w + 64 + lane_addr);
-            if (nseg == 2) weight_to_tmem(p.W[1], p.w_ns[1], p.w_ks[1], n, tmem_w + 144 + lane_addr, tmem_w + 208 + lane_addr);
-        } else if (has_ext) {
+        const float floor_ = p.relu ? 0.f : -INFINITY;                     // relu as max(z, floor): no branch in the store loop
+        const int nres = (p.R1 != nullptr) + (p.R1 != nullptr && p.R2 != nullptr);
+        // W -> tensor memory, shared by the two warps of a lane quadrant (32-column groups 2*half, 2*half+1)
+        weight_to_tmem(p.W[0], p.w_ns[0], p.w_ks[0], n, tmem_w + lane_addr, tmem_w + 64 + lane_addr, 2 * half, 2 * half + 2);
+        if (nseg == 2)
+            weight_to_tmem(p.W[1], p.w_ns[1], p.w_ks[1], n, tmem_w + 144 + lane_addr, tmem_w + 208 + lane_addr, 2 * half, 2 * half + 2);
+        if (has_ext && half == 1) {
             // extension weights: K step of 16 = (w0 w1)(w2 w3) then zeros; hi in columns +0..7, lo in +8..15
             uint2 h, l;
             split4(ldg4(p.Wext + n * 4), h, l);
@@ -100,29 +105,47 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { mbar_arrive(tm_empty); if (d_stages == 2) mbar_arrive(tm_empty + 8); }
+        if (warp == 0) TL(3, 0, 0);
         int i = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int b = (d_stages == 2) ? (i & 1) : 0;
             const uint32_t ph = (uint32_t)((d_stages == 2) ? (i >> 1) : i) & 1u;
             mbar_wait(tm_full + 8 * b, ph);
+            if (warp == 0) TL(3, i, 1);
             tc_fence_after();
             const uint32_t d_addr = tmem_d + lane_addr + b * GT + half * 64;
             uint32_t v[32];
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 tmem_ld32_async(d_addr + c * 32, v);
-                tmem_wait_ld(v);
                 const int64_t m0 = t * GT + half * 64 + c * 32;
+                const int rows = (int)((p.M - m0 < 32) ? (p.M - m0 < 0 ? 0 : p.M - m0) : 32);     // warp-uniform
+                float* cp = p.C + m0 * p.ldc + n;
+                if (nres == 0) {
+                    tmem_wait_ld(v);
+                    if (rows == 32) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int64_t m = m0 + j;
-                    if (m < p.M) {                                         // warp-uniform
-                        float z = __uint_as_float(v[j]);
-                        if (p.relu) z = fmaxf(z, 0.f);
-                        if (p.R1) z += p.R1[m * p.ldr1 + n];               // plain loads: a residual may alias C
-                        if (p.R2) z += p.R2[m * p.ldr2 + n];
-                        p.C[m * p.ldc + n] = z;
+                        for (int j = 0; j < 32; ++j) { *cp = fmaxf(__uint_as_float(v[j]), floor_); cp += p.ldc; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { if (j < rows) *cp = fmaxf(__uint_as_float(v[j]), floor_); cp += p.ldc; }
                     }
+                } else {
+                    // residuals first, all loads in flight (a residual may alias C, but only element-wise: every thread
+                    // reads exactly the elements it writes afterwards)
+                    float res[32];
+                    const float* r1 = p.R1 + m0 * p.ldr1 + n;
+                    const float* r2 = (nres == 2) ? p.R2 + m0 * p.ldr2 + n : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        res[j] = 0.f;
+                        if (j < rows) { res[j] = *r1; if (nres == 2) res[j] += *r2; }
+                        r1 += p.ldr1;
+                        if (nres == 2) r2 += p.ldr2;
+                    }
+                    tmem_wait_ld(v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { if (j < rows) *cp = fmaxf(__uint_as_float(v[j]), floor_) + res[j]; cp += p.ldc; }
                 }
             }
             tmem_fill32(d_addr, bias_bits);
@@ -131,37 +154,41 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tm_empty + 8 * b);
+            if (warp == 0) TL(3, i, 2);
         }
     } else if (warp < G_MMA_WARP) {
         // ------------------------------------------------------------------ builders: warp w -> rows 16w .. 16w+15 of a tile
+        if (warp == G_EPI_WARPS) TL(0, 0, 4);
         reg_inc<G_BLD_REGS>();
+        if (warp == G_EPI_WARPS) TL(0, 0, 5);
         const int w = warp - G_EPI_WARPS;
         const int row0 = w * 16;
         // stream of half-stages u = 0, 1, ...: stage j = u >> 1 (tile j / nseg, segment j % nseg), rows row0 + 8*(u&1) ..
-        auto load8 = [&](float4 (&r)[8], int64_t u) {
-            const int64_t j = u >> 1;
-            const int64_t t = (int64_t)blockIdx.x + (j / nseg) * gridDim.x;
-            const int seg = (int)(j % nseg);
-            const float* base = p.A[seg];
+        // (32-bit counters, shifts instead of divisions: 64-bit division costs ~1000 clocks a piece)
+        const int sh = (nseg == 2) ? 1 : 0;
+        const int my_tiles = ((int64_t)blockIdx.x < n_tiles) ? (int)(((uint32_t)(n_tiles - blockIdx.x) + gridDim.x - 1) / gridDim.x) : 0;
+        const int n_half = my_tiles * nseg * 2;
+        auto load8 = [&](float4 (&r)[8], int u) {
+            const int j = u >> 1, ti = j >> sh, seg = j & sh;
+            const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * GT + row0 + 8 * (u & 1);
+            const float* base = p.A[seg] + m0 * p.lda[seg] + lane * 4;
             const int64_t ld = p.lda[seg];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const int64_t m = t * GT + row0 + 8 * (int)(u & 1) + k;
                 r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t < n_tiles && m < p.M) r[k] = ldg4(base + m * ld + lane * 4);
+                if (ti < my_tiles && m0 + k < p.M) r[k] = ldg4(base + k * ld);
             }
         };
-        const int64_t my_tiles = ((int64_t)blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const int64_t n_half = my_tiles * nseg * 2;
         float4 ra[8], rb[8];
         if (n_half > 0) load8(ra, 0);
-        for (int64_t u = 0; u < n_half; u += 2) {
-            const int64_t j = u >> 1;
-            const int sb = (int)(j & 1);
-            const int64_t ti = j / nseg;
-            const int seg = (int)(j % nseg);
+        for (int u = 0; u < n_half; u += 2) {
+            const int j = u >> 1;
+            const int sb = j & 1;
+            const int ti = j >> sh, seg = j & sh;
+            if (w == 0) TL(0, j, 0);
             load8(rb, u + 1);
             mbar_wait(h_empty + 8 * sb, ((uint32_t)(j >> 1) & 1u) ^ 1u);
+            if (w == 0) TL(0, j, 1);
             const uint32_t img = sbase + GemmSmem::SEG + sb * (2 * G_IMG);
 #pragma unroll
             for (int k = 0; k < 8; ++k) store_split<GT>(img, row0 + k, lane, ra[k]);
@@ -170,7 +197,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
             for (int k = 0; k < 8; ++k) store_split<GT>(img, row0 + 8 + k, lane, rb[k]);
             if (has_ext && seg == nseg - 1) {
                 // extension K step: columns 0..3 = node4[m], 4..15 = 0.  16 rows x 4 pieces of 8 bytes (hi image; lo follows)
-                const int64_t t = (int64_t)blockIdx.x + ti * gridDim.x;
+                const int64_t t = (int64_t)blockIdx.x + (int64_t)ti * gridDim.x;
                 const uint32_t ximg = sbase + GemmSmem::EXT + (uint32_t)(ti & 1) * (2 * G_XIMG);
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
@@ -186,6 +213,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(h_full + 8 * sb);
+            if (w == 0) TL(0, j, 2);
         }
     } else {
         // ------------------------------------------------------------------ MMA issuer (one thread)
@@ -198,6 +226,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
                 const int b = (d_stages == 2) ? (i & 1) : 0;
                 const uint32_t ph = (uint32_t)((d_stages == 2) ? (i >> 1) : i) & 1u;
                 mbar_wait(tm_empty + 8 * b, ph);
+                TL(2, i, 0);
                 for (int seg = 0; seg < nseg; ++seg, ++j) {
                     const int sb = (int)(j & 1);
                     mbar_wait(h_full + 8 * sb, (uint32_t)(j >> 1) & 1u);
@@ -223,12 +252,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
                     umma_commit(h_empty + 8 * sb);
                 }
                 umma_commit(tm_full + 8 * b);
+                TL(2, i, 2);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, N_TMEM_COLS);
+    if (warp == 0) { TL(3, 0, 7); tmem_dealloc(tmem_base, N_TMEM_COLS); }
 }
 
 // ================================================================================================================
@@ -266,9 +296,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
         mbar_init(all_done, 1);
         fence_mbar_init();
     }
-    // the extension tiles only ever receive features 0..4: zero the rest (and everything else) once
-    for (uint32_t o = tid * 16; o < 2 * WgradSmem::STAGE; o += W_THREADS * 16)
-        *reinterpret_cast<uint4*>(sm + o) = make_uint4(0u, 0u, 0u, 0u);
+    // the extension tiles only ever receive features 0..4: zero them once (rows 5..15 stay zero)
+    for (uint32_t o = tid * 16; o < 2 * 2 * W_XIMG; o += W_THREADS * 16) {
+        const uint32_t stage = o / (2 * W_XIMG), off = o % (2 * W_XIMG);
+        *reinterpret_cast<uint4*>(sm + stage * WgradSmem::STAGE + 4 * W_IMG + off) = make_uint4(0u, 0u, 0u, 0u);
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -276,7 +308,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_d = tmem_base, tmem_dx = tmem_base + 128;
     const int64_t n_tiles = (p.M + WT - 1) / WT;
-    const int64_t my_tiles = ((int64_t)blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t my_tiles = ((int64_t)blockIdx.x < n_tiles) ? (int64_t)(((uint32_t)(n_tiles - blockIdx.x) + gridDim.x - 1) / gridDim.x) : 0;
 
     if (warp < W_EPI_WARPS) {
         // ------------------------------------------------------------------ epilogue (once): lane = row i of dW
@@ -321,39 +353,33 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
         reg_inc<W_BLD_REGS>();
         const int w = warp - W_EPI_WARPS;
         const int row0 = w * 8;
-        const int per_tile = has_b ? 2 : 1;                                // half-steps per tile: A rows, then B rows
-        auto load8 = [&](float4 (&r)[8], int64_t u) {
-            const int64_t ti = u / per_tile;
-            const bool is_b = (u % per_tile) == 1;
+        // per tile: 8 rows of A and 8 rows of B per warp; the NEXT tile's 16 rows are already in flight while this
+        // tile is converted (two register sets swapped by copy: the loads were issued a whole tile ago)
+        auto load16 = [&](float4 (&ra)[8], float4 (&rb)[8], int64_t ti) {
             const int64_t t = (int64_t)blockIdx.x + ti * gridDim.x;
-            const float* base = is_b ? p.B : p.A;
-            const int64_t ld = is_b ? p.ldb : p.lda;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int64_t m = t * WT + row0 + k;
-                r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ti < my_tiles && m < p.M) r[k] = ldg4(base + m * ld + lane * 4);
+                ra[k] = rb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ti < my_tiles && m < p.M) {
+                    ra[k] = ldg4(p.A + m * p.lda + lane * 4);
+                    if (has_b) rb[k] = ldg4(p.B + m * p.ldb + lane * 4);
+                }
             }
         };
-        const int64_t n_steps = my_tiles * per_tile;
-        float4 ra[8], rb[8];
-        if (n_steps > 0) load8(ra, 0);
+        float4 ra[8], rb[8], na[8], nb[8];
+        load16(ra, rb, 0);
         for (int64_t ti = 0; ti < my_tiles; ++ti) {
             const int sb = (int)(ti & 1);
-            const int64_t u = ti * per_tile;
             const int64_t t = (int64_t)blockIdx.x + ti * gridDim.x;
-            if (u + 1 < n_steps) load8(rb, u + 1);
+            load16(na, nb, ti + 1);
             mbar_wait(s_empty + 8 * sb, ((uint32_t)(ti >> 1) & 1u) ^ 1u);
             const uint32_t stage = sbase + sb * WgradSmem::STAGE;
 #pragma unroll
             for (int k = 0; k < 8; ++k) store_split<WT>(stage, row0 + k, lane, ra[k]);
             if (has_b) {
-                if (u + 2 < n_steps) load8(ra, u + 2);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) store_split<WT>(stage + 2 * W_IMG, row0 + k, lane, rb[k]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) ra[k] = rb[k];
             }
             if (has_ext && lane < 8) {
                 // extension tile, K-major and transposed: feature f (row of the tile), node r (column): f 0..3 = node4, 4 = 1
@@ -376,6 +402,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_full + 8 * sb);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { ra[k] = na[k]; rb[k] = nb[k]; }
         }
     } else {
         // ------------------------------------------------------------------ MMA issuer (one thread)
@@ -419,6 +447,10 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
 }  // namespace mmpde
 
 using namespace mmpde;
+
+#ifdef MMPDE_TIMELINE
+extern "C" int mmpde_debug_timeline_node(long long* buf) { return (int)cudaMemcpyToSymbol(g_timeline, &buf, sizeof(buf)); }
+#endif
 
 extern "C" int mmpde_node_gemm(const float* A0, int64_t lda0, const float* A1, int64_t lda1,
                                const float* W0, int64_t w0_ns, int64_t w0_ks, const float* W1, int64_t w1_ns, int64_t w1_ks,

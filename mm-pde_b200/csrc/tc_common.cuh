@@ -234,25 +234,38 @@ __device__ __forceinline__ void store_split(uint32_t img, int row, int lane, con
 }
 
 // W (fp32, element (r, k) at w[r*rs + k*ks], 128 x 128) -> TMEM A operand of the TS-form MMA: lane r, 64 columns hi at
-// t_hi, 64 columns lo at t_lo (one 32-bit column = two consecutive k).  Called by the 4 warps owning the 128 lanes.
-__device__ __forceinline__ void weight_to_tmem(const float* __restrict__ w, int64_t rs, int64_t ks, int r, uint32_t t_hi, uint32_t t_lo) {
+// t_hi, 64 columns lo at t_lo (one 32-bit column = two consecutive k).  Called by the warps owning the 128 lanes; the
+// four 32-column groups g0 <= g < g1 let two warps of the same lane quadrant share the work.
+__device__ __forceinline__ void weight_to_tmem(const float* __restrict__ w, int64_t rs, int64_t ks, int r, uint32_t t_hi, uint32_t t_lo,
+                                               int g0 = 0, int g1 = 4) {
     const bool vec = (ks == 1) && ((rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);   // 128-bit loads need alignment
+    const float* row = w + r * rs;
 #pragma unroll 1
-    for (int g = 0; g < 4; ++g) {
-        uint32_t hi[16], lo[16];
+    for (int g = g0; g < g1; g += 2) {                         // two groups (64 values) in flight per round
+        float4 x[16];
+        if (vec) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            const int k = g * 32 + v * 4;
-            float4 x;
-            if (vec) x = ldg4(w + r * rs + k);
-            else x = make_float4(__ldg(w + r * rs + k * ks), __ldg(w + r * rs + (k + 1) * ks), __ldg(w + r * rs + (k + 2) * ks),
-                                 __ldg(w + r * rs + (k + 3) * ks));
-            uint2 h, l;
-            split4(x, h, l);
-            hi[2 * v] = h.x; hi[2 * v + 1] = h.y; lo[2 * v] = l.x; lo[2 * v + 1] = l.y;
+            for (int v = 0; v < 16; ++v) x[v] = ldg4(row + g * 32 + v * 4);
+        } else {
+            const float* q = row + (int64_t)(g * 32) * ks;
+#pragma unroll
+            for (int v = 0; v < 16; ++v) {
+                x[v] = make_float4(__ldg(q), __ldg(q + ks), __ldg(q + 2 * ks), __ldg(q + 3 * ks));
+                q += 4 * ks;
+            }
         }
-        tmem_st16(t_hi + g * 16, hi);
-        tmem_st16(t_lo + g * 16, lo);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                uint2 a, b;
+                split4(x[h * 8 + v], a, b);
+                hi[2 * v] = a.x; hi[2 * v + 1] = a.y; lo[2 * v] = b.x; lo[2 * v + 1] = b.y;
+            }
+            tmem_st16(t_hi + (g + h) * 16, hi);
+            tmem_st16(t_lo + (g + h) * 16, lo);
+        }
     }
 }
 

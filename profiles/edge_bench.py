@@ -53,6 +53,20 @@ def main():
     gemm_nt = lambda: ops.gemm(ops._ptr(X), 256, 1, ops._ptr(W), 260, 1, ops._ptr(C), 128, N, 128, 128, st=st)
     gemm_tn = lambda: ops.gemm(ops._ptr(C), 128, 0, ops._ptr(X), 256, 0, ops._ptr(dW), 260, 128, 128, N, split_k=ops._split_for(N), st=st)
     knn = lambda: ops.knn_indices(pts, off, pts, off, k, 0, True, bbox=(-0.02, -0.02, 1.02, 1.02), per_sample=n)
+    b1 = torch.randn(128, device=dev)
+    n4 = torch.randn(N, 4, device=dev)
+    wx = torch.randn(128, 4, device=dev)
+    ng_lin = lambda: ops.node_gemm(ops._ptr(X), 256, ops._ptr(W), 260, 1, ops._ptr(C), 128, N, ext=(ops._ptr(n4), ops._ptr(wx)),
+                                   bias=ops._ptr(b1), st=st)
+    ng_k256 = lambda: ops.node_gemm(ops._ptr(X), 256, ops._ptr(W), 260, 1, ops._ptr(C), 128, N, A1=ops._ptr(X, 128), lda1=256,
+                                    W1=ops._ptr(W, 128), w1_ns=260, w1_ks=1, bias=ops._ptr(b1), relu=1, st=st)
+    ng_dgrad = lambda: ops.node_gemm(ops._ptr(X), 256, ops._ptr(W), 1, 260, ops._ptr(C), 128, N, R1=ops._ptr(C), ldr1=128, st=st)
+    dWt = torch.zeros(128, 260, device=dev)
+    dWx, dbt = torch.zeros(128, 4, device=dev), torch.zeros(128, device=dev)
+    nw = lambda: ops.node_wgrad(ops._ptr(C), 128, N, B=ops._ptr(X), ldb=256, dW=ops._ptr(dWt), ldw=260, Bext=ops._ptr(n4),
+                                dWext=ops._ptr(dWx), dbias=ops._ptr(dbt), st=st)
+    print(f"node_gemm K=128+ext {timeit(ng_lin, iters):7.1f} us   K=256 relu {timeit(ng_k256, iters):7.1f} us   "
+          f"dgrad+residual {timeit(ng_dgrad, iters):7.1f} us   node_wgrad {timeit(nw, iters):7.1f} us")
     t_f, t_b = timeit(fwd, iters), timeit(bwd, iters)
     flop = 99328 * E
     print(f"edge_fwd {t_f:8.1f} us  {flop / t_f / 1e6:7.1f} TFLOP/s algorithmic  ({3 * 32768 * E / t_f / 1e6:6.1f} executed bf16)")

@@ -36,6 +36,16 @@ LAYERS = 6
 FLOP_PER_EDGE_FWD = 99328          # 2*260*128 + 2*128*128 (reference formulation)
 
 
+def _ncu_traffic():
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed ncu --set full capture
+    (profiles/r01_edge_bwd_ncu.json, written by profiles/ncu_summary.py --json on this CPU box)."""
+    path = os.path.join(ROOT, "profiles", "r01_edge_bwd_ncu.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("dram_bytes_read", 0) + d.get("dram_bytes_write", 0)
+    return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -63,19 +73,25 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock and the throttle reasons seen between t_begin and t_end (perf_counter stamps of the timed
+        region; nvidia-smi is started well before it because its first sample can take a second on an 8-GPU box)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = [r for t, r in self.rows if t_begin is None or (t_begin - 0.05 <= t <= t_end + 0.15)]
+        window = "timed region"
+        if not rows:                                   # region shorter than the sampling period: nearest samples under load
+            rows, window = [r for _, r in self.rows[-5:]], "last samples before the end of the timed region"
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -196,12 +212,12 @@ def run_ours(args):
 
     import random
     random.seed(1234 + rank)
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         train_step(fields_dev)
 
     # ---- device-resident timing (value) with per-launch events on the dominant kernel -----------------------
-    sampler = ClockSampler(dev.index or 0)
-    sampler.start()
     _cabi_profile = []
     real_call = _cabi.call
 
@@ -219,21 +235,44 @@ def run_ours(args):
     ops_mod._cabi.call = profiled_call
     launches0 = _cabi.launches
     torch.cuda.profiler.start()          # ncu --profile-from-start off captures exactly the timed region
+    t_begin = time.perf_counter()
     ms_step = timed(lambda: train_step(fields_dev), args.steps)
+    t_end = time.perf_counter()
     torch.cuda.profiler.stop()
     launches = _cabi.launches - launches0
     ops_mod._cabi.call = real_call
-    clocks = sampler.stop()
     kern_ms = [s.elapsed_time(e) for s, e in _cabi_profile]
     kern_avg_ms = sum(kern_ms) / max(len(kern_ms), 1)
 
     # ---- end to end through the public API with host buffers -----------------------------------------------
-    def e2e_step():
-        losses = train_step(fields_host)          # create_graph moves the step's slices host -> device
-        return float(losses[-1])                   # D2H read of the loss
+    # Every step: H2D of that step's input slices from the pinned trajectory batch (inside create_graph) and a D2H
+    # read of that step's loss.  The read is the usual asynchronous logging pattern: the loss is copied to pinned
+    # host memory on the stream and looked at one step later (the last one before the clock stops), so the host
+    # keeps queueing work instead of draining the GPU after every step.
+    host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+    seen = []
 
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    def e2e_step():
+        if e2e_step.pending is not None:
+            e2e_step.pending.synchronize()
+            seen.append(float(host_loss[0]))       # loss of the previous step, now on the host
+        losses = train_step(fields_host)           # create_graph moves the step's slices host -> device
+        host_loss.copy_(losses[-1].reshape(1), non_blocking=True)
+        e2e_step.pending = torch.cuda.Event()
+        e2e_step.pending.record()
+
+    def e2e_run(steps):
+        e2e_step.pending = None
+        for _ in range(steps):
+            e2e_step()
+        e2e_step.pending.synchronize()
+        seen.append(float(host_loss[0]))           # the last step's loss is read inside the timed region too
+
+    e2e_run(1)
+    n_seen = len(seen)
+    ms_e2e = timed(lambda: e2e_run(args.steps), 1) / args.steps
+    assert len(seen) - n_seen == args.steps and all(v == v for v in seen), "every timed step must deliver its loss"
+    clocks = sampler.stop(t_begin, time.perf_counter())
     h2d = 2 * BATCH * RES[1] * RES[2] * 4          # data + labels slices, fp32
     d2h = 4
 
@@ -276,7 +315,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"kernel": "mmpde_edge_bwd", "bound": "tensor", "achieved": achieved, "peak": peaks["bf16"],
-                         "unit": "TFLOP/s", "frac": achieved / peaks["bf16"], "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peaks["bf16"], "traffic": _ncu_traffic(),
                          "avg_launch_ms": kern_avg_ms, "launches_timed": len(kern_ms),
                          "algorithmic_flops_per_launch": alg_flops, "peak_source": peaks["source"],
                          "share_of_step": kern_avg_ms * len(kern_ms) / args.steps / ms_step if ms_step > 0 else None},

@@ -39,6 +39,7 @@ SIGNATURES = {
     "mmpde_itp_bwd": [_p, _p, _p, _p, _l, _p, _p, _p, _p, _p],
     "mmpde_rows_gather": [_p, _l, _p, _l, _i, _p, _p],
     "mmpde_rows_scatter_add": [_p, _p, _l, _i, _p, _l, _p],
+    "mmpde_rows_dot": [_p, _l, _i, _p, _p, _l, _l, _i, _p],
 }
 
 launches = 0          # number of kernel-launching C-ABI calls made so far (bench.py reports the delta)

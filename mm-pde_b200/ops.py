@@ -319,17 +319,18 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st):
     dev = W1.device
     f32 = dict(dtype=torch.float32, device=dev)
     w1c, w1cq = _edge_feature_weights(W1)
+    wu = torch.cat((w1c[:, 0], w1cq[:, 0])).contiguous()          # dL/du = [dP' | dQ'] . wu
     # BatchNorm backward: y = h + r4
     g_ys = [torch.empty(part.n_own, H, **f32) for part in parts]
     items = [(_ptr(g_h), H, None, 0, _ptr(Xl), 2 * H, _ptr(sv[3]), H, part.n_own, _ptr(g_y), H)
              for part, Xl, sv, g_h, g_y in zip(parts, Xs, saved, g_hs, g_ys)]
     dgam, dbet = _bn_backward(items, 0, bn, gam, st)
-    dW1, db1 = torch.zeros(H, 260, **f32), torch.zeros(H, **f32)
-    dW2, db2 = torch.zeros(H, H, **f32), torch.zeros(H, **f32)
-    dW3, db3 = torch.zeros(H, 2 * H + 1, **f32), torch.zeros(H, **f32)
-    dW4, db4 = torch.zeros(H, H, **f32), torch.zeros(H, **f32)
-    dW1c = torch.zeros(2, H, 4, **f32)
-    dW3x = torch.zeros(H, 4, **f32)
+    # all accumulators of this layer in ONE zeroed buffer (every block is a multiple of 4 floats: 16-byte aligned rows)
+    sizes = [H * 260, H, H * H, H, H * 257, H, H * H, H, 2 * H * 4, H * 4]
+    flat = torch.zeros(sum(sizes), **f32)
+    dW1, db1, dW2, db2, dW3, db3, dW4, db4, dW1c, dW3x = torch.split(flat, sizes)
+    dW1, dW2, dW3, dW4 = dW1.view(H, 260), dW2.view(H, H), dW3.view(H, 257), dW4.view(H, H)
+    dW1c, dW3x = dW1c.view(2, H, 4), dW3x.view(H, 4)
     dPQs = []
     for part, Xl, sv, g_y in zip(parts, Xs, saved, g_ys):
         PQ, mask2, h3, r4 = sv
@@ -363,9 +364,8 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st):
         node_wgrad(_ptr(dPQ), 2 * H, N, B=x, ldb=2 * H, dW=_ptr(dW1), ldw=260, Bext=n4, dWext=_ptr(dW1c), dbias=_ptr(db1), st=st)
         node_wgrad(_ptr(dPQ, H), 2 * H, N, B=x, ldb=2 * H, dW=_ptr(dW1, H), ldw=260, Bext=n4, dWext=_ptr(dW1c, 4 * H), st=st)
         g_node4 = g_node4s[idx] if g_node4s is not None else None
-        if g_node4 is not None:      # dL/du (column 0 of node4): dP' W1c[:,0] - dQ' W1c[:,0]
-            gemm(_ptr(dPQ), 2 * H, 1, _ptr(w1c), 4, 0, _ptr(g_node4), 4, N, 1, H, acc=1, st=st)
-            gemm(_ptr(dPQ, H), 2 * H, 1, _ptr(w1cq), 4, 0, _ptr(g_node4), 4, N, 1, H, acc=1, st=st)
+        if g_node4 is not None:      # dL/du (column 0 of node4): dP' W1c[:,0] - dQ' W1c[:,0], one pass over dPQ
+            _cabi.call("mmpde_rows_dot", _ptr(dPQ), 2 * H, 2 * H, _ptr(wu), _ptr(g_node4), 4, N, 1, st)
         # dL/dh_in += dP' W1a + dQ' W1b
         node_gemm(_ptr(dPQ), 2 * H, _ptr(W1), 1, 260, _ptr(g_y), H, N, A1=_ptr(dPQ, H), lda1=2 * H, W1=_ptr(W1, H), w1_ns=1,
                   w1_ks=260, R1=_ptr(g_y), ldr1=H, st=st)

@@ -77,6 +77,24 @@ __global__ void __launch_bounds__(WARPS * 32) decoder_bwd_kernel(const float* __
     float gp[17];
 #pragma unroll
     for (int i = 0; i < 17; ++i) gp[i] = 0.f;
+    // Everything that does not depend on the node is decoded ONCE: the scratch offsets of each parameter slot ...
+    //   w1[c][t] (pi <  64): sum_p g1[c*38+p] * h[3p+t]         -> offA = c*38, offB = t,        n = 38, stride 3
+    //   w2[o][c][t]        : sum_p g2[o*9+p]  * a1[c*38+3p+t]   -> offA = o*9,  offB = c*38 + t, n = 9,  stride 3
+    int offA[17], offB[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+        const int pi = lane + 32 * i;
+        offA[i] = offB[i] = 0;
+        if (pi < OFF_B1) { offA[i] = (pi >> 4) * 38; offB[i] = pi & 15; }
+        else if (pi >= OFF_W2 && pi < OFF_B2) { const int r = pi - OFF_W2; offA[i] = (r / 48) * 9; offB[i] = ((r % 48) / 12) * 38 + r % 12; }
+    }
+    // ... and, for the two transposed convolutions, quotient / remainder by the stride 3 of each output this lane owns
+    int q1d[5], q1m[5];                                  // layer-1 outputs idx = lane + 32*j < 152: position q = idx % 38
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { const int idx = lane + 32 * j, q = idx % 38; q1d[j] = q / 3; q1m[j] = q - 3 * (q / 3); }
+    int q0d[4], q0m[4];                                  // input positions q = 4*lane + i
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const int q = lane * 4 + i; q0d[i] = q / 3; q0m[i] = q - 3 * (q / 3); }
 
     for (int64_t n = (int64_t)blockIdx.x * WARPS + warp; n < M; n += (int64_t)gridDim.x * WARPS) {
         __syncwarp();
@@ -91,34 +109,37 @@ __global__ void __launch_bounds__(WARPS * 32) decoder_bwd_kernel(const float* __
             s.g2[idx] = s.a2[idx] > 0.f ? g : 0.f;
         }
         __syncwarp();
-        // layer 2 -> g wrt pre-activation of layer 1
-        for (int idx = lane; idx < 152; idx += 32) {
-            int c = idx / 38, q = idx - c * 38;
-            float acc = 0.f;
-            for (int t = 0; t < 12; ++t) {
-                int r = q - t;
-                if (r < 0 || r % 3) continue;
-                int p = r / 3;
-                if (p >= 9) continue;
+        // layer 2 -> g wrt pre-activation of layer 1: g1[c][q] = sum over (p, t) with 3p + t = q, t < 12, p < 9
 #pragma unroll
-                for (int o = 0; o < 8; ++o) acc = fmaf(s.g2[o * 9 + p], sp[OFF_W2 + (o * 4 + c) * 12 + t], acc);
+        for (int j = 0; j < 5; ++j) {
+            const int idx = lane + 32 * j;
+            if (idx < 152) {
+                const int c = idx / 38;
+                float acc = 0.f;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {              // t = q%3 + 3m, p = q/3 - m
+                    const int t = q1m[j] + 3 * m, p = q1d[j] - m;
+                    if (p >= 0 && p < 9) {
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) acc = fmaf(s.g2[o * 9 + p], sp[OFF_W2 + (o * 4 + c) * 12 + t], acc);
+                    }
+                }
+                s.g1[idx] = s.a1[idx] > 0.f ? acc : 0.f;
             }
-            s.g1[idx] = s.a1[idx] > 0.f ? acc : 0.f;
         }
         __syncwarp();
-        // layer 1 -> g_h
+        // layer 1 -> g_h[q] = sum over (p, t) with 3p + t = q, t < 16, p < 38
         float gh[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            int q = lane * 4 + i;
             float acc = 0.f;
-            for (int t = 0; t < 16; ++t) {
-                int r = q - t;
-                if (r < 0 || r % 3) continue;
-                int p = r / 3;
-                if (p >= 38) continue;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc = fmaf(s.g1[c * 38 + p], sp[OFF_W1 + c * 16 + t], acc);
+            for (int m = 0; m < 6; ++m) {
+                const int t = q0m[i] + 3 * m, p = q0d[i] - m;
+                if (t < 16 && p >= 0 && p < 38) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc = fmaf(s.g1[c * 38 + p], sp[OFF_W1 + c * 16 + t], acc);
+                }
             }
             gh[i] = acc;
         }
@@ -126,19 +147,17 @@ __global__ void __launch_bounds__(WARPS * 32) decoder_bwd_kernel(const float* __
         // parameter gradients
 #pragma unroll
         for (int i = 0; i < 17; ++i) {
-            int pi = lane + 32 * i;
+            const int pi = lane + 32 * i;
             if (pi >= DEC_NP) break;
             float acc = 0.f;
             if (pi < OFF_B1) {                       // w1[c][t]
-                int c = pi >> 4, t = pi & 15;
-                for (int p = 0; p < 38; ++p) acc = fmaf(s.g1[c * 38 + p], s.h[3 * p + t], acc);
+                for (int p = 0; p < 38; ++p) acc = fmaf(s.g1[offA[i] + p], s.h[3 * p + offB[i]], acc);
             } else if (pi < OFF_W2) {                // b1[c]
                 int c = pi - OFF_B1;
                 for (int p = 0; p < 38; ++p) acc += s.g1[c * 38 + p];
             } else if (pi < OFF_B2) {                // w2[o][c][t]
-                int r = pi - OFF_W2;
-                int o = r / 48, c = (r % 48) / 12, t = r % 12;
-                for (int p = 0; p < 9; ++p) acc = fmaf(s.g2[o * 9 + p], s.a1[c * 38 + 3 * p + t], acc);
+#pragma unroll
+                for (int p = 0; p < 9; ++p) acc = fmaf(s.g2[offA[i] + p], s.a1[offB[i] + 3 * p], acc);
             } else if (pi < OFF_W3) {                // b2[o]
                 int o = pi - OFF_B2;
                 for (int p = 0; p < 9; ++p) acc += s.g2[o * 9 + p];

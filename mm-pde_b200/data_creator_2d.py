@@ -71,15 +71,20 @@ class GraphCreator_FS_2D(nn.Module):
         return (-px, -py, self.pde.Lx + px, self.pde.Ly + py)
 
     # ------------------------------------------------------------------ interpolation (:46-85)
-    def interpolate(self, itp_model, u, init_x, init_y, x, y, mode):
-        """u (nu, ...) known at (init_x, init_y) [nu*P,1]; returns values at (x, y) [nu*Q,1], flattened."""
+    def interpolate(self, itp_model, u, init_x, init_y, x, y, mode, idx=None):
+        """u (nu, ...) known at (init_x, init_y) [nu*P,1]; returns values at (x, y) [nu*Q,1], flattened.
+        ``idx`` (optional, not in the reference signature): the ordered neighbour lists of an earlier call with the
+        same source and query points (create_graph interpolates data and labels onto the same moved mesh), saved in
+        ``self.last_itp_idx`` by every call."""
         nu = u.shape[0]
         src = torch.cat((init_x, init_y), dim=-1).detach().to(torch.float32).contiguous()
         qry = torch.cat((x, y), dim=-1).detach().to(torch.float32).contiguous()
         P, Q = src.shape[0] // nu, qry.shape[0] // nu
         dev = src.device
-        idx = ops.knn_indices(src, _offsets(nu, P, dev), qry, _offsets(nu, Q, dev), itp_model.n, rule=1,
-                              exclude_self=False, bbox=self._bbox(), per_sample=P)
+        if idx is None:
+            idx = ops.knn_indices(src, _offsets(nu, P, dev), qry, _offsets(nu, Q, dev), itp_model.n, rule=1,
+                                  exclude_self=False, bbox=self._bbox(), per_sample=P)
+        self.last_itp_idx = idx
         vals = u.reshape(-1).to(torch.float32).contiguous()
         return ops.InterpolateFn.apply(vals, src, qry, idx, itp_model.flat_params(mode))
 
@@ -164,7 +169,7 @@ class GraphCreator_FS_2D(nn.Module):
                 data = self.interpolate(itp_model, data.reshape(-1, onx, ony), og[:, 0:1], og[:, 1:2],
                                         mesh_x, mesh_y, mode="1").reshape(-1, self.tw, nx, ny)
                 labels = self.interpolate(itp_model, labels.reshape(-1, onx, ony), og[:, 0:1], og[:, 1:2],
-                                          mesh_x, mesh_y, mode="1").reshape(-1, self.tw, nx, ny)
+                                          mesh_x, mesh_y, mode="1", idx=self.last_itp_idx).reshape(-1, self.tw, nx, ny)
                 static_key = None
             else:
                 mesh = grid

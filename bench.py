@@ -249,24 +249,22 @@ def run_ours(args):
     # read of that step's loss.  The read is the usual asynchronous logging pattern: the loss is copied to pinned
     # host memory on the stream and looked at one step later (the last one before the clock stops), so the host
     # keeps queueing work instead of draining the GPU after every step.
-    host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+    host_loss = torch.zeros(2, dtype=torch.float32).pin_memory()     # two slots: step i is in flight while i-1 is read
     seen = []
 
-    def e2e_step():
-        if e2e_step.pending is not None:
-            e2e_step.pending.synchronize()
-            seen.append(float(host_loss[0]))       # loss of the previous step, now on the host
-        losses = train_step(fields_host)           # create_graph moves the step's slices host -> device
-        host_loss.copy_(losses[-1].reshape(1), non_blocking=True)
-        e2e_step.pending = torch.cuda.Event()
-        e2e_step.pending.record()
-
     def e2e_run(steps):
-        e2e_step.pending = None
-        for _ in range(steps):
-            e2e_step()
-        e2e_step.pending.synchronize()
-        seen.append(float(host_loss[0]))           # the last step's loss is read inside the timed region too
+        pending = None
+        for i in range(steps):
+            losses = train_step(fields_host)       # create_graph moves the step's slices host -> device
+            host_loss[i & 1:(i & 1) + 1].copy_(losses[-1].reshape(1), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            if pending is not None:                # step i is queued: now look at the loss of step i-1
+                pending[0].synchronize()
+                seen.append(float(host_loss[pending[1]]))
+            pending = (ev, i & 1)
+        pending[0].synchronize()
+        seen.append(float(host_loss[pending[1]]))  # the last step's loss is read inside the timed region too
 
     e2e_run(1)
     n_seen = len(seen)

@@ -385,7 +385,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
             mbar_wait(all_done, 0);
             tc_fence_after();
 #pragma unroll 1
-            for (int chunk = 0; chunk < 4; ++chunk) {
+            for (int cc = 0; cc < 4; ++cc) {                              // rotated per CTA: spreads the same-address atomics
+                const int chunk = (cc + (int)blockIdx.x) & 3;
                 uint32_t v[32];
                 tmem_ld32_async(tmem_d2 + lane_addr + chunk * 32, v);
                 tmem_wait_ld(v);

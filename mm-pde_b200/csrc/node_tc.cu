@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool has_b = p.B != nullptr, has_ext = (p.Bext != nullptr) || p.want_bias;
 
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+    if (warp == 0) { TL(3, 0, 6); tmem_alloc(smem_u32(tmem_slot), 256); }
     if (tid == 32) {
         for (int b = 0; b < 2; ++b) { mbar_init(s_full + 8 * b, W_BLD_WARPS); mbar_init(s_empty + 8 * b, 1); }
         mbar_init(all_done, 1);
@@ -317,20 +317,31 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
         if (my_tiles > 0) {
             mbar_wait(all_done, 0);
+            if (warp == 0) TL(3, 0, 1);
             tc_fence_after();
             if (has_b) {
                 const bool vec = (p.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0;
+                // every CTA adds its 128x128 partial onto the same 64 KB: walk the chunks in a per-CTA rotated order so that
+                // the CTAs do not all hammer the same addresses at the same moment (same-address atomics serialise in L2)
 #pragma unroll 1
-                for (int chunk = 0; chunk < 4; ++chunk) {
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int chunk = (cc + (int)blockIdx.x) & 3;
                     uint32_t v[32];
                     tmem_ld32_async(tmem_d + lane_addr + chunk * 32, v);
                     tmem_wait_ld(v);
                     float* row = p.dW + (int64_t)i_row * p.ldw + chunk * 32;
                     if (vec) {
+                        if ((blockIdx.x >> 2) & 1) {
 #pragma unroll
-                        for (int m = 0; m < 8; ++m)
-                            red_add_v4(row + 4 * m, make_float4(__uint_as_float(v[4 * m]), __uint_as_float(v[4 * m + 1]),
-                                                                 __uint_as_float(v[4 * m + 2]), __uint_as_float(v[4 * m + 3])));
+                            for (int m = 7; m >= 0; --m)
+                                red_add_v4(row + 4 * m, make_float4(__uint_as_float(v[4 * m]), __uint_as_float(v[4 * m + 1]),
+                                                                     __uint_as_float(v[4 * m + 2]), __uint_as_float(v[4 * m + 3])));
+                        } else {
+#pragma unroll
+                            for (int m = 0; m < 8; ++m)
+                                red_add_v4(row + 4 * m, make_float4(__uint_as_float(v[4 * m]), __uint_as_float(v[4 * m + 1]),
+                                                                     __uint_as_float(v[4 * m + 2]), __uint_as_float(v[4 * m + 3])));
+                        }
                     } else {
 #pragma unroll
                         for (int m = 0; m < 32; ++m) atomicAdd(row + m, __uint_as_float(v[m]));
@@ -347,6 +358,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
                 }
                 if (p.dbias) atomicAdd(p.dbias + i_row, __uint_as_float(v[4]));
             }
+            if (warp == 0) TL(3, 0, 2);
         }
     } else if (warp < W_MMA_WARP) {
         // ------------------------------------------------------------------ builders: warp w -> rows 8w .. 8w+7 of the A and B tiles
@@ -372,8 +384,10 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
         for (int64_t ti = 0; ti < my_tiles; ++ti) {
             const int sb = (int)(ti & 1);
             const int64_t t = (int64_t)blockIdx.x + ti * gridDim.x;
+            if (w == 0) TL(0, (int)ti, 0);
             load16(na, nb, ti + 1);
             mbar_wait(s_empty + 8 * sb, ((uint32_t)(ti >> 1) & 1u) ^ 1u);
+            if (w == 0) TL(0, (int)ti, 1);
             const uint32_t stage = sbase + sb * WgradSmem::STAGE;
 #pragma unroll
             for (int k = 0; k < 8; ++k) store_split<WT>(stage, row0 + k, lane, ra[k]);
@@ -402,6 +416,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_full + 8 * sb);
+            if (w == 0) TL(0, (int)ti, 2);
 #pragma unroll
             for (int k = 0; k < 8; ++k) { ra[k] = na[k]; rb[k] = nb[k]; }
         }
@@ -414,6 +429,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
             for (int64_t ti = 0; ti < my_tiles; ++ti) {
                 const int sb = (int)(ti & 1);
                 mbar_wait(s_full + 8 * sb, (uint32_t)(ti >> 1) & 1u);
+                TL(2, (int)ti, 0);
                 tc_fence_after();
                 const uint32_t a_addr = sbase + sb * WgradSmem::STAGE, b_addr = a_addr + 2 * W_IMG, x_addr = a_addr + 4 * W_IMG;
 #pragma unroll
@@ -435,13 +451,14 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
                     }
                 }
                 umma_commit(s_empty + 8 * sb);
+                TL(2, (int)ti, 2);
             }
             if (my_tiles > 0) umma_commit(all_done);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 256);
+    if (warp == 0) { TL(3, 0, 7); tmem_dealloc(tmem_base, 256); }
 }
 
 }  // namespace mmpde

@@ -13,6 +13,8 @@ Differences a caller can observe, both deliberate (SURVEY.md 8a-5, appendix C.10
 """
 import numpy as np
 import torch
+
+from ._h2d import to_device
 import torch.nn.functional as F
 from torch import nn
 
@@ -64,6 +66,7 @@ class GraphCreator_FS_2D(nn.Module):
         self.tw = time_window
         self.t_res = t_resolution
         self._static_edges = {}
+        self._mm_grids = {}
 
     def _bbox(self):
         """Box handed to the cell-binned k-NN (a hint: points outside are clamped, results stay exact)."""
@@ -102,7 +105,11 @@ class GraphCreator_FS_2D(nn.Module):
         gx = np.linspace(0, self.pde.Lx, n_grid_x)
         gy = np.linspace(0, self.pde.Ly, n_grid_y)
         # x-fastest node order, as np.meshgrid gives it (:94-96)
-        grid = torch.tensor(np.array(np.meshgrid(gx, gy)), dtype=torch.float).reshape(2, -1).t().to(u.device)
+        key = (n_grid_x, n_grid_y, float(self.pde.Lx), float(self.pde.Ly), str(u.device))
+        grid = self._mm_grids.get(key)
+        if grid is None:                      # static: built and moved to the device once, not every call
+            grid = torch.tensor(np.array(np.meshgrid(gx, gy)), dtype=torch.float).reshape(2, -1).t().to(u.device)
+            self._mm_grids[key] = grid
         nu = u.shape[0]
         xi1 = grid[:, 0:1].repeat(nu, 1)
         xi2 = grid[:, 1:2].repeat(nu, 1)
@@ -145,7 +152,7 @@ class GraphCreator_FS_2D(nn.Module):
         return edges
 
     def create_graph(self, itp_model, data, labels, steps, device, mesh_model=None):
-        data, labels = data.to(device), labels.to(device)
+        data, labels = to_device(data, device), to_device(labels, device)
         pde = self.pde
         B = data.shape[0]
         if len(pde.grid_size) == 3:
@@ -194,7 +201,7 @@ class GraphCreator_FS_2D(nn.Module):
         u_new = data[:B].reshape(B, self.tw, n).permute(0, 2, 1).reshape(B * n, self.tw)
         y_new = labels[:B].reshape(B, self.tw, n).permute(0, 2, 1).reshape(B * n, self.tw)
         x_new = mesh[:B].reshape(B * n, 2)
-        t_new = t[torch.as_tensor(list(steps[:B]), device=device)].repeat_interleave(n)
+        t_new = t[to_device(torch.as_tensor(list(steps[:B])), device)].repeat_interleave(n)
         batch = torch.arange(B, device=device).repeat_interleave(n)
         if static_key is not None:
             static_key = static_key + (B,)
@@ -206,7 +213,7 @@ class GraphCreator_FS_2D(nn.Module):
 
     # ------------------------------------------------------------------ prediction back on the grid (:270-305)
     def interpolate_pred(self, itp_model, pred, graph, data, device):
-        data = data.to(device)
+        data = to_device(data, device)
         pde = self.pde
         if len(pde.grid_size) == 3:
             onx, ony = pde.ori_grid_size[1], pde.ori_grid_size[2]

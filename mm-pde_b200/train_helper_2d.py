@@ -9,6 +9,8 @@ import random
 
 import torch
 
+from ._h2d import to_device
+
 
 def _sample_steps(graph_creator, unrolling, batch_size):
     # random.choice / random.choices in this order, like the reference, so seeded runs pick the same steps
@@ -54,7 +56,7 @@ def training_itp(itp_model, mesh_model, unrolling, batch_size, optimizer, optimi
         data, labels = graph_creator.create_data(u_super, steps)
         moved = graph_creator.create_graph(itp_model, data, labels, steps, device, mesh_model)
         round_trip = graph_creator.interpolate_pred(itp_model, moved.x, moved, data, device)
-        loss = criterion(round_trip, data.to(device).reshape(-1, 1))
+        loss = criterion(round_trip, to_device(data, device).reshape(-1, 1))
         loss.backward()
         if after_backward is not None:
             after_backward()
@@ -73,9 +75,9 @@ def training_loop_branch(model, model_b, itp_model, mesh_model, unrolling, batch
         data, labels = graph_creator.create_data(u_super, steps)
         if _is_gnn(model):
             pred = _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, steps, device)
-            loss = criterion(pred, labels.to(device).reshape(-1, 1))
+            loss = criterion(pred, to_device(labels, device).reshape(-1, 1))
         else:
-            data, labels = data.to(device), labels.to(device)
+            data, labels = to_device(data, device), to_device(labels, device)
             loss = criterion(model(data), labels.squeeze())
         loss.backward()
         if after_backward is not None:
@@ -99,9 +101,9 @@ def test_timestep_losses(model, model_b, itp_model, mesh_model, steps, batch_siz
                 if _is_gnn(model):
                     pred = _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels,
                                         [step] * batch_size, device)
-                    per_batch.append(criterion(pred, labels.to(device).reshape(-1, 1)))
+                    per_batch.append(criterion(pred, to_device(labels, device).reshape(-1, 1)))
                 else:
-                    data, labels = data.to(device), labels.to(device)
+                    data, labels = to_device(data, device), to_device(labels, device)
                     per_batch.append(criterion(model(data), labels.squeeze()))
         curve.append(torch.stack(per_batch).mean())
         if step % 2 == 1:

@@ -27,3 +27,17 @@ print("kernel start -> (clks)  W in TMEM:", rel(t[3,0,0]), " end:", rel(t[3,0,7]
       " builder before/after setmaxnreg:", rel(t[0,0,4]), rel(t[0,0,5]))
 for i in range(2):
     print(f" tile {i}: builder start {rel(t[0,i,0])} empty-ok {rel(t[0,i,1])} built {rel(t[0,i,2])} | mma tm_empty-ok {rel(t[2,i,0])} issued {rel(t[2,i,2])} | epi acc-ready {rel(t[3,i,1])} stored {rel(t[3,i,2])}")
+
+# ---- wgrad
+lib.mmpde_node_wgrad.argtypes = _cabi.SIGNATURES["mmpde_node_wgrad"]
+n4 = torch.randn(N, 4, device=dev)
+dW, dWx, db = torch.zeros(128, 260, device=dev), torch.zeros(128, 4, device=dev), torch.zeros(128, device=dev)
+def runw():
+    assert lib.mmpde_node_wgrad(pp(C), 128, pp(X), 256, pp(n4), pp(dW), 260, pp(dWx), 4, pp(db), N, st) == 0
+for _ in range(3): runw()
+torch.cuda.synchronize(); buf.zero_(); lib.mmpde_debug_timeline_node(pp(buf)); runw(); torch.cuda.synchronize(); lib.mmpde_debug_timeline_node(None)
+t = buf.cpu().numpy().reshape(4, 48, 8)
+t0 = t[3, 0, 6]
+print("wgrad: kernel start -> all MMAs done:", rel(t[3,0,1]), " reductions done:", rel(t[3,0,2]), " end:", rel(t[3,0,7]))
+for i in range(4):
+    print(f" tile {i}: builder start {rel(t[0,i,0])} empty-ok {rel(t[0,i,1])} built {rel(t[0,i,2])} | mma full-ok {rel(t[2,i,0])} issued {rel(t[2,i,2])}")

@@ -30,6 +30,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 RES = [31, 48, 48]
+CY_RES = [30, 2521]
 BATCH = 16
 K_NEIGH = 35
 LAYERS = 6
@@ -168,11 +169,24 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
     _cabi.lib()
     torch.manual_seed(0)
-    pde = burgers()
-    pde.grid_size = pde.movingmesh_grid_size = pde.ori_grid_size = RES
-    gc = GraphCreator_FS_2D(pde, K_NEIGH, "knn", 1, RES[0])
+    cyl = args.workload == "cylinder"
+    if cyl:                                  # BASELINE.json configs[2]: flow around a cylinder, base_resolution 30,2521
+        from mmpde_b200.PDEs import cy
+        cloud = synthetic.cylinder_cloud(CY_RES[1], seed=0)
+        pde = cy(ori_grid=cloud, device=dev)
+        pde.grid_size = pde.movingmesh_grid_size = pde.ori_grid_size = CY_RES
+        gc = GraphCreator_FS_2D(pde, K_NEIGH, "knn", 1, CY_RES[0])
+        net = ItpNet(CY_RES[1], None, [128, 64], [128, 64], [1, 4, 16, 4, 1]).to(dev)
+        nodes_per_sample, workload = CY_RES[1], ("Flow around a cylinder MM-PDE training step (moved nodes + interpolation + 2x 6-layer "
+                                                 "processor), 30x2521 unstructured nodes, k=35")
+    else:
+        pde = burgers()
+        pde.grid_size = pde.movingmesh_grid_size = pde.ori_grid_size = RES
+        gc = GraphCreator_FS_2D(pde, K_NEIGH, "knn", 1, RES[0])
+        net = ItpNet(RES[1], RES[2], [128, 64], [128, 64], [1, 4, 16, 4, 1]).to(dev)
+        nodes_per_sample, workload = RES[1] * RES[2], ("Burgers 2D MM-PDE training step (moved mesh + interpolation + 2x 6-layer "
+                                                       "processor), 31x48x48, k=35")
     model, model_b = MP_PDE_Solver_2D(pde).to(dev), MP_PDE_Solver_2D(pde).to(dev)
-    net = ItpNet(RES[1], RES[2], [128, 64], [128, 64], [1, 4, 16, 4, 1]).to(dev)
     mover = synthetic.AnalyticMover().to(dev)
     params = [p for m in (model, model_b, net) for p in m.parameters()]
     opt = torch.optim.AdamW([{"params": model.parameters()}, {"params": model_b.parameters()},
@@ -180,9 +194,12 @@ def run_ours(args):
     bucket = mdist.GradBucket(params) if world > 1 else None
     after = bucket.allreduce if bucket is not None else None
     # weak scaling: every rank owns its own batch of 16 trajectories (global batch 16*G), seeded per rank
-    fields_host = synthetic.burgers_fields(BATCH, RES[0], RES[1], RES[2], seed=100 + rank).pin_memory()
+    if cyl:
+        fields_host = synthetic.cylinder_fields(BATCH, cloud, CY_RES[0], seed=100 + rank).pin_memory()
+    else:
+        fields_host = synthetic.burgers_fields(BATCH, RES[0], RES[1], RES[2], seed=100 + rank).pin_memory()
     fields_dev = fields_host.to(dev)
-    n_nodes = BATCH * RES[1] * RES[2]
+    n_nodes = BATCH * nodes_per_sample
     n_edges = n_nodes * K_NEIGH
     edge_updates_per_step = 2 * n_edges * LAYERS
 
@@ -271,7 +288,7 @@ def run_ours(args):
     ms_e2e = timed(lambda: e2e_run(args.steps), 1) / args.steps
     assert len(seen) - n_seen == args.steps and all(v == v for v in seen), "every timed step must deliver its loss"
     clocks = sampler.stop(t_begin, time.perf_counter())
-    h2d = 2 * BATCH * RES[1] * RES[2] * 4          # data + labels slices, fp32
+    h2d = 2 * BATCH * nodes_per_sample * 4         # data + labels slices, fp32
     d2h = 4
 
     # ---- rollout (teacher-forced per-time-step test sweep, no_grad) ----------------------------------------
@@ -294,7 +311,7 @@ def run_ours(args):
     achieved = alg_flops / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else 0.0
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not cyl:      # the CPU arm times the headline workload
         v, sec, cores = cpu_reference_step_time(2, 1, 1)
         cpu = {"value": v, "unit": "edge-updates/s", "cores": cores, "kind": "port",
                "sample": f"batch 2 of the batch-{BATCH} step, 1 warm-up + 1 timed step ({sec:.1f} s); oracle port "
@@ -304,8 +321,7 @@ def run_ours(args):
             "metric": "edge-updates/sec (fwd+bwd)", "value": value, "unit": "edge-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Burgers 2D MM-PDE training step (moved mesh + interpolation + 2x 6-layer processor), "
-                                   "31x48x48, k=35", "per_gpu_batch": BATCH, "nodes_per_gpu": n_nodes,
+            "config": {"workload": workload, "per_gpu_batch": BATCH, "nodes_per_gpu": n_nodes,
                        "edges_per_graph": n_edges, "parallelism": f"batch-sharded dp{world}, sync-BN, flat grad all-reduce",
                        "l2": "per-step working set ~1.7 GB > 126 MB L2, no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "edge-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -334,6 +350,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--workload", default="burgers", choices=["burgers", "cylinder"],
+                    help="burgers = BASELINE.json configs[1] (the headline, default); cylinder = configs[2]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -67,10 +67,14 @@ __device__ __forceinline__ void gather8(Gather8& g, const float* __restrict__ PQ
 __device__ __forceinline__ float4 sel4(bool c, const float4& a, const float4& b) {
     return make_float4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
 }
-__device__ __forceinline__ float4 relu_add(const float4& a, const float4& b) {
-    return make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
+// 2*relu(a + b) = z + |z|: two adds on the (mostly idle, full-rate) FMA pipe instead of an add plus a max on the ALU
+// pipe, which is the busiest unit of these kernels (profiles/r01_edge_bwd_ncu.json).  The factor 2 is exact; the forward
+// folds 1/2 into W2 when it loads it into tensor memory, the backward into the final dW2 reduction.
+__device__ __forceinline__ float4 relu2_add(const float4& a, const float4& b) {
+    const float4 z = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    return make_float4(z.x + fabsf(z.x), z.y + fabsf(z.y), z.z + fabsf(z.z), z.w + fabsf(z.w));
 }
-// h1 = relu(P'[dst] + Q'[src]) of 8 gathered rows -> operand image rows rowbase .. rowbase+7.  Straight-line code
+// 2*h1 = 2*relu(P'[dst] + Q'[src]) of 8 gathered rows -> operand image rows rowbase .. rowbase+7.  Straight-line code
 // (rows beyond the last edge come out as zero: their Q' and the last row's P' are zero), then the rare patch loop.
 template <int ROWS>
 __device__ __forceinline__ void build_h8(uint32_t img, int rowbase, const Gather8& g, RowIdx idx, int r0,
@@ -78,13 +82,13 @@ __device__ __forceinline__ void build_h8(uint32_t img, int rowbase, const Gather
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int d = __shfl_sync(0xffffffffu, idx.d, r0 + k);
-        store_split<ROWS>(img, rowbase + k, lane, relu_add(sel4(d == g.da, g.pa, g.pb), g.q[k]));
+        store_split<ROWS>(img, rowbase + k, lane, relu2_add(sel4(d == g.da, g.pa, g.pb), g.q[k]));
     }
     for (uint32_t odd = g.odd; odd != 0u; odd &= odd - 1u) {
         const int k = __ffs(odd) - 1;
         const int d = __shfl_sync(0xffffffffu, idx.d, r0 + k), sr = __shfl_sync(0xffffffffu, idx.s, r0 + k);
         store_split<ROWS>(img, rowbase + k, lane,
-                          relu_add(ldg4(PQ + (int64_t)d * 256 + lane * 4), ldg4(PQ + (int64_t)sr * 256 + 128 + lane * 4)));
+                          relu2_add(ldg4(PQ + (int64_t)d * 256 + lane * 4), ldg4(PQ + (int64_t)sr * 256 + 128 + lane * 4)));
     }
 }
 
@@ -95,12 +99,13 @@ __device__ __noinline__ void flush_mean(float* agg, int64_t ld, int cur, float i
 __device__ __forceinline__ int lds_i32(uint32_t saddr) { return (int)lds_b32(saddr); }
 
 // ================================================================================================================
-// Forward warp roles (640 threads): 8 epilogue warps (TMEM lane quadrant = warp & 3, column half = warp >> 2),
-// 8 builder warps, 1 MMA warp (+ 3 idle to fill the warpgroup).  Register budget per thread moved with setmaxnreg
-// from the launch value 96 (the CTA's pool is what it was launched with: 640*96 = 61440):
-// 8*32*72 + 8*32*144 + 4*32*40 = 60416 <= 61440.
-constexpr int F_EPI_WARPS = 8, F_BLD_WARPS = 8, F_MMA_WARP = F_EPI_WARPS + F_BLD_WARPS, F_THREADS = 640;
-constexpr int F_EPI_REGS = 72, F_BLD_REGS = 144, F_MMA_REGS = 40;
+// Forward warp roles (896 threads): 16 epilogue warps (TMEM lane quadrant = warp & 3, 32-column quarter = warp >> 2),
+// 8 builder warps, 1 MMA warp (+ 3 idle to fill the warpgroup).  Every role is a latency-bound instruction stream
+// (~0.2 IPC per warp), so throughput comes from the NUMBER of warps per sub-partition: 4 epilogue + 2 builder each.
+// Register budget per thread moved with setmaxnreg from the launch value 72 (the CTA's pool is what it was launched
+// with: 896*72 = 64512): 16*32*56 + 8*32*120 + 4*32*40 = 64512.
+constexpr int F_EPI_WARPS = 16, F_BLD_WARPS = 8, F_MMA_WARP = F_EPI_WARPS + F_BLD_WARPS, F_THREADS = 896;
+constexpr int F_EPI_REGS = 56, F_BLD_REGS = 120, F_MMA_REGS = 40;
 
 // ================================================================================================================
 // Forward:  agg[i] = mean_{e: dst=i} relu(W2 relu(P'[i] + Q'[src_e]) + b2);  mask2 = sign bits of z2.
@@ -147,14 +152,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
     if (warp < F_EPI_WARPS) {
         // ------------------------------------------------------------------ epilogue: thread = out-channel o
         reg_dec<F_EPI_REGS>();
-        const int q = warp & 3, half = warp >> 2;                          // TMEM lane quadrant, column half
+        const int q = warp & 3, quarter = warp >> 2;                       // TMEM lane quadrant, 32-column quarter of the tile
         const int o = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const uint32_t bias_bits = __float_as_uint(__ldg(p.b2 + o));
-        if (half == 0) weight_to_tmem(p.w2, 128, 1, o, tmem_w_hi + lane_addr, tmem_w_lo + lane_addr);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_fill32(tmem_d + lane_addr + (c >> 1) * FTE + half * 64 + (c & 1) * 32, bias_bits);
-        tmem_wait_st();                                                    // accumulators start at b2
+        const float bias = __ldg(p.b2 + o);
+        if (quarter < 2)                                                   // W2/2 (the operand tile holds 2*h1) -> tensor memory
+            weight_to_tmem(p.w2, 128, 1, o, tmem_w_hi + lane_addr, tmem_w_lo + lane_addr, 2 * quarter, 2 * quarter + 2, 0.5f);
+        tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { mbar_arrive(tm_empty); mbar_arrive(tm_empty + 8); }
@@ -166,58 +170,71 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
             mbar_wait(tm_full + 8 * b, ph);
             if (warp == 0) TL(3, i, 0);
             tc_fence_after();
-            const uint32_t d_addr = tmem_d + lane_addr + b * FTE + half * 64;
+            const uint32_t d_addr = tmem_d + lane_addr + b * FTE + quarter * 32;
             int cur = -1;
-            float run = 0.f, cur_inv = 0.f;
-            // 32 edges of this thread's channel: ReLU, sign mask, running per-target sum.  Targets are contiguous
-            // runs of edges; `bm` marks the first edge of each run (warp-uniform), so groups of 4 edges without a
-            // boundary take the short path.  A warp's 64 columns always start a new run (partial runs add atomically).
-            auto process = [&](uint32_t (&vc)[32], int chunk) {
-                const int e = chunk * 32 + lane;
-                const int d_me = lds_i32(dsts + 4 * e);
-                const int d_pv = (e > half * 64) ? lds_i32(dsts + 4 * e - 4) : -2;
-                const uint32_t bm = __ballot_sync(0xffffffffu, d_me != d_pv);
-                uint32_t word = 0;
+            float run_s = 0.f, run_a = 0.f, cur_inv = 0.f;                 // sum z, sum |z| of the current run
+            // The thread's 32 edges in 4 pieces of 8 (a rolled loop over small tcgen05.ld.x8 pieces keeps the body short).
+            // Per edge: sign mask + running per-target sum of relu(z), kept off the busy ALU pipe:
+            //   sum relu(z) = (sum z + sum |z|) / 2   -> two adds per edge (|.| is an operand modifier);
+            //   mask bit    = sign of (0 - z)         -> one add (exact: set iff z > 0, both zeros give +0) + one funnel shift.
+            // Targets are contiguous runs of edges; `bm` marks the first edge of each run (warp-uniform), so groups of 4
+            // edges without a boundary take the short path.  A warp's 32 columns always start a new run (partial runs
+            // add up atomically).
+            const int e_first = quarter * 32;
+            const int d_me = lds_i32(dsts + 4 * (e_first + lane));
+            const int d_pv = (lane > 0) ? lds_i32(dsts + 4 * (e_first + lane) - 4) : -2;
+            const uint32_t bm = __ballot_sync(0xffffffffu, d_me != d_pv);
+            uint32_t word = 0;                                             // filled MSB-first: bit 31-j <- edge j
+            auto process8 = [&](uint32_t (&vc)[8], int pc) {              // piece pc: columns e_first + 8*pc .. +7
+                const int e0 = e_first + pc * 8;
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const float z0 = __uint_as_float(vc[4 * g]), z1 = __uint_as_float(vc[4 * g + 1]),
-                                z2 = __uint_as_float(vc[4 * g + 2]), z3 = __uint_as_float(vc[4 * g + 3]);
-                    const float r0 = fmaxf(z0, 0.f), r1 = fmaxf(z1, 0.f), r2 = fmaxf(z2, 0.f), r3 = fmaxf(z3, 0.f);
-                    const uint32_t nib = (bm >> (4 * g)) & 15u;
+                for (int g = 0; g < 2; ++g) {
+                    const float z0 = __uint_as_float(vc[4 * g]) + bias, z1 = __uint_as_float(vc[4 * g + 1]) + bias,
+                                z2 = __uint_as_float(vc[4 * g + 2]) + bias, z3 = __uint_as_float(vc[4 * g + 3]) + bias;
+                    const uint32_t nib = (bm >> (pc * 8 + 4 * g)) & 15u;
                     if (nib == 0u) {
-                        run += (r0 + r1) + (r2 + r3);
+                        run_s += (z0 + z1) + (z2 + z3);
+                        run_a += (fabsf(z0) + fabsf(z1)) + (fabsf(z2) + fabsf(z3));
                     } else {
-                        const float r[4] = {r0, r1, r2, r3};
+                        const float z[4] = {z0, z1, z2, z3};
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if (nib & (1u << k)) {
-                                flush_mean(p.agg, p.ld_agg, cur, cur_inv, o, run);
-                                cur = lds_i32(dsts + 4 * (chunk * 32 + 4 * g + k));           // used at the NEXT flush:
-                                cur_inv = __uint_as_float(lds_b32(dsts + 4 * FTE * 4 + 4 * (chunk * 32 + 4 * g + k)));
-                                run = 0.f;                                                    // latency stays hidden
+                                flush_mean(p.agg, p.ld_agg, cur, cur_inv, o, 0.5f * (run_s + run_a));
+                                cur = lds_i32(dsts + 4 * (e0 + 4 * g + k));                   // used at the NEXT flush:
+                                cur_inv = __uint_as_float(lds_b32(dsts + 4 * FTE * 4 + 4 * (e0 + 4 * g + k)));
+                                run_s = run_a = 0.f;                                          // latency stays hidden
                             }
-                            run += r[k];
+                            run_s += z[k];
+                            run_a += fabsf(z[k]);
                         }
                     }
-                    word |= ((z0 > 0.f ? 1u : 0u) | (z1 > 0.f ? 2u : 0u) | (z2 > 0.f ? 4u : 0u) | (z3 > 0.f ? 8u : 0u)) << (4 * g);
+                    word = __funnelshift_l(__float_as_uint(0.f - z0), word, 1);
+                    word = __funnelshift_l(__float_as_uint(0.f - z1), word, 1);
+                    word = __funnelshift_l(__float_as_uint(0.f - z2), word, 1);
+                    word = __funnelshift_l(__float_as_uint(0.f - z3), word, 1);
                 }
-                // mask2[chunk of 32 edges][channel]: bit j = (z2 > 0) of edge 32*chunk + j
-                p.mask2[((t * 4 + chunk) * 128) + o] = word;
             };
-            uint32_t v[32];
+            uint32_t va[8], vb[8];
+            tmem_ld8_async(d_addr, va);
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                tmem_ld32_async(d_addr + c * 32, v);
-                tmem_wait_ld(v);
-                process(v, 2 * half + c);
+            for (int pc = 0; pc < 4; pc += 2) {
+                tmem_wait_ld8(va);
+                tmem_ld8_async(d_addr + (pc + 1) * 8, vb);
+                process8(va, pc);
+                tmem_wait_ld8(vb);
+                if (pc + 2 < 4) {
+                    tmem_ld8_async(d_addr + (pc + 2) * 8, va);
+                } else {                                                   // all 32 columns are in registers: release the stage
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tm_empty + 8 * b);
+                }
+                process8(vb, pc + 1);
             }
-            flush_mean(p.agg, p.ld_agg, cur, cur_inv, o, run);
-            tmem_fill32(d_addr, bias_bits);
-            tmem_fill32(d_addr + 32, bias_bits);
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tm_empty + 8 * b);
+            // mask2[chunk of 32 edges][channel]: bit j = (z2 > 0) of edge 32*chunk + j
+            p.mask2[((t * 4 + quarter) * 128) + o] = __brev(word);
+            flush_mean(p.agg, p.ld_agg, cur, cur_inv, o, 0.5f * (run_s + run_a));
             if (warp == 0) TL(3, i, 2);
         }
     } else if (warp < F_MMA_WARP) {
@@ -270,15 +287,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
             mbar_wait(tm_empty + 8 * b, ph);
             TL(2, i, 1);
             tc_fence_after();
-            const uint32_t h_addr = sbase + FwdSmem::H + b * (2 * F_IMG);
+            const uint32_t b_lo = desc_lo_sw128(sbase + FwdSmem::H + b * (2 * F_IMG), 16);
+            constexpr uint32_t b_hi = desc_hi_sw128(1024);
+            const uint32_t d_tm = tmem_d + b * FTE;
 #pragma unroll
             for (int prod = 0; prod < 3; ++prod) {                         // hi*hi + hi*lo + lo*hi
                 const uint32_t a = (prod == 2) ? tmem_w_lo : tmem_w_hi;
-                const uint32_t bb = h_addr + (prod == 1 ? F_IMG : 0);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    umma_bf16_ts(tmem_d + b * FTE, a + ks * 8,
-                                 smem_desc_sw128(bb + (ks >> 2) * (FTE * 128) + (ks & 3) * 32, 16, 1024), idesc, 1u);
+                    umma_bf16_ts_lh(d_tm, a + ks * 8,
+                                    b_lo + (((prod == 1 ? F_IMG : 0) + (ks >> 2) * (FTE * 128) + (ks & 3) * 32) >> 4), b_hi, idesc,
+                                    (prod | ks) ? 1u : 0u);
             }
             umma_commit(h_empty + 8 * b);
             umma_commit(tm_full + 8 * b);
@@ -392,9 +411,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
                 tmem_wait_ld(v);
 #pragma unroll
                 for (int m = 0; m < 8; ++m)
-                    red_add_v4(p.dW2 + c * 128 + chunk * 32 + 4 * m,
-                               make_float4(__uint_as_float(v[4 * m]), __uint_as_float(v[4 * m + 1]),
-                                           __uint_as_float(v[4 * m + 2]), __uint_as_float(v[4 * m + 3])));
+                    red_add_v4(p.dW2 + c * 128 + chunk * 32 + 4 * m,             // the h1 tile holds 2*h1: halve (exact)
+                               make_float4(0.5f * __uint_as_float(v[4 * m]), 0.5f * __uint_as_float(v[4 * m + 1]),
+                                           0.5f * __uint_as_float(v[4 * m + 2]), 0.5f * __uint_as_float(v[4 * m + 3])));
             }
         }
     } else if (warp < MMA_WARP) {
@@ -547,28 +566,27 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
             TL(2, i, 1);
             tc_fence_after();
             const uint32_t h_addr = sbase + BwdSmem::HG + b * (4 * B_IMG), g_addr = h_addr + 2 * B_IMG;
-            uint32_t acc = 0;
+            constexpr uint32_t d_hi = desc_hi_sw128(1024);
+            const uint32_t gk_lo = desc_lo_sw128(g_addr, 16);              // G read K-major (MMA-A)
+            const uint32_t gm_lo = desc_lo_sw128(g_addr, BTE * 128), hm_lo = desc_lo_sw128(h_addr, BTE * 128);   // MN-major (MMA-B)
 #pragma unroll
             for (int prod = 0; prod < 3; ++prod) {                         // W2^T hi * G hi + hi * G lo + lo * G hi
                 const uint32_t a = (prod == 2) ? tmem_w_lo : tmem_w_hi;
-                const uint32_t bb = g_addr + (prod == 1 ? B_IMG : 0);
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {                           // 16 values of o per step
-                    umma_bf16_ts(tmem_d1 + b * BTE, a + ks * 8,
-                                 smem_desc_sw128(bb + (ks >> 2) * (BTE * 128) + (ks & 3) * 32, 16, 1024), idesc_a, acc);
-                    acc = 1;
-                }
+                for (int ks = 0; ks < 8; ++ks)                             // 16 values of o per step
+                    umma_bf16_ts_lh(tmem_d1 + b * BTE, a + ks * 8,
+                                    gk_lo + (((prod == 1 ? B_IMG : 0) + (ks >> 2) * (BTE * 128) + (ks & 3) * 32) >> 4), d_hi, idesc_a,
+                                    (prod | ks) ? 1u : 0u);
             }
             umma_commit(d1_full + 8 * b);
             TL(2, i, 2);
 #pragma unroll
             for (int prod = 0; prod < 3; ++prod) {                         // G hi * h hi + G hi * h lo + G lo * h hi
-                const uint32_t a = g_addr + (prod == 2 ? B_IMG : 0);
-                const uint32_t bb = h_addr + (prod == 1 ? B_IMG : 0);
 #pragma unroll
                 for (int ks = 0; ks < BTE / 16; ++ks)                      // 16 edges per step
-                    umma_bf16(tmem_d2, smem_desc_sw128(a + ks * 16 * 128, BTE * 128, 1024),
-                              smem_desc_sw128(bb + ks * 16 * 128, BTE * 128, 1024), idesc_b, (i > 0 || prod > 0 || ks > 0) ? 1u : 0u);
+                    umma_bf16_lh(tmem_d2, gm_lo + (((prod == 2 ? B_IMG : 0) + ks * 16 * 128) >> 4), d_hi,
+                                 hm_lo + (((prod == 1 ? B_IMG : 0) + ks * 16 * 128) >> 4), d_hi, idesc_b,
+                                 (i > 0 || prod > 0 || ks > 0) ? 1u : 0u);
             }
             umma_commit(hg_empty + 8 * b);
             TL(2, i, 3);

@@ -231,23 +231,23 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
                     const int sb = (int)(j & 1);
                     mbar_wait(h_full + 8 * sb, (uint32_t)(j >> 1) & 1u);
                     tc_fence_after();
-                    const uint32_t h_addr = sbase + GemmSmem::SEG + sb * (2 * G_IMG);
+                    const uint32_t b_lo = desc_lo_sw128(sbase + GemmSmem::SEG + sb * (2 * G_IMG), 16);
+                    constexpr uint32_t b_hi = desc_hi_sw128(1024);
                     const uint32_t w_hi = tmem_w + (seg == 0 ? 0 : 144), w_lo = w_hi + 64;
 #pragma unroll
                     for (int prod = 0; prod < 3; ++prod) {                 // hi*hi + hi*lo + lo*hi
                         const uint32_t a = (prod == 2) ? w_lo : w_hi;
-                        const uint32_t bb = h_addr + (prod == 1 ? G_IMG : 0);
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
-                            umma_bf16_ts(tmem_d + b * GT, a + ks * 8,
-                                         smem_desc_sw128(bb + (ks >> 2) * (GT * 128) + (ks & 3) * 32, 16, 1024), idesc, 1u);
+                            umma_bf16_ts_lh(tmem_d + b * GT, a + ks * 8,
+                                            b_lo + (((prod == 1 ? G_IMG : 0) + (ks >> 2) * (GT * 128) + (ks & 3) * 32) >> 4), b_hi, idesc, 1u);
                     }
                     if (has_ext && seg == nseg - 1) {
-                        const uint32_t x_addr = sbase + GemmSmem::EXT + (uint32_t)(i & 1) * (2 * G_XIMG);
+                        const uint32_t x_lo = desc_lo_sw128(sbase + GemmSmem::EXT + (uint32_t)(i & 1) * (2 * G_XIMG), 16);
 #pragma unroll
                         for (int prod = 0; prod < 3; ++prod)
-                            umma_bf16_ts(tmem_d + b * GT, (prod == 2) ? tmem_x_lo : tmem_x_hi,
-                                         smem_desc_sw128(x_addr + (prod == 1 ? G_XIMG : 0), 16, 1024), idesc, 1u);
+                            umma_bf16_ts_lh(tmem_d + b * GT, (prod == 2) ? tmem_x_lo : tmem_x_hi,
+                                            x_lo + ((prod == 1 ? G_XIMG : 0) >> 4), b_hi, idesc, 1u);
                     }
                     umma_commit(h_empty + 8 * sb);
                 }
@@ -433,21 +433,23 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
                 tc_fence_after();
                 const uint32_t a_addr = sbase + sb * WgradSmem::STAGE, b_addr = a_addr + 2 * W_IMG, x_addr = a_addr + 4 * W_IMG;
 #pragma unroll
+                constexpr uint32_t d_hi = desc_hi_sw128(1024);
+                const uint32_t a_lo = desc_lo_sw128(a_addr, WT * 128), bm_lo = desc_lo_sw128(b_addr, WT * 128), x_lo = desc_lo_sw128(x_addr, 16);
+#pragma unroll
                 for (int prod = 0; prod < 3; ++prod) {
-                    const uint32_t a = a_addr + (prod == 2 ? W_IMG : 0);
                     if (has_b) {
-                        const uint32_t bb = b_addr + (prod == 1 ? W_IMG : 0);
 #pragma unroll
                         for (int ks = 0; ks < WT / 16; ++ks)               // 16 node rows per step
-                            umma_bf16(tmem_d, smem_desc_sw128(a + ks * 16 * 128, WT * 128, 1024),
-                                      smem_desc_sw128(bb + ks * 16 * 128, WT * 128, 1024), idesc_main, (ti > 0 || prod > 0 || ks > 0) ? 1u : 0u);
+                            umma_bf16_lh(tmem_d, a_lo + (((prod == 2 ? W_IMG : 0) + ks * 16 * 128) >> 4), d_hi,
+                                         bm_lo + (((prod == 1 ? W_IMG : 0) + ks * 16 * 128) >> 4), d_hi, idesc_main,
+                                         (ti > 0 || prod > 0 || ks > 0) ? 1u : 0u);
                     }
                     if (has_ext) {
-                        const uint32_t xx = x_addr + (prod == 1 ? W_XIMG : 0);
 #pragma unroll
                         for (int ks = 0; ks < WT / 16; ++ks)
-                            umma_bf16(tmem_dx, smem_desc_sw128(a + ks * 16 * 128, WT * 128, 1024),
-                                      smem_desc_sw128(xx + ks * 32, 16, 1024), idesc_ext, (ti > 0 || prod > 0 || ks > 0) ? 1u : 0u);
+                            umma_bf16_lh(tmem_dx, a_lo + (((prod == 2 ? W_IMG : 0) + ks * 16 * 128) >> 4), d_hi,
+                                         x_lo + (((prod == 1 ? W_XIMG : 0) + ks * 32) >> 4), d_hi, idesc_ext,
+                                         (ti > 0 || prod > 0 || ks > 0) ? 1u : 0u);
                     }
                 }
                 umma_commit(s_empty + 8 * sb);

@@ -21,6 +21,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 // Wait on a phase parity.  try_wait suspends the thread in hardware for a bounded time, so the loop rarely
 // iterates; the clock is only read every 256 failed polls.  A wait that outlives ~4 s of SM clocks can only be a
 // protocol bug: trap (the launch fails with an error) instead of hanging the GPU.
+// (A leaner loop -- one try_wait per iteration with an iteration-count watchdog -- measured 25 % SLOWER on the
+// backward edge kernel: the wake-up from the longer hardware suspend is slower than this poll.)
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
@@ -107,6 +109,19 @@ __device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
                  :
                  : "memory");
 }
+// 8-column variants (small epilogue loop bodies that stay inside the instruction cache)
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+}
 // 32 lanes x 16 consecutive 32-bit columns <- 16 registers per thread
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
@@ -166,6 +181,37 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// The same two instructions with the shared-memory descriptors given as (low word, high word): the MMA-issuing
+// thread shares its scheduler with busy warps, so its instruction count per MMA is what paces the tensor pipe.  Only the
+// start-address field (bits 0..13 of the low word, in 16-byte units) changes between the MMAs of a tile, so a
+// descriptor is "low word of the tile base + compile-time constant".
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi_sw128(uint32_t sbo_bytes) {     // SBO, version 1, SWIZZLE_128B
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ void umma_bf16_ts_lh(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // All MMAs issued so far by this thread -> arrive (count 1) on the mbarrier when they have completed.
@@ -237,7 +283,7 @@ __device__ __forceinline__ void store_split(uint32_t img, int row, int lane, con
 // t_hi, 64 columns lo at t_lo (one 32-bit column = two consecutive k).  Called by the warps owning the 128 lanes; the
 // four 32-column groups g0 <= g < g1 let two warps of the same lane quadrant share the work.
 __device__ __forceinline__ void weight_to_tmem(const float* __restrict__ w, int64_t rs, int64_t ks, int r, uint32_t t_hi, uint32_t t_lo,
-                                               int g0 = 0, int g1 = 4) {
+                                               int g0 = 0, int g1 = 4, float scale = 1.f) {
     const bool vec = (ks == 1) && ((rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);   // 128-bit loads need alignment
     const float* row = w + r * rs;
 #pragma unroll 1
@@ -260,7 +306,8 @@ __device__ __forceinline__ void weight_to_tmem(const float* __restrict__ w, int6
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
                 uint2 a, b;
-                split4(x[h * 8 + v], a, b);
+                const float4 xs = make_float4(x[h * 8 + v].x * scale, x[h * 8 + v].y * scale, x[h * 8 + v].z * scale, x[h * 8 + v].w * scale);
+                split4(xs, a, b);
                 hi[2 * v] = a.x; hi[2 * v + 1] = a.y; lo[2 * v] = b.x; lo[2 * v + 1] = b.y;
             }
             tmem_st16(t_hi + (g + h) * 16, hi);

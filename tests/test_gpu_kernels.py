@@ -484,3 +484,31 @@ def test_node_wgrad_tensor_core(M):
     assert _rel(db, Ad[:, 128:].sum(0)) < 2e-5
     assert _rel(dW3[:, 128:256], Ad[:, :128].t() @ Bd[:, 128:]) < 2e-5 and float(dW3[:, 256].abs().max()) == 0.0
     assert _rel(db_only, Ad[:, :128].sum(0)) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------- halo / row helpers
+def test_rows_gather_scatter_add_and_dot():
+    """Pack / unpack kernels of the halo exchange and the N = 1 row contraction, against plain torch."""
+    from mmpde_b200 import ops, _cabi
+    dev = _dev()
+    g = torch.Generator().manual_seed(11)
+    M, n = 5000, 1777
+    buf = torch.randn(M, 256, generator=g).to(dev)
+    idx = torch.randint(0, M, (n,), generator=g, dtype=torch.int32).to(dev)           # repeats on purpose
+    st = ops._stream()
+    out = torch.empty(n, 128, device=dev)
+    _cabi.call("mmpde_rows_gather", ops._ptr(buf, 128), 256, ops._ptr(idx), n, 128, ops._ptr(out), st)
+    assert torch.equal(out, buf[idx.long(), 128:])
+    dst = torch.randn(M, 256, generator=g).to(dev)
+    ref = dst.clone()
+    ref[:, 128:].index_add_(0, idx.long(), out)
+    _cabi.call("mmpde_rows_scatter_add", ops._ptr(out), ops._ptr(idx), n, 128, ops._ptr(dst, 128), 256, st)
+    assert _rel(dst, ref) < 1e-6 and torch.equal(dst[:, :128], ref[:, :128])
+    w = torch.randn(256, generator=g).to(dev)
+    acc = torch.randn(M, 4, generator=g).to(dev)
+    want = acc.clone()
+    want[:, 0] += (buf.double() @ w.double()).float()
+    _cabi.call("mmpde_rows_dot", ops._ptr(buf), 256, 256, ops._ptr(w), ops._ptr(acc), 4, M, 1, st)
+    assert _rel(acc[:, 0], want[:, 0]) < 1e-5 and torch.equal(acc[:, 1:], want[:, 1:])
+    _cabi.call("mmpde_rows_dot", ops._ptr(buf), 256, 128, ops._ptr(w), ops._ptr(acc), 4, M, 0, st)
+    assert _rel(acc[:, 0], buf[:, :128].double() @ w[:128].double()) < 1e-5

@@ -5,7 +5,9 @@
 
 namespace mmpde {
 
-constexpr int ROWS_PER_CTA = 256;   // rows reduced by one CTA before it touches the fp64 accumulators
+constexpr int ROWS_PER_WARP = 8;                 // rows whose loads one warp keeps in flight together
+constexpr int ROWS_PER_CTA = 8 * ROWS_PER_WARP;  // rows reduced by one CTA before it touches the fp64 accumulators
+constexpr int APPLY_ROWS = 4;                    // rows per warp of the elementwise kernels (CTA = 32 rows)
 
 __device__ __forceinline__ float4 load_y(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t r, int c4) {
     float4 y = ldg4(A + r * lda + c4 * 4);
@@ -37,11 +39,18 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
     const int c4 = threadIdx.x & 31, rg = threadIdx.x >> 5;
     for (int64_t base = (int64_t)blockIdx.x * ROWS_PER_CTA; base < M; base += (int64_t)gridDim.x * ROWS_PER_CTA) {
         float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
-        int64_t end = (base + ROWS_PER_CTA < M) ? base + ROWS_PER_CTA : M;
-        for (int64_t r = base + rg; r < end; r += 8) {
-            float4 y = load_y(A, lda, B, ldb, r, c4);
+        auto acc = [&](float4 y) {
             s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
             q.x = fmaf(y.x, y.x, q.x); q.y = fmaf(y.y, y.y, q.y); q.z = fmaf(y.z, y.z, q.z); q.w = fmaf(y.w, y.w, q.w);
+        };
+        if (base + ROWS_PER_CTA <= M) {                 // full block: all loads of the warp's rows in flight at once
+            float4 y[ROWS_PER_WARP];
+#pragma unroll
+            for (int k = 0; k < ROWS_PER_WARP; ++k) y[k] = load_y(A, lda, B, ldb, base + rg + 8 * k, c4);
+#pragma unroll
+            for (int k = 0; k < ROWS_PER_WARP; ++k) acc(y[k]);
+        } else {
+            for (int64_t r = base + rg; r < M; r += 8) acc(load_y(A, lda, B, ldb, r, c4));
         }
         block_reduce_to_double(s, sums);
         block_reduce_to_double(q, sums + 128);
@@ -72,12 +81,23 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
     float4 mu = ldg4(mean_rstd + c4 * 4), rs = ldg4(mean_rstd + 128 + c4 * 4);
     float4 ga = ldg4(gamma + c4 * 4), be = ldg4(beta + c4 * 4);
     float4 sc = make_float4(ga.x * rs.x, ga.y * rs.y, ga.z * rs.z, ga.w * rs.w);
-    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < M; r += (int64_t)gridDim.x * 8) {
-        float4 y = load_y(A, lda, B, ldb, r, c4);
+    const int rg = threadIdx.x >> 5;
+    auto apply = [&](float4 y, int64_t r) {
         float4 o = make_float4(fmaf(y.x - mu.x, sc.x, be.x), fmaf(y.y - mu.y, sc.y, be.y),
                                fmaf(y.z - mu.z, sc.z, be.z), fmaf(y.w - mu.w, sc.w, be.w));
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         *reinterpret_cast<float4*>(out + r * ldo + c4 * 4) = o;
+    };
+    for (int64_t base = (int64_t)blockIdx.x * (8 * APPLY_ROWS); base < M; base += (int64_t)gridDim.x * (8 * APPLY_ROWS)) {
+        if (base + 8 * APPLY_ROWS <= M) {
+            float4 y[APPLY_ROWS];
+#pragma unroll
+            for (int k = 0; k < APPLY_ROWS; ++k) y[k] = load_y(A, lda, B, ldb, base + rg + 8 * k, c4);
+#pragma unroll
+            for (int k = 0; k < APPLY_ROWS; ++k) apply(y[k], base + rg + 8 * k);
+        } else {
+            for (int64_t r = base + rg; r < M; r += 8) apply(load_y(A, lda, B, ldb, r, c4), r);
+        }
     }
 }
 
@@ -100,13 +120,26 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     float4 mu = ldg4(mean_rstd + c4 * 4), rs = ldg4(mean_rstd + 128 + c4 * 4);
     for (int64_t base = (int64_t)blockIdx.x * ROWS_PER_CTA; base < M; base += (int64_t)gridDim.x * ROWS_PER_CTA) {
         float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
-        int64_t end = (base + ROWS_PER_CTA < M) ? base + ROWS_PER_CTA : M;
-        for (int64_t r = base + rg; r < end; r += 8) {
-            float4 gv = gated_grad(g, ldg, out, ldo, relu, r, c4);
-            float4 y = load_y(A, lda, B, ldb, r, c4);
+        auto acc = [&](float4 gv, float4 y) {
             s.x += gv.x; s.y += gv.y; s.z += gv.z; s.w += gv.w;
             q.x = fmaf(gv.x, (y.x - mu.x) * rs.x, q.x); q.y = fmaf(gv.y, (y.y - mu.y) * rs.y, q.y);
             q.z = fmaf(gv.z, (y.z - mu.z) * rs.z, q.z); q.w = fmaf(gv.w, (y.w - mu.w) * rs.w, q.w);
+        };
+        if (base + ROWS_PER_CTA <= M) {
+#pragma unroll
+            for (int h = 0; h < ROWS_PER_WARP; h += APPLY_ROWS) {
+                float4 gv[APPLY_ROWS], y[APPLY_ROWS];
+#pragma unroll
+                for (int k = 0; k < APPLY_ROWS; ++k) {
+                    gv[k] = gated_grad(g, ldg, out, ldo, relu, base + rg + 8 * (h + k), c4);
+                    y[k] = load_y(A, lda, B, ldb, base + rg + 8 * (h + k), c4);
+                }
+#pragma unroll
+                for (int k = 0; k < APPLY_ROWS; ++k) acc(gv[k], y[k]);
+            }
+        } else {
+            for (int64_t r = base + rg; r < M; r += 8)
+                acc(gated_grad(g, ldg, out, ldo, relu, r, c4), load_y(A, lda, B, ldb, r, c4));
         }
         block_reduce_to_double(s, bsums);
         block_reduce_to_double(q, bsums + 128);
@@ -128,17 +161,33 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
         mgy[j] = (float)(bsums[128 + c4 * 4 + j] / count);
     }
     float4 sc = make_float4(ga.x * rs.x, ga.y * rs.y, ga.z * rs.z, ga.w * rs.w);
-    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < M; r += (int64_t)gridDim.x * 8) {
-        float4 gv = gated_grad(g, ldg, out, ldo, relu, r, c4);
-        float4 y = load_y(A, lda, B, ldb, r, c4);
+    const int rg = threadIdx.x >> 5;
+    auto apply = [&](float4 gv, float4 y, float4 p, int64_t r) {
         float4 o;
-        o.x = sc.x * (gv.x - mg[0] - (y.x - mu.x) * rs.x * mgy[0]);
-        o.y = sc.y * (gv.y - mg[1] - (y.y - mu.y) * rs.y * mgy[1]);
-        o.z = sc.z * (gv.z - mg[2] - (y.z - mu.z) * rs.z * mgy[2]);
-        o.w = sc.w * (gv.w - mg[3] - (y.w - mu.w) * rs.w * mgy[3]);
-        float4* dst = reinterpret_cast<float4*>(gy + r * ldgy + c4 * 4);
-        if (accumulate) { float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-        *dst = o;
+        o.x = sc.x * (gv.x - mg[0] - (y.x - mu.x) * rs.x * mgy[0]) + p.x;
+        o.y = sc.y * (gv.y - mg[1] - (y.y - mu.y) * rs.y * mgy[1]) + p.y;
+        o.z = sc.z * (gv.z - mg[2] - (y.z - mu.z) * rs.z * mgy[2]) + p.z;
+        o.w = sc.w * (gv.w - mg[3] - (y.w - mu.w) * rs.w * mgy[3]) + p.w;
+        *reinterpret_cast<float4*>(gy + r * ldgy + c4 * 4) = o;
+    };
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t base = (int64_t)blockIdx.x * (8 * APPLY_ROWS); base < M; base += (int64_t)gridDim.x * (8 * APPLY_ROWS)) {
+        if (base + 8 * APPLY_ROWS <= M) {
+            float4 gv[APPLY_ROWS], y[APPLY_ROWS], p[APPLY_ROWS];
+#pragma unroll
+            for (int k = 0; k < APPLY_ROWS; ++k) {
+                const int64_t r = base + rg + 8 * k;
+                gv[k] = gated_grad(g, ldg, out, ldo, relu, r, c4);
+                y[k] = load_y(A, lda, B, ldb, r, c4);
+                p[k] = accumulate ? *reinterpret_cast<const float4*>(gy + r * ldgy + c4 * 4) : zero;
+            }
+#pragma unroll
+            for (int k = 0; k < APPLY_ROWS; ++k) apply(gv[k], y[k], p[k], base + rg + 8 * k);
+        } else {
+            for (int64_t r = base + rg; r < M; r += 8)
+                apply(gated_grad(g, ldg, out, ldo, relu, r, c4), load_y(A, lda, B, ldb, r, c4),
+                      accumulate ? *reinterpret_cast<const float4*>(gy + r * ldgy + c4 * 4) : zero, r);
+        }
     }
 }
 
@@ -148,12 +197,29 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__
     __shared__ float4 red[8][32];
     const int c4 = threadIdx.x & 31, rg = threadIdx.x >> 5;
     float4 s = make_float4(0, 0, 0, 0);
-    for (int64_t r = (int64_t)blockIdx.x * 8 + rg; r < M; r += (int64_t)gridDim.x * 8) {
-        float4 gv = ldg4(g + r * ldg + c4 * 4), a = ldg4(act + r * lda + c4 * 4);
+    auto apply = [&](float4 gv, float4 a, int64_t r) {
         gv.x = a.x > 0.f ? gv.x : 0.f; gv.y = a.y > 0.f ? gv.y : 0.f;
         gv.z = a.z > 0.f ? gv.z : 0.f; gv.w = a.w > 0.f ? gv.w : 0.f;
         *reinterpret_cast<float4*>(out + r * ldo + c4 * 4) = gv;
         s.x += gv.x; s.y += gv.y; s.z += gv.z; s.w += gv.w;
+    };
+    for (int64_t base = (int64_t)blockIdx.x * ROWS_PER_CTA; base < M; base += (int64_t)gridDim.x * ROWS_PER_CTA) {
+        if (base + ROWS_PER_CTA <= M) {
+#pragma unroll
+            for (int h = 0; h < ROWS_PER_WARP; h += APPLY_ROWS) {
+                float4 gv[APPLY_ROWS], a[APPLY_ROWS];
+#pragma unroll
+                for (int k = 0; k < APPLY_ROWS; ++k) {
+                    const int64_t r = base + rg + 8 * (h + k);
+                    gv[k] = ldg4(g + r * ldg + c4 * 4);
+                    a[k] = ldg4(act + r * lda + c4 * 4);
+                }
+#pragma unroll
+                for (int k = 0; k < APPLY_ROWS; ++k) apply(gv[k], a[k], base + rg + 8 * (h + k));
+            }
+        } else {
+            for (int64_t r = base + rg; r < M; r += 8) apply(ldg4(g + r * ldg + c4 * 4), ldg4(act + r * lda + c4 * 4), r);
+        }
     }
     if (colsum) {
         red[rg][c4] = s;
@@ -207,7 +273,7 @@ extern "C" int mmpde_bn_apply(const float* A, int64_t lda, const float* B, int64
                               const float* gamma, const float* beta, int relu, float* out, int64_t ldo, void* stream) {
     if (M < 0 || lda % 4 || (B && ldb % 4) || ldo % 4) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
-    bn_apply_kernel<<<row_grid(M, 32), 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, M, mean_rstd, gamma, beta, relu, out, ldo);
+    bn_apply_kernel<<<row_grid(M, 8 * APPLY_ROWS), 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, M, mean_rstd, gamma, beta, relu, out, ldo);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }
@@ -228,7 +294,7 @@ extern "C" int mmpde_bn_bwd_apply(const float* g, int64_t ldg, const float* out,
                                   int accumulate, void* stream) {
     if (M < 0 || count <= 0 || ldg % 4 || lda % 4 || (B && ldb % 4) || ldgy % 4 || (relu && (!out || ldo % 4))) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
-    bn_bwd_apply_kernel<<<row_grid(M, 32), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, gamma, bsums, count, gy, ldgy, accumulate);
+    bn_bwd_apply_kernel<<<row_grid(M, 8 * APPLY_ROWS), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, gamma, bsums, count, gy, ldgy, accumulate);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }
@@ -237,7 +303,7 @@ extern "C" int mmpde_relu_bwd(const float* g, int64_t ldg, const float* act, int
                               int64_t ldo, float* colsum, void* stream) {
     if (M < 0 || ldg % 4 || lda % 4 || ldo % 4) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
-    relu_bwd_kernel<<<row_grid(M, 64), 256, 0, (cudaStream_t)stream>>>(g, ldg, act, lda, M, out, ldo, colsum);
+    relu_bwd_kernel<<<row_grid(M, ROWS_PER_CTA), 256, 0, (cudaStream_t)stream>>>(g, ldg, act, lda, M, out, ldo, colsum);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }

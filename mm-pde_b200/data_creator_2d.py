@@ -201,7 +201,9 @@ class GraphCreator_FS_2D(nn.Module):
         u_new = data[:B].reshape(B, self.tw, n).permute(0, 2, 1).reshape(B * n, self.tw)
         y_new = labels[:B].reshape(B, self.tw, n).permute(0, 2, 1).reshape(B * n, self.tw)
         x_new = mesh[:B].reshape(B * n, 2)
-        t_new = t[to_device(torch.as_tensor(list(steps[:B])), device)].repeat_interleave(n)
+        # ``steps`` may already be a device tensor (train_helper_2d.StepGraph: the step indices are a graph input)
+        step_idx = steps[:B] if torch.is_tensor(steps) else to_device(torch.as_tensor(list(steps[:B])), device)
+        t_new = t[step_idx].repeat_interleave(n)
         batch = torch.arange(B, device=device).repeat_interleave(n)
         if static_key is not None:
             static_key = static_key + (B,)

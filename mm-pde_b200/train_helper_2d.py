@@ -2,14 +2,83 @@
 ``training_itp`` :9-62, ``training_loop_branch`` :65-134, ``test_timestep_losses`` :137-200).
 
 The loops are host-side control flow only; everything they call (graph creation, both solvers, the
-interpolation) runs on the sm_100a kernels.  ``after_backward`` is the one addition: the multi-GPU
-driver passes the flat-bucket gradient all-reduce there (mmpde_b200.dist.allreduce_gradients).
+interpolation) runs on the sm_100a kernels.  Two additions, both optional keyword arguments:
+``after_backward`` -- the multi-GPU driver passes the flat-bucket gradient all-reduce there
+(mmpde_b200.dist.GradBucket.allreduce); ``step_graph`` -- a StepGraph that records the device work of one
+step (~800 launches: both solvers, k-NN, interpolation, backward, optimizer) into a CUDA graph and replays
+it, because queueing those launches from Python costs about as long as the GPU needs to run them.
 """
 import random
 
 import torch
 
+from . import _cabi
 from ._h2d import to_device
+
+
+class StepGraph:
+    """CUDA-graph record/replay of the per-batch device work of the step loops.
+
+    The first ``eager_steps`` calls with a given signature (input shapes, train/eval mode, optimizer
+    hyper-parameters) run eagerly -- they fill the static caches (uniform-grid edges, optimizer state, cuDNN
+    plans) -- the next one is captured on static input buffers, later ones copy the step's inputs into those
+    buffers and replay.  Shapes are static by construction (fixed k, fixed batch); a new shape or a changed
+    learning rate simply records a new graph.  Training needs optimizers built with ``capturable=True`` (their
+    step counter must live on the device)."""
+
+    def __init__(self, eager_steps=2, max_graphs=3):
+        self.eager_steps = eager_steps
+        self.max_graphs = max_graphs  # recordings kept per loop (e.g. full batch + the loader's last short batch)
+        self._seen = {}
+        self._graphs = {}            # signature -> (graph, static inputs, static output, launches per replay)
+        self.replays = 0
+
+    @staticmethod
+    def hyper(*optimizers):
+        sig = []
+        for opt in optimizers:
+            if opt is None:
+                continue
+            for g in opt.param_groups:
+                if not g.get("capturable", False):
+                    raise ValueError("StepGraph needs optimizers built with capturable=True")
+                sig.append(tuple((k, v) for k, v in sorted(g.items())
+                                 if isinstance(v, (int, float, bool, str, tuple)) and k != "params"))
+        return tuple(sig)
+
+    def run(self, signature, body, inputs, prepare=None):
+        """body(*device tensors) -> device tensor.  ``inputs``: tensors already on the device.  ``prepare`` runs
+        before every eager call and once before the recording (zero_grad: a replay rewrites the gradients the
+        recording allocated, it never accumulates)."""
+        n = self._seen.get(signature, 0)
+        self._seen[signature] = n + 1
+        if n < self.eager_steps or not inputs[0].is_cuda:
+            if prepare is not None:
+                prepare()
+            return body(*inputs)
+        hit = self._graphs.get(signature)
+        if hit is None:
+            same_loop = [k for k in self._graphs if k[0] == signature[0]]
+            for k in same_loop[:max(0, len(same_loop) - self.max_graphs + 1)]:
+                del self._graphs[k]          # oldest recordings of this loop: free their memory pools
+            static = [torch.empty_like(t) for t in inputs]
+            for s_, t in zip(static, inputs):
+                s_.copy_(t)
+            if prepare is not None:
+                prepare()
+            graph = torch.cuda.CUDAGraph()
+            l0 = _cabi.launches
+            with torch.cuda.graph(graph):
+                out = body(*static)
+            hit = self._graphs[signature] = (graph, static, out, _cabi.launches - l0)
+            _cabi.launches = l0
+        graph, static, out, launches = hit
+        for s_, t in zip(static, inputs):
+            s_.copy_(t, non_blocking=True)
+        graph.replay()
+        _cabi.launches += launches
+        self.replays += 1
+        return out.clone()
 
 
 def _sample_steps(graph_creator, unrolling, batch_size):
@@ -32,6 +101,10 @@ def _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, lab
         return model(uniform)
     moved = graph_creator.create_graph(itp_model, data, labels, steps, device, mesh_model)
     return graph_creator.interpolate_pred(itp_model, model_b(moved), moved, data, device) + model(uniform)
+
+
+def _steps_tensor(steps, device):
+    return to_device(torch.as_tensor(list(steps), dtype=torch.int64), device)
 
 
 def _step_optimizers(optimizer, optimizer2):
@@ -66,19 +139,35 @@ def training_itp(itp_model, mesh_model, unrolling, batch_size, optimizer, optimi
 
 
 def training_loop_branch(model, model_b, itp_model, mesh_model, unrolling, batch_size, optimizer, optimizer2,
-                         loader, graph_creator, criterion, device="cpu", after_backward=None):
+                         loader, graph_creator, criterion, device="cpu", after_backward=None, step_graph=None):
     """One pass over the loader with a random start step per trajectory."""
     history = []
+
+    def gnn_step(data, labels, steps):
+        pred = _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, steps, device)
+        loss = criterion(pred, to_device(labels, device).reshape(-1, 1))
+        loss.backward()
+        if after_backward is not None:
+            after_backward()
+        _step_optimizers(optimizer, optimizer2)
+        return loss.detach()
+
     for (_, u_super) in loader:
-        _zero(optimizer, optimizer2)
         steps = _sample_steps(graph_creator, unrolling, batch_size)
         data, labels = graph_creator.create_data(u_super, steps)
-        if _is_gnn(model):
-            pred = _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, steps, device)
-            loss = criterion(pred, to_device(labels, device).reshape(-1, 1))
-        else:
+        if _is_gnn(model) and step_graph is not None:
             data, labels = to_device(data, device), to_device(labels, device)
-            loss = criterion(model(data), labels.squeeze())
+            sig = ("train", tuple(data.shape), model.training, model_b.training if model_b is not None else None,
+                   mesh_model is None, StepGraph.hyper(optimizer, optimizer2))
+            history.append(step_graph.run(sig, gnn_step, (data, labels, _steps_tensor(steps, device)),
+                                          prepare=lambda: _zero(optimizer, optimizer2)))
+            continue
+        _zero(optimizer, optimizer2)
+        if _is_gnn(model):
+            history.append(gnn_step(data, labels, steps))
+            continue
+        data, labels = to_device(data, device), to_device(labels, device)
+        loss = criterion(model(data), labels.squeeze())
         loss.backward()
         if after_backward is not None:
             after_backward()
@@ -88,9 +177,14 @@ def training_loop_branch(model, model_b, itp_model, mesh_model, unrolling, batch
 
 
 def test_timestep_losses(model, model_b, itp_model, mesh_model, steps, batch_size, loader, graph_creator,
-                         criterion, device="cpu", return_curve=False):
+                         criterion, device="cpu", return_curve=False, step_graph=None):
     """Teacher-forced one-step error for every start step (the reference's "rollout" curve)."""
     curve = []
+
+    def gnn_eval(data, labels, step_idx):
+        pred = _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, step_idx, device)
+        return criterion(pred, to_device(labels, device).reshape(-1, 1))
+
     for step in steps:
         if step != graph_creator.tw and step % graph_creator.tw != 0:
             continue
@@ -98,10 +192,13 @@ def test_timestep_losses(model, model_b, itp_model, mesh_model, steps, batch_siz
         for (_, u_super) in loader:
             data, labels = graph_creator.create_data(u_super, [step] * batch_size)
             with torch.no_grad():
-                if _is_gnn(model):
-                    pred = _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels,
-                                        [step] * batch_size, device)
-                    per_batch.append(criterion(pred, to_device(labels, device).reshape(-1, 1)))
+                if _is_gnn(model) and step_graph is not None:
+                    data, labels = to_device(data, device), to_device(labels, device)
+                    sig = ("eval", tuple(data.shape), model.training, model_b.training if model_b is not None else None,
+                           mesh_model is None)
+                    per_batch.append(step_graph.run(sig, gnn_eval, (data, labels, _steps_tensor([step] * batch_size, device))))
+                elif _is_gnn(model):
+                    per_batch.append(gnn_eval(data, labels, [step] * batch_size))
                 else:
                     data, labels = to_device(data, device), to_device(labels, device)
                     per_batch.append(criterion(model(data), labels.squeeze()))

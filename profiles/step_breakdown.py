@@ -41,6 +41,18 @@ def main():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
+    # host cost of queueing one step (no sync inside) next to the GPU time of the same steps: if the two are close the
+    # step is launch-bound and the kernels' speed no longer shows
+    import time
+    h0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(steps):
+        step()
+    g1.record()
+    host_ms = (time.perf_counter() - h0) * 1e3 / steps
+    torch.cuda.synchronize()
+    print(f"host queueing {host_ms:.2f} ms/step, GPU {g0.elapsed_time(g1) / steps:.2f} ms/step")
     events = []
     real = _cabi.call
 

@@ -141,6 +141,54 @@ def test_training_and_rollout_loops_golden_fixture(golden_dir):
     assert torch.allclose(curve, g["curve"], rtol=1e-2, atol=1e-7)          # "within 1 %" of the reference curve
 
 
+def test_step_graph_replay_equals_eager_loops():
+    """The recorded-and-replayed step (train_helper_2d.StepGraph) must train exactly like the eager loop: same
+    per-step losses over several epochs (different random start steps and inputs every replay), same weights at
+    the end, same rollout error -- and it must really have replayed."""
+    from mmpde_b200.data_creator_2d import GraphCreator_FS_2D
+    from mmpde_b200.gnn_2d import MP_PDE_Solver_2D
+    from mmpde_b200.interpolate import ItpNet
+    from mmpde_b200.mmpde import criterion
+    from mmpde_b200.train_helper_2d import StepGraph, test_timestep_losses, training_loop_branch
+    dev = _dev()
+    pde = _pde12()
+    fields = synth_fields(4, 31, 12, 12, seed=3)
+    loader = [(fields[:2], fields[:2]), (fields[2:], fields[2:])]
+    mover = SmoothMover()
+
+    def run(step_graph):
+        gc = GraphCreator_FS_2D(pde, 35, "knn", 1, 31)
+        model_a = fill_params(MP_PDE_Solver_2D(pde, time_window=1, hidden_layer=2), 11).to(dev)
+        model_b = fill_params(MP_PDE_Solver_2D(pde, time_window=1, hidden_layer=2), 12).to(dev)
+        net = fill_params(ItpNet(12, 12, [128, 64], [128, 64], [1, 4, 16, 4, 1]), 13).to(dev)
+        opt = torch.optim.AdamW([{"params": model_a.parameters()}, {"params": model_b.parameters()},
+                                 {"params": net.parameters()}], lr=1e-3, capturable=True)
+        model_a.train(); model_b.train(); net.train()
+        random.seed(77)
+        losses = torch.cat([training_loop_branch(model_a, model_b, net, mover, [0], 2, opt, None, loader, gc, criterion,
+                                                 dev, step_graph=step_graph) for _ in range(4)])
+        model_a.eval(); model_b.eval(); net.eval()
+        curve = torch.stack([test_timestep_losses(model_a, model_b, net, mover, [s], 2, loader, gc, criterion, dev,
+                                                  step_graph=step_graph) for s in (3, 9, 9, 17, 25)])
+        weights = torch.cat([p.detach().reshape(-1) for m in (model_a, model_b, net) for p in m.parameters()])
+        stats = torch.cat([b.detach().reshape(-1).float() for m in (model_a, model_b) for b in m.buffers()])
+        return losses.cpu(), curve.cpu(), weights.cpu(), stats.cpu()
+
+    eager = run(None)
+    sg = StepGraph(eager_steps=2)
+    graphed = run(sg)
+    assert sg.replays >= 5 + 2, sg.replays                   # 8 training batches - 2 eager, 10 eval batches - 2 eager
+    assert torch.isfinite(graphed[0]).all()
+    assert torch.allclose(graphed[0], eager[0], rtol=2e-3, atol=1e-7), (graphed[0], eager[0])
+    assert torch.allclose(graphed[1], eager[1], rtol=2e-3, atol=1e-7), (graphed[1], eager[1])
+    assert _rel(graphed[2], eager[2]) < 2e-3
+    assert _rel(graphed[3], eager[3]) < 2e-3                 # BatchNorm running statistics + batch counters
+    # an optimizer whose step counter lives on the host cannot be recorded
+    model = MP_PDE_Solver_2D(pde, time_window=1, hidden_layer=1).to(dev)
+    with pytest.raises(ValueError):
+        StepGraph.hyper(torch.optim.AdamW(model.parameters(), lr=1e-3))
+
+
 def test_dmm_golden_fixture(golden_dir):
     from mmpde_b200.data_creator_2d import GraphCreator_FS_2D
     from mmpde_b200.mesh.dmm_model import DMM

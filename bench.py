@@ -190,7 +190,8 @@ def run_ours(args):
     mover = synthetic.AnalyticMover().to(dev)
     params = [p for m in (model, model_b, net) for p in m.parameters()]
     opt = torch.optim.AdamW([{"params": model.parameters()}, {"params": model_b.parameters()},
-                             {"params": net.parameters()}], lr=2e-3, capturable=not args.no_graph)
+                             {"params": net.parameters()}], lr=2e-3, capturable=not args.no_graph,
+                            fused=True if not args.no_graph else None)
     step_graph = None if args.no_graph else StepGraph()
     bucket = mdist.GradBucket(params) if world > 1 else None
     after = bucket.allreduce if bucket is not None else None

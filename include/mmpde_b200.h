@@ -86,7 +86,9 @@ int mmpde_gemm(const float* A, int64_t lda, int a_kmajor, const float* B, int64_
  *   A0 / A1 [M, >=128] fp32 row-major (ld multiple of 4, 16-byte aligned); A1 / W1 NULL for K = 128;
  *   W element (n,k) at W[n*w_ns + k*w_ks]  (nn.Linear weight [out,in]: w_ns = ld, w_ks = 1; its transpose for the
  *   data gradient: w_ns = 1, w_ks = ld);  Aext [M,4] / Wext [128,4] (ld 4) optional extra K columns (the node scalars);
- *   bias [128], R1, R2 (residuals, may alias C) optional;  relu applies before the residuals.
+ *   bias [128], R1, R2 (residuals, may alias C) optional;  relu = 1 applies before the residuals.
+ *   relu = 2 is the ReLU BACKWARD gate fused into a dgrad: C = acc where R1 > 0, else 0 (R1 = the saved forward
+ *   activation, R2 must be NULL).
  * mmpde_node_wgrad:  dW[i][j] += sum_m A[m][i] B[m][j]   (i, j < 128);   dWext[i][f] += sum_m A[m][i] Bext[m][f] (f < 4);
  *                    dbias[i] += sum_m A[m][i].   Any of (B, dW), (Bext, dWext), dbias may be NULL.  Accumulates
  *   atomically: zero the outputs first (or let several calls add up). */
@@ -127,27 +129,33 @@ int mmpde_edge_bwd(const float* PQ, const int32_t* edge_src, const int32_t* edge
 
 /* ---- BatchNorm over all nodes (PyG BatchNorm / nn.BatchNorm1d, gnn_2d.py:51,56,101,104) ---------
  * y = A (+ B if non-NULL), [M,128] with leading dims lda/ldb.
- * stats: sums [2,128] fp64 += (sum_c, sum_c^2)   (zero first; all-reduce across ranks for sync-BN)
- * finalize: from sums and the GLOBAL row count -> mean_rstd [2,128] fp32, and, if running_* given,
+ * stats: sums [MMPDE_BN_REPLICAS][2,128] fp64 += (sum_c, sum_c^2), zero first.  The column sums are spread over
+ *        MMPDE_BN_REPLICAS copies (same-address atomics of all CTAs would serialise in L2); the true sums are the
+ *        sum over the copies.  For sync-BN fold the copies, all-reduce [2,128] and finalize with n_rep = 1.
+ * finalize: from n_rep copies of sums and the GLOBAL row count -> mean_rstd [2,128] fp32, and, if running_* given,
  *           running stats update with momentum and the unbiased variance.
  * apply : out = gamma*(y-mean)*rstd + beta, optional ReLU. */
+#define MMPDE_BN_REPLICAS 16
 int mmpde_bn_stats(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, double* sums, void* stream);
-int mmpde_bn_finalize(const double* sums, double count, float eps, float momentum,
+int mmpde_bn_finalize(const double* sums, int n_rep, double count, float eps, float momentum,
                       float* mean_rstd, float* running_mean, float* running_var, void* stream);
 int mmpde_bn_apply(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
                    const float* mean_rstd, const float* gamma, const float* beta, int relu,
                    float* out, int64_t ldo, void* stream);
 /* backward: g [M,128] (ldg) is dL/d(out).  If relu, `out` (the forward output) gates g first.
- * reduce: bsums [2,128] fp64 += (sum g, sum g*yhat)  -> dbeta, dgamma (all-reduce for sync-BN)
- * apply : gy = gamma*rstd*( g - sum_g/count - yhat*sum_gyhat/count ); written to gy (ldgy);
- *         accumulate!=0 adds into gy instead. */
+ * reduce: bsums [MMPDE_BN_REPLICAS][2,128] fp64 += (sum g, sum g*yhat), spread over copies like `sums`; folded
+ *         they are dbeta, dgamma (all-reduce the folded [2,128] for sync-BN)
+ * apply : takes the FOLDED bsums [2,128]: gy = gamma*rstd*( g - sum_g/count - yhat*sum_gyhat/count ); written to gy (ldgy);
+ *         accumulate!=0 adds into gy instead.  gy_gated (ldgg), if non-NULL, additionally receives gy * (B > 0): with
+ *         y = x + relu_branch (B = the ReLU output of the residual branch) that is dL/d(pre-activation) of the branch,
+ *         so the separate ReLU-backward pass over [M,128] disappears. */
 int mmpde_bn_bwd_reduce(const float* g, int64_t ldg, const float* out, int64_t ldo, int relu,
                         const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
                         const float* mean_rstd, double* bsums, void* stream);
 int mmpde_bn_bwd_apply(const float* g, int64_t ldg, const float* out, int64_t ldo, int relu,
                        const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
                        const float* mean_rstd, const float* gamma, const double* bsums, double count,
-                       float* gy, int64_t ldgy, int accumulate, void* stream);
+                       float* gy, int64_t ldgy, int accumulate, float* gy_gated, int64_t ldgg, void* stream);
 
 /* ---- small elementwise helpers of the node path -------------------------------------------------
  * relu_bwd: out = g * (act > 0); colsum[128] += column sums of out (NULL to skip).  [M,128] */

@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
         const int n = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const uint32_t bias_bits = p.bias ? __float_as_uint(__ldg(p.bias + n)) : 0u;
-        const float floor_ = p.relu ? 0.f : -INFINITY;                     // relu as max(z, floor): no branch in the store loop
-        const int nres = (p.R1 != nullptr) + (p.R1 != nullptr && p.R2 != nullptr);
+        const float floor_ = (p.relu == 1) ? 0.f : -INFINITY;              // relu as max(z, floor): no branch in the store loop
+        const bool gate = p.relu == 2;                                     // ReLU backward: C = acc where R1 > 0, else 0
+        const int nres = gate ? 1 : (p.R1 != nullptr) + (p.R1 != nullptr && p.R2 != nullptr);
         // W -> tensor memory, shared by the two warps of a lane quadrant (32-column groups 2*half, 2*half+1)
         weight_to_tmem(p.W[0], p.w_ns[0], p.w_ks[0], n, tmem_w + lane_addr, tmem_w + 64 + lane_addr, 2 * half, 2 * half + 2);
         if (nseg == 2)
@@ -144,8 +145,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
                         if (nres == 2) r2 += p.ldr2;
                     }
                     tmem_wait_ld(v);
+                    if (gate) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { if (j < rows) *cp = fmaxf(__uint_as_float(v[j]), floor_) + res[j]; cp += p.ldc; }
+                        for (int j = 0; j < 32; ++j) { if (j < rows) *cp = res[j] > 0.f ? __uint_as_float(v[j]) : 0.f; cp += p.ldc; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { if (j < rows) *cp = fmaxf(__uint_as_float(v[j]), floor_) + res[j]; cp += p.ldc; }
+                    }
                 }
             }
             tmem_fill32(d_addr, bias_bits);
@@ -479,6 +485,7 @@ extern "C" int mmpde_node_gemm(const float* A0, int64_t lda0, const float* A1, i
     if (M < 0 || A0 == nullptr || W0 == nullptr || C == nullptr) return MMPDE_EINVAL;
     if ((A1 == nullptr) != (W1 == nullptr) || (Aext == nullptr) != (Wext == nullptr)) return MMPDE_EINVAL;
     if ((lda0 & 3) || (A1 && (lda1 & 3))) return MMPDE_EINVAL;
+    if (relu < 0 || relu > 2 || (relu == 2 && (R1 == nullptr || R2 != nullptr))) return MMPDE_EINVAL;
     if ((reinterpret_cast<uintptr_t>(A0) | reinterpret_cast<uintptr_t>(A1) | reinterpret_cast<uintptr_t>(Aext) |
          reinterpret_cast<uintptr_t>(Wext)) & 15) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;

@@ -2,6 +2,7 @@
 // Replaces PyG BatchNorm / nn.BatchNorm1d (/root/reference/gnn_2d.py:51,56,101,104) and autograd's ReLU masks.
 // Row-major [M,128] fp32; every thread moves one float4 (4 channels), a warp one 512-byte row.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace mmpde {
 
@@ -37,8 +38,12 @@ __device__ __forceinline__ void block_reduce_to_double(float4 v, double* dst) {
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
                                                        int64_t ldb, int64_t M, double* __restrict__ sums) {
     const int c4 = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    // fp32 partials over the CTA's row blocks (a thread sees M / (8 * grid) rows), ONE fp64 reduction per CTA into
+    // replica blockIdx % MMPDE_BN_REPLICAS: same-address atomics serialise in L2 (~30-50 ns each when every CTA
+    // arrives at once), so the time of the tail is the number of CTAs per replica (profiles/r01_norm_bench.txt)
+    sums += (blockIdx.x % MMPDE_BN_REPLICAS) * 256;
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
     for (int64_t base = (int64_t)blockIdx.x * ROWS_PER_CTA; base < M; base += (int64_t)gridDim.x * ROWS_PER_CTA) {
-        float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
         auto acc = [&](float4 y) {
             s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
             q.x = fmaf(y.x, y.x, q.x); q.y = fmaf(y.y, y.y, q.y); q.z = fmaf(y.z, y.z, q.z); q.w = fmaf(y.w, y.w, q.w);
@@ -52,17 +57,19 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
         } else {
             for (int64_t r = base + rg; r < M; r += 8) acc(load_y(A, lda, B, ldb, r, c4));
         }
-        block_reduce_to_double(s, sums);
-        block_reduce_to_double(q, sums + 128);
     }
+    block_reduce_to_double(s, sums);
+    block_reduce_to_double(q, sums + 128);
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, float eps, float momentum,
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int n_rep, double count, float eps, float momentum,
                                    float* __restrict__ mean_rstd, float* __restrict__ rmean, float* __restrict__ rvar) {
     int c = threadIdx.x;
     if (c >= 128) return;
-    double mean = sums[c] / count;
-    double var = sums[128 + c] / count - mean * mean;
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < n_rep; ++r) { s += sums[r * 256 + c]; q += sums[r * 256 + 128 + c]; }
+    double mean = s / count;
+    double var = q / count - mean * mean;
     if (var < 0) var = 0;
     mean_rstd[c] = (float)mean;
     mean_rstd[128 + c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -118,8 +125,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ mean_rstd, double* __restrict__ bsums) {
     const int c4 = threadIdx.x & 31, rg = threadIdx.x >> 5;
     float4 mu = ldg4(mean_rstd + c4 * 4), rs = ldg4(mean_rstd + 128 + c4 * 4);
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    bsums += (blockIdx.x % MMPDE_BN_REPLICAS) * 256;
     for (int64_t base = (int64_t)blockIdx.x * ROWS_PER_CTA; base < M; base += (int64_t)gridDim.x * ROWS_PER_CTA) {
-        float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
         auto acc = [&](float4 gv, float4 y) {
             s.x += gv.x; s.y += gv.y; s.z += gv.z; s.w += gv.w;
             q.x = fmaf(gv.x, (y.x - mu.x) * rs.x, q.x); q.y = fmaf(gv.y, (y.y - mu.y) * rs.y, q.y);
@@ -141,9 +149,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
             for (int64_t r = base + rg; r < M; r += 8)
                 acc(gated_grad(g, ldg, out, ldo, relu, r, c4), load_y(A, lda, B, ldb, r, c4));
         }
-        block_reduce_to_double(s, bsums);
-        block_reduce_to_double(q, bsums + 128);
     }
+    block_reduce_to_double(s, bsums);
+    block_reduce_to_double(q, bsums + 128);
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ out,
@@ -151,7 +159,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ B, int64_t ldb, int64_t M,
                                                            const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                                            const double* __restrict__ bsums, double count,
-                                                           float* __restrict__ gy, int64_t ldgy, int accumulate) {
+                                                           float* __restrict__ gy, int64_t ldgy, int accumulate,
+                                                           float* __restrict__ gyg, int64_t ldgg) {
     const int c4 = threadIdx.x & 31;
     float4 mu = ldg4(mean_rstd + c4 * 4), rs = ldg4(mean_rstd + 128 + c4 * 4), ga = ldg4(gamma + c4 * 4);
     float mg[4], mgy[4];
@@ -169,6 +178,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
         o.z = sc.z * (gv.z - mg[2] - (y.z - mu.z) * rs.z * mgy[2]) + p.z;
         o.w = sc.w * (gv.w - mg[3] - (y.w - mu.w) * rs.w * mgy[3]) + p.w;
         *reinterpret_cast<float4*>(gy + r * ldgy + c4 * 4) = o;
+        if (gyg) {                                     // B is re-read from L1/L2: it was loaded for y a moment ago
+            const float4 b = ldg4(B + r * ldb + c4 * 4);
+            *reinterpret_cast<float4*>(gyg + r * ldgg + c4 * 4) =
+                make_float4(b.x > 0.f ? o.x : 0.f, b.y > 0.f ? o.y : 0.f, b.z > 0.f ? o.z : 0.f, b.w > 0.f ? o.w : 0.f);
+        }
     };
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t base = (int64_t)blockIdx.x * (8 * APPLY_ROWS); base < M; base += (int64_t)gridDim.x * (8 * APPLY_ROWS)) {
@@ -244,6 +258,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A
     atomicAdd(colsum + c, s);
 }
 
+// grid of the column-reducing kernels: a few CTAs per SM, each looping over its row blocks
+inline int reduce_grid(int64_t M) {
+    static const int per_sm = [] { const char* e = getenv("MMPDE_REDUCE_CTAS_PER_SM"); return e ? atoi(e) : 2; }();
+    int64_t g = (M + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+    return (int)imin64(g > 0 ? g : 1, (int64_t)sm_count() * per_sm);
+}
+
 inline int row_grid(int64_t M, int rows_per_cta) {
     int64_t g = (M + rows_per_cta - 1) / rows_per_cta;
     return (int)imin64(g > 0 ? g : 1, (int64_t)sm_count() * 8);
@@ -256,15 +277,15 @@ using namespace mmpde;
 extern "C" int mmpde_bn_stats(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, double* sums, void* stream) {
     if (M < 0 || lda % 4 || (B && ldb % 4)) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
-    bn_stats_kernel<<<row_grid(M, ROWS_PER_CTA), 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, M, sums);
+    bn_stats_kernel<<<reduce_grid(M), 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, M, sums);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }
 
-extern "C" int mmpde_bn_finalize(const double* sums, double count, float eps, float momentum, float* mean_rstd,
+extern "C" int mmpde_bn_finalize(const double* sums, int n_rep, double count, float eps, float momentum, float* mean_rstd,
                                  float* running_mean, float* running_var, void* stream) {
-    if (count <= 0 || ((running_mean == nullptr) != (running_var == nullptr))) return MMPDE_EINVAL;
-    bn_finalize_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(sums, count, eps, momentum, mean_rstd, running_mean, running_var);
+    if (count <= 0 || n_rep < 1 || ((running_mean == nullptr) != (running_var == nullptr))) return MMPDE_EINVAL;
+    bn_finalize_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(sums, n_rep, count, eps, momentum, mean_rstd, running_mean, running_var);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }
@@ -283,7 +304,7 @@ extern "C" int mmpde_bn_bwd_reduce(const float* g, int64_t ldg, const float* out
                                    double* bsums, void* stream) {
     if (M < 0 || ldg % 4 || lda % 4 || (B && ldb % 4) || (relu && (!out || ldo % 4))) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
-    bn_bwd_reduce_kernel<<<row_grid(M, ROWS_PER_CTA), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, bsums);
+    bn_bwd_reduce_kernel<<<reduce_grid(M), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, bsums);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }
@@ -291,10 +312,11 @@ extern "C" int mmpde_bn_bwd_reduce(const float* g, int64_t ldg, const float* out
 extern "C" int mmpde_bn_bwd_apply(const float* g, int64_t ldg, const float* out, int64_t ldo, int relu, const float* A,
                                   int64_t lda, const float* B, int64_t ldb, int64_t M, const float* mean_rstd,
                                   const float* gamma, const double* bsums, double count, float* gy, int64_t ldgy,
-                                  int accumulate, void* stream) {
+                                  int accumulate, float* gy_gated, int64_t ldgg, void* stream) {
     if (M < 0 || count <= 0 || ldg % 4 || lda % 4 || (B && ldb % 4) || ldgy % 4 || (relu && (!out || ldo % 4))) return MMPDE_EINVAL;
+    if (gy_gated && (!B || ldgg % 4)) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
-    bn_bwd_apply_kernel<<<row_grid(M, 8 * APPLY_ROWS), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, gamma, bsums, count, gy, ldgy, accumulate);
+    bn_bwd_apply_kernel<<<row_grid(M, 8 * APPLY_ROWS), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, gamma, bsums, count, gy, ldgy, accumulate, gy_gated, ldgg);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }
@@ -303,7 +325,7 @@ extern "C" int mmpde_relu_bwd(const float* g, int64_t ldg, const float* act, int
                               int64_t ldo, float* colsum, void* stream) {
     if (M < 0 || ldg % 4 || lda % 4 || ldo % 4) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
-    relu_bwd_kernel<<<row_grid(M, ROWS_PER_CTA), 256, 0, (cudaStream_t)stream>>>(g, ldg, act, lda, M, out, ldo, colsum);
+    relu_bwd_kernel<<<reduce_grid(M) * 2, 256, 0, (cudaStream_t)stream>>>(g, ldg, act, lda, M, out, ldo, colsum);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }

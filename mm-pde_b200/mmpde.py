@@ -23,7 +23,7 @@ from .data_creator_2d import GraphCreator_FS_2D
 from .gnn_2d import MP_PDE_Solver_2D
 from .interpolate import ItpNet
 from .mesh.dmm_model import DMM
-from .train_helper_2d import test_timestep_losses, training_itp, training_loop_branch
+from .train_helper_2d import StepGraph, test_timestep_losses, training_itp, training_loop_branch
 
 
 def check_directory():
@@ -36,7 +36,7 @@ def criterion(x, y):
 
 
 def train(args, pde, epoch, model, model_b, itp_model, mesh_model, optimizer, optimizer2, loader, graph_creator,
-          criterion, device="cpu", after_backward=None):
+          criterion, device="cpu", after_backward=None, step_graph=None):
     print(f"Starting epoch {epoch}...")
     model.train()
     if model_b is not None:
@@ -57,14 +57,16 @@ def train(args, pde, epoch, model, model_b, itp_model, mesh_model, optimizer, op
     train_losses = []
     for i in range(passes):
         losses = training_loop_branch(model, model_b, itp_model, mesh_model, unrolling, args.batch_size, optimizer,
-                                      optimizer2, loader, graph_creator, criterion, device, after_backward)
+                                      optimizer2, loader, graph_creator, criterion, device, after_backward,
+                                      step_graph=step_graph)
         if i % args.print_interval == 0:
             print(f"Training Loss (progress: {i / graph_creator.t_res:.2f}): {torch.mean(losses)}")
         train_losses.append(torch.mean(losses))
     return train_losses, itp_losses
 
 
-def test(args, pde, model, model_b, itp_model, mesh_model, loader, graph_creator, criterion, device="cpu"):
+def test(args, pde, model, model_b, itp_model, mesh_model, loader, graph_creator, criterion, device="cpu",
+         step_graph=None):
     model.eval()
     if model_b is not None:
         model_b.eval()
@@ -73,7 +75,7 @@ def test(args, pde, model, model_b, itp_model, mesh_model, loader, graph_creator
     steps = list(range(graph_creator.tw, graph_creator.t_res - graph_creator.tw + 1))
     return test_timestep_losses(model=model, model_b=model_b, itp_model=itp_model, mesh_model=mesh_model, steps=steps,
                                 batch_size=args.batch_size, loader=loader, graph_creator=graph_creator,
-                                criterion=criterion, device=device)
+                                criterion=criterion, device=device, step_graph=step_graph)
 
 
 def _load_data(args, device):
@@ -167,7 +169,12 @@ def main(args):
     groups = [{"params": model.parameters()}]
     if mesh_model is not None:
         groups += [{"params": model_b.parameters()}, {"params": itp_model.parameters()}]
-    optimizer = optim.AdamW(groups, lr=args.lr)
+    # step_graph: record the step once, replay it afterwards (train_helper_2d.StepGraph).  The optimizer then keeps
+    # its step counters on the device (capturable) and updates all tensors in one fused multi-tensor kernel instead of
+    # ~800 single-tensor launches per step.
+    use_graph = bool(getattr(args, "step_graph", True)) and str(device).startswith("cuda")
+    step_graph = StepGraph() if use_graph else None
+    optimizer = optim.AdamW(groups, lr=args.lr, capturable=use_graph, fused=use_graph or None)
     scheduler = optim.lr_scheduler.MultiStepLR(optimizer, milestones=[args.unrolling, 30, 50, 70], gamma=args.lr_decay)
     after_backward = None
     if world > 1:
@@ -178,12 +185,12 @@ def main(args):
     for epoch in range(args.num_epochs):
         print(f"Epoch {epoch}")
         tl, il = train(args, pde, epoch, model, model_b, itp_model, mesh_model, optimizer, None, train_loader,
-                       graph_creator, criterion, device=device, after_backward=after_backward)
+                       graph_creator, criterion, device=device, after_backward=after_backward, step_graph=step_graph)
         train_losses.append(tl)
         itp_losses.append(il)
         print("Testing:")
         test_losses.append(test(args, pde, model, model_b, itp_model, mesh_model, test_loader, graph_creator,
-                                criterion, device=device))
+                                criterion, device=device, step_graph=step_graph))
         if rank == 0:
             state = {"model_state_dict": model.state_dict(), "args": args, "train_losses": train_losses,
                      "itp_losses": itp_losses, "test_timestep_losses": test_losses}
@@ -225,6 +232,7 @@ def build_parser():
     # additions
     p.add_argument("--synthetic", type=eval, default=True, help="seeded synthetic data / analytic mesh mover")
     p.add_argument("--n_traj", type=int, default=20, help="synthetic trajectories")
+    p.add_argument("--step_graph", type=eval, default=True, help="replay the recorded step as a CUDA graph")
     p.add_argument("--max_passes", type=int, default=None, help="bound the passes per epoch (default t_res)")
     return p
 

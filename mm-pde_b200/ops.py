@@ -16,6 +16,7 @@ ITP_NPARAM = 18270
 DEC_NPARAM = 525
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+BN_REPLICAS = 16            # include/mmpde_b200.h: MMPDE_BN_REPLICAS
 
 
 # ------------------------------------------------------------------------------------------------
@@ -202,13 +203,15 @@ def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st):
     dev = gamma.device
     state.rows = sum(it[4] for it in items)
     if training:
-        sums = torch.zeros(2 * H, dtype=torch.float64, device=dev)
+        sums = torch.zeros(BN_REPLICAS, 2 * H, dtype=torch.float64, device=dev)
         for A, lda, B, ldb, M, _, _ in items:
             _cabi.call("mmpde_bn_stats", A, lda, B, ldb, M, _ptr(sums), st)
-        COMM.allreduce_(sums)
         state.count = COMM.global_rows(state.rows)
+        n_rep = BN_REPLICAS
+        if state.count != float(state.rows):          # other ranks / parts hold rows too: fold, then all-reduce [2,128]
+            sums, n_rep = COMM.allreduce_(sums.sum(0)), 1
         state.mean_rstd = torch.empty(2 * H, dtype=torch.float32, device=dev)
-        _cabi.call("mmpde_bn_finalize", _ptr(sums), state.count, BN_EPS, BN_MOMENTUM, _ptr(state.mean_rstd),
+        _cabi.call("mmpde_bn_finalize", _ptr(sums), n_rep, state.count, BN_EPS, BN_MOMENTUM, _ptr(state.mean_rstd),
                    _ptr(rmean), _ptr(rvar), st)
         if nbt is not None:
             nbt += 1
@@ -221,19 +224,22 @@ def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st):
 
 
 def _bn_backward(items, relu, state, gamma, st):
-    """items: one (g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy) per local part.  Returns this rank's
+    """items: one (g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy[, gy_gated, ldgg]) per local part (gy_gated =
+    gy * (B > 0), the ReLU backward of a residual branch B fused into this pass).  Returns this rank's
     (dgamma, dbeta); writes dL/dy into gy.  With several ranks the two column sums are all-reduced for the
     normalisation term (sync-BN), while the parameter grads stay per-rank sums (the gradient all-reduce adds
     them up afterwards)."""
-    local = torch.zeros(2 * H, dtype=torch.float64, device=gamma.device)
-    for g, ldg, out, ldo, A, lda, B, ldb, M, _, _ in items:
-        _cabi.call("mmpde_bn_bwd_reduce", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(local), st)
+    spread = torch.zeros(BN_REPLICAS, 2 * H, dtype=torch.float64, device=gamma.device)
+    for g, ldg, out, ldo, A, lda, B, ldb, M, *_ in items:
+        _cabi.call("mmpde_bn_bwd_reduce", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(spread), st)
+    local = spread.sum(0)
     glob = local
     if COMM.global_rows(state.rows) != float(state.rows):
         glob = COMM.allreduce_(local.clone())
-    for g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy in items:
+    for g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy, *gated in items:
+        gyg, ldgg = gated if gated else (None, 0)
         _cabi.call("mmpde_bn_bwd_apply", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(gamma),
-                   _ptr(glob), state.count, gy, ldgy, 0, st)
+                   _ptr(glob), state.count, gy, ldgy, 0, gyg, ldgg, st)
     return local[H:].to(torch.float32), local[:H].to(torch.float32)
 
 
@@ -321,9 +327,11 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st):
     w1c, w1cq = _edge_feature_weights(W1)
     wu = torch.cat((w1c[:, 0], w1cq[:, 0])).contiguous()          # dL/du = [dP' | dQ'] . wu
     # BatchNorm backward: y = h + r4
+    # (its second output g_z4 = g_y * (r4 > 0) is the ReLU backward of update_net_2, fused into the same pass)
     g_ys = [torch.empty(part.n_own, H, **f32) for part in parts]
-    items = [(_ptr(g_h), H, None, 0, _ptr(Xl), 2 * H, _ptr(sv[3]), H, part.n_own, _ptr(g_y), H)
-             for part, Xl, sv, g_h, g_y in zip(parts, Xs, saved, g_hs, g_ys)]
+    g_z4s = [torch.empty(part.n_own, H, **f32) for part in parts]
+    items = [(_ptr(g_h), H, None, 0, _ptr(Xl), 2 * H, _ptr(sv[3]), H, part.n_own, _ptr(g_y), H, _ptr(g_z4), H)
+             for part, Xl, sv, g_h, g_y, g_z4 in zip(parts, Xs, saved, g_hs, g_ys, g_z4s)]
     dgam, dbet = _bn_backward(items, 0, bn, gam, st)
     # all accumulators of this layer in ONE zeroed buffer (every block is a multiple of 4 floats: 16-byte aligned rows)
     sizes = [H * 260, H, H * H, H, H * 257, H, H * H, H, 2 * H * 4, H * 4]
@@ -332,23 +340,21 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st):
     dW1, dW2, dW3, dW4 = dW1.view(H, 260), dW2.view(H, H), dW3.view(H, 257), dW4.view(H, H)
     dW1c, dW3x = dW1c.view(2, H, 4), dW3x.view(H, 4)
     dPQs = []
-    for part, Xl, sv, g_y in zip(parts, Xs, saved, g_ys):
+    for part, Xl, sv, g_y, g_z4 in zip(parts, Xs, saved, g_ys, g_z4s):
         PQ, mask2, h3, r4 = sv
         N, E, edges = part.n_own, part.edges.n_edges, part.edges
         x, n4 = _ptr(Xl), _ptr(part.node4)
-        # node MLP backward (update_net_2, update_net_1)
-        g_z4 = torch.empty(N, H, **f32)
-        _cabi.call("mmpde_relu_bwd", _ptr(g_y), H, _ptr(r4), H, N, _ptr(g_z4), H, _ptr(db4), st)
-        node_wgrad(_ptr(g_z4), H, N, B=_ptr(h3), ldb=H, dW=_ptr(dW4), ldw=H, st=st)
-        g_h3 = torch.empty(N, H, **f32)
-        node_gemm(_ptr(g_z4), H, _ptr(W4), 1, H, _ptr(g_h3), H, N, st=st)
-        g_z3 = g_z4                                               # reuse
-        _cabi.call("mmpde_relu_bwd", _ptr(g_h3), H, _ptr(h3), H, N, _ptr(g_z3), H, _ptr(db3), st)
-        node_wgrad(_ptr(g_z3), H, N, B=x, ldb=2 * H, dW=_ptr(dW3), ldw=257, Bext=n4, dWext=_ptr(dW3x), st=st)
+        # node MLP backward (update_net_2, update_net_1).  No stand-alone ReLU-backward passes: g_z4 came out of the
+        # BatchNorm backward, g_z3 = (g_z4 W4) * (h3 > 0) is gated in the epilogue of its dgrad, and the bias
+        # gradients are the ones-column of the weight-gradient contractions.
+        node_wgrad(_ptr(g_z4), H, N, B=_ptr(h3), ldb=H, dW=_ptr(dW4), ldw=H, dbias=_ptr(db4), st=st)
+        g_z3 = torch.empty(N, H, **f32)
+        node_gemm(_ptr(g_z4), H, _ptr(W4), 1, H, _ptr(g_z3), H, N, relu=2, R1=_ptr(h3), ldr1=H, st=st)
+        node_wgrad(_ptr(g_z3), H, N, B=x, ldb=2 * H, dW=_ptr(dW3), ldw=257, Bext=n4, dWext=_ptr(dW3x), dbias=_ptr(db3), st=st)
         node_wgrad(_ptr(g_z3), H, N, B=_ptr(Xl, H), ldb=2 * H, dW=_ptr(dW3, H), ldw=257, st=st)
         # dL/dh_in so far: g_y (residual) + g_z3 W3[:, :128];  dL/d(mean message) = g_z3 W3[:, 128:256]
         node_gemm(_ptr(g_z3), H, _ptr(W3), 1, 257, _ptr(g_y), H, N, R1=_ptr(g_y), ldr1=H, st=st)
-        g_agg = g_h3                                              # reuse
+        g_agg = g_z4                                              # reuse
         node_gemm(_ptr(g_z3), H, _ptr(W3, H), 1, 257, _ptr(g_agg), H, N, st=st)
         # message passing backward
         dPQ = torch.zeros(part.n_src, 2 * H, **f32)

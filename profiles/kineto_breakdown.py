@@ -1,0 +1,77 @@
+"""GPU-time breakdown of the bench step as it really runs (replayed from the CUDA graph): kernel durations from CUPTI
+activity records through torch.profiler, summed per kernel name.  Unlike step_breakdown.py (events around eager calls)
+this carries no per-launch event overhead and sees the torch glue kernels too.
+usage: python profiles/kineto_breakdown.py [steps] [--eager]"""
+import collections
+import os
+import random
+import sys
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from mmpde_b200 import synthetic  # noqa: E402
+from mmpde_b200.PDEs import burgers  # noqa: E402
+from mmpde_b200.data_creator_2d import GraphCreator_FS_2D  # noqa: E402
+from mmpde_b200.gnn_2d import MP_PDE_Solver_2D  # noqa: E402
+from mmpde_b200.interpolate import ItpNet  # noqa: E402
+from mmpde_b200.mmpde import criterion  # noqa: E402
+from mmpde_b200.train_helper_2d import StepGraph, training_loop_branch  # noqa: E402
+
+
+def main():
+    argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    steps = int(argv[0]) if argv else 5
+    eager = "--eager" in sys.argv
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    random.seed(0)
+    pde = burgers()
+    pde.grid_size = pde.movingmesh_grid_size = pde.ori_grid_size = bench.RES
+    gc = GraphCreator_FS_2D(pde, bench.K_NEIGH, "knn", 1, bench.RES[0])
+    model, model_b = MP_PDE_Solver_2D(pde).to(dev), MP_PDE_Solver_2D(pde).to(dev)
+    net = ItpNet(bench.RES[1], bench.RES[2], [128, 64], [128, 64], [1, 4, 16, 4, 1]).to(dev)
+    mover = synthetic.AnalyticMover().to(dev)
+    opt = torch.optim.AdamW([{"params": model.parameters()}, {"params": model_b.parameters()}, {"params": net.parameters()}],
+                            lr=2e-3, capturable=True, fused=True)
+    fields = synthetic.burgers_fields(bench.BATCH, *bench.RES, seed=100).to(dev)
+    sg = None if eager else StepGraph()
+
+    def step():
+        training_loop_branch(model, model_b, net, mover, [0], bench.BATCH, opt, None, [(fields, fields)], gc, criterion, dev,
+                             step_graph=sg)
+
+    for _ in range(4):
+        step()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        t0.record()
+        for _ in range(steps):
+            step()
+        t1.record()
+        torch.cuda.synchronize()
+    wall = t0.elapsed_time(t1) / steps
+    tot, cnt = collections.Counter(), collections.Counter()
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            name = ev.name
+            for cut in ("<", "("):
+                name = name.split(cut)[0]
+            tot[name] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+            cnt[name] += 1
+    busy = sum(tot.values()) / steps / 1e3
+    print(f"{'eager' if eager else 'graph replay'}: step {wall:.2f} ms under the profiler; kernels+copies busy {busy:.2f} ms/step")
+    for name, v in tot.most_common(45):
+        print(f"  {v / steps / 1e3:8.3f} ms {100 * v / steps / 1e3 / wall:5.1f}%  x{cnt[name] / steps:6.1f}  avg {v / cnt[name]:8.1f} us  {name[:90]}")
+
+
+    if "--ops" in sys.argv:          # eager only: which aten ops the small torch kernels come from
+        print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=60))
+
+
+if __name__ == "__main__":
+    main()

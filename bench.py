@@ -354,9 +354,17 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    if step_graph is not None:
+        step_graph.release()             # recorded graphs hold captured NCCL work: drop them before the communicator
     if world > 1:
-        mdist.shutdown()
+        # The line is out.  Leave without the interpreter / NCCL teardown: with collectives captured in CUDA graphs
+        # destroy_process_group() was seen to block after the run had finished (profiles/r01_bench_2gpu_v12.json).
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -13,6 +13,12 @@ _lib = None
 
 _p, _i, _l, _f, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 
+class WgradTask(ctypes.Structure):
+    """include/mmpde_b200.h: mmpde_wgrad_task."""
+    _fields_ = [("A", _p), ("lda", _l), ("B", _p), ("ldb", _l), ("Bext", _p), ("dW", _p), ("ldw", _l),
+                ("dWext", _p), ("ldwext", _l), ("dbias", _p), ("M", _l)]
+
+
 # name -> argtypes, exactly mirroring include/mmpde_b200.h
 SIGNATURES = {
     "mmpde_abi_version": [],
@@ -24,6 +30,7 @@ SIGNATURES = {
     "mmpde_gemm": [_p, _l, _i, _p, _l, _i, _p, _l, _l, _i, _l, _p, _p, _l, _p, _i, _i, _i, _p],
     "mmpde_node_gemm": [_p, _l, _p, _l, _p, _l, _l, _p, _l, _l, _p, _p, _p, _i, _p, _l, _p, _l, _p, _l, _l, _p],
     "mmpde_node_wgrad": [_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _l, _p],
+    "mmpde_node_wgrad_grouped": [_p, _i, _p],
     "mmpde_edge_fwd": [_p, _p, _p, _p, _l, _p, _p, _p, _l, _p, _p],
     "mmpde_edge_bwd": [_p, _p, _p, _p, _l, _p, _p, _p, _l, _p, _p, _p, _p],
     "mmpde_bn_stats": [_p, _l, _p, _l, _l, _p, _p],

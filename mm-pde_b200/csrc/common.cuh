@@ -26,6 +26,7 @@ inline int sm_count() {
 }
 
 inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+inline int64_t imax64(int64_t a, int64_t b) { return a > b ? a : b; }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 

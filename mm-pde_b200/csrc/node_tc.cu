@@ -280,13 +280,27 @@ struct NodeWgradArgs {
     const float* A; int64_t lda; const float* B; int64_t ldb; const float* Bext; int want_bias;
     float* dW; int64_t ldw; float* dWext; int64_t ldwext; float* dbias; int64_t M;
 };
+// Several independent contractions in ONE launch: the CTAs are divided between the tasks (task k owns CTAs
+// cta_begin[k] .. cta_begin[k+1]-1), so an output tile is summed over grid/n_tasks partials instead of grid: the
+// atomic flush of the 64 KB partial tiles -- half the time of a single-task launch at 36 k rows -- shrinks with it.
+constexpr int W_MAX_TASKS = 8;
+struct NodeWgradGroup {
+    NodeWgradArgs t[W_MAX_TASKS];
+    int cta_begin[W_MAX_TASKS + 1];
+};
 struct WgradSmem {
     static constexpr uint32_t STAGE = 4 * W_IMG + 2 * W_XIMG;             // A hi lo | B hi lo | ext hi lo  = 68 KB
     static constexpr uint32_t BAR = 2 * STAGE;
     static constexpr uint32_t TOTAL = BAR + 128;
 };
 
-__global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradArgs p) {
+__global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(const __grid_constant__ NodeWgradGroup grp) {
+    int task = 0;
+#pragma unroll
+    for (int k = 1; k < W_MAX_TASKS; ++k) task += ((int)blockIdx.x >= grp.cta_begin[k]) ? 1 : 0;
+    const NodeWgradArgs p = grp.t[task];
+    const uint32_t bx = blockIdx.x - (uint32_t)grp.cta_begin[task];                 // this CTA within its task
+    const uint32_t gx = (uint32_t)(grp.cta_begin[task + 1] - grp.cta_begin[task]);  // CTAs of the task
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(sm);
@@ -314,7 +328,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_d = tmem_base, tmem_dx = tmem_base + 128;
     const int64_t n_tiles = (p.M + WT - 1) / WT;
-    const int64_t my_tiles = ((int64_t)blockIdx.x < n_tiles) ? (int64_t)(((uint32_t)(n_tiles - blockIdx.x) + gridDim.x - 1) / gridDim.x) : 0;
+    const int64_t my_tiles = ((int64_t)bx < n_tiles) ? (int64_t)(((uint32_t)(n_tiles - bx) + gx - 1) / gx) : 0;
 
     if (warp < W_EPI_WARPS) {
         // ------------------------------------------------------------------ epilogue (once): lane = row i of dW
@@ -331,13 +345,13 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
                 // the CTAs do not all hammer the same addresses at the same moment (same-address atomics serialise in L2)
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
-                    const int chunk = (cc + (int)blockIdx.x) & 3;
+                    const int chunk = (cc + (int)bx) & 3;
                     uint32_t v[32];
                     tmem_ld32_async(tmem_d + lane_addr + chunk * 32, v);
                     tmem_wait_ld(v);
                     float* row = p.dW + (int64_t)i_row * p.ldw + chunk * 32;
                     if (vec) {
-                        if ((blockIdx.x >> 2) & 1) {
+                        if ((bx >> 2) & 1) {
 #pragma unroll
                             for (int m = 7; m >= 0; --m)
                                 red_add_v4(row + 4 * m, make_float4(__uint_as_float(v[4 * m]), __uint_as_float(v[4 * m + 1]),
@@ -374,7 +388,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
         // per tile: 8 rows of A and 8 rows of B per warp; the NEXT tile's 16 rows are already in flight while this
         // tile is converted (two register sets swapped by copy: the loads were issued a whole tile ago)
         auto load16 = [&](float4 (&ra)[8], float4 (&rb)[8], int64_t ti) {
-            const int64_t t = (int64_t)blockIdx.x + ti * gridDim.x;
+            const int64_t t = (int64_t)bx + ti * gx;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int64_t m = t * WT + row0 + k;
@@ -389,7 +403,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(NodeWgradAr
         load16(ra, rb, 0);
         for (int64_t ti = 0; ti < my_tiles; ++ti) {
             const int sb = (int)(ti & 1);
-            const int64_t t = (int64_t)blockIdx.x + ti * gridDim.x;
+            const int64_t t = (int64_t)bx + ti * gx;
             if (w == 0) TL(0, (int)ti, 0);
             load16(na, nb, ti + 1);
             mbar_wait(s_empty + 8 * sb, ((uint32_t)(ti >> 1) & 1u) ^ 1u);
@@ -507,12 +521,19 @@ extern "C" int mmpde_node_gemm(const float* A0, int64_t lda0, const float* A1, i
     return MMPDE_OK;
 }
 
-extern "C" int mmpde_node_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, const float* Bext,
-                                float* dW, int64_t ldw, float* dWext, int64_t ldwext, float* dbias, int64_t M, void* stream) {
-    if (M < 0 || A == nullptr || (lda & 3) || (B && (ldb & 3))) return MMPDE_EINVAL;
-    if ((B == nullptr) != (dW == nullptr) || (Bext == nullptr) != (dWext == nullptr)) return MMPDE_EINVAL;
-    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(Bext)) & 15) return MMPDE_EINVAL;
-    if (M == 0 || (B == nullptr && Bext == nullptr && dbias == nullptr)) return MMPDE_OK;
+static int check_wgrad_task(const mmpde_wgrad_task& t) {
+    if (t.M < 0) return MMPDE_EINVAL;
+    if (t.M == 0) return MMPDE_OK;                                         // empty part: nothing to read, pointers may be NULL
+    if (t.A == nullptr || (t.lda & 3) || (t.B && (t.ldb & 3))) return MMPDE_EINVAL;
+    if ((t.B == nullptr) != (t.dW == nullptr) || (t.Bext == nullptr) != (t.dWext == nullptr)) return MMPDE_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(t.A) | reinterpret_cast<uintptr_t>(t.B) | reinterpret_cast<uintptr_t>(t.Bext)) & 15) return MMPDE_EINVAL;
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_node_wgrad_grouped(const mmpde_wgrad_task* tasks, int n_tasks, void* stream) {
+    if (n_tasks < 0 || (n_tasks > 0 && tasks == nullptr)) return MMPDE_EINVAL;
+    for (int k = 0; k < n_tasks; ++k)
+        if (int rc = check_wgrad_task(tasks[k])) return rc;
     constexpr size_t smem = WgradSmem::TOTAL + 1024;
     static bool attr = false;
     if (!attr) {
@@ -520,11 +541,48 @@ extern "C" int mmpde_node_wgrad(const float* A, int64_t lda, const float* B, int
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    NodeWgradArgs p;
-    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.Bext = Bext; p.want_bias = dbias != nullptr;
-    p.dW = dW; p.ldw = ldw; p.dWext = dWext; p.ldwext = ldwext; p.dbias = dbias; p.M = M;
-    const int64_t n_tiles = (M + WT - 1) / WT;
-    node_wgrad_tc_kernel<<<(int)imin64(n_tiles, sm_count()), W_THREADS, smem, (cudaStream_t)stream>>>(p);
-    MMPDE_CHECK_LAUNCH();
+    int k0 = 0;
+    while (k0 < n_tasks) {
+        // next launch: up to W_MAX_TASKS tasks that have work
+        NodeWgradGroup g;
+        int64_t tiles[W_MAX_TASKS], total = 0;
+        int n = 0;
+        for (; k0 < n_tasks && n < W_MAX_TASKS; ++k0) {
+            const mmpde_wgrad_task& t = tasks[k0];
+            if (t.M == 0 || (t.B == nullptr && t.Bext == nullptr && t.dbias == nullptr)) continue;
+            NodeWgradArgs& a = g.t[n];
+            a.A = t.A; a.lda = t.lda; a.B = t.B; a.ldb = t.ldb; a.Bext = t.Bext; a.want_bias = t.dbias != nullptr;
+            a.dW = t.dW; a.ldw = t.ldw; a.dWext = t.dWext; a.ldwext = t.ldwext; a.dbias = t.dbias; a.M = t.M;
+            tiles[n] = (t.M + WT - 1) / WT;
+            total += tiles[n];
+            ++n;
+        }
+        if (n == 0) break;
+        // CTAs per task in proportion to its K tiles (every task at least one, none more than it has tiles)
+        const int64_t grid = imin64(total, imax64((int64_t)sm_count(), (int64_t)n));
+        int64_t given = 0;
+        g.cta_begin[0] = 0;
+        for (int k = 0; k < n; ++k) {
+            int64_t share = (k == n - 1) ? grid - given : (tiles[k] * grid + total / 2) / total;
+            const int64_t left_for_rest = (int64_t)(n - 1 - k);
+            if (share < 1) share = 1;
+            if (share > tiles[k]) share = tiles[k];
+            if (given + share > grid - left_for_rest) share = grid - left_for_rest - given;
+            if (share < 1) share = 1;
+            given += share;
+            g.cta_begin[k + 1] = (int)given;
+        }
+        for (int k = n; k < W_MAX_TASKS; ++k) { g.t[k] = g.t[0]; g.cta_begin[k + 1] = 0x7fffffff; }
+        node_wgrad_tc_kernel<<<(int)given, W_THREADS, smem, (cudaStream_t)stream>>>(g);
+        MMPDE_CHECK_LAUNCH();
+    }
     return MMPDE_OK;
+}
+
+extern "C" int mmpde_node_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, const float* Bext,
+                                float* dW, int64_t ldw, float* dWext, int64_t ldwext, float* dbias, int64_t M, void* stream) {
+    mmpde_wgrad_task t;
+    t.A = A; t.lda = lda; t.B = B; t.ldb = ldb; t.Bext = Bext; t.dW = dW; t.ldw = ldw; t.dWext = dWext; t.ldwext = ldwext;
+    t.dbias = dbias; t.M = M;
+    return mmpde_node_wgrad_grouped(&t, 1, stream);
 }

@@ -200,6 +200,8 @@ def main(args):
             torch.save(state, save_path)
             print(f"Saved model at {save_path}\n")
         scheduler.step()
+    if step_graph is not None:
+        step_graph.release()
     return train_losses, test_losses
 
 

@@ -185,6 +185,18 @@ def node_wgrad(A, lda, M, B=None, ldb=0, dW=None, ldw=0, Bext=None, dWext=None, 
                st if st is not None else _stream())
 
 
+def wgrad_task(A, lda, M, B=None, ldb=0, dW=None, ldw=0, Bext=None, dWext=None, dbias=None):
+    """One entry of a grouped weight-gradient launch (same arguments as node_wgrad)."""
+    return _cabi.WgradTask(A, lda, B, ldb, Bext, dW, ldw, dWext, 4 if dWext is not None else 0, dbias, M)
+
+
+def node_wgrad_grouped(tasks, st=None):
+    """All weight gradients of one layer in ONE launch (mmpde_node_wgrad_grouped)."""
+    import ctypes
+    arr = (_cabi.WgradTask * len(tasks))(*tasks)
+    _cabi.call("mmpde_node_wgrad_grouped", ctypes.addressof(arr), len(tasks), st if st is not None else _stream())
+
+
 def _split_for(rows):
     """split-K factor of the weight-gradient contractions (K = node count): ~one 256-row chunk per CTA so the
     1-2 output tiles still spread over the whole chip."""
@@ -339,7 +351,7 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st):
     dW1, db1, dW2, db2, dW3, db3, dW4, db4, dW1c, dW3x = torch.split(flat, sizes)
     dW1, dW2, dW3, dW4 = dW1.view(H, 260), dW2.view(H, H), dW3.view(H, 257), dW4.view(H, H)
     dW1c, dW3x = dW1c.view(2, H, 4), dW3x.view(H, 4)
-    dPQs = []
+    dPQs, wtasks, keep = [], [], []
     for part, Xl, sv, g_y, g_z4 in zip(parts, Xs, saved, g_ys, g_z4s):
         PQ, mask2, h3, r4 = sv
         N, E, edges = part.n_own, part.edges.n_edges, part.edges
@@ -347,15 +359,18 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st):
         # node MLP backward (update_net_2, update_net_1).  No stand-alone ReLU-backward passes: g_z4 came out of the
         # BatchNorm backward, g_z3 = (g_z4 W4) * (h3 > 0) is gated in the epilogue of its dgrad, and the bias
         # gradients are the ones-column of the weight-gradient contractions.
-        node_wgrad(_ptr(g_z4), H, N, B=_ptr(h3), ldb=H, dW=_ptr(dW4), ldw=H, dbias=_ptr(db4), st=st)
+        # The five weight-gradient contractions of the layer are only queued here: they run as ONE grouped launch
+        # at the end (nothing but the optimizer waits for them), so their operands stay alive until then.
+        wtasks.append(wgrad_task(_ptr(g_z4), H, N, B=_ptr(h3), ldb=H, dW=_ptr(dW4), ldw=H, dbias=_ptr(db4)))
         g_z3 = torch.empty(N, H, **f32)
         node_gemm(_ptr(g_z4), H, _ptr(W4), 1, H, _ptr(g_z3), H, N, relu=2, R1=_ptr(h3), ldr1=H, st=st)
-        node_wgrad(_ptr(g_z3), H, N, B=x, ldb=2 * H, dW=_ptr(dW3), ldw=257, Bext=n4, dWext=_ptr(dW3x), dbias=_ptr(db3), st=st)
-        node_wgrad(_ptr(g_z3), H, N, B=_ptr(Xl, H), ldb=2 * H, dW=_ptr(dW3, H), ldw=257, st=st)
+        wtasks.append(wgrad_task(_ptr(g_z3), H, N, B=x, ldb=2 * H, dW=_ptr(dW3), ldw=257, Bext=n4, dWext=_ptr(dW3x), dbias=_ptr(db3)))
+        wtasks.append(wgrad_task(_ptr(g_z3), H, N, B=_ptr(Xl, H), ldb=2 * H, dW=_ptr(dW3, H), ldw=257))
         # dL/dh_in so far: g_y (residual) + g_z3 W3[:, :128];  dL/d(mean message) = g_z3 W3[:, 128:256]
         node_gemm(_ptr(g_z3), H, _ptr(W3), 1, 257, _ptr(g_y), H, N, R1=_ptr(g_y), ldr1=H, st=st)
-        g_agg = g_z4                                              # reuse
+        g_agg = torch.empty(N, H, **f32)
         node_gemm(_ptr(g_z3), H, _ptr(W3, H), 1, 257, _ptr(g_agg), H, N, st=st)
+        keep.append((g_z3, g_z4))
         # message passing backward
         dPQ = torch.zeros(part.n_src, 2 * H, **f32)
         _cabi.call("mmpde_edge_bwd", _ptr(PQ), _ptr(edges.src), _ptr(edges.dst), _ptr(edges.inv_deg), E,
@@ -367,14 +382,16 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st):
         N = part.n_own
         x, n4 = _ptr(Xl), _ptr(part.node4)
         # message_net_1 parameters from dP', dQ':  dW1a = dP'^T h, dW1b = dQ'^T h, dW1c = dP'^T node4 - dQ'^T node4[:, :3]
-        node_wgrad(_ptr(dPQ), 2 * H, N, B=x, ldb=2 * H, dW=_ptr(dW1), ldw=260, Bext=n4, dWext=_ptr(dW1c), dbias=_ptr(db1), st=st)
-        node_wgrad(_ptr(dPQ, H), 2 * H, N, B=x, ldb=2 * H, dW=_ptr(dW1, H), ldw=260, Bext=n4, dWext=_ptr(dW1c, 4 * H), st=st)
+        wtasks.append(wgrad_task(_ptr(dPQ), 2 * H, N, B=x, ldb=2 * H, dW=_ptr(dW1), ldw=260, Bext=n4, dWext=_ptr(dW1c), dbias=_ptr(db1)))
+        wtasks.append(wgrad_task(_ptr(dPQ, H), 2 * H, N, B=x, ldb=2 * H, dW=_ptr(dW1, H), ldw=260, Bext=n4, dWext=_ptr(dW1c, 4 * H)))
         g_node4 = g_node4s[idx] if g_node4s is not None else None
         if g_node4 is not None:      # dL/du (column 0 of node4): dP' W1c[:,0] - dQ' W1c[:,0], one pass over dPQ
             _cabi.call("mmpde_rows_dot", _ptr(dPQ), 2 * H, 2 * H, _ptr(wu), _ptr(g_node4), 4, N, 1, st)
         # dL/dh_in += dP' W1a + dQ' W1b
         node_gemm(_ptr(dPQ), 2 * H, _ptr(W1), 1, 260, _ptr(g_y), H, N, A1=_ptr(dPQ, H), lda1=2 * H, W1=_ptr(W1, H), w1_ns=1,
                   w1_ks=260, R1=_ptr(g_y), ldr1=H, st=st)
+    node_wgrad_grouped(wtasks, st)
+    del keep
     dW3[:, 2 * H] = dW3x[:, 3]
     dW1[:, 2 * H:2 * H + 4] = dW1c[0]
     dW1[:, 2 * H:2 * H + 3] -= dW1c[1, :, :3]

@@ -46,6 +46,17 @@ class StepGraph:
                                  if isinstance(v, (int, float, bool, str, tuple)) and k != "params"))
         return tuple(sig)
 
+    def release(self):
+        """Drop every recording (their memory pools and, with several ranks, the NCCL work captured in them).  Call
+        it before the process group is destroyed: a graph that still holds collectives of a dead communicator can
+        block the teardown."""
+        import gc
+        self._graphs.clear()
+        self._seen.clear()
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def run(self, signature, body, inputs, prepare=None):
         """body(*device tensors) -> device tensor.  ``inputs``: tensors already on the device.  ``prepare`` runs
         before every eager call and once before the recording (zero_grad: a replay rewrites the gradients the

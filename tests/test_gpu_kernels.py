@@ -486,6 +486,45 @@ def test_node_wgrad_tensor_core(M):
     assert _rel(db_only, Ad[:, :128].sum(0)) < 2e-5
 
 
+@pytest.mark.parametrize("sizes", [(36864,) * 5, (1, 64, 65, 1000, 7, 300, 129, 5000, 20000, 3), (0, 500, 0)])
+def test_node_wgrad_grouped(sizes):
+    """mmpde_node_wgrad_grouped: several contractions in one launch (CTAs divided between the tasks; more than 8 tasks
+    take several launches; empty tasks are skipped) -- each against its fp64 definition, two tasks adding into the same
+    output on purpose."""
+    from mmpde_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(len(sizes))
+    tasks, checks, keep = [], [], []
+    shared_dW = torch.zeros(128, 128, device=dev)
+    shared_ref = torch.zeros(128, 128, dtype=torch.float64)
+    for k, M in enumerate(sizes):
+        A = torch.randn(max(M, 1), 128, generator=g).to(dev)[:M]
+        B = torch.randn(max(M, 1), 256, generator=g).to(dev)[:M]
+        n4 = torch.randn(max(M, 1), 4, generator=g).to(dev)[:M]
+        keep += [A, B, n4]
+        Ad, Bd = A.double().cpu(), B.double().cpu()
+        if k % 3 == 0:          # full: dW + extension + bias
+            dW, dWe, db = torch.zeros(128, 260, device=dev), torch.zeros(128, 4, device=dev), torch.zeros(128, device=dev)
+            tasks.append(ops.wgrad_task(ops._ptr(A), 128, M, B=ops._ptr(B, 128), ldb=256, dW=ops._ptr(dW, 4), ldw=260,
+                                        Bext=ops._ptr(n4), dWext=ops._ptr(dWe), dbias=ops._ptr(db)))
+            checks += [(dW[:, 4:132], Ad.t() @ Bd[:, 128:]), (dWe, Ad.t() @ n4.double().cpu()), (db, Ad.sum(0))]
+        elif k % 3 == 1:        # plain, summed into an output another task also writes
+            tasks.append(ops.wgrad_task(ops._ptr(A), 128, M, B=ops._ptr(B), ldb=256, dW=ops._ptr(shared_dW), ldw=128))
+            shared_ref += Ad.t() @ Bd[:, :128]
+        else:                   # bias only
+            db = torch.zeros(128, device=dev)
+            tasks.append(ops.wgrad_task(ops._ptr(A), 128, M, dbias=ops._ptr(db)))
+            checks.append((db, Ad.sum(0)))
+    ops.node_wgrad_grouped(tasks)
+    torch.cuda.synchronize()
+    checks.append((shared_dW, shared_ref))
+    for got, want in checks:
+        if float(want.abs().max()) == 0.0:
+            assert float(got.abs().max()) == 0.0
+        else:
+            assert _rel(got, want) < 2e-5
+
+
 # ------------------------------------------------------------------------------------------- halo / row helpers
 def test_rows_gather_scatter_add_and_dot():
     """Pack / unpack kernels of the halo exchange and the N = 1 row contraction, against plain torch."""

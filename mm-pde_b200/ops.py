@@ -208,14 +208,15 @@ class _BNState:
     __slots__ = ("mean_rstd", "count", "rows")
 
 
-def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st):
+def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st, sums=None):
     """BatchNorm over the rows of ALL local parts (and all ranks, through COMM).
     items: one (A, lda, B, ldb, M, out, ldo) per local part, y = A (+ B)."""
     state = _BNState()
     dev = gamma.device
     state.rows = sum(it[4] for it in items)
     if training:
-        sums = torch.zeros(BN_REPLICAS, 2 * H, dtype=torch.float64, device=dev)
+        if sums is None:                               # else: a zeroed [BN_REPLICAS, 256] slice handed in by the solver
+            sums = torch.zeros(BN_REPLICAS, 2 * H, dtype=torch.float64, device=dev)
         for A, lda, B, ldb, M, _, _ in items:
             _cabi.call("mmpde_bn_stats", A, lda, B, ldb, M, _ptr(sums), st)
         state.count = COMM.global_rows(state.rows)
@@ -235,13 +236,14 @@ def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st):
     return state
 
 
-def _bn_backward(items, relu, state, gamma, st):
+def _bn_backward(items, relu, state, gamma, st, spread=None):
     """items: one (g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy[, gy_gated, ldgg]) per local part (gy_gated =
     gy * (B > 0), the ReLU backward of a residual branch B fused into this pass).  Returns this rank's
-    (dgamma, dbeta); writes dL/dy into gy.  With several ranks the two column sums are all-reduced for the
+    (dgamma, dbeta) as fp64 views; writes dL/dy into gy.  With several ranks the two column sums are all-reduced for the
     normalisation term (sync-BN), while the parameter grads stay per-rank sums (the gradient all-reduce adds
     them up afterwards)."""
-    spread = torch.zeros(BN_REPLICAS, 2 * H, dtype=torch.float64, device=gamma.device)
+    if spread is None:
+        spread = torch.zeros(BN_REPLICAS, 2 * H, dtype=torch.float64, device=gamma.device)
     for g, ldg, out, ldo, A, lda, B, ldb, M, *_ in items:
         _cabi.call("mmpde_bn_bwd_reduce", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(spread), st)
     local = spread.sum(0)
@@ -252,7 +254,7 @@ def _bn_backward(items, relu, state, gamma, st):
         gyg, ldgg = gated if gated else (None, 0)
         _cabi.call("mmpde_bn_bwd_apply", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(gamma),
                    _ptr(glob), state.count, gy, ldgy, 0, gyg, ldgg, st)
-    return local[H:].to(torch.float32), local[:H].to(torch.float32)
+    return local[H:], local[:H]                        # fp64 views; callers convert all of a solver's at once
 
 
 # ------------------------------------------------------------------------------------------------
@@ -280,23 +282,30 @@ def mask_words(n_edges):
     return max((n_edges + 127) // 128, 1) * 512
 
 
-def _edge_feature_weights(W1):
-    """W1c = W1[:, 256:260] acting on e_ij = (u_i-u_j, px_i-px_j, py_i-py_j, v_i) (gnn_2d.py:61), as the two
-    per-node matrices of the split: target side W1c, source side -W1c with the v column removed."""
-    w1c = W1[:, 2 * H:2 * H + 4].contiguous()
+def _layer_prep(W1s, W3s):
+    """Derived weights of SEVERAL layers in a handful of launches (instead of ~9 tiny ones per layer and pass).
+    W1c = W1[:, 256:260] acts on e_ij = (u_i-u_j, px_i-px_j, py_i-py_j, v_i) (gnn_2d.py:61); split per node it is W1c on
+    the target side and -W1c with the v column removed on the source side.  Returns per-layer tuples
+    (w1c [128,4], w1cq [128,4], w3x [128,4], wu [256])."""
+    L = len(W1s)
+    w1c = torch.stack([W[:, 2 * H:2 * H + 4] for W in W1s])              # [L,128,4]
     w1cq = -w1c
-    w1cq[:, 3] = 0.0
-    return w1c, w1cq
+    w1cq[:, :, 3] = 0.0
+    w3x = torch.zeros(L, H, 4, dtype=torch.float32, device=w1c.device)   # update_net_1 sees [x, agg, v]: v = node4[:, 3]
+    w3x[:, :, 3] = torch.stack([W[:, 2 * H] for W in W3s])
+    wu = torch.cat((w1c[:, :, 0], w1cq[:, :, 0]), dim=1)                 # [L,256]: dL/du = [dP' | dQ'] . wu
+    return [(w1c[l], w1cq[l], w3x[l], wu[l]) for l in range(L)]
 
 
-def _layer_forward(parts, Xs, lp, bnbuf, training, nxts, exch, st):
+LAYER_GRAD_SIZES = [H * 260, H, H * H, H, H * 257, H, H * H, H, 2 * H * 4, H * 4]    # dW1 db1 dW2 db2 dW3 db3 dW4 db4 dW1c dW3x
+
+
+def _layer_forward(parts, Xs, lp, bnbuf, training, nxts, exch, st, prep=None, bn_sums=None):
     """One GNN_Layer_FS_2D (gnn_2d.py:53-69) on every part.  Xs[p] [n_own,256]: cols 0..127 hold the layer input
     h, cols 128..255 must be ZERO on entry and receive the mean message.  Output BN(h + update) -> nxts[p] =
     (pointer, leading dimension)."""
     W1, b1, W2, b2, W3, b3, W4, b4, gam, bet = lp
-    w1c, w1cq = _edge_feature_weights(W1)
-    w3x = torch.zeros(H, 4, dtype=torch.float32, device=W3.device)       # update_net_1 sees [x, agg, v]: v = node4[:, 3]
-    w3x[:, 3] = W3[:, 2 * H]
+    w1c, w1cq, w3x, _ = prep if prep is not None else _layer_prep([W1], [W3])[0]
     # message_net_1 split per node (gnn_2d.py:61): z1_ij = P'[i] + Q'[j] with
     #   P' = h W1a^T + b1 + node4 W1c^T,   Q' = h W1b^T - node4[:, :3] W1c[:, :3]^T
     PQs = []
@@ -326,29 +335,29 @@ def _layer_forward(parts, Xs, lp, bnbuf, training, nxts, exch, st):
         node_gemm(_ptr(h3), H, _ptr(W4), H, 1, _ptr(r4), H, N, bias=_ptr(b4), relu=1, st=st)
         saved.append((PQ, mask2, h3, r4))
         bn_items.append((x, 2 * H, _ptr(r4), H, N, nxt[0], nxt[1]))
-    bn = _bn_forward(bn_items, gam, bet, 0, training, *bnbuf, st)
+    bn = _bn_forward(bn_items, gam, bet, 0, training, *bnbuf, st, sums=bn_sums)
     return saved, bn
 
 
-def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st):
+def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st, prep=None, flat=None, bn_spread=None):
     """Backward of _layer_forward.  g_hs[p] [n_own,128] = dL/d(output).  Returns ([dL/dh_in per part], 10 param
     grads summed over the local parts); adds the layer's dL/du into g_node4s[p][:,0] when given."""
     W1, b1, W2, b2, W3, b3, W4, b4, gam, bet = lp
     dev = W1.device
     f32 = dict(dtype=torch.float32, device=dev)
-    w1c, w1cq = _edge_feature_weights(W1)
-    wu = torch.cat((w1c[:, 0], w1cq[:, 0])).contiguous()          # dL/du = [dP' | dQ'] . wu
+    wu = (prep if prep is not None else _layer_prep([W1], [W3])[0])[3]
     # BatchNorm backward: y = h + r4
     # (its second output g_z4 = g_y * (r4 > 0) is the ReLU backward of update_net_2, fused into the same pass)
     g_ys = [torch.empty(part.n_own, H, **f32) for part in parts]
     g_z4s = [torch.empty(part.n_own, H, **f32) for part in parts]
     items = [(_ptr(g_h), H, None, 0, _ptr(Xl), 2 * H, _ptr(sv[3]), H, part.n_own, _ptr(g_y), H, _ptr(g_z4), H)
              for part, Xl, sv, g_h, g_y, g_z4 in zip(parts, Xs, saved, g_hs, g_ys, g_z4s)]
-    dgam, dbet = _bn_backward(items, 0, bn, gam, st)
+    dgam, dbet = _bn_backward(items, 0, bn, gam, st, spread=bn_spread)
     # all accumulators of this layer in ONE zeroed buffer (every block is a multiple of 4 floats: 16-byte aligned rows)
-    sizes = [H * 260, H, H * H, H, H * 257, H, H * H, H, 2 * H * 4, H * 4]
-    flat = torch.zeros(sum(sizes), **f32)
-    dW1, db1, dW2, db2, dW3, db3, dW4, db4, dW1c, dW3x = torch.split(flat, sizes)
+    fold_here = flat is None
+    if fold_here:
+        flat = torch.zeros(sum(LAYER_GRAD_SIZES), **f32)
+    dW1, db1, dW2, db2, dW3, db3, dW4, db4, dW1c, dW3x = torch.split(flat, LAYER_GRAD_SIZES)
     dW1, dW2, dW3, dW4 = dW1.view(H, 260), dW2.view(H, H), dW3.view(H, 257), dW4.view(H, H)
     dW1c, dW3x = dW1c.view(2, H, 4), dW3x.view(H, 4)
     dPQs, wtasks, keep = [], [], []
@@ -392,10 +401,27 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st):
                   w1_ks=260, R1=_ptr(g_y), ldr1=H, st=st)
     node_wgrad_grouped(wtasks, st)
     del keep
-    dW3[:, 2 * H] = dW3x[:, 3]
-    dW1[:, 2 * H:2 * H + 4] = dW1c[0]
-    dW1[:, 2 * H:2 * H + 3] -= dW1c[1, :, :3]
+    if fold_here:
+        _fold_extension_grads(flat.view(1, -1))
+        dgam, dbet = dgam.to(torch.float32), dbet.to(torch.float32)
     return g_ys, [dW1, db1, dW2, db2, dW3, db3, dW4, db4, dgam, dbet]
+
+
+def _fold_extension_grads(flat2d):
+    """flat2d [L, sum(LAYER_GRAD_SIZES)]: move the node-scalar extension gradients of every layer into the weight
+    columns they belong to -- dW3[:, 256] = dW3x[:, 3];  dW1[:, 256:260] = dW1c[P'] - dW1c[Q'] (no v column on the
+    source side) -- with one launch per term for all layers."""
+    L = flat2d.shape[0]
+    off = [0]
+    for n in LAYER_GRAD_SIZES:
+        off.append(off[-1] + n)
+    dW1 = flat2d[:, off[0]:off[1]].view(L, H, 260)
+    dW3 = flat2d[:, off[4]:off[5]].view(L, H, 257)
+    dW1c = flat2d[:, off[8]:off[9]].view(L, 2, H, 4)
+    dW3x = flat2d[:, off[9]:off[10]].view(L, H, 4)
+    dW3[:, :, 2 * H] = dW3x[:, :, 3]
+    dW1[:, :, 2 * H:2 * H + 4] = dW1c[:, 0]
+    dW1[:, :, 2 * H:2 * H + 3] -= dW1c[:, 1, :, :3]
 
 
 class LayerFn(torch.autograd.Function):
@@ -430,6 +456,8 @@ def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st):
     We1, be1, g1, bt1, We2, be2, g2, bt2 = params[:N_ENC]
     dec = params[N_ENC + N_LAYER * L]
     # ---- encoder: Linear(4,128) BN ReLU Linear(128,128) BN        (gnn_2d.py:99-106,130-131)
+    preps = _layer_prep([params[N_ENC + N_LAYER * l] for l in range(L)], [params[N_ENC + N_LAYER * l + 4] for l in range(L)]) if L else []
+    bn_sums = torch.zeros(2 + L, BN_REPLICAS, 2 * H, dtype=torch.float64, device=dev) if training else [None] * (2 + L)
     e1s, e1ns, e2s = [], [], []
     for part in parts:
         e1 = torch.empty(part.n_own, H, **f32)
@@ -437,7 +465,7 @@ def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st):
         e1s.append(e1)
         e1ns.append(torch.empty(part.n_own, H, **f32))
     bn1 = _bn_forward([(_ptr(e1), H, None, 0, part.n_own, _ptr(e1n), H) for part, e1, e1n in zip(parts, e1s, e1ns)],
-                      g1, bt1, 1, training, *bn_buffers[0], st)
+                      g1, bt1, 1, training, *bn_buffers[0], st, sums=bn_sums[0])
     for part, e1n in zip(parts, e1ns):
         e2 = torch.empty(part.n_own, H, **f32)
         node_gemm(_ptr(e1n), H, _ptr(We2), H, 1, _ptr(e2), H, part.n_own, bias=_ptr(be2), st=st)
@@ -450,18 +478,19 @@ def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st):
         return [(_ptr(t), 2 * H) for t in X[l]] if l < L else [(_ptr(t), H) for t in hL]
 
     bn2 = _bn_forward([(_ptr(e2), H, None, 0, part.n_own, d[0], d[1]) for part, e2, d in zip(parts, e2s, dest(0))],
-                      g2, bt2, 0, training, *bn_buffers[1], st)
+                      g2, bt2, 0, training, *bn_buffers[1], st, sums=bn_sums[1])
     layers = []
     for l in range(L):
         lp = params[N_ENC + N_LAYER * l: N_ENC + N_LAYER * (l + 1)]
-        layers.append(_layer_forward(parts, X[l], lp, bn_buffers[2 + l], training, dest(l + 1), exch, st))
+        layers.append(_layer_forward(parts, X[l], lp, bn_buffers[2 + l], training, dest(l + 1), exch, st,
+                                     prep=preps[l], bn_sums=bn_sums[2 + l]))
     outs = []
     for part, h in zip(parts, hL):
         out = torch.empty(part.n_own, **f32)
         _cabi.call("mmpde_decoder_fwd", _ptr(h), H, part.n_own, _ptr(dec), float(scale), _ptr(out), st)
         outs.append(out)
     return outs, dict(parts=parts, L=L, scale=float(scale), params=params, enc=(e1s, e1ns, e2s, bn1, bn2), X=X, hL=hL,
-                      layers=layers, exch=exch)
+                      layers=layers, exch=exch, preps=preps)
 
 
 def _solver_backward(sv, g_outs, need_u, st):
@@ -482,15 +511,20 @@ def _solver_backward(sv, g_outs, need_u, st):
                    _ptr(g_h), H, _ptr(g_dec), st)
         g_hs.append(g_h)
     grads[N_ENC + N_LAYER * L] = g_dec
+    flat_all = torch.zeros(max(L, 1), sum(LAYER_GRAD_SIZES), **f32)   # every layer's gradient accumulators, zeroed at once
+    spread_all = torch.zeros(2 + L, BN_REPLICAS, 2 * H, dtype=torch.float64, device=dev)
     for l in reversed(range(L)):
         base = N_ENC + N_LAYER * l
         saved, bn = sv["layers"][l]
-        g_hs, lg = _layer_backward(parts, sv["X"][l], params[base:base + N_LAYER], saved, bn, g_hs, g_node4s, exch, st)
+        g_hs, lg = _layer_backward(parts, sv["X"][l], params[base:base + N_LAYER], saved, bn, g_hs, g_node4s, exch, st,
+                                   prep=sv["preps"][l], flat=flat_all[l], bn_spread=spread_all[2 + l])
         grads[base:base + N_LAYER] = lg
+    if L:
+        _fold_extension_grads(flat_all)
     # ---- encoder backward
     g_e2s = [torch.empty(part.n_own, H, **f32) for part in parts]
     dg2, db2_ = _bn_backward([(_ptr(g_h), H, None, 0, _ptr(e2), H, None, 0, part.n_own, _ptr(g_e2), H)
-                              for part, g_h, e2, g_e2 in zip(parts, g_hs, e2s, g_e2s)], 0, bn2, g2, st)
+                              for part, g_h, e2, g_e2 in zip(parts, g_hs, e2s, g_e2s)], 0, bn2, g2, st, spread=spread_all[1])
     dWe2, dbe2 = torch.zeros(H, H, **f32), torch.zeros(H, **f32)
     dWe1, dbe1 = torch.zeros(H, 4, **f32), torch.zeros(H, **f32)
     g_e1ns = []
@@ -501,12 +535,18 @@ def _solver_backward(sv, g_outs, need_u, st):
         g_e1ns.append(g_e1n)
     g_e1s = g_e2s                                                     # reuse
     dg1, db1_ = _bn_backward([(_ptr(g_e1n), H, _ptr(e1n), H, _ptr(e1), H, None, 0, part.n_own, _ptr(g_e1), H)
-                              for part, g_e1n, e1n, e1, g_e1 in zip(parts, g_e1ns, e1ns, e1s, g_e1s)], 1, bn1, g1, st)
+                              for part, g_e1n, e1n, e1, g_e1 in zip(parts, g_e1ns, e1ns, e1s, g_e1s)], 1, bn1, g1, st,
+                             spread=spread_all[0])
     for idx, (part, g_e1) in enumerate(zip(parts, g_e1s)):
         node_wgrad(_ptr(g_e1), H, part.n_own, Bext=_ptr(part.node4), dWext=_ptr(dWe1), dbias=_ptr(dbe1), st=st)
         if need_u:      # only the u column: positions/time feed the frozen mesh mover only
             gemm(_ptr(g_e1), H, 1, _ptr(We1), 4, 0, _ptr(g_node4s[idx]), 4, part.n_own, 1, H, acc=1, st=st)
     grads[:N_ENC] = [dWe1, dbe1, dg1, db1_, dWe2, dbe2, dg2, db2_]
+    # BatchNorm parameter gradients come back as fp64 views: convert all of them with two launches
+    bn_idx = [2, 3, 6, 7] + [N_ENC + N_LAYER * l + k for l in range(L) for k in (8, 9)]
+    bn32 = torch.stack([grads[k] for k in bn_idx]).to(torch.float32)
+    for row, k in enumerate(bn_idx):
+        grads[k] = bn32[row]
     return g_node4s, grads
 
 

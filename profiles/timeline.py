@@ -85,6 +85,13 @@ def main():
                             (3, 0, "epi sees acc"), (3, 2, "epi released acc")):
             print(f"      {label:20s} at +{(t[r, lo:hi, j] - ref).mean():8.0f} clk after builder w0 started the tile")
         print("    first 6 tiles, MMA 'full ok' stamps:", [int(x - t0) for x in t[2, :6, 0]])
+        if kname == "bwd":          # raw stamps of a few steady-state tiles, relative to builder w0's start of tile 8
+            base = t[0, 8, 0]
+            for i in range(8, 15):
+                row = f"    tile {i:2d}:"
+                for r in range(4):
+                    row += f" | {roles[r]}: " + " ".join(f"{int(t[r, i, j] - base):6d}" if t[r, i, j] > 0 else "     -" for j in range(len(slots[r])))
+                print(row)
 
 
 if __name__ == "__main__":

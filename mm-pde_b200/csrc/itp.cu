@@ -178,10 +178,12 @@ __global__ void __launch_bounds__(IW * 32, 1) itp_bwd_kernel(const float2* __res
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dWc[i][j] = 0.f;
-    const int ta_o = (tid >> 4) * 8, ta_k = (tid & 15) * 4;      // dWa tile: 8 outputs x 4 inputs (k padded to 64)
-    const int tb_o = (tid >> 4) * 4, tb_k = (tid & 15) * 8;      // dWb tile: 4 outputs x 8 inputs
-    const int tc_o = (tid >> 4) * 2, tc_k = (tid & 15) * 4;      // dWc tile: 2 outputs x 4 inputs (outputs padded to 32)
-
+    // Tiles: outputs og*8.. (dWa) / og*4.. (dWb) / og*2.. (dWc) x inputs kl + 16 j.  The inputs of neighbouring lanes are
+    // NEIGHBOURING feature rows (8 floats apart) and every row is read as float4 over 4 queries: a quarter-warp covers
+    // 256 contiguous bytes (2-way bank conflict).  The first version gave each lane 4 / 8 consecutive rows and read
+    // scalars: all 16 lanes on one bank, and this phase was ~60 % of the kernel.
+    const int og = tid >> 4, kl = tid & 15;
+    const int ta_o = og * 8, tb_o = og * 4, tc_o = og * 2;
     const int64_t stride = (int64_t)gridDim.x * IW * QW;
     const int64_t n_iter = (nq + stride - 1) / stride;           // uniform trip count: block-wide barriers inside
     for (int64_t it = 0; it < n_iter; ++it) {
@@ -251,39 +253,51 @@ __global__ void __launch_bounds__(IW * 32, 1) itp_bwd_kernel(const float2* __res
         for (int w = 0; w < IW; ++w) {
             const ItpWarp& aw = wa[w];
             const ItpWarpGrad& gw = wg[w];
-#pragma unroll 2
-            for (int qq = 0; qq < QW; ++qq) {
-                float ga[8], xa[4];
+#pragma unroll 1
+            for (int h = 0; h < QW; h += 4) {                              // 4 queries at a time
+                auto ld4 = [&](const float* base, int row) { return *reinterpret_cast<const float4*>(base + row * QW + h); };
+                {
+                    float4 ga[8], xa[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) ga[i] = gw.gza[(ta_o + i) * QW + qq];
+                    for (int i = 0; i < 8; ++i) ga[i] = ld4(gw.gza, ta_o + i);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) xa[j] = aw.p[(ta_k + j) * QW + qq];
+                    for (int j = 0; j < 4; ++j) xa[j] = ld4(aw.p, kl + 16 * j);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dWa[i][j] = fmaf(ga[i], xa[j], dWa[i][j]);
-                float gb[4], xb[8];
+                        for (int j = 0; j < 4; ++j)
+                            dWa[i][j] = fmaf(ga[i].x, xa[j].x, fmaf(ga[i].y, xa[j].y, fmaf(ga[i].z, xa[j].z, fmaf(ga[i].w, xa[j].w, dWa[i][j]))));
+                }
+                {
+                    float4 gb[4], xb[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) gb[i] = gw.gzb[(tb_o + i) * QW + qq];
+                    for (int i = 0; i < 4; ++i) gb[i] = ld4(gw.gzb, tb_o + i);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) xb[j] = aw.ha[(tb_k + j) * QW + qq];
+                    for (int j = 0; j < 8; ++j) xb[j] = ld4(aw.ha, kl + 16 * j);
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dWb[i][j] = fmaf(gb[i], xb[j], dWb[i][j]);
-                float gc[2], xc[4];
+                        for (int j = 0; j < 8; ++j)
+                            dWb[i][j] = fmaf(gb[i].x, xb[j].x, fmaf(gb[i].y, xb[j].y, fmaf(gb[i].z, xb[j].z, fmaf(gb[i].w, xb[j].w, dWb[i][j]))));
+                }
+                {
+                    float4 gc[2], xc[4];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) gc[i] = aw.w[(tc_o + i) * QW + qq];
+                    for (int i = 0; i < 2; ++i) gc[i] = ld4(aw.w, tc_o + i);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) xc[j] = aw.hb[(tc_k + j) * QW + qq];
+                    for (int j = 0; j < 4; ++j) xc[j] = ld4(aw.hb, kl + 16 * j);
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
+                    for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dWc[i][j] = fmaf(gc[i], xc[j], dWc[i][j]);
+                        for (int j = 0; j < 4; ++j)
+                            dWc[i][j] = fmaf(gc[i].x, xc[j].x, fmaf(gc[i].y, xc[j].y, fmaf(gc[i].z, xc[j].z, fmaf(gc[i].w, xc[j].w, dWc[i][j]))));
+                }
                 // biases: thread t < 128 -> ba[t]; 128..191 -> bb; 192..221 -> bc
-                if (tid < H1) dbias += gw.gza[tid * QW + qq];
-                else if (tid < H1 + H2) dbias += gw.gzb[(tid - H1) * QW + qq];
-                else if (tid < H1 + H2 + KN) dbias += aw.w[(tid - H1 - H2) * QW + qq];
+                float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tid < H1) bsum = ld4(gw.gza, tid);
+                else if (tid < H1 + H2) bsum = ld4(gw.gzb, tid - H1);
+                else if (tid < H1 + H2 + KN) bsum = ld4(aw.w, tid - H1 - H2);
+                dbias += (bsum.x + bsum.y) + (bsum.z + bsum.w);
             }
         }
         __syncthreads();
@@ -292,16 +306,16 @@ __global__ void __launch_bounds__(IW * 32, 1) itp_bwd_kernel(const float2* __res
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (ta_k + j < IN0) atomicAdd(g_params + P_WA + (ta_o + i) * IN0 + ta_k + j, dWa[i][j]);
+            if (kl + 16 * j < IN0) atomicAdd(g_params + P_WA + (ta_o + i) * IN0 + kl + 16 * j, dWa[i][j]);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(g_params + P_WB + (tb_o + i) * H1 + tb_k + j, dWb[i][j]);
+        for (int j = 0; j < 8; ++j) atomicAdd(g_params + P_WB + (tb_o + i) * H1 + kl + 16 * j, dWb[i][j]);
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (tc_o + i < KN) atomicAdd(g_params + P_WC + (tc_o + i) * H2 + tc_k + j, dWc[i][j]);
+            if (tc_o + i < KN) atomicAdd(g_params + P_WC + (tc_o + i) * H2 + kl + 16 * j, dWc[i][j]);
     if (tid < H1) atomicAdd(g_params + P_BA + tid, dbias);
     else if (tid < H1 + H2) atomicAdd(g_params + P_BB + tid - H1, dbias);
     else if (tid < H1 + H2 + KN) atomicAdd(g_params + P_BC + tid - H1 - H2, dbias);

@@ -59,6 +59,18 @@ int mmpde_knn_grid(const float* pts, const int32_t* pts_off, const float* qry, c
                    int n_samples, int64_t n_queries, float x0, float y0, float inv_cell, int gx, int gy,
                    const int32_t* cell_start, const int32_t* order,
                    int k, int rule, int exclude_self, int32_t* out_idx, void* stream);
+/* Several such searches in ONE launch (they are latency-bound with one thread per query and leave most warp slots
+ * empty, so the three searches of a training step -- graph on the moved mesh, interpolation to it and back -- run side
+ * by side).  Every task has its own points / queries / cell grid (from mmpde_knn_grid_build) and output. */
+typedef struct mmpde_knn_task {
+    const float* pts; const int32_t* pts_off; const float* qry; const int32_t* qry_off;
+    int32_t n_samples; int32_t k; int64_t n_queries;
+    float x0, y0, inv_cell; int32_t gx, gy;
+    const int32_t* cell_start; const int32_t* order;
+    int32_t rule, exclude_self;
+    int32_t* out_idx;
+} mmpde_knn_task;
+int mmpde_knn_grid_multi(const mmpde_knn_task* tasks, int n_tasks, void* stream);
 
 /* radius_graph (data_creator_2d.py:258): first <= max_nb points in index order with d2 < r*r. */
 int mmpde_radius(const float* pts, const int32_t* off, int n_samples, int64_t n_pts, float r,

@@ -19,6 +19,13 @@ class WgradTask(ctypes.Structure):
                 ("dWext", _p), ("ldwext", _l), ("dbias", _p), ("M", _l)]
 
 
+class KnnTask(ctypes.Structure):
+    """include/mmpde_b200.h: mmpde_knn_task."""
+    _fields_ = [("pts", _p), ("pts_off", _p), ("qry", _p), ("qry_off", _p), ("n_samples", ctypes.c_int32), ("k", ctypes.c_int32),
+                ("n_queries", _l), ("x0", _f), ("y0", _f), ("inv_cell", _f), ("gx", ctypes.c_int32), ("gy", ctypes.c_int32),
+                ("cell_start", _p), ("order", _p), ("rule", ctypes.c_int32), ("exclude_self", ctypes.c_int32), ("out_idx", _p)]
+
+
 # name -> argtypes, exactly mirroring include/mmpde_b200.h
 SIGNATURES = {
     "mmpde_abi_version": [],
@@ -26,6 +33,7 @@ SIGNATURES = {
     "mmpde_knn": [_p, _p, _p, _p, _i, _l, _i, _i, _i, _p, _p],
     "mmpde_knn_grid_build": [_p, _p, _i, _l, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p],
     "mmpde_knn_grid": [_p, _p, _p, _p, _i, _l, _f, _f, _f, _i, _i, _p, _p, _i, _i, _i, _p, _p],
+    "mmpde_knn_grid_multi": [_p, _i, _p],
     "mmpde_radius": [_p, _p, _i, _l, _f, _i, _p, _p],
     "mmpde_gemm": [_p, _l, _i, _p, _l, _i, _p, _l, _l, _i, _l, _p, _p, _l, _p, _i, _i, _i, _p],
     "mmpde_node_gemm": [_p, _l, _p, _l, _p, _l, _l, _p, _l, _l, _p, _p, _p, _i, _p, _l, _p, _l, _p, _l, _l, _p],

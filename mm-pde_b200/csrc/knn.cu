@@ -37,6 +37,33 @@ struct TopK {
     }
 };
 
+// The same list in SHARED memory, entry j of thread t at [j * 128 + t] (conflict-free).  The cell-binned search keeps its
+// lists here: in local memory they are ~400 B per thread, and with several searches resident per SM they fall out of
+// L1 (three grouped searches ran barely faster than one after the other).
+template <typename D>
+struct TopKShared {
+    D* d;
+    int* i;
+    int cnt, k;
+    static constexpr int S = 128;                 // = blockDim.x of knn_grid_kernel
+    __device__ __forceinline__ void init(int k_, void* d_base, int* i_base) {
+        cnt = 0; k = k_;
+        d = reinterpret_cast<D*>(d_base) + threadIdx.x;
+        i = i_base + threadIdx.x;
+    }
+    __device__ __forceinline__ bool before(D a, int ai, D b, int bi) const { return a < b || (a == b && ai < bi); }
+    __device__ __forceinline__ D worst() const { return d[(k - 1) * S]; }
+    __device__ __forceinline__ void push(D dv, int iv) {
+        if (cnt == k && !before(dv, iv, d[(k - 1) * S], i[(k - 1) * S])) return;
+        int pos = (cnt < k) ? cnt : k - 1;
+        while (pos > 0 && before(dv, iv, d[(pos - 1) * S], i[(pos - 1) * S])) {
+            d[pos * S] = d[(pos - 1) * S]; i[pos * S] = i[(pos - 1) * S]; --pos;
+        }
+        d[pos * S] = dv; i[pos * S] = iv;
+        if (cnt < k) ++cnt;
+    }
+};
+
 constexpr int KNN_KMAX = 64;
 constexpr int KNN_TILE = 512;
 
@@ -141,22 +168,33 @@ __global__ void grid_fill_kernel(const int* __restrict__ cell_of_pt, int64_t n, 
     }
 }
 
+// One search = one task; a launch carries up to KNN_MAX_TASKS of them, the CTAs divided between the tasks.  A search
+// is latency-bound with one thread per query (10 % of the warp slots at 36 k queries), so the three searches of a
+// training step (graph on the moved mesh, interpolation to it and back) run side by side in one launch.
+constexpr int KNN_MAX_TASKS = 4;
+struct KnnGroup {
+    mmpde_knn_task t[KNN_MAX_TASKS];
+    int cta_begin[KNN_MAX_TASKS + 1];
+    int kmax;                                     // largest k of the group: the shared-memory lists are sized for it
+};
+
 template <typename D>
-__global__ void __launch_bounds__(128) knn_grid_kernel(const float2* __restrict__ pts, const int* __restrict__ pts_off,
-                                                       const float2* __restrict__ qry, const int* __restrict__ qry_off,
-                                                       int n_samples, int64_t nq, float x0, float y0, float inv_cell,
-                                                       int gx, int gy, const int* __restrict__ cell_start,
-                                                       const int* __restrict__ order, int k, int exclude_self,
-                                                       int* __restrict__ out) {
+__device__ __forceinline__ void knn_grid_body(const mmpde_knn_task& a, int64_t bx, int64_t nb, void* d_base, int* i_base) {
+    const float2* __restrict__ pts = reinterpret_cast<const float2*>(a.pts);
+    const float2* __restrict__ qry = reinterpret_cast<const float2*>(a.qry);
+    const int* __restrict__ cell_start = a.cell_start;
+    const int* __restrict__ order = a.order;
+    const int gx = a.gx, gy = a.gy, k = a.k;
+    const float x0 = a.x0, y0 = a.y0, inv_cell = a.inv_cell;
     const float cell = 1.0f / inv_cell;
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t q = bx * (int64_t)blockDim.x + threadIdx.x; q < a.n_queries; q += nb * blockDim.x) {
         float2 qq = qry[q];
         int cx = cell_coord(qq.x, x0, inv_cell, gx), cy = cell_coord(qq.y, y0, inv_cell, gy);
-        const int smp = sample_of(qry_off, n_samples, q);
+        const int smp = sample_of(a.qry_off, a.n_samples, q);
         const int cell0 = smp * gx * gy;
-        int self = exclude_self ? (int)(__ldg(pts_off + smp) + (q - __ldg(qry_off + smp))) : -1;
-        TopK<D, KNN_KMAX> best;
-        best.init(k);
+        int self = a.exclude_self ? (int)(__ldg(a.pts_off + smp) + (q - __ldg(a.qry_off + smp))) : -1;
+        TopKShared<D> best;
+        best.init(k, d_base, i_base);
         int rmax = max(max(cx, gx - 1 - cx), max(cy, gy - 1 - cy));
         for (int r = 0; r <= rmax; ++r) {
             if (best.cnt == k && r > 0) {
@@ -171,7 +209,7 @@ __global__ void __launch_bounds__(128) knn_grid_kernel(const float2* __restrict_
                 if (cy - (r - 1) > 0) gap = fminf(gap, qq.y - lo_y);
                 if (cy + r < gy) gap = fminf(gap, hi_y - qq.y);
                 gap = gap * (1.0f - 1e-5f) - 2e-6f * (gx + gy) * cell;   // conservative (cell-assignment rounding): never stop early
-                if (gap > 0.f && (double)best.d[k - 1] < (double)gap * (double)gap) break;
+                if (gap > 0.f && (double)best.worst() < (double)gap * (double)gap) break;
             }
             int ylo = cy - r, yhi = cy + r, xlo = cx - r, xhi = cx + r;
             for (int yy = max(ylo, 0); yy <= min(yhi, gy - 1); ++yy) {
@@ -189,8 +227,20 @@ __global__ void __launch_bounds__(128) knn_grid_kernel(const float2* __restrict_
                 }
             }
         }
-        for (int j = 0; j < k; ++j) out[q * k + j] = (j < best.cnt) ? best.i[j] : -1;
+        for (int j = 0; j < k; ++j) a.out_idx[q * k + j] = (j < best.cnt) ? best.i[j * TopKShared<D>::S] : -1;
     }
+}
+
+__global__ void __launch_bounds__(128) knn_grid_kernel(const __grid_constant__ KnnGroup g) {
+    int task = 0;
+#pragma unroll
+    for (int j = 1; j < KNN_MAX_TASKS; ++j) task += ((int)blockIdx.x >= g.cta_begin[j]) ? 1 : 0;
+    const mmpde_knn_task& a = g.t[task];
+    const int64_t bx = (int64_t)blockIdx.x - g.cta_begin[task], nb = g.cta_begin[task + 1] - g.cta_begin[task];
+    extern __shared__ __align__(16) unsigned char knn_smem[];      // [kmax][128] distances (8 B slots), then [kmax][128] indices
+    int* i_base = reinterpret_cast<int*>(knn_smem + (size_t)g.kmax * 128 * sizeof(double));
+    if (a.rule == 0) knn_grid_body<float>(a, bx, nb, knn_smem, i_base);
+    else knn_grid_body<double>(a, bx, nb, knn_smem, i_base);
 }
 
 __global__ void radius_kernel(const float2* __restrict__ pts, const int* __restrict__ off, int n_samples, float r2,
@@ -246,20 +296,52 @@ extern "C" int mmpde_knn_grid_build(const float* pts, const int32_t* pts_off, in
     return MMPDE_OK;
 }
 
+extern "C" int mmpde_knn_grid_multi(const mmpde_knn_task* tasks, int n_tasks, void* stream) {
+    if (n_tasks < 0 || (n_tasks > 0 && tasks == nullptr)) return MMPDE_EINVAL;
+    for (int j = 0; j < n_tasks; ++j) {
+        const mmpde_knn_task& t = tasks[j];
+        if (t.k <= 0 || t.k > KNN_KMAX || (t.rule != 0 && t.rule != 1) || t.gx <= 0 || t.gy <= 0 || t.n_samples <= 0 || t.n_queries < 0)
+            return MMPDE_EINVAL;
+    }
+    auto st = (cudaStream_t)stream;
+    int j0 = 0;
+    while (j0 < n_tasks) {
+        KnnGroup g;
+        int n = 0;
+        int64_t begin = 0;
+        g.cta_begin[0] = 0;
+        g.kmax = 1;
+        for (; j0 < n_tasks && n < KNN_MAX_TASKS; ++j0) {
+            if (tasks[j0].n_queries == 0) continue;
+            g.t[n] = tasks[j0];
+            if (tasks[j0].k > g.kmax) g.kmax = tasks[j0].k;
+            begin += imin64((tasks[j0].n_queries + 127) / 128, (int64_t)sm_count() * 32);
+            g.cta_begin[++n] = (int)begin;
+        }
+        if (n == 0) break;
+        for (int j = n; j < KNN_MAX_TASKS; ++j) { g.t[j] = g.t[0]; g.cta_begin[j + 1] = 0x7fffffff; }
+        const size_t smem = (size_t)g.kmax * 128 * (sizeof(double) + sizeof(int));     // <= 96 KB at k = 64
+        static size_t smem_ok = 48 * 1024;
+        if (smem > smem_ok) {
+            cudaError_t e = cudaFuncSetAttribute(knn_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 12);
+            if (e != cudaSuccess) return (int)e;
+            smem_ok = 64 * 128 * 12;
+        }
+        knn_grid_kernel<<<(int)begin, 128, smem, st>>>(g);
+        MMPDE_CHECK_LAUNCH();
+    }
+    return MMPDE_OK;
+}
+
 extern "C" int mmpde_knn_grid(const float* pts, const int32_t* pts_off, const float* qry, const int32_t* qry_off,
                               int n_samples, int64_t n_queries, float x0, float y0, float inv_cell, int gx, int gy,
                               const int32_t* cell_start, const int32_t* order, int k, int rule, int exclude_self,
                               int32_t* out_idx, void* stream) {
-    if (k <= 0 || k > KNN_KMAX || (rule != 0 && rule != 1) || gx <= 0 || gy <= 0 || n_samples <= 0) return MMPDE_EINVAL;
-    if (n_queries == 0) return MMPDE_OK;
-    auto st = (cudaStream_t)stream;
-    int blocks = (int)imin64((n_queries + 127) / 128, (int64_t)sm_count() * 32);
-    if (rule == 0)
-        knn_grid_kernel<float><<<blocks, 128, 0, st>>>((const float2*)pts, pts_off, (const float2*)qry, qry_off, n_samples, n_queries, x0, y0, inv_cell, gx, gy, cell_start, order, k, exclude_self, out_idx);
-    else
-        knn_grid_kernel<double><<<blocks, 128, 0, st>>>((const float2*)pts, pts_off, (const float2*)qry, qry_off, n_samples, n_queries, x0, y0, inv_cell, gx, gy, cell_start, order, k, exclude_self, out_idx);
-    MMPDE_CHECK_LAUNCH();
-    return MMPDE_OK;
+    mmpde_knn_task t;
+    t.pts = pts; t.pts_off = pts_off; t.qry = qry; t.qry_off = qry_off; t.n_samples = n_samples; t.k = k;
+    t.n_queries = n_queries; t.x0 = x0; t.y0 = y0; t.inv_cell = inv_cell; t.gx = gx; t.gy = gy;
+    t.cell_start = cell_start; t.order = order; t.rule = rule; t.exclude_self = exclude_self; t.out_idx = out_idx;
+    return mmpde_knn_grid_multi(&t, 1, stream);
 }
 
 extern "C" int mmpde_radius(const float* pts, const int32_t* off, int n_samples, int64_t n_pts, float r, int max_nb,

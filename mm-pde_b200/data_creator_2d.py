@@ -67,11 +67,42 @@ class GraphCreator_FS_2D(nn.Module):
         self.t_res = t_resolution
         self._static_edges = {}
         self._mm_grids = {}
+        self._ref_cache = {}
 
     def _bbox(self):
         """Box handed to the cell-binned k-NN (a hint: points outside are clamped, results stay exact)."""
         px, py = 0.02 * self.pde.Lx, 0.02 * self.pde.Ly
         return (-px, -py, self.pde.Lx + px, self.pde.Ly + py)
+
+    # ------------------------------------------------------------------ neighbour searches of one moved-mesh step
+    def _ref_points(self, key, make):
+        """The reference points (regular grid / original cloud, repeated per sample) never move: the tensor and its
+        cell bins are built once per (shape, batch, device)."""
+        hit = self._ref_cache.get(key)
+        if hit is None:
+            pts = make().to(torch.float32).contiguous()
+            hit = self._ref_cache[key] = [pts, None]
+        return hit
+
+    def _moved_searches(self, itp_model, mesh_pts, B, n, ref, to_mesh):
+        """All neighbour searches a step needs once the mesh has moved -- graph edges on the moved mesh (fp32 rule),
+        interpolation reference -> mesh (``to_mesh``) and mesh -> reference (fp64 rule) -- in ONE launch: each search
+        alone is latency-bound at ~10 % of the GPU's warp slots.  Returns None when the cell-binned path does not
+        apply (small samples, radius graphs): the callers then search one by one as before."""
+        ref_pts, P = ref[0], ref[0].shape[0] // B
+        if self.e != "knn" or min(n, P) < ops.GRID_MIN_POINTS or not mesh_pts.is_cuda:
+            return None
+        dev = mesh_pts.device
+        mesh_pts = mesh_pts.detach().to(torch.float32).contiguous()
+        off_m, off_r = _offsets(B, n, dev), _offsets(B, P, dev)
+        if ref[1] is None:
+            ref[1] = ops.CellBins(ref_pts, off_r, self._bbox(), P)
+        bins_m = ops.CellBins(mesh_pts, off_m, self._bbox(), n)
+        searches = [(bins_m, mesh_pts, off_m, self.n, 0, True), (bins_m, ref_pts, off_r, itp_model.n, 1, False)]
+        if to_mesh:
+            searches.append((ref[1], mesh_pts, off_m, itp_model.n, 1, False))
+        outs = ops.knn_grid_multi(searches)
+        return {"graph": outs[0], "back": outs[1], "to_mesh": outs[2] if to_mesh else None}
 
     # ------------------------------------------------------------------ interpolation (:46-85)
     def interpolate(self, itp_model, u, init_x, init_y, x, y, mode, idx=None):
@@ -134,9 +165,11 @@ class GraphCreator_FS_2D(nn.Module):
         return dp[rows, (idx[:, None] - self.tw + win)], dp[rows, (idx[:, None] + win)]
 
     # ------------------------------------------------------------------ graph assembly (:157-267)
-    def _edges(self, x_new, n_samples, per_sample, static_key=None):
+    def _edges(self, x_new, n_samples, per_sample, static_key=None, nbr=None):
         if static_key is not None and static_key in self._static_edges:
             return self._static_edges[static_key]
+        if nbr is not None:                       # searched together with the interpolation lists (_moved_searches)
+            return ops.EdgeList.from_knn(nbr, has_pad=per_sample - 1 < self.n)
         dev = x_new.device
         off = _offsets(n_samples, per_sample, dev)
         pts = x_new.detach().to(torch.float32).contiguous()
@@ -155,6 +188,7 @@ class GraphCreator_FS_2D(nn.Module):
         data, labels = to_device(data, device), to_device(labels, device)
         pde = self.pde
         B = data.shape[0]
+        pre = None                                   # neighbour lists searched together once the mesh has moved
         if len(pde.grid_size) == 3:
             onx, ony = data.shape[-2], data.shape[-1]
             nt, nx, ny = pde.grid_size
@@ -170,11 +204,14 @@ class GraphCreator_FS_2D(nn.Module):
                 coarse = data.reshape(-1, onx, ony)[:, ::int(onx / mm_nx), ::int(ony / mm_ny)]
                 mesh_x, mesh_y = self.moving_mesh(coarse, mesh_model, nx, ny)
                 mesh = torch.cat((mesh_x, mesh_y), dim=-1).reshape(-1, n, 2)
-                og = torch.stack(torch.meshgrid(torch.linspace(0, pde.Lx, onx, device=device),
-                                                torch.linspace(0, pde.Ly, ony, device=device), indexing="ij"), dim=2)
-                og = og.reshape(1, -1, 2).expand(B, -1, 2).reshape(-1, 2)
-                data = self.interpolate(itp_model, data.reshape(-1, onx, ony), og[:, 0:1], og[:, 1:2],
-                                        mesh_x, mesh_y, mode="1").reshape(-1, self.tw, nx, ny)
+                ref = self._ref_points(("grid", B, onx, ony, str(device)), lambda: torch.stack(torch.meshgrid(
+                    torch.linspace(0, pde.Lx, onx, device=device), torch.linspace(0, pde.Ly, ony, device=device),
+                    indexing="ij"), dim=2).reshape(1, -1, 2).expand(B, -1, 2).reshape(-1, 2))
+                og = ref[0]
+                if self.tw == 1 and len(steps) >= B:
+                    pre = self._moved_searches(itp_model, mesh.reshape(-1, 2), B, n, ref, to_mesh=True)
+                data = self.interpolate(itp_model, data.reshape(-1, onx, ony), og[:, 0:1], og[:, 1:2], mesh_x, mesh_y, mode="1",
+                                        idx=pre["to_mesh"] if pre else None).reshape(-1, self.tw, nx, ny)
                 labels = self.interpolate(itp_model, labels.reshape(-1, onx, ony), og[:, 0:1], og[:, 1:2],
                                           mesh_x, mesh_y, mode="1", idx=self.last_itp_idx).reshape(-1, self.tw, nx, ny)
                 static_key = None
@@ -193,6 +230,9 @@ class GraphCreator_FS_2D(nn.Module):
                 mesh_x, mesh_y = self.moving_mesh_tri(data.reshape(-1, n), mesh_model,
                                                       grid[:, :, 0].contiguous(), grid[:, :, 1].contiguous())
                 mesh = torch.cat((mesh_x, mesh_y), dim=-1).reshape(-1, n, 2)
+                if len(steps) >= B:
+                    ref = self._ref_points(("cloud", B, n, str(device)), lambda: grid.reshape(-1, 2))
+                    pre = self._moved_searches(itp_model, mesh.reshape(-1, 2), B, n, ref, to_mesh=False)
                 static_key = None
             else:
                 mesh = grid
@@ -207,7 +247,8 @@ class GraphCreator_FS_2D(nn.Module):
         batch = torch.arange(B, device=device).repeat_interleave(n)
         if static_key is not None:
             static_key = static_key + (B,)
-        graph = Data(x=u_new, edges=self._edges(x_new, B, n, static_key))
+        graph = Data(x=u_new, edges=self._edges(x_new, B, n, static_key, nbr=pre["graph"] if pre else None))
+        graph._itp_back_idx = pre["back"] if pre else None      # mesh -> reference lists for interpolate_pred
         graph.y = y_new
         graph.pos = torch.cat((t_new[:, None], x_new), dim=1)
         graph.batch = batch
@@ -225,13 +266,14 @@ class GraphCreator_FS_2D(nn.Module):
                                             torch.linspace(0, pde.Ly, ony, device=device), indexing="ij"), dim=2)
             og = og.reshape(1, -1, 2).expand(nu, -1, 2).reshape(-1, 2)
             on_grid = self.interpolate(itp_model, pred.reshape(-1, nx, ny), graph.pos[:, 1:2], graph.pos[:, 2:3],
-                                       og[:, 0:1], og[:, 1:2], mode="2").reshape(-1, 1, onx, ony)
+                                       og[:, 0:1], og[:, 1:2], mode="2",
+                                       idx=getattr(graph, "_itp_back_idx", None)).reshape(-1, 1, onx, ony)
             out = itp_model(None, None, mode="res_cut", data=data).reshape(-1, 1, onx, ony) + on_grid
         else:
             n = pde.ori_grid_size[1]
             nu = pred.shape[0] // n
             g = pde.ori_grid.to(device)[None].expand(nu, n, 2).reshape(-1, 2)
             on_grid = self.interpolate(itp_model, pred.reshape(-1, n), graph.pos[:, 1:2], graph.pos[:, 2:3],
-                                       g[:, 0:1], g[:, 1:2], mode="2").reshape(-1, n)
+                                       g[:, 0:1], g[:, 1:2], mode="2", idx=getattr(graph, "_itp_back_idx", None)).reshape(-1, n)
             out = itp_model(None, None, mode="res_cut", data=data.reshape(-1, n)).reshape(-1, n) + on_grid
         return out.reshape(-1, 1)

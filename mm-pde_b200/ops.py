@@ -121,27 +121,53 @@ def knn_indices(pts, pts_off, qry, qry_off, k, rule, exclude_self, bbox=None, pe
     return out
 
 
+class CellBins:
+    """Points binned into the uniform cell grid of the exact search (mmpde_knn_grid_build): reusable for every search
+    over the same points (and across steps for points that never move, e.g. the reference grid)."""
+
+    def __init__(self, pts, pts_off, bbox, per_sample, pts_per_cell=6.0):
+        x0, y0, x1, y1 = [float(v) for v in bbox]
+        S = pts_off.numel() - 1
+        P = pts.shape[0]
+        area = max((x1 - x0) * (y1 - y0), 1e-30)
+        cell = max((area * pts_per_cell / max(per_sample, 1)) ** 0.5, 1e-9)
+        self.x0, self.y0, self.inv_cell = x0, y0, 1.0 / cell
+        self.gx = max(int((x1 - x0) / cell) + 1, 1)
+        self.gy = max(int((y1 - y0) / cell) + 1, 1)
+        self.pts, self.pts_off, self.S = pts, pts_off, S
+        dev = pts.device
+        ncell = S * self.gx * self.gy
+        cell_of = torch.empty(P, dtype=torch.int32, device=dev)
+        self.cell_start = torch.empty(ncell + 1, dtype=torch.int32, device=dev)
+        cursor = torch.empty(ncell, dtype=torch.int32, device=dev)
+        self.order = torch.empty(P, dtype=torch.int32, device=dev)
+        _cabi.call("mmpde_knn_grid_build", _ptr(pts), _ptr(pts_off), S, P, x0, y0, self.inv_cell, self.gx, self.gy, _ptr(cell_of),
+                   _ptr(self.cell_start), _ptr(cursor), _ptr(self.order), _stream())
+
+    def task(self, qry, qry_off, k, rule, exclude_self, out):
+        return _cabi.KnnTask(_ptr(self.pts), _ptr(self.pts_off), _ptr(qry), _ptr(qry_off), self.S, k, qry.shape[0], self.x0,
+                             self.y0, self.inv_cell, self.gx, self.gy, _ptr(self.cell_start), _ptr(self.order), rule,
+                             int(exclude_self), _ptr(out))
+
+
+def knn_grid_multi(searches):
+    """Several cell-binned searches in ONE launch.  searches: (bins, qry, qry_off, k, rule, exclude_self) each; returns the
+    int32 [Q,k] neighbour lists.  One search alone fills ~10 % of the GPU's warp slots."""
+    import ctypes
+    outs, tasks = [], []
+    for bins, qry, qry_off, k, rule, exclude_self in searches:
+        _chk(qry, name="qry"); _chk(qry_off, torch.int32, "qry_off")
+        out = torch.empty((qry.shape[0], k), dtype=torch.int32, device=qry.device)
+        outs.append(out)
+        tasks.append(bins.task(qry, qry_off, k, rule, exclude_self, out))
+    arr = (_cabi.KnnTask * len(tasks))(*tasks)
+    _cabi.call("mmpde_knn_grid_multi", ctypes.addressof(arr), len(tasks), _stream())
+    return outs
+
+
 def _knn_grid(pts, pts_off, qry, qry_off, k, rule, exclude_self, bbox, per_sample, pts_per_cell=6.0):
-    x0, y0, x1, y1 = [float(v) for v in bbox]
-    S = pts_off.numel() - 1
-    P, Q = pts.shape[0], qry.shape[0]
-    area = max((x1 - x0) * (y1 - y0), 1e-30)
-    cell = max((area * pts_per_cell / max(per_sample, 1)) ** 0.5, 1e-9)
-    gx = max(int((x1 - x0) / cell) + 1, 1)
-    gy = max(int((y1 - y0) / cell) + 1, 1)
-    dev = pts.device
-    ncell = S * gx * gy
-    cell_of = torch.empty(P, dtype=torch.int32, device=dev)
-    cell_start = torch.empty(ncell + 1, dtype=torch.int32, device=dev)
-    cursor = torch.empty(ncell, dtype=torch.int32, device=dev)
-    order = torch.empty(P, dtype=torch.int32, device=dev)
-    st = _stream()
-    _cabi.call("mmpde_knn_grid_build", _ptr(pts), _ptr(pts_off), S, P, x0, y0, 1.0 / cell, gx, gy, _ptr(cell_of),
-               _ptr(cell_start), _ptr(cursor), _ptr(order), st)
-    out = torch.empty((Q, k), dtype=torch.int32, device=dev)
-    _cabi.call("mmpde_knn_grid", _ptr(pts), _ptr(pts_off), _ptr(qry), _ptr(qry_off), S, Q, x0, y0, 1.0 / cell, gx, gy,
-               _ptr(cell_start), _ptr(order), k, rule, int(exclude_self), _ptr(out), st)
-    return out
+    bins = CellBins(pts, pts_off, bbox, per_sample, pts_per_cell)
+    return knn_grid_multi([(bins, qry, qry_off, k, rule, exclude_self)])[0]
 
 
 def knn_indices_grid(pts, qry, k, rule, exclude_self):

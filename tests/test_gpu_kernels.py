@@ -100,6 +100,33 @@ def test_knn_grid_search_equals_brute_force(n, rule, excl):
     assert np.array_equal(got, ref)
 
 
+def test_knn_grid_multi_equals_single_searches():
+    """mmpde_knn_grid_multi: the three searches of a moved-mesh step in one launch (shared cell bins for the searches over
+    the same points, a different rule / k / self-exclusion per task, an empty task) == the oracle, task by task."""
+    from mmpde_b200 import ops
+    dev = _dev()
+    S, n = 3, 700
+    mesh = np.concatenate([_cloud(n, 60 + s) for s in range(S)])
+    ref_pts = np.concatenate([_cloud(n, 70, jitter=0.0)] * S)
+    off = _off([n] * S, dev)
+    mesh_d, ref_d = torch.from_numpy(mesh).to(dev), torch.from_numpy(ref_pts).to(dev)
+    bbox = (-0.05, -0.05, 1.05, 1.05)
+    bins_m, bins_r = ops.CellBins(mesh_d, off, bbox, n), ops.CellBins(ref_d, off, bbox, n)
+    empty = torch.zeros(0, 2, device=dev)
+    off0 = torch.zeros(S + 1, dtype=torch.int32, device=dev)
+    outs = ops.knn_grid_multi([(bins_m, mesh_d, off, 35, 0, True), (bins_m, ref_d, off, 30, 1, False),
+                               (bins_r, empty, off0, 30, 1, False), (bins_r, mesh_d, off, 30, 1, False),
+                               (bins_m, mesh_d, off, 7, 1, True)])          # 5 tasks: two launches
+    assert outs[2].shape == (0, 30)
+    for got, (pts, qry, k, excl, rule) in zip([outs[0], outs[1], outs[3], outs[4]],
+                                              [(mesh, mesh, 35, True, "f32"), (mesh, ref_pts, 30, False, "f64"),
+                                               (ref_pts, mesh, 30, False, "f64"), (mesh, mesh, 7, True, "f64")]):
+        got = got.cpu().numpy()
+        for s in range(S):
+            want, _ = oknn.knn_indices(pts[s * n:(s + 1) * n], qry[s * n:(s + 1) * n], k, exclude_self=excl, rule=rule)
+            assert np.array_equal(got[s * n:(s + 1) * n], want + s * n)
+
+
 def test_radius_bit_exact():
     from mmpde_b200 import ops
     dev = _dev()

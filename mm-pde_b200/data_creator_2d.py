@@ -74,6 +74,15 @@ class GraphCreator_FS_2D(nn.Module):
         px, py = 0.02 * self.pde.Lx, 0.02 * self.pde.Ly
         return (-px, -py, self.pde.Lx + px, self.pde.Ly + py)
 
+    def _ori_grid(self, device):
+        """pde.ori_grid on the device, copied once (the reference re-uploads it on every call; under CUDA-graph
+        capture a pageable host copy is not even allowed)."""
+        src = self.pde.ori_grid
+        hit = self._ref_cache.get(("ori_grid", str(device)))
+        if hit is None or hit[0] is not src:
+            hit = self._ref_cache[("ori_grid", str(device))] = (src, src.to(device))
+        return hit[1]
+
     # ------------------------------------------------------------------ neighbour searches of one moved-mesh step
     def _ref_points(self, key, make):
         """The reference points (regular grid / original cloud, repeated per sample) never move: the tensor and its
@@ -220,7 +229,7 @@ class GraphCreator_FS_2D(nn.Module):
         else:
             n = pde.ori_grid_size[1]
             nt = pde.grid_size[0]
-            grid = pde.ori_grid.to(device)[None].expand(B, n, 2)
+            grid = self._ori_grid(device)[None].expand(B, n, 2)
             if self.e == "radius":
                 side = int(np.sqrt(pde.grid_size[1]))
                 hx = pde.Lx / (side - 1)
@@ -272,7 +281,7 @@ class GraphCreator_FS_2D(nn.Module):
         else:
             n = pde.ori_grid_size[1]
             nu = pred.shape[0] // n
-            g = pde.ori_grid.to(device)[None].expand(nu, n, 2).reshape(-1, 2)
+            g = self._ori_grid(device)[None].expand(nu, n, 2).reshape(-1, 2)
             on_grid = self.interpolate(itp_model, pred.reshape(-1, n), graph.pos[:, 1:2], graph.pos[:, 2:3],
                                        g[:, 0:1], g[:, 1:2], mode="2", idx=getattr(graph, "_itp_back_idx", None)).reshape(-1, n)
             out = itp_model(None, None, mode="res_cut", data=data.reshape(-1, n)).reshape(-1, n) + on_grid

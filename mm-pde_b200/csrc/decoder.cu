@@ -115,15 +115,16 @@ __global__ void __launch_bounds__(WARPS * 32) decoder_bwd_kernel(const float* __
             const int idx = lane + 32 * j;
             if (idx < 152) {
                 const int c = idx / 38;
-                float acc = 0.f;
+                float accm[4] = {0.f, 0.f, 0.f, 0.f};      // one chain per m: 4 independent 8-term chains
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {              // t = q%3 + 3m, p = q/3 - m
                     const int t = q1m[j] + 3 * m, p = q1d[j] - m;
                     if (p >= 0 && p < 9) {
 #pragma unroll
-                        for (int o = 0; o < 8; ++o) acc = fmaf(s.g2[o * 9 + p], sp[OFF_W2 + (o * 4 + c) * 12 + t], acc);
+                        for (int o = 0; o < 8; ++o) accm[m] = fmaf(s.g2[o * 9 + p], sp[OFF_W2 + (o * 4 + c) * 12 + t], accm[m]);
                     }
                 }
+                const float acc = (accm[0] + accm[1]) + (accm[2] + accm[3]);
                 s.g1[idx] = s.a1[idx] > 0.f ? acc : 0.f;
             }
         }
@@ -132,16 +133,16 @@ __global__ void __launch_bounds__(WARPS * 32) decoder_bwd_kernel(const float* __
         float gh[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float acc = 0.f;
+            float accm[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int m = 0; m < 6; ++m) {
                 const int t = q0m[i] + 3 * m, p = q0d[i] - m;
                 if (t < 16 && p >= 0 && p < 38) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) acc = fmaf(s.g1[c * 38 + p], sp[OFF_W1 + c * 16 + t], acc);
+                    for (int c = 0; c < 4; ++c) accm[m] = fmaf(s.g1[c * 38 + p], sp[OFF_W1 + c * 16 + t], accm[m]);
                 }
             }
-            gh[i] = acc;
+            gh[i] = ((accm[0] + accm[1]) + (accm[2] + accm[3])) + (accm[4] + accm[5]);
         }
         *reinterpret_cast<float4*>(g_h + n * ldg + lane * 4) = make_float4(gh[0], gh[1], gh[2], gh[3]);
         // parameter gradients
@@ -150,14 +151,34 @@ __global__ void __launch_bounds__(WARPS * 32) decoder_bwd_kernel(const float* __
             const int pi = lane + 32 * i;
             if (pi >= DEC_NP) break;
             float acc = 0.f;
+            // (several partial sums per chain: a single 38-term FMA chain is 38 x the FMA latency)
             if (pi < OFF_B1) {                       // w1[c][t]
-                for (int p = 0; p < 38; ++p) acc = fmaf(s.g1[offA[i] + p], s.h[3 * p + offB[i]], acc);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int p = 0; p < 36; p += 4) {
+                    a0 = fmaf(s.g1[offA[i] + p], s.h[3 * p + offB[i]], a0);
+                    a1 = fmaf(s.g1[offA[i] + p + 1], s.h[3 * p + 3 + offB[i]], a1);
+                    a2 = fmaf(s.g1[offA[i] + p + 2], s.h[3 * p + 6 + offB[i]], a2);
+                    a3 = fmaf(s.g1[offA[i] + p + 3], s.h[3 * p + 9 + offB[i]], a3);
+                }
+                a0 = fmaf(s.g1[offA[i] + 36], s.h[108 + offB[i]], a0);
+                a1 = fmaf(s.g1[offA[i] + 37], s.h[111 + offB[i]], a1);
+                acc = (a0 + a1) + (a2 + a3);
             } else if (pi < OFF_W2) {                // b1[c]
                 int c = pi - OFF_B1;
-                for (int p = 0; p < 38; ++p) acc += s.g1[c * 38 + p];
-            } else if (pi < OFF_B2) {                // w2[o][c][t]
+                float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                for (int p = 0; p < 9; ++p) acc = fmaf(s.g2[offA[i] + p], s.a1[offB[i] + 3 * p], acc);
+                for (int p = 0; p < 38; p += 2) { a0 += s.g1[c * 38 + p]; a1 += s.g1[c * 38 + p + 1]; }
+                acc = a0 + a1;
+            } else if (pi < OFF_B2) {                // w2[o][c][t]
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int p = 0; p < 9; p += 3) {
+                    a0 = fmaf(s.g2[offA[i] + p], s.a1[offB[i] + 3 * p], a0);
+                    a1 = fmaf(s.g2[offA[i] + p + 1], s.a1[offB[i] + 3 * p + 3], a1);
+                    a2 = fmaf(s.g2[offA[i] + p + 2], s.a1[offB[i] + 3 * p + 6], a2);
+                }
+                acc = (a0 + a1) + a2;
             } else if (pi < OFF_W3) {                // b2[o]
                 int o = pi - OFF_B2;
                 for (int p = 0; p < 9; ++p) acc += s.g2[o * 9 + p];

@@ -80,21 +80,24 @@ class GradBucket:
         self.nbytes = n * 4
 
     def allreduce(self, average=True):
+        """Gradients -> flat bucket -> ONE all-reduce -> back.  The two copies are multi-tensor launches
+        (torch._foreach_copy_): one tiny kernel per parameter costs ~0.7 ms per step for the ~180 tensors here."""
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        have = [(p, v) for p, v in zip(self.params, self.views) if p.grad is not None]
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()
-            else:
-                v.copy_(p.grad)
+        if have:
+            torch._foreach_copy_([v for _, v in have], [p.grad for p, _ in have])
         if world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             if average:
                 self.flat.div_(world)
+        if have:
+            torch._foreach_copy_([p.grad for p, _ in have], [v for _, v in have])
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
 
 
 class HaloExchange:

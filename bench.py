@@ -165,6 +165,8 @@ def run_ours(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    # stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, dev = mdist.init_from_env()
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
     _cabi.lib()
@@ -335,7 +337,10 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "per_gpu_batch": BATCH, "nodes_per_gpu": n_nodes,
-                       "edges_per_graph": n_edges, "parallelism": f"batch-sharded dp{world}, sync-BN, flat grad all-reduce",
+                       "edges_per_graph": n_edges,
+                       "parallelism": f"batch-sharded dp{world}, sync-BN ("
+                                      + ("sums exchanged over NVLink peer memory in one kernel" if getattr(ops_mod.COMM, "peer", None) is not None
+                                         else "NCCL all-reduce of the sums" if world > 1 else "single rank") + "), flat grad all-reduce",
                        "launch": "eager" if step_graph is None else "CUDA graph replay of the whole step (StepGraph)",
                        "l2": "per-step working set ~1.7 GB > 126 MB L2, no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "edge-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

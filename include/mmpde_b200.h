@@ -183,6 +183,18 @@ int mmpde_bn_bwd_apply(const float* g, int64_t ldg, const float* out, int64_t ld
                        const float* mean_rstd, const float* gamma, const double* bsums, double count,
                        float* gy, int64_t ldgy, int accumulate, float* gy_gated, int64_t ldgg, void* stream);
 
+/* ---- sync-BatchNorm sums across GPUs over NVLink peer memory (no reference counterpart) -------------
+ * One kernel replaces the NCCL all-reduce of the [2,128] fp64 sums: it folds the n_rep local accumulator copies,
+ * stores them into a slot of EVERY peer's exchange buffer, raises a flag there, waits for all peers' flags and adds
+ * the world slots in rank order (identical bits on every rank) into out [2,128].
+ * peer_base: device array [world] of the addresses (valid on THIS device) of every rank's exchange buffer of
+ * MMPDE_BN_EXCHANGE_BYTES bytes, zero-initialised once, peer-mapped by the caller (e.g. torch symmetric memory).
+ * All ranks must issue the same sequence of exchanges; the sequence number lives in the buffer, so the call can be
+ * replayed from a CUDA graph.  A peer that never arrives makes the kernel trap after ~10 s instead of hanging. */
+#define MMPDE_BN_EXCHANGE_BYTES (1024 + 4 * 16 * 256 * 8)      /* counter, flags, 4 slots x 16 ranks x 256 doubles */
+int mmpde_bn_exchange(const double* sums, int n_rep, const int64_t* peer_base, int rank, int world, double* out,
+                      void* stream);
+
 /* ---- small elementwise helpers of the node path -------------------------------------------------
  * relu_bwd: out = g * (act > 0); colsum[128] += column sums of out (NULL to skip).  [M,128] */
 int mmpde_relu_bwd(const float* g, int64_t ldg, const float* act, int64_t lda, int64_t M,

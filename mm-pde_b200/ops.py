@@ -51,6 +51,10 @@ class _Comm:
     def allreduce_(self, t):
         return t
 
+    def reduce_bn_sums(self, spread):
+        """[n_rep, 256] local accumulator copies -> [256] sums over all ranks (here: one rank)."""
+        return spread.sum(0) if spread.dim() == 2 else spread
+
     def global_rows(self, n):
         return float(n) if self.total_rows is None else float(self.total_rows)
 
@@ -247,8 +251,8 @@ def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st, sums=N
             _cabi.call("mmpde_bn_stats", A, lda, B, ldb, M, _ptr(sums), st)
         state.count = COMM.global_rows(state.rows)
         n_rep = BN_REPLICAS
-        if state.count != float(state.rows):          # other ranks / parts hold rows too: fold, then all-reduce [2,128]
-            sums, n_rep = COMM.allreduce_(sums.sum(0)), 1
+        if state.count != float(state.rows):          # other ranks hold rows too: fold + sum over the ranks -> [2,128]
+            sums, n_rep = COMM.reduce_bn_sums(sums), 1
         state.mean_rstd = torch.empty(2 * H, dtype=torch.float32, device=dev)
         _cabi.call("mmpde_bn_finalize", _ptr(sums), n_rep, state.count, BN_EPS, BN_MOMENTUM, _ptr(state.mean_rstd),
                    _ptr(rmean), _ptr(rvar), st)
@@ -275,7 +279,7 @@ def _bn_backward(items, relu, state, gamma, st, spread=None):
     local = spread.sum(0)
     glob = local
     if COMM.global_rows(state.rows) != float(state.rows):
-        glob = COMM.allreduce_(local.clone())
+        glob = COMM.reduce_bn_sums(spread)
     for g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy, *gated in items:
         gyg, ldgg = gated if gated else (None, 0)
         _cabi.call("mmpde_bn_bwd_apply", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(gamma),

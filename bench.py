@@ -37,6 +37,9 @@ LAYERS = 6
 FLOP_PER_EDGE_FWD = 99328          # 2*260*128 + 2*128*128 (reference formulation)
 
 
+RESULT_OUT = sys.stdout
+
+
 def _ncu_traffic():
     """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed ncu --set full capture
     (profiles/r01_edge_bwd_ncu.json, written by profiles/ncu_summary.py --json on this CPU box)."""
@@ -149,7 +152,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -165,8 +168,6 @@ def run_ours(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    # stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, dev = mdist.init_from_env()
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
     _cabi.lib()
@@ -359,7 +360,7 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     if step_graph is not None:
         step_graph.release()             # recorded graphs hold captured NCCL work: drop them before the communicator
     if world > 1:
@@ -384,6 +385,12 @@ def main():
     ap.add_argument("--workload", default="burgers", choices=["burgers", "cylinder"],
                     help="burgers = BASELINE.json configs[1] (the headline, default); cylinder = configs[2]")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: whatever libraries write to file descriptor 1 (the NCCL version
+    # banner, cuDNN notices) is sent to stderr, the result goes to a private copy of the original stdout.
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

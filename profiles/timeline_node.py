@@ -28,6 +28,17 @@ print("kernel start -> (clks)  W in TMEM:", rel(t[3,0,0]), " end:", rel(t[3,0,7]
 for i in range(2):
     print(f" tile {i}: builder start {rel(t[0,i,0])} empty-ok {rel(t[0,i,1])} built {rel(t[0,i,2])} | mma tm_empty-ok {rel(t[2,i,0])} issued {rel(t[2,i,2])} | epi acc-ready {rel(t[3,i,1])} stored {rel(t[3,i,2])}")
 
+# ---- dgrad + residual in place: W^T by strides, R1 = C
+def run_d():
+    assert lib.mmpde_node_gemm(pp(X), 256, None, 0, pp(W), 1, 260, None, 0, 0, None, None, None, 0, pp(C), 128, None, 0, pp(C), 128, N, st) == 0
+for _ in range(3): run_d()
+torch.cuda.synchronize(); buf.zero_(); lib.mmpde_debug_timeline_node(pp(buf)); run_d(); torch.cuda.synchronize(); lib.mmpde_debug_timeline_node(None)
+t = buf.cpu().numpy().reshape(4, 48, 8)
+t0 = t[3, 0, 6]
+print("dgrad+residual: W in TMEM:", rel(t[3,0,0]), " end:", rel(t[3,0,7]))
+for i in range(2):
+    print(f" tile {i}: builder start {rel(t[0,i,0])} empty-ok {rel(t[0,i,1])} built {rel(t[0,i,2])} | mma tm_empty-ok {rel(t[2,i,0])} issued {rel(t[2,i,2])} | epi acc-ready {rel(t[3,i,1])} stored {rel(t[3,i,2])}")
+
 # ---- wgrad
 lib.mmpde_node_wgrad.argtypes = _cabi.SIGNATURES["mmpde_node_wgrad"]
 n4 = torch.randn(N, 4, device=dev)

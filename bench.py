@@ -138,7 +138,8 @@ def run_reference(args):
     if rank != 0:
         return
     sample = 2
-    value, sec, cores = cpu_reference_step_time(sample, max(1, min(args.steps, 3)), 1 if args.warmup > 0 else 0)
+    # exactly --steps timed steps of the bounded sample (1.5 s each on the GPU box's 16 cores), at most 2 warm-ups
+    value, sec, cores = cpu_reference_step_time(sample, max(1, args.steps), min(max(args.warmup, 0), 2))
     line = {
         "impl": "reference", "metric": "edge-updates/sec (fwd+bwd)", "value": value, "unit": "edge-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
@@ -328,9 +329,9 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not cyl:      # the CPU arm times the headline workload
-        v, sec, cores = cpu_reference_step_time(2, 1, 1)
+        v, sec, cores = cpu_reference_step_time(4, 2, 1)
         cpu = {"value": v, "unit": "edge-updates/s", "cores": cores, "kind": "port",
-               "sample": f"batch 2 of the batch-{BATCH} step, 1 warm-up + 1 timed step ({sec:.1f} s); oracle port "
+               "sample": f"batch 4 of the batch-{BATCH} step, 1 warm-up + 2 timed steps (best {sec:.1f} s); oracle port "
                          "(reference needs PyG, not installable offline)"}
     if rank == 0:
         line = {

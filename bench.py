@@ -329,9 +329,9 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not cyl:      # the CPU arm times the headline workload
-        v, sec, cores = cpu_reference_step_time(4, 2, 1)
+        v, sec, cores = cpu_reference_step_time(4, 3, 1)
         cpu = {"value": v, "unit": "edge-updates/s", "cores": cores, "kind": "port",
-               "sample": f"batch 4 of the batch-{BATCH} step, 1 warm-up + 2 timed steps (best {sec:.1f} s); oracle port "
+               "sample": f"batch 4 of the batch-{BATCH} step, 1 warm-up + 3 timed steps (best {sec:.1f} s); oracle port "
                          "(reference needs PyG, not installable offline)"}
     if rank == 0:
         line = {

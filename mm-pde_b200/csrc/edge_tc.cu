@@ -9,13 +9,15 @@
 // (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM: ~2^-16 relative error per term).
 //
 // Both kernels are persistent (one CTA per SM) and warp-specialised:
-//   warps 0-3   epilogue : thread = TMEM lane = channel; tcgen05.ld, ReLU / masks / per-target sums
-//   warps 4-11  builders : gather P'/Q' rows with 128-bit loads (next tile prefetched into registers), ReLU, split
-//                          into bf16 hi/lo and write the SWIZZLE_128B operand tile -- the neighbour gather IS the
-//                          operand load of the GEMM, no [E,260] / [E,128] tensor ever exists
-//   warp  12    MMA      : one thread issues tcgen05.mma; W2 (hi, lo) lives in TENSOR MEMORY as the A operand for the
-//                          whole kernel, so only the per-tile operand is read from shared memory
-// connected by mbarrier pipelines (operand tiles and accumulators are double-buffered).
+//   epilogue warps : thread = TMEM lane = channel; tcgen05.ld, bias, ReLU / masks / per-target sums
+//                    (forward: 16 warps, lane quadrant x 32-column quarter; backward: 4 warps)
+//   builder warps  : gather P'/Q' rows with 128-bit loads (next tile prefetched into registers), ReLU, split into bf16
+//     (8)            hi/lo and write the SWIZZLE_128B operand tile -- the neighbour gather IS the operand load of the
+//                    GEMM, no [E,260] / [E,128] tensor ever exists; in the backward they also run the row phase
+//   MMA warp       : one thread issues tcgen05.mma; W2 (hi, lo) lives in TENSOR MEMORY as the A operand for the whole
+//                    kernel, so only the per-tile operand is read from shared memory
+// connected by mbarrier pipelines (operand tiles and accumulators are double-buffered); registers are moved between the
+// roles with setmaxnreg (forward 896 threads: 56 / 120 / 40 per thread; backward 512 threads: 104 / 184 / 40).
 #include "tc_common.cuh"
 
 namespace mmpde {

@@ -48,6 +48,37 @@ def test_ctypes_table_matches_header():
         assert len(_cabi.SIGNATURES[name]) == n_args, name
 
 
+def test_argument_errors_are_reported_before_any_device_work():
+    """Entry points validate their arguments on the host and return MMPDE_EINVAL (-1) without touching a device, so a
+    wrong call fails loudly even on a box without a GPU; the struct layouts of the grouped launches match the header."""
+    _cabi = _ensure_built()
+    lib = _cabi.lib()
+    assert lib.mmpde_node_wgrad_grouped(None, -1, None) == -1
+    assert lib.mmpde_node_wgrad_grouped(None, 2, None) == -1                      # tasks missing
+    bad = (_cabi.WgradTask * 1)(_cabi.WgradTask(0x1000, 130, None, 0, None, None, 0, None, 0, None, 64))   # lda % 4 != 0
+    assert lib.mmpde_node_wgrad_grouped(ctypes.addressof(bad), 1, None) == -1
+    unpaired = (_cabi.WgradTask * 1)(_cabi.WgradTask(0x1000, 128, 0x2000, 128, None, None, 0, None, 0, None, 64))   # B without dW
+    assert lib.mmpde_node_wgrad_grouped(ctypes.addressof(unpaired), 1, None) == -1
+    assert lib.mmpde_knn_grid_multi(None, 1, None) == -1
+    k0 = (_cabi.KnnTask * 1)(_cabi.KnnTask(0x1000, 0x1000, 0x1000, 0x1000, 1, 0, 10, 0.0, 0.0, 1.0, 4, 4, 0x1000, 0x1000, 0, 0, 0x1000))
+    assert lib.mmpde_knn_grid_multi(ctypes.addressof(k0), 1, None) == -1          # k = 0
+    k65 = (_cabi.KnnTask * 1)(_cabi.KnnTask(0x1000, 0x1000, 0x1000, 0x1000, 1, 65, 10, 0.0, 0.0, 1.0, 4, 4, 0x1000, 0x1000, 0, 0, 0x1000))
+    assert lib.mmpde_knn_grid_multi(ctypes.addressof(k65), 1, None) == -1         # k > 64
+    assert lib.mmpde_bn_exchange(0x1000, 16, 0x1000, 3, 2, 0x1000, None) == -1    # rank >= world
+    assert lib.mmpde_bn_exchange(0x1000, 16, 0x1000, 0, 17, 0x1000, None) == -1   # world > 16
+    assert lib.mmpde_bn_finalize(0x1000, 0, 10.0, 1e-5, 0.1, 0x1000, None, None, None) == -1     # n_rep < 1
+    assert lib.mmpde_node_gemm(0x1000, 128, None, 0, 0x1000, 128, 1, None, 0, 0, None, None, None, 2, None, 0, None, 0,
+                               0x1000, 128, 64, None) == -1                      # gate mode without the activation
+    # struct sizes as the C compiler lays them out (header: mmpde_wgrad_task, mmpde_knn_task)
+    assert ctypes.sizeof(_cabi.WgradTask) == 11 * 8
+    assert ctypes.sizeof(_cabi.KnnTask) == 104
+    from mmpde_b200 import ops
+    assert ops.BN_REPLICAS == 16
+    with open(os.path.join(ROOT, "include", "mmpde_b200.h")) as f:
+        hdr = f.read()
+    assert "#define MMPDE_BN_REPLICAS 16" in hdr and "#define MMPDE_BN_EXCHANGE_BYTES (1024 + 4 * 16 * 256 * 8)" in hdr
+
+
 def test_no_cpu_fallback():
     from mmpde_b200 import ops, _cabi
     from mmpde_b200.gnn_2d import GNN_Layer_FS_2D

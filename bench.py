@@ -269,10 +269,12 @@ def run_ours(args):
     launches = _cabi.launches - launches0
     if step_graph is not None:
         ops_mod._cabi.call = profiled_call
+        os.environ["MMPDE_OVERLAP_SOLVERS"] = "0"      # time the kernel alone: on one stream, not beside the other solver's kernels
         barrier()
         for _ in range(args.steps):
             train_step(fields_dev, graph=None)
         barrier()
+        os.environ.pop("MMPDE_OVERLAP_SOLVERS")
     ops_mod._cabi.call = real_call
     kern_ms = [s.elapsed_time(e) for s, e in _cabi_profile]
     kern_avg_ms = sum(kern_ms) / max(len(kern_ms), 1)
@@ -343,7 +345,8 @@ def run_ours(args):
                        "parallelism": f"batch-sharded dp{world}, sync-BN ("
                                       + ("sums exchanged over NVLink peer memory in one kernel" if getattr(ops_mod.COMM, "peer", None) is not None
                                          else "NCCL all-reduce of the sums" if world > 1 else "single rank") + "), flat grad all-reduce",
-                       "launch": "eager" if step_graph is None else "CUDA graph replay of the whole step (StepGraph)",
+                       "launch": "eager" if step_graph is None else "CUDA graph replay of the whole step (StepGraph)"
+                                 + (", the two solvers as parallel graph branches" if world == 1 else ""),
                        "l2": "per-step working set ~1.7 GB > 126 MB L2, no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "edge-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
@@ -353,8 +356,8 @@ def run_ours(args):
                          "unit": "TFLOP/s", "frac": achieved / peaks["bf16"], "traffic": _ncu_traffic(),
                          "avg_launch_ms": kern_avg_ms, "launches_timed": len(kern_ms),
                          "algorithmic_flops_per_launch": alg_flops, "peak_source": peaks["source"],
-                         "timed_in": "timed region" if step_graph is None else "eager pass of the same step after the timed region "
-                                     "(graph nodes cannot carry events)",
+                         "timed_in": "timed region" if step_graph is None else "eager single-stream pass of the same step after the "
+                                     "timed region (graph nodes cannot carry events)",
                          "share_of_step": kern_avg_ms * len(kern_ms) / args.steps / ms_step if ms_step > 0 else None},
             "rollout": {"steps_per_s": world * 1e3 / ms_roll, "ms_per_step": ms_roll,
                         "definition": "one pass of train_helper_2d.py:173-185 for one batch of 16, eval, no_grad"},

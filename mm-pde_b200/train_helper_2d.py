@@ -12,7 +12,7 @@ import random
 
 import torch
 
-from . import _cabi
+from . import _cabi, ops
 from ._h2d import to_device
 
 
@@ -104,12 +104,44 @@ def _is_gnn(model):
     return f"{model}" == "GNN"
 
 
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def _overlap_solvers(device):
+    """The two solvers of a step (uniform grid, moved mesh) are independent until their outputs are added.  Their big
+    kernels are persistent one-CTA-per-SM kernels, so they cannot share an SM -- but issued on two streams (two parallel
+    branches of the step's CUDA graph) the launch ramp and the tail of every kernel of one branch are filled by the
+    other branch.  Off with several ranks: the cross-GPU exchanges need the same order on every rank."""
+    import os
+    from . import ops
+    if os.environ.get("MMPDE_OVERLAP_SOLVERS", "1") == "0" or not torch.cuda.is_available():
+        return False
+    return torch.device(device).type == "cuda" and type(ops.COMM) is ops._Comm
+
+
 def _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, steps, device):
     """Both branches of the MM-PDE prediction (train_helper_2d.py:107-118): the branch solver on the moved
     mesh, interpolated back to the grid (+ residual net), plus the solver on the uniform grid."""
     uniform = graph_creator.create_graph(itp_model, data, labels, steps, device, None)
     if mesh_model is None:
         return model(uniform)
+    if _overlap_solvers(device):
+        cur, side = torch.cuda.current_stream(), _side_stream(device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            on_uniform = model(uniform)
+        moved = graph_creator.create_graph(itp_model, data, labels, steps, device, mesh_model)
+        on_moved = graph_creator.interpolate_pred(itp_model, model_b(moved), moved, data, device)
+        cur.wait_stream(side)
+        on_uniform.record_stream(cur)
+        return on_moved + on_uniform
     moved = graph_creator.create_graph(itp_model, data, labels, steps, device, mesh_model)
     return graph_creator.interpolate_pred(itp_model, model_b(moved), moved, data, device) + model(uniform)
 

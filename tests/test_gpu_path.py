@@ -189,6 +189,48 @@ def test_step_graph_replay_equals_eager_loops():
         StepGraph.hyper(torch.optim.AdamW(model.parameters(), lr=1e-3))
 
 
+def test_step_graph_new_shape_and_learning_rate_record_new_graphs():
+    """A loader whose last batch is shorter and a learning-rate change (what MultiStepLR does) must each get their own
+    recording; the losses stay those of the eager loop, and no more than `max_graphs` recordings are kept per loop."""
+    from mmpde_b200.data_creator_2d import GraphCreator_FS_2D
+    from mmpde_b200.gnn_2d import MP_PDE_Solver_2D
+    from mmpde_b200.interpolate import ItpNet
+    from mmpde_b200.mmpde import criterion
+    from mmpde_b200.train_helper_2d import StepGraph, training_loop_branch
+    dev = _dev()
+    pde = _pde12()
+    fields = synth_fields(3, 31, 12, 12, seed=5)
+    loader = [(fields[:2], fields[:2]), (fields[2:], fields[2:])]          # batch 2, then the short batch 1
+    mover = SmoothMover()
+
+    def run(step_graph):
+        gc = GraphCreator_FS_2D(pde, 35, "knn", 1, 31)
+        model_a = fill_params(MP_PDE_Solver_2D(pde, time_window=1, hidden_layer=1), 21).to(dev)
+        model_b = fill_params(MP_PDE_Solver_2D(pde, time_window=1, hidden_layer=1), 22).to(dev)
+        net = fill_params(ItpNet(12, 12, [128, 64], [128, 64], [1, 4, 16, 4, 1]), 23).to(dev)
+        opt = torch.optim.AdamW([{"params": model_a.parameters()}, {"params": model_b.parameters()},
+                                 {"params": net.parameters()}], lr=1e-3, capturable=True)
+        model_a.train(); model_b.train(); net.train()
+        random.seed(9)
+        out = []
+        for epoch in range(8):
+            if epoch == 4:
+                for g in opt.param_groups:
+                    g["lr"] = 4e-4
+            out.append(training_loop_branch(model_a, model_b, net, mover, [0], 2, opt, None, loader, gc, criterion, dev,
+                                            step_graph=step_graph))
+        return torch.cat(out).cpu()
+
+    eager = run(None)
+    sg = StepGraph(eager_steps=1, max_graphs=3)
+    graphed = run(sg)
+    assert torch.allclose(graphed, eager, rtol=2e-3, atol=1e-7), (graphed, eager)
+    assert sg.replays >= 8                                   # 16 batches, 4 signatures x (1 eager + 1 recording)
+    assert len(sg._graphs) <= 3                              # 4 signatures seen, the oldest recording was dropped
+    sg.release()
+    assert len(sg._graphs) == 0
+
+
 def test_dmm_golden_fixture(golden_dir):
     from mmpde_b200.data_creator_2d import GraphCreator_FS_2D
     from mmpde_b200.mesh.dmm_model import DMM

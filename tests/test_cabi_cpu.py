@@ -136,3 +136,23 @@ def test_create_data_matches_oracle_slicing():
     a = GraphCreator_FS_2D(burgers(), 35, "knn", 1, 31).create_data(u, steps)
     b = creator.GraphCreator_FS_2D(pdes.burgers(), 35, "knn", 1, 31).create_data(u, steps)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[0].shape == (4, 1, 6, 6)
+
+
+def test_step_graph_host_logic_on_cpu():
+    """StepGraph on a box without CUDA: the optimizer check is a host-side check, CPU inputs run eagerly (prepare +
+    body every call, nothing recorded), release() is safe to call at any time."""
+    from mmpde_b200.train_helper_2d import StepGraph
+    w = torch.nn.Parameter(torch.zeros(3))
+    with pytest.raises(ValueError):
+        StepGraph.hyper(torch.optim.AdamW([w], lr=1e-3))
+    sig_a = StepGraph.hyper(torch.optim.AdamW([w], lr=1e-3, capturable=True))
+    sig_b = StepGraph.hyper(torch.optim.AdamW([w], lr=4e-4, capturable=True))
+    assert sig_a != sig_b and sig_a == StepGraph.hyper(torch.optim.AdamW([w], lr=1e-3, capturable=True), None)
+    sg = StepGraph(eager_steps=1)
+    calls = []
+    for i in range(4):
+        out = sg.run(("train", (2, 3)), lambda x: (calls.append("body"), x * 2)[1], (torch.ones(2, 3) * i,),
+                     prepare=lambda: calls.append("prepare"))
+        assert torch.equal(out, torch.ones(2, 3) * 2 * i)
+    assert calls == ["prepare", "body"] * 4 and sg.replays == 0 and len(sg._graphs) == 0
+    sg.release()

@@ -190,10 +190,13 @@ int mmpde_bn_bwd_apply(const float* g, int64_t ldg, const float* out, int64_t ld
  * peer_base: device array [world] of the addresses (valid on THIS device) of every rank's exchange buffer of
  * MMPDE_BN_EXCHANGE_BYTES bytes, zero-initialised once, peer-mapped by the caller (e.g. torch symmetric memory).
  * All ranks must issue the same sequence of exchanges; the sequence number lives in the buffer, so the call can be
- * replayed from a CUDA graph.  A peer that never arrives makes the kernel trap after ~10 s instead of hanging. */
+ * replayed from a CUDA graph.  A peer that never arrives makes the kernel trap after a wall-clock limit instead of
+ * hanging: 600 s by default (a peer may legitimately be late -- checkpoint save on one rank, a re-recorded step graph),
+ * overridden by the environment variable MMPDE_PEER_TIMEOUT_S or mmpde_bn_exchange_set_timeout(seconds). */
 #define MMPDE_BN_EXCHANGE_BYTES (1024 + 4 * 16 * 256 * 8)      /* counter, flags, 4 slots x 16 ranks x 256 doubles */
 int mmpde_bn_exchange(const double* sums, int n_rep, const int64_t* peer_base, int rank, int world, double* out,
                       void* stream);
+int mmpde_bn_exchange_set_timeout(double seconds);
 
 /* ---- small elementwise helpers of the node path -------------------------------------------------
  * relu_bwd: out = g * (act > 0); colsum[128] += column sums of out (NULL to skip).  [M,128] */

@@ -44,6 +44,7 @@ SIGNATURES = {
     "mmpde_bn_stats": [_p, _l, _p, _l, _l, _p, _p],
     "mmpde_bn_finalize": [_p, _i, _d, _f, _f, _p, _p, _p, _p],
     "mmpde_bn_exchange": [_p, _i, _p, _i, _i, _p, _p],
+    "mmpde_bn_exchange_set_timeout": [_d],
     "mmpde_bn_apply": [_p, _l, _p, _l, _l, _p, _p, _p, _i, _p, _l, _p],
     "mmpde_bn_bwd_reduce": [_p, _l, _p, _l, _i, _p, _l, _p, _l, _l, _p, _p, _p],
     "mmpde_bn_bwd_apply": [_p, _l, _p, _l, _i, _p, _l, _p, _l, _l, _p, _p, _p, _d, _p, _l, _i, _p, _l, _p],

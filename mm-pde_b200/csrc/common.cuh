@@ -14,16 +14,33 @@ namespace mmpde {
 
 constexpr int H = MMPDE_H;
 
-inline int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
+// Host-side caches are keyed by the CURRENT device: one process may drive several GPUs (mmpde.py --device cuda:1).
+constexpr int MAX_DEVICES = 64;
+inline int cur_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
 }
+inline int sm_count() {
+    static int n[MAX_DEVICES] = {0};
+    const int dev = cur_device();
+    if (n[dev] == 0) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
+    }
+    return n[dev];
+}
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel AND device
+#define MMPDE_ENSURE_SMEM(kernel, bytes)                                                                              \
+    do {                                                                                                              \
+        static bool done__[mmpde::MAX_DEVICES] = {false};                                                             \
+        const int dev__ = mmpde::cur_device();                                                                        \
+        if (!done__[dev__]) {                                                                                         \
+            cudaError_t e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+            if (e__ != cudaSuccess) return (int)e__;                                                                  \
+            done__[dev__] = true;                                                                                     \
+        }                                                                                                             \
+    } while (0)
 
 inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 inline int64_t imax64(int64_t a, int64_t b) { return a > b ? a : b; }

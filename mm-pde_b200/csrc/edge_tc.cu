@@ -121,9 +121,14 @@ struct EdgeFwdArgs {
 };
 struct FwdSmem {
     static constexpr uint32_t H = 0;                       // 2 stages x (hi, lo)
-    static constexpr uint32_t DST = 2 * 2 * F_IMG;         // int dst[4][128]  (slot = tile iteration & 3)
-    static constexpr uint32_t INV = DST + 4 * FTE * 4;     // float inv_deg[dst][4][128]
-    static constexpr uint32_t BAR = INV + 4 * FTE * 4;     // h_full[2] h_empty[2] tm_full[2] tm_empty[2], tmem slot
+    // Targets of the tile's edges for the epilogue, slot = tile iteration & 7.  The epilogue still reads slot i after it
+    // has released accumulator stage i (boundary targets of its last piece); the builders may then run up to tile i+4
+    // (operand stage free <=> MMA of tile i+2 done <=> accumulator stage of tile i released), so 8 slots keep the
+    // slot being read and the slot being written apart by construction, not by timing.
+    static constexpr int SLOTS = 8;
+    static constexpr uint32_t DST = 2 * 2 * F_IMG;         // int dst[SLOTS][128]
+    static constexpr uint32_t INV = DST + SLOTS * FTE * 4; // float inv_deg[dst][SLOTS][128]
+    static constexpr uint32_t BAR = INV + SLOTS * FTE * 4; // h_full[2] h_empty[2] tm_full[2] tm_empty[2], tmem slot
     static constexpr uint32_t TOTAL = BAR + 128;
 };
 
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int b = i & 1;
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-            const uint32_t dsts = sbase + FwdSmem::DST + (uint32_t)(i & 3) * (FTE * 4);
+            const uint32_t dsts = sbase + FwdSmem::DST + (uint32_t)(i & (FwdSmem::SLOTS - 1)) * (FTE * 4);
             mbar_wait(tm_full + 8 * b, ph);
             if (warp == 0) TL(3, i, 0);
             tc_fence_after();
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
                             if (nib & (1u << k)) {
                                 flush_mean(p.agg, p.ld_agg, cur, cur_inv, o, 0.5f * (run_s + run_a));
                                 cur = lds_i32(dsts + 4 * (e0 + 4 * g + k));                   // used at the NEXT flush:
-                                cur_inv = __uint_as_float(lds_b32(dsts + 4 * FTE * 4 + 4 * (e0 + 4 * g + k)));
+                                cur_inv = __uint_as_float(lds_b32(dsts + FwdSmem::SLOTS * FTE * 4 + 4 * (e0 + 4 * g + k)));
                                 run_s = run_a = 0.f;                                          // latency stays hidden
                             }
                             run_s += z[k];
@@ -262,9 +267,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
             if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 1);
             const uint32_t img = sbase + FwdSmem::H + b * (2 * F_IMG);
             if (lane < 16) {
-                const uint32_t slot = sbase + FwdSmem::DST + (uint32_t)((i & 3) * FTE + row0 + lane) * 4;
+                const uint32_t slot = sbase + FwdSmem::DST + (uint32_t)((i & (FwdSmem::SLOTS - 1)) * FTE + row0 + lane) * 4;
                 sts_b32(slot, (uint32_t)idx.d);
-                sts_b32(slot + 4 * FTE * 4, __float_as_uint(inv));
+                sts_b32(slot + FwdSmem::SLOTS * FTE * 4, __float_as_uint(inv));
             }
             build_h8<FTE>(img, row0, ga, idx, 0, p.PQ, lane);
             gather8(ga, p.PQ, idx_n, 0, lane);                             // first half of the NEXT tile
@@ -618,12 +623,7 @@ extern "C" int mmpde_edge_fwd(const float* PQ, const int32_t* edge_src, const in
     if (n_edges < 0 || ld_agg < 128) return MMPDE_EINVAL;
     if (n_edges == 0) return MMPDE_OK;
     constexpr size_t smem = FwdSmem::TOTAL + 1024;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(edge_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = true;
-    }
+    MMPDE_ENSURE_SMEM(edge_fwd_tc_kernel, smem);
     EdgeFwdArgs p;
     p.PQ = PQ; p.src = edge_src; p.dst = edge_dst; p.inv_deg = inv_deg; p.n_edges = n_edges; p.w2 = w2; p.b2 = b2;
     p.agg = agg; p.ld_agg = ld_agg; p.mask2 = mask2;
@@ -638,12 +638,7 @@ extern "C" int mmpde_edge_bwd(const float* PQ, const int32_t* edge_src, const in
     if (n_edges < 0 || ld_gagg < 128) return MMPDE_EINVAL;
     if (n_edges == 0) return MMPDE_OK;
     constexpr size_t smem = BwdSmem::TOTAL + 1024;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(edge_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = true;
-    }
+    MMPDE_ENSURE_SMEM(edge_bwd_tc_kernel, smem);
     EdgeBwdArgs p;
     p.PQ = PQ; p.src = edge_src; p.dst = edge_dst; p.inv_deg = inv_deg; p.n_edges = n_edges; p.w2 = w2; p.mask2 = mask2;
     p.g_agg = g_agg; p.ld_gagg = ld_gagg; p.dPQ = dPQ; p.dW2 = dW2; p.db2 = db2;

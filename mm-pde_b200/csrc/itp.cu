@@ -332,12 +332,7 @@ extern "C" int mmpde_itp_fwd(const float* src_xy, const float* src_val, const fl
                              int64_t n_queries, const float* params, float* out, void* stream) {
     if (n_queries < 0) return MMPDE_EINVAL;
     if (n_queries == 0) return MMPDE_OK;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(itp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITP_FWD_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr = true;
-    }
+    MMPDE_ENSURE_SMEM(itp_fwd_kernel, ITP_FWD_SMEM);
     int grid = (int)imin64((n_queries + IW * QW - 1) / (IW * QW), sm_count());
     itp_fwd_kernel<<<grid, IW * 32, ITP_FWD_SMEM, (cudaStream_t)stream>>>((const float2*)src_xy, src_val, (const float2*)qry_xy, idx, n_queries, params, out);
     MMPDE_CHECK_LAUNCH();
@@ -349,12 +344,7 @@ extern "C" int mmpde_itp_bwd(const float* src_xy, const float* src_val, const fl
                              float* g_src_val, void* stream) {
     if (n_queries < 0) return MMPDE_EINVAL;
     if (n_queries == 0) return MMPDE_OK;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(itp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ITP_BWD_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr = true;
-    }
+    MMPDE_ENSURE_SMEM(itp_bwd_kernel, ITP_BWD_SMEM);
     int grid = (int)imin64((n_queries + IW * QW - 1) / (IW * QW), sm_count());
     itp_bwd_kernel<<<grid, IW * 32, ITP_BWD_SMEM, (cudaStream_t)stream>>>((const float2*)src_xy, src_val, (const float2*)qry_xy, idx, n_queries, params, g_out, g_params, g_src_val);
     MMPDE_CHECK_LAUNCH();

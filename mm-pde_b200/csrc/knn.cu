@@ -321,12 +321,7 @@ extern "C" int mmpde_knn_grid_multi(const mmpde_knn_task* tasks, int n_tasks, vo
         if (n == 0) break;
         for (int j = n; j < KNN_MAX_TASKS; ++j) { g.t[j] = g.t[0]; g.cta_begin[j + 1] = 0x7fffffff; }
         const size_t smem = (size_t)g.kmax * 128 * (sizeof(double) + sizeof(int));     // <= 96 KB at k = 64
-        static size_t smem_ok = 48 * 1024;
-        if (smem > smem_ok) {
-            cudaError_t e = cudaFuncSetAttribute(knn_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 12);
-            if (e != cudaSuccess) return (int)e;
-            smem_ok = 64 * 128 * 12;
-        }
+        if (smem > 48 * 1024) MMPDE_ENSURE_SMEM(knn_grid_kernel, 64 * 128 * 12);
         knn_grid_kernel<<<(int)begin, 128, smem, st>>>(g);
         MMPDE_CHECK_LAUNCH();
     }

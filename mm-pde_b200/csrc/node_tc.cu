@@ -504,12 +504,7 @@ extern "C" int mmpde_node_gemm(const float* A0, int64_t lda0, const float* A1, i
          reinterpret_cast<uintptr_t>(Wext)) & 15) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
     constexpr size_t smem = GemmSmem::TOTAL + 1024;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(node_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = true;
-    }
+    MMPDE_ENSURE_SMEM(node_gemm_tc_kernel, smem);
     NodeGemmArgs p;
     p.A[0] = A0; p.A[1] = A1; p.lda[0] = lda0; p.lda[1] = lda1; p.nseg = A1 ? 2 : 1;
     p.W[0] = W0; p.W[1] = W1; p.w_ns[0] = w0_ns; p.w_ks[0] = w0_ks; p.w_ns[1] = w1_ns; p.w_ks[1] = w1_ks;
@@ -535,12 +530,7 @@ extern "C" int mmpde_node_wgrad_grouped(const mmpde_wgrad_task* tasks, int n_tas
     for (int k = 0; k < n_tasks; ++k)
         if (int rc = check_wgrad_task(tasks[k])) return rc;
     constexpr size_t smem = WgradSmem::TOTAL + 1024;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(node_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = true;
-    }
+    MMPDE_ENSURE_SMEM(node_wgrad_tc_kernel, smem);
     int k0 = 0;
     while (k0 < n_tasks) {
         // next launch: up to W_MAX_TASKS tasks that have work

@@ -16,6 +16,7 @@
 // The sequence number lives on the device, which makes the kernel replayable from a CUDA graph.
 #include "common.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 namespace mmpde {
 
@@ -36,9 +37,15 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {         
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(256) bn_exchange_kernel(const double* __restrict__ sums, int n_rep,
                                                           const int64_t* __restrict__ peer_base, int rank, int world,
-                                                          double* __restrict__ out) {
+                                                          double* __restrict__ out, unsigned long long timeout_ns) {
     __shared__ uint32_t s_seq;
     const int c = threadIdx.x;
     unsigned char* mine = reinterpret_cast<unsigned char*>(peer_base[rank]);
@@ -58,9 +65,13 @@ __global__ void __launch_bounds__(256) bn_exchange_kernel(const double* __restri
         st_release_sys(reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(peer_base[c]) + PEER_FLAGS_OFF) +
                            slot * PEER_MAX_WORLD + rank, seq);
         const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + PEER_FLAGS_OFF) + slot * PEER_MAX_WORLD + c;
-        const long long t0 = clock64();
+        // A peer may legitimately be late by many seconds (rank-0-only checkpoint save, a re-recorded step graph, a
+        // data-loader stall), so the wait is bounded in WALL time (globaltimer, independent of the SM clock) by a
+        // generous, configurable limit (default 10 min, like a collective watchdog): only a dead peer trips it.
+        const unsigned long long t0 = global_ns();
+        unsigned spins = 0;
         while (ld_acquire_sys(flag) != seq) {
-            if (clock64() - t0 > 20000000000LL) {                                  // ~10 s: a peer is gone; fail loudly
+            if ((++spins & 1023u) == 0u && global_ns() - t0 > timeout_ns) {
                 printf("mmpde_bn_exchange: rank %d timed out waiting for rank %d (exchange %u)\n", rank, c, seq);
                 __trap();
             }
@@ -81,11 +92,24 @@ using namespace mmpde;
 
 static_assert(MMPDE_BN_EXCHANGE_BYTES == PEER_SLOTS_OFF + 4 * PEER_MAX_WORLD * 256 * sizeof(double), "header and kernel layout differ");
 
+static double g_peer_timeout_s = -1.0;
+
+extern "C" int mmpde_bn_exchange_set_timeout(double seconds) {
+    if (!(seconds > 0.0)) return MMPDE_EINVAL;
+    g_peer_timeout_s = seconds;
+    return MMPDE_OK;
+}
+
 extern "C" int mmpde_bn_exchange(const double* sums, int n_rep, const int64_t* peer_base, int rank, int world, double* out,
                                  void* stream) {
     if (!sums || !peer_base || !out || n_rep < 1 || world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world)
         return MMPDE_EINVAL;
-    bn_exchange_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, n_rep, peer_base, rank, world, out);
+    if (g_peer_timeout_s < 0.0) {
+        const char* e = getenv("MMPDE_PEER_TIMEOUT_S");
+        g_peer_timeout_s = (e && atof(e) > 0.0) ? atof(e) : 600.0;
+    }
+    bn_exchange_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, n_rep, peer_base, rank, world, out,
+                                                            (unsigned long long)(g_peer_timeout_s * 1e9));
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }

@@ -123,6 +123,8 @@ def main(args):
     rank, world, device = mdist.init_from_env()
     if args.device != "auto":
         device = torch.device(args.device)
+        if device.type == "cuda":
+            torch.cuda.set_device(device)      # the C ABI launches on the current device's current stream
     check_directory()
     pde, u = _load_data(args, device)
     split = int(0.8 * u.shape[0]) if u.shape[0] < 100 else 80
@@ -140,9 +142,14 @@ def main(args):
         mesh_model = _mesh_mover(args, pde, device)
 
     per_rank = args.batch_size
-    if world > 1:                          # batch sharding: every rank loads its own slice of each global batch
-        u_train = u_train[rank::world]
-        u_test = u_test[rank::world]
+    if world > 1:
+        # Batch sharding: every rank loads its own slice of each global batch.  All ranks must run the SAME number of
+        # steps with the SAME per-rank batch sizes (sync-BatchNorm counts rows as n * world and every step is a sequence
+        # of collectives), so the trajectories that do not divide evenly are dropped.
+        u_train = mdist.shard_batch(u_train[:u_train.shape[0] // world * world], rank, world)
+        u_test = mdist.shard_batch(u_test[:u_test.shape[0] // world * world], rank, world)
+        if u_train.shape[0] == 0 or u_test.shape[0] == 0:
+            raise ValueError(f"fewer trajectories than ranks ({world}): nothing to shard")
     train_loader = DataLoader(TensorDataset(u_train, u_train), batch_size=per_rank, shuffle=True, num_workers=0)
     test_loader = DataLoader(TensorDataset(u_test, u_test), batch_size=per_rank, shuffle=False, num_workers=0)
 
@@ -199,6 +206,8 @@ def main(args):
                              itp_model_state_dict=itp_model.state_dict())
             torch.save(state, save_path)
             print(f"Saved model at {save_path}\n")
+        if world > 1:
+            torch.distributed.barrier()        # rank-0-only work above: keep the ranks' exchange sequences aligned
         scheduler.step()
     if step_graph is not None:
         step_graph.release()

@@ -32,9 +32,20 @@ def _ptr(t, off=0):
     return t.data_ptr() + off * t.element_size()
 
 
+def _on(t):
+    """Context that makes ``t``'s GPU the current device: the C ABI launches on torch's current stream of the current
+    device and keeps its host-side caches (SM count, shared-memory opt-ins) per current device."""
+    if not t.is_cuda:
+        raise _cabi.MMPDEError("expected a CUDA tensor: the MM-PDE hot path has no CPU fallback")
+    return torch.cuda.device(t.device)
+
+
 def _chk(t, dtype=torch.float32, name="tensor"):
     if not t.is_cuda:
         raise _cabi.MMPDEError(f"{name} must be a CUDA tensor: the MM-PDE hot path has no CPU fallback")
+    if t.device.index != torch.cuda.current_device():
+        raise _cabi.MMPDEError(f"{name} lives on {t.device} but the current device is cuda:{torch.cuda.current_device()}: "
+                               "all tensors of one call must be on the GPU the call is launched on")
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -114,15 +125,16 @@ def knn_indices(pts, pts_off, qry, qry_off, k, rule, exclude_self, bbox=None, pe
     ``bbox`` = (x0, y0, x1, y1) enclosing (most of) the points and ``per_sample`` = points per sample (host
     ints, so no device sync) switch large samples to the cell-binned search; both paths are exact and
     return identical indices."""
-    _chk(pts, name="pts"); _chk(qry, name="qry")
-    _chk(pts_off, torch.int32, "pts_off"); _chk(qry_off, torch.int32, "qry_off")
-    if bbox is not None and per_sample is not None and per_sample >= GRID_MIN_POINTS:
-        return _knn_grid(pts, pts_off, qry, qry_off, k, rule, exclude_self, bbox, per_sample)
-    Q = qry.shape[0]
-    out = torch.empty((Q, k), dtype=torch.int32, device=pts.device)
-    _cabi.call("mmpde_knn", _ptr(pts), _ptr(pts_off), _ptr(qry), _ptr(qry_off), pts_off.numel() - 1, Q, k, rule,
-               int(exclude_self), _ptr(out), _stream())
-    return out
+    with _on(pts):
+        _chk(pts, name="pts"); _chk(qry, name="qry")
+        _chk(pts_off, torch.int32, "pts_off"); _chk(qry_off, torch.int32, "qry_off")
+        if bbox is not None and per_sample is not None and per_sample >= GRID_MIN_POINTS:
+            return _knn_grid(pts, pts_off, qry, qry_off, k, rule, exclude_self, bbox, per_sample)
+        Q = qry.shape[0]
+        out = torch.empty((Q, k), dtype=torch.int32, device=pts.device)
+        _cabi.call("mmpde_knn", _ptr(pts), _ptr(pts_off), _ptr(qry), _ptr(qry_off), pts_off.numel() - 1, Q, k, rule,
+                   int(exclude_self), _ptr(out), _stream())
+        return out
 
 
 class CellBins:
@@ -145,8 +157,9 @@ class CellBins:
         self.cell_start = torch.empty(ncell + 1, dtype=torch.int32, device=dev)
         cursor = torch.empty(ncell, dtype=torch.int32, device=dev)
         self.order = torch.empty(P, dtype=torch.int32, device=dev)
-        _cabi.call("mmpde_knn_grid_build", _ptr(pts), _ptr(pts_off), S, P, x0, y0, self.inv_cell, self.gx, self.gy, _ptr(cell_of),
-                   _ptr(self.cell_start), _ptr(cursor), _ptr(self.order), _stream())
+        with _on(pts):
+            _cabi.call("mmpde_knn_grid_build", _ptr(pts), _ptr(pts_off), S, P, x0, y0, self.inv_cell, self.gx, self.gy,
+                       _ptr(cell_of), _ptr(self.cell_start), _ptr(cursor), _ptr(self.order), _stream())
 
     def task(self, qry, qry_off, k, rule, exclude_self, out):
         return _cabi.KnnTask(_ptr(self.pts), _ptr(self.pts_off), _ptr(qry), _ptr(qry_off), self.S, k, qry.shape[0], self.x0,
@@ -159,13 +172,14 @@ def knn_grid_multi(searches):
     int32 [Q,k] neighbour lists.  One search alone fills ~10 % of the GPU's warp slots."""
     import ctypes
     outs, tasks = [], []
-    for bins, qry, qry_off, k, rule, exclude_self in searches:
-        _chk(qry, name="qry"); _chk(qry_off, torch.int32, "qry_off")
-        out = torch.empty((qry.shape[0], k), dtype=torch.int32, device=qry.device)
-        outs.append(out)
-        tasks.append(bins.task(qry, qry_off, k, rule, exclude_self, out))
-    arr = (_cabi.KnnTask * len(tasks))(*tasks)
-    _cabi.call("mmpde_knn_grid_multi", ctypes.addressof(arr), len(tasks), _stream())
+    with _on(searches[0][1]):
+        for bins, qry, qry_off, k, rule, exclude_self in searches:
+            _chk(qry, name="qry"); _chk(qry_off, torch.int32, "qry_off")
+            out = torch.empty((qry.shape[0], k), dtype=torch.int32, device=qry.device)
+            outs.append(out)
+            tasks.append(bins.task(qry, qry_off, k, rule, exclude_self, out))
+        arr = (_cabi.KnnTask * len(tasks))(*tasks)
+        _cabi.call("mmpde_knn_grid_multi", ctypes.addressof(arr), len(tasks), _stream())
     return outs
 
 
@@ -186,9 +200,10 @@ def knn_indices_grid(pts, qry, k, rule, exclude_self):
 
 
 def radius_indices(pts, off, r, max_nb=32):
-    _chk(pts, name="pts"); _chk(off, torch.int32, "off")
-    out = torch.empty((pts.shape[0], max_nb), dtype=torch.int32, device=pts.device)
-    _cabi.call("mmpde_radius", _ptr(pts), _ptr(off), off.numel() - 1, pts.shape[0], float(r), max_nb, _ptr(out), _stream())
+    with _on(pts):
+        _chk(pts, name="pts"); _chk(off, torch.int32, "off")
+        out = torch.empty((pts.shape[0], max_nb), dtype=torch.int32, device=pts.device)
+        _cabi.call("mmpde_radius", _ptr(pts), _ptr(off), off.numel() - 1, pts.shape[0], float(r), max_nb, _ptr(out), _stream())
     return out
 
 
@@ -235,7 +250,7 @@ def _split_for(rows):
 
 class _BNState:
     """mean/rstd [2,128] of one BatchNorm application (saved for the backward)."""
-    __slots__ = ("mean_rstd", "count", "rows")
+    __slots__ = ("mean_rstd", "count", "rows", "training")
 
 
 def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st, sums=None):
@@ -244,6 +259,7 @@ def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st, sums=N
     state = _BNState()
     dev = gamma.device
     state.rows = sum(it[4] for it in items)
+    state.training = bool(training)
     if training:
         if sums is None:                               # else: a zeroed [BN_REPLICAS, 256] slice handed in by the solver
             sums = torch.zeros(BN_REPLICAS, 2 * H, dtype=torch.float64, device=dev)
@@ -278,7 +294,11 @@ def _bn_backward(items, relu, state, gamma, st, spread=None):
         _cabi.call("mmpde_bn_bwd_reduce", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(spread), st)
     local = spread.sum(0)
     glob = local
-    if COMM.global_rows(state.rows) != float(state.rows):
+    if not state.training:
+        # eval mode normalised with the running statistics: they do not depend on the batch, so the two batch-mean
+        # terms vanish and dL/dy = g * gamma * rstd (what nn.BatchNorm1d.eval() gives); dgamma / dbeta stay the sums.
+        glob = torch.zeros_like(local)
+    elif COMM.global_rows(state.rows) != float(state.rows):
         glob = COMM.reduce_bn_sums(spread)
     for g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy, *gated in items:
         gyg, ldgg = gated if gated else (None, 0)
@@ -459,23 +479,25 @@ class LayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, node4, edges, training, bnbuf, *lp):
-        _chk(x, name="x"); _chk(node4, name="node4")
-        st = _stream()
-        N = x.shape[0]
-        Xl = torch.zeros(N, 2 * H, dtype=torch.float32, device=x.device)
-        Xl[:, :H] = x
-        out = torch.empty(N, H, dtype=torch.float32, device=x.device)
-        parts = [GraphPart(node4, edges)]
-        saved, bn = _layer_forward(parts, [Xl], lp, bnbuf, training, [(_ptr(out), H)], None, st)
+        with _on(x):
+            _chk(x, name="x"); _chk(node4, name="node4")
+            st = _stream()
+            N = x.shape[0]
+            Xl = torch.zeros(N, 2 * H, dtype=torch.float32, device=x.device)
+            Xl[:, :H] = x
+            out = torch.empty(N, H, dtype=torch.float32, device=x.device)
+            parts = [GraphPart(node4, edges)]
+            saved, bn = _layer_forward(parts, [Xl], lp, bnbuf, training, [(_ptr(out), H)], None, st)
         ctx.stuff = (parts, Xl, lp, saved, bn)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         parts, Xl, lp, saved, bn = ctx.stuff
-        g_node4 = torch.zeros_like(parts[0].node4) if ctx.needs_input_grad[1] else None
-        g_xs, grads = _layer_backward(parts, [Xl], lp, saved, bn, [g_out.contiguous()],
-                                      [g_node4] if g_node4 is not None else None, None, _stream())
+        with _on(Xl):
+            g_node4 = torch.zeros_like(parts[0].node4) if ctx.needs_input_grad[1] else None
+            g_xs, grads = _layer_backward(parts, [Xl], lp, saved, bn, [g_out.contiguous()],
+                                          [g_node4] if g_node4 is not None else None, None, _stream())
         return (g_xs[0], g_node4, None, None, None, *grads)
 
 
@@ -586,15 +608,18 @@ class SolverFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, node4, edges, n_layers, training, scale, bn_buffers, *params):
-        _chk(node4, name="node4")
-        for i, p in enumerate(params):
-            _chk(p, name=f"param{i}")
-        outs, ctx.sv = _solver_forward([GraphPart(node4, edges)], n_layers, training, scale, bn_buffers, params, None, _stream())
+        with _on(node4):
+            _chk(node4, name="node4")
+            for i, p in enumerate(params):
+                _chk(p, name=f"param{i}")
+            outs, ctx.sv = _solver_forward([GraphPart(node4, edges)], n_layers, training, scale, bn_buffers, params, None,
+                                           _stream())
         return outs[0].view(-1, 1)
 
     @staticmethod
     def backward(ctx, g_out):
-        g_node4s, grads = _solver_backward(ctx.sv, [g_out], ctx.needs_input_grad[0], _stream())
+        with _on(g_out):
+            g_node4s, grads = _solver_backward(ctx.sv, [g_out], ctx.needs_input_grad[0], _stream())
         return (g_node4s[0] if g_node4s is not None else None, None, None, None, None, None, *grads)
 
 
@@ -613,7 +638,8 @@ class PartitionedSolverFn(torch.autograd.Function):
         gps = [GraphPart(n4, edges, plan) for n4, (edges, plan) in zip(node4s, parts)]
         COMM.total_rows = float(parts[0][1].n_total)
         try:
-            outs, ctx.sv = _solver_forward(gps, n_layers, training, scale, bn_buffers, params, exch, _stream())
+            with _on(node4s[0]):
+                outs, ctx.sv = _solver_forward(gps, n_layers, training, scale, bn_buffers, params, exch, _stream())
         finally:
             COMM.total_rows = None
         ctx.n = n
@@ -624,7 +650,8 @@ class PartitionedSolverFn(torch.autograd.Function):
         need_u = any(ctx.needs_input_grad[6:6 + ctx.n])
         COMM.total_rows = float(ctx.sv["parts"][0].plan.n_total)
         try:
-            g_node4s, grads = _solver_backward(ctx.sv, list(g_outs), need_u, _stream())
+            with _on(g_outs[0]):
+                g_node4s, grads = _solver_backward(ctx.sv, list(g_outs), need_u, _stream())
         finally:
             COMM.total_rows = None
         g4 = g_node4s if g_node4s is not None else [None] * ctx.n
@@ -641,13 +668,14 @@ class InterpolateFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, src_val, src_xy, qry_xy, idx, flat_params):
-        _chk(src_val, name="src_val"); _chk(src_xy, name="src_xy"); _chk(qry_xy, name="qry_xy")
-        _chk(idx, torch.int32, "idx"); _chk(flat_params, name="flat_params")
         assert flat_params.numel() == ITP_NPARAM and idx.shape[1] == KN
         Q = qry_xy.shape[0]
-        out = torch.empty(Q, dtype=torch.float32, device=src_val.device)
-        _cabi.call("mmpde_itp_fwd", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), Q, _ptr(flat_params),
-                   _ptr(out), _stream())
+        with _on(src_val):
+            _chk(src_val, name="src_val"); _chk(src_xy, name="src_xy"); _chk(qry_xy, name="qry_xy")
+            _chk(idx, torch.int32, "idx"); _chk(flat_params, name="flat_params")
+            out = torch.empty(Q, dtype=torch.float32, device=src_val.device)
+            _cabi.call("mmpde_itp_fwd", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), Q, _ptr(flat_params),
+                       _ptr(out), _stream())
         ctx.save_for_backward(src_val, src_xy, qry_xy, idx, flat_params)
         return out
 
@@ -657,6 +685,7 @@ class InterpolateFn(torch.autograd.Function):
         g_out = g_out.contiguous()
         g_params = torch.zeros_like(flat_params)
         g_val = torch.zeros_like(src_val) if ctx.needs_input_grad[0] else None
-        _cabi.call("mmpde_itp_bwd", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), qry_xy.shape[0],
-                   _ptr(flat_params), _ptr(g_out), _ptr(g_params), _ptr(g_val), _stream())
+        with _on(src_val):
+            _cabi.call("mmpde_itp_bwd", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), qry_xy.shape[0],
+                       _ptr(flat_params), _ptr(g_out), _ptr(g_params), _ptr(g_val), _stream())
         return g_val, None, None, None, g_params

@@ -1,0 +1,113 @@
+"""Run under torchrun with N >= 2 GPUs (tests/test_gpu_multi.py does, N = 2 / 4 / 8):
+
+    the 6-layer processor on a graph PARTITIONED over N ranks, one part per rank, halo rows of Q' / dL/dQ' moved by
+    dist.HaloExchange over NCCL / NVLink, BatchNorm sums exchanged across the ranks, parameter gradients summed
+        ==
+    MP_PDE_Solver_2D.forward on the WHOLE graph (every rank recomputes it on its own GPU with the single-rank COMM)
+
+for the outputs and dL/du of the rank's own nodes, EVERY parameter gradient and the BatchNorm buffers, at >= 100 k nodes
+(env MMPDE_HALO_NODES, default 102 400; k = 35).  The reference has no counterpart of the partitioning; the contract is
+equality with /root/reference/gnn_2d.py:119-141 on the unpartitioned graph.
+Prints `HALO_PARITY_OK {json}` on rank 0; optional argv[1] = path to append the json to."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from mmpde_b200 import dist as mdist, ops, partition as pt  # noqa: E402
+from mmpde_b200.PDEs import burgers  # noqa: E402
+from mmpde_b200.gnn_2d import MP_PDE_Solver_2D  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def main():
+    rank, world, dev = mdist.init_from_env()
+    assert world >= 2 and isinstance(ops.COMM, mdist.DistComm)
+    nodes = int(os.environ.get("MMPDE_HALO_NODES", "102400"))
+    layers = int(os.environ.get("MMPDE_PARITY_LAYERS", "6"))
+    side = int(round(nodes ** 0.5))
+    n = side * side
+    rng = np.random.default_rng(0)                                     # identical mesh on every rank
+    g = np.stack(np.meshgrid(np.linspace(0, 1, side), np.linspace(0, 1, side), indexing="ij"), -1).reshape(-1, 2)
+    xy = torch.from_numpy((g + rng.uniform(-0.3, 0.3, g.shape) / (side - 1)).astype(np.float32)).to(dev)
+    xy = xy[pt.morton_order(xy)].contiguous()
+    edges = ops.EdgeList.from_knn(ops.knn_indices_grid(xy, xy, 35, 0, True), has_pad=False)
+    torch.manual_seed(0)
+    u = torch.randn(n, 1, device=dev)
+    pos = torch.cat((torch.full((n, 1), 7.0, device=dev), xy), 1)
+    r = torch.randn(n, 1, device=dev)
+    model = MP_PDE_Solver_2D(burgers(), hidden_layer=layers).to(dev)
+    model.train()
+    state0 = {k: v.clone() for k, v in model.state_dict().items()}
+    params = list(model.parameters())
+    names = [k for k, _ in model.named_parameters()]
+
+    # ---- partitioned over the ranks
+    (part,), (plan,) = pt.split_graph(u, pos, edges.src, edges.dst, world, ranks=[rank])
+    part.x = part.x.clone().requires_grad_(True)
+    exch = mdist.HaloExchange(plan)
+    (out_p,) = model.forward_partitioned([part], exch)
+    ((out_p * r[plan.owned]).sum() / n).backward()
+    bucket = mdist.GradBucket(params)
+    bucket.allreduce(average=False)                                    # every rank holds the partial sums of its part
+    grads_p = [p.grad.detach().clone() for p in params]
+    gu_p = part.x.grad.detach().clone()
+    bn_p = {k: v.detach().clone() for k, v in model.state_dict().items() if "running" in k}
+    torch.cuda.synchronize()
+
+    # ---- whole graph on this GPU
+    comm = ops.COMM
+    ops.COMM = ops._Comm()
+    try:
+        model.load_state_dict(state0)
+        model.zero_grad(set_to_none=True)
+
+        class Whole:
+            pass
+        whole = Whole()
+        whole.x, whole.pos, whole.edge_index, whole.batch, whole._edges = u.clone().requires_grad_(True), pos, None, None, edges
+        out_w = model(whole)
+        ((out_w * r).sum() / n).backward()
+    finally:
+        ops.COMM = comm
+    out = {"world": world, "nodes": n, "edges": int(edges.n_edges), "layers": layers, "halo_rows": plan.n_halo,
+           "own_rows": plan.n_own, "bn_exchange": "peer" if comm.peer is not None else "nccl",
+           "out_rel": rel(out_p, out_w[plan.owned]), "du_rel": rel(gu_p, whole.x.grad[plan.owned])}
+    worst, worst_name = 0.0, ""
+    for nm, a, p in zip(names, grads_p, params):
+        b = p.grad
+        if float(b.norm()) < 1e-9:
+            assert float((a - b).norm()) < 1e-7, nm
+            continue
+        rr = rel(a, b)
+        if rr > worst:
+            worst, worst_name = rr, nm
+    out["grad_rel_max"], out["grad_rel_argmax"] = worst, worst_name
+    out["bn_buffers_rel_max"] = max(rel(bn_p[k].float(), model.state_dict()[k].float()) for k in bn_p)
+    flag = torch.tensor([out["out_rel"], out["du_rel"], worst, out["bn_buffers_rel_max"]], device=dev, dtype=torch.float64)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    out["max_over_ranks"] = {"out_rel": float(flag[0]), "du_rel": float(flag[1]), "grad_rel": float(flag[2]),
+                             "bn_rel": float(flag[3])}
+    ok = float(flag[0]) < 2e-5 and float(flag[1]) < 1e-3 and float(flag[2]) < 1e-3 and float(flag[3]) < 1e-5
+    dist.barrier()
+    if rank == 0:
+        print(("HALO_PARITY_OK " if ok else "HALO_PARITY_FAIL ") + json.dumps(out), flush=True)
+        if len(sys.argv) > 1:
+            with open(sys.argv[1], "a") as f:
+                f.write(json.dumps(out) + "\n")
+    sys.stdout.flush()
+    torch.cuda.synchronize()
+    os._exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

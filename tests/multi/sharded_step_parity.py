@@ -1,0 +1,143 @@
+"""Run under torchrun with N >= 2 GPUs (tests/test_gpu_multi.py does, N = 2 and 4):
+
+    one MM-mode training step, the global batch SHARDED over N ranks (sync-BatchNorm sums over NVLink peer memory or
+    NCCL, flat gradient bucket all-reduced and averaged)
+        ==
+    the same global batch in ONE process (every rank recomputes it on its own GPU with the single-rank COMM)
+
+for the loss, the prediction rows of the rank's own samples, EVERY parameter gradient and the BatchNorm buffers.  The
+only legitimate difference is summation order (fp64 column sums added per rank first; fp32 gradient partial sums added
+by the all-reduce), so the bars are 1e-5 relative on loss / predictions / buffers and 1e-4 on gradients (a ReLU whose
+pre-activation moves by one ulp can flip: single terms, far below the bar at these sizes).
+Couplings checked: /root/reference/gnn_2d.py:56 (BatchNorm over the whole batch), /root/reference/mmpde.py:33-36
+(global-mean MSE), /root/reference/train_helper_2d.py:95-131 (the step).
+Prints one line `SHARDED_STEP_OK {json}` on rank 0; optional argv[1] = path to append the json to."""
+import json
+import os
+import random
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from mmpde_b200 import dist as mdist, ops, synthetic  # noqa: E402
+from mmpde_b200.PDEs import burgers  # noqa: E402
+from mmpde_b200.data_creator_2d import GraphCreator_FS_2D  # noqa: E402
+from mmpde_b200.gnn_2d import MP_PDE_Solver_2D  # noqa: E402
+from mmpde_b200.interpolate import ItpNet  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def build(dev, res, layers, seed):
+    pde = burgers()
+    pde.grid_size = pde.movingmesh_grid_size = pde.ori_grid_size = res
+    torch.manual_seed(seed)                     # same weights on every rank
+    model = MP_PDE_Solver_2D(pde, hidden_layer=layers).to(dev)
+    model_b = MP_PDE_Solver_2D(pde, hidden_layer=layers).to(dev)
+    net = ItpNet(res[1], res[2], [128, 64], [128, 64], [1, 4, 16, 4, 1]).to(dev)
+    for m in (model, model_b, net):
+        m.train()
+    return pde, model, model_b, net
+
+
+def step(pde, model, model_b, net, mover, fields, steps, dev):
+    gc = GraphCreator_FS_2D(pde, 35, "knn", 1, pde.grid_size[0])
+    for m in (model, model_b, net):
+        m.zero_grad(set_to_none=True)
+    data, labels = gc.create_data(fields, steps)
+    moved = gc.create_graph(net, data, labels, steps, dev, mover)
+    uniform = gc.create_graph(net, data, labels, steps, dev, None)
+    pred = gc.interpolate_pred(net, model_b(moved), moved, data, dev) + model(uniform)
+    loss = torch.nn.functional.mse_loss(pred, labels.to(dev).reshape(-1, 1))
+    loss.backward()
+    return pred.detach(), loss.detach()
+
+
+def main():
+    rank, world, dev = mdist.init_from_env()
+    assert world >= 2 and isinstance(ops.COMM, mdist.DistComm)
+    res = [31, 48, 48]
+    layers = int(os.environ.get("MMPDE_PARITY_LAYERS", "6"))
+    per = int(os.environ.get("MMPDE_PARITY_PER_RANK", "4"))
+    G = per * world
+    n = res[1] * res[2]
+    fields = synthetic.burgers_fields(G, res[0], res[1], res[2], seed=11)          # identical on every rank
+    random.seed(3)
+    steps = [random.randrange(1, 30) for _ in range(G)]
+    mover = synthetic.AnalyticMover().to(dev)
+
+    # ---- sharded: this rank's samples, DistComm, gradient bucket
+    pde, model, model_b, net = build(dev, res, layers, seed=7)
+    state0 = [{k: v.clone() for k, v in m.state_dict().items()} for m in (model, model_b, net)]
+    params = [p for m in (model, model_b, net) for p in m.parameters()]
+    bucket = mdist.GradBucket(params)
+    lo, hi = rank * per, (rank + 1) * per
+    pred_s, loss_s = step(pde, model, model_b, net, mover, fields[lo:hi], steps[lo:hi], dev)
+    bucket.allreduce()
+    loss_glob = loss_s.clone()
+    dist.all_reduce(loss_glob)
+    loss_glob /= world
+    grads_s = [p.grad.detach().clone() if p.grad is not None else None for p in params]
+    bufs_s = [{k: v.detach().clone() for k, v in m.state_dict().items() if "running" in k or "num_batches" in k}
+              for m in (model, model_b)]
+    torch.cuda.synchronize()
+
+    # ---- reference: the whole global batch on this GPU, single-rank COMM, same initial state
+    comm = ops.COMM
+    ops.COMM = ops._Comm()
+    try:
+        for m, s0 in zip((model, model_b, net), state0):
+            m.load_state_dict(s0)
+        pred_g, loss_g = step(pde, model, model_b, net, mover, fields, steps, dev)
+    finally:
+        ops.COMM = comm
+    grads_g = [p.grad.detach().clone() if p.grad is not None else None for p in params]
+    bufs_g = [{k: v.detach().clone() for k, v in m.state_dict().items() if "running" in k or "num_batches" in k}
+              for m in (model, model_b)]
+
+    names = [f"{tag}.{k}" for tag, m in (("model", model), ("model_b", model_b), ("itp", net)) for k, _ in m.named_parameters()]
+    out = {"world": world, "per_rank": per, "layers": layers, "nodes_global": G * n,
+           "bn_exchange": "peer" if comm.peer is not None else "nccl",
+           "loss_rel": abs(float(loss_glob) - float(loss_g)) / abs(float(loss_g)),
+           "pred_rel": rel(pred_s, pred_g[lo * n:hi * n])}
+    worst, worst_name = 0.0, ""
+    for nm, a, b in zip(names, grads_s, grads_g):
+        if b is None:
+            continue
+        nb = float(b.norm())
+        if nb < 1e-9:                                # biases in front of a BatchNorm: analytically zero
+            assert float((a - b).norm()) < 1e-7, nm
+            continue
+        r = rel(a, b)
+        if r > worst:
+            worst, worst_name = r, nm
+    out["grad_rel_max"], out["grad_rel_argmax"] = worst, worst_name
+    bn = 0.0
+    for bs, bg in zip(bufs_s, bufs_g):
+        for k in bg:
+            bn = max(bn, rel(bs[k].float(), bg[k].float()))
+    out["bn_buffers_rel_max"] = bn
+    flag = torch.tensor([out["loss_rel"], out["pred_rel"], worst, bn], device=dev, dtype=torch.float64)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    out["max_over_ranks"] = {"loss_rel": float(flag[0]), "pred_rel": float(flag[1]), "grad_rel": float(flag[2]),
+                             "bn_rel": float(flag[3])}
+    ok = float(flag[0]) < 1e-5 and float(flag[1]) < 1e-5 and float(flag[2]) < 1e-4 and float(flag[3]) < 1e-5
+    dist.barrier()
+    if rank == 0:
+        print(("SHARDED_STEP_OK " if ok else "SHARDED_STEP_FAIL ") + json.dumps(out), flush=True)
+        if len(sys.argv) > 1:
+            with open(sys.argv[1], "a") as f:
+                f.write(json.dumps(out) + "\n")
+    sys.stdout.flush()
+    torch.cuda.synchronize()
+    os._exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

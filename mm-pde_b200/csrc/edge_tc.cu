@@ -19,6 +19,7 @@
 // connected by mbarrier pipelines (operand tiles and accumulators are double-buffered); registers are moved between the
 // roles with setmaxnreg (forward 896 threads: 56 / 120 / 40 per thread; backward 512 threads: 104 / 184 / 40).
 #include "tc_common.cuh"
+#include "tma_host.cuh"
 
 namespace mmpde {
 using namespace tc;
@@ -102,16 +103,114 @@ __device__ __forceinline__ int lds_i32(uint32_t saddr) { return (int)lds_b32(sad
 
 // ================================================================================================================
 // Forward warp roles (896 threads): 16 epilogue warps (TMEM lane quadrant = warp & 3, 32-column quarter = warp >> 2),
-// 8 builder warps, 1 MMA warp (+ 3 idle to fill the warpgroup).  Every role is a latency-bound instruction stream
-// (~0.2 IPC per warp), so throughput comes from the NUMBER of warps per sub-partition: 4 epilogue + 2 builder each.
+// 8 builder warps, 1 MMA warp (+ 3 idle to fill the warpgroup).  Every role is an instruction-issue-bound stream, so
+// what counts is the number of instructions per edge: the Q'[src] rows are fetched by the TMA (gather4 into a
+// shared-memory ring, no address arithmetic / predicates / register prefetch in the builders), element-wise math uses
+// the packed fp32x2 forms, and the bias lives in the accumulator (tcgen05.st) instead of an add per element.
 // Register budget per thread moved with setmaxnreg from the launch value 72 (the CTA's pool is what it was launched
 // with: 896*72 = 64512): 16*32*56 + 8*32*120 + 4*32*40 = 64512.
 constexpr int F_EPI_WARPS = 16, F_BLD_WARPS = 8, F_MMA_WARP = F_EPI_WARPS + F_BLD_WARPS, F_THREADS = 896;
 constexpr int F_EPI_REGS = 56, F_BLD_REGS = 120, F_MMA_REGS = 40;
 
+// ---- packed fp32x2 (sm_100: FADD2 -- one issue slot for two fp32 additions) ---------------------------------------------
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// One operand row: 2*h1 = 2*relu(p + q) = z + |z| of this lane's 4 channels, split into bf16 hi / lo and written into
+// the two SWIZZLE_128B images (the lo image follows the hi image).  Same arithmetic as relu2_add + split4, 16 instead of
+// 24 instructions.
+template <int ROWS>
+__device__ __forceinline__ void build_row(uint32_t img, int row, int lane, const float4& p, const float4& q) {
+    float z0, z1, z2, z3, l0, l1, l2, l3;
+    unpack2(add2(pack2(p.x, p.y), pack2(q.x, q.y)), z0, z1);
+    unpack2(add2(pack2(p.z, p.w), pack2(q.z, q.w)), z2, z3);
+    const float r0 = z0 + fabsf(z0), r1 = z1 + fabsf(z1), r2 = z2 + fabsf(z2), r3 = z3 + fabsf(z3);
+    const uint32_t h01 = cvt_bf16x2(r0, r1), h23 = cvt_bf16x2(r2, r3);
+    unpack2(sub2(pack2(r0, r1), pack2(__uint_as_float(h01 << 16), __uint_as_float(h01 & 0xFFFF0000u))), l0, l1);
+    unpack2(sub2(pack2(r2, r3), pack2(__uint_as_float(h23 << 16), __uint_as_float(h23 & 0xFFFF0000u))), l2, l3);
+    const uint32_t a = img + tile_off<ROWS>(row, lane * 4);
+    sts_v2(a, make_uint2(h01, h23));
+    sts_v2(a + 2 * ROWS * 128, make_uint2(cvt_bf16x2(l0, l1), cvt_bf16x2(l2, l3)));
+}
+
+// P'[dst] of 8 consecutive rows of one builder warp (lane = 4 channels): a target's rows are consecutive, so 8 rows span
+// <= 2 targets unless some in-degree is < 4; such rows are listed in `odd` and patched afterwards.
+struct PRows {
+    float4 pa, pb;
+    int da, db;
+    uint32_t odd;
+};
+__device__ __forceinline__ void gather_p(PRows& g, const float* __restrict__ PQ, int d_lane, int r0, int lane) {
+    g.da = __shfl_sync(0xffffffffu, d_lane, r0);
+    g.db = __shfl_sync(0xffffffffu, d_lane, r0 + 7);
+    g.pa = g.pb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.da >= 0) g.pa = ldg4(PQ + (int64_t)g.da * 256 + lane * 4);
+    if (g.db >= 0) g.pb = ldg4(PQ + (int64_t)g.db * 256 + lane * 4);
+    g.odd = (__ballot_sync(0xffffffffu, d_lane >= 0 && d_lane != g.da && d_lane != g.db) >> r0) & 0xFFu;
+}
+// Source indices of a builder warp's rows, four per lane: lane l (< ROWS/4) holds rows 4l .. 4l+3 (-1 beyond the last edge:
+// the TMA fills such rows with zeros).  e is a multiple of 4 and the edge list is 16-byte aligned (checked on the host).
+template <int ROWS>
+__device__ __forceinline__ int4 load_src4(const int* __restrict__ src, int64_t e0, int row0, int64_t n_edges, bool valid_tile) {
+    int4 r = make_int4(-1, -1, -1, -1);
+    const int lane = threadIdx.x & 31;
+    const int64_t e = e0 + row0 + 4 * lane;
+    if (valid_tile && lane < ROWS / 4 && e < n_edges) {
+        if (e + 3 < n_edges) {
+            r = __ldg(reinterpret_cast<const int4*>(src + e));
+        } else {
+            r.x = __ldg(src + e);
+            if (e + 1 < n_edges) r.y = __ldg(src + e + 1);
+            if (e + 2 < n_edges) r.z = __ldg(src + e + 2);
+        }
+    }
+    return r;
+}
+__device__ __forceinline__ int src_of_row(const int4& s4, int r) {           // r warp-uniform
+    const int c = r & 3;
+    const int v = (c == 0) ? s4.x : (c == 1) ? s4.y : (c == 2) ? s4.z : s4.w;
+    return __shfl_sync(0xffffffffu, v, r >> 2);
+}
+// 8 gathered Q' rows (fp32, 512 bytes each, in the shared-memory ring at `rows`) + P' of their targets -> operand image
+// rows rowbase .. rowbase+7; then the rare patch loop (rows of a third target).
+template <int ROWS>
+__device__ __forceinline__ void build8(uint32_t img, int rowbase, uint32_t rows, const PRows& g, int d_lane, const int4& s4, int r0,
+                                       const float* __restrict__ PQ, int lane) {
+    float4 q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = lds_v4f(rows + k * 512 + lane * 16);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int d = __shfl_sync(0xffffffffu, d_lane, r0 + k);
+        if (d == g.da) build_row<ROWS>(img, rowbase + k, lane, g.pa, q[k]);
+        else build_row<ROWS>(img, rowbase + k, lane, g.pb, q[k]);
+    }
+    for (uint32_t odd = g.odd; odd != 0u; odd &= odd - 1u) {
+        const int k = __ffs(odd) - 1;
+        const int d = __shfl_sync(0xffffffffu, d_lane, r0 + k), sr = src_of_row(s4, r0 + k);
+        build_row<ROWS>(img, rowbase + k, lane, ldg4(PQ + (int64_t)d * 256 + lane * 4), ldg4(PQ + (int64_t)sr * 256 + 128 + lane * 4));
+    }
+}
+
 // ================================================================================================================
 // Forward:  agg[i] = mean_{e: dst=i} relu(W2 relu(P'[i] + Q'[src_e]) + b2);  mask2 = sign bits of z2.
-// Tile = 128 edges.  D[o][e] = sum_c W2[o][c] h1[e][c]  (M = 128 channels on TMEM lanes, N = 128 edges).
+// Tile = 128 edges.  D[o][e] = -b2[o] - sum_c W2[o][c] h1[e][c] = -z2  (M = 128 channels on TMEM lanes, N = 128 edges):
+// the NEGATED pre-activation, so that the sign bit of an accumulator element IS the mask bit (z2 > 0; a sum that
+// cancels to zero is +0 in the accumulator, so z2 = 0 gives 0 like relu'(0)) and no negation is needed per element.
 // ================================================================================================================
 constexpr int FTE = 128;
 constexpr uint32_t F_IMG = 2 * FTE * 128;                  // one [128][128] bf16 image (2 column blocks) = 32 KB
@@ -120,25 +219,27 @@ struct EdgeFwdArgs {
     const float* w2; const float* b2; float* agg; int64_t ld_agg; uint32_t* mask2;
 };
 struct FwdSmem {
-    static constexpr uint32_t H = 0;                       // 2 stages x (hi, lo)
     // Targets of the tile's edges for the epilogue, slot = tile iteration & 7.  The epilogue still reads slot i after it
     // has released accumulator stage i (boundary targets of its last piece); the builders may then run up to tile i+4
     // (operand stage free <=> MMA of tile i+2 done <=> accumulator stage of tile i released), so 8 slots keep the
     // slot being read and the slot being written apart by construction, not by timing.
     static constexpr int SLOTS = 8;
-    static constexpr uint32_t DST = 2 * 2 * F_IMG;         // int dst[SLOTS][128]
+    static constexpr uint32_t H = 0;                       // 2 stages x (hi, lo)
+    static constexpr uint32_t RING = 2 * 2 * F_IMG;        // Q' rows of one tile: 8 builder warps x 16 rows x 512 B (TMA destination)
+    static constexpr uint32_t DST = RING + FTE * 512;      // int dst[SLOTS][128]
     static constexpr uint32_t INV = DST + SLOTS * FTE * 4; // float inv_deg[dst][SLOTS][128]
-    static constexpr uint32_t BAR = INV + SLOTS * FTE * 4; // h_full[2] h_empty[2] tm_full[2] tm_empty[2], tmem slot
-    static constexpr uint32_t TOTAL = BAR + 128;
+    static constexpr uint32_t BAR = INV + SLOTS * FTE * 4; // h_full[2] h_empty[2] tm_full[2] tm_empty[2] q_full[8][2], tmem slot
+    static constexpr uint32_t TOTAL = BAR + 256;
 };
 
-__global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p) {
+__global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p, const __grid_constant__ CUtensorMap q_map) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(sm);
     const uint32_t bar0 = sbase + FwdSmem::BAR;
     const uint32_t h_full = bar0, h_empty = bar0 + 16, tm_full = bar0 + 32, tm_empty = bar0 + 48;   // [b] at +8*b
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + FwdSmem::BAR + 64);
+    const uint32_t q_full = bar0 + 64;                                                              // [warp][half] at +16*w + 8*h
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + FwdSmem::BAR + 64 + F_BLD_WARPS * 16);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -147,6 +248,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
             mbar_init(h_full + 8 * b, F_BLD_WARPS); mbar_init(h_empty + 8 * b, 1);
             mbar_init(tm_full + 8 * b, 1); mbar_init(tm_empty + 8 * b, F_EPI_WARPS);
         }
+        for (int k = 0; k < 2 * F_BLD_WARPS; ++k) mbar_init(q_full + 8 * k, 1);
         fence_mbar_init();
     }
     tc_fence_before();
@@ -162,9 +264,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
         const int q = warp & 3, quarter = warp >> 2;                       // TMEM lane quadrant, 32-column quarter of the tile
         const int o = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const float bias = __ldg(p.b2 + o);
-        if (quarter < 2)                                                   // W2/2 (the operand tile holds 2*h1) -> tensor memory
-            weight_to_tmem(p.w2, 128, 1, o, tmem_w_hi + lane_addr, tmem_w_lo + lane_addr, 2 * quarter, 2 * quarter + 2, 0.5f);
+        const uint32_t nbias = __float_as_uint(0.f - __ldg(p.b2 + o));     // accumulators start at -b2 (never -0)
+        if (quarter < 2)                                                   // -W2/2 (the operand tile holds 2*h1) -> tensor memory
+            weight_to_tmem(p.w2, 128, 1, o, tmem_w_hi + lane_addr, tmem_w_lo + lane_addr, 2 * quarter, 2 * quarter + 2, -0.5f);
+        tmem_fill32(tmem_d + lane_addr + quarter * 32, nbias);
+        tmem_fill32(tmem_d + lane_addr + FTE + quarter * 32, nbias);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -179,11 +283,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
             tc_fence_after();
             const uint32_t d_addr = tmem_d + lane_addr + b * FTE + quarter * 32;
             int cur = -1;
-            float run_s = 0.f, run_a = 0.f, cur_inv = 0.f;                 // sum z, sum |z| of the current run
+            uint64_t run_s = 0ull;                                         // packed pair of partial sums of a = -z2
+            float run_a = 0.f, cur_inv = 0.f;                              // sum |a| of the current run
             // The thread's 32 edges in 4 pieces of 8 (a rolled loop over small tcgen05.ld.x8 pieces keeps the body short).
-            // Per edge: sign mask + running per-target sum of relu(z), kept off the busy ALU pipe:
-            //   sum relu(z) = (sum z + sum |z|) / 2   -> two adds per edge (|.| is an operand modifier);
-            //   mask bit    = sign of (0 - z)         -> one add (exact: set iff z > 0, both zeros give +0) + one funnel shift.
+            // Per edge: running per-target sum of relu(z2) and the sign mask, kept off the busy ALU pipe:
+            //   sum relu(z2) = (sum |a| - sum a) / 2   -> 1.5 adds per edge (the sum of a as packed pairs);
+            //   mask bit     = sign bit of a           -> one funnel shift.
             // Targets are contiguous runs of edges; `bm` marks the first edge of each run (warp-uniform), so groups of 4
             // edges without a boundary take the short path.  A warp's 32 columns always start a new run (partial runs
             // add up atomically).
@@ -192,34 +297,36 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
             const int d_pv = (lane > 0) ? lds_i32(dsts + 4 * (e_first + lane) - 4) : -2;
             const uint32_t bm = __ballot_sync(0xffffffffu, d_me != d_pv);
             uint32_t word = 0;                                             // filled MSB-first: bit 31-j <- edge j
+            auto run_sum = [&]() { float s0, s1; unpack2(run_s, s0, s1); return 0.5f * (run_a - (s0 + s1)); };
             auto process8 = [&](uint32_t (&vc)[8], int pc) {              // piece pc: columns e_first + 8*pc .. +7
                 const int e0 = e_first + pc * 8;
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    const float z0 = __uint_as_float(vc[4 * g]) + bias, z1 = __uint_as_float(vc[4 * g + 1]) + bias,
-                                z2 = __uint_as_float(vc[4 * g + 2]) + bias, z3 = __uint_as_float(vc[4 * g + 3]) + bias;
+                    const float a0 = __uint_as_float(vc[4 * g]), a1 = __uint_as_float(vc[4 * g + 1]),
+                                a2 = __uint_as_float(vc[4 * g + 2]), a3 = __uint_as_float(vc[4 * g + 3]);
                     const uint32_t nib = (bm >> (pc * 8 + 4 * g)) & 15u;
                     if (nib == 0u) {
-                        run_s += (z0 + z1) + (z2 + z3);
-                        run_a += (fabsf(z0) + fabsf(z1)) + (fabsf(z2) + fabsf(z3));
+                        run_s = add2(add2(run_s, pack2(a0, a1)), pack2(a2, a3));
+                        run_a += (fabsf(a0) + fabsf(a1)) + (fabsf(a2) + fabsf(a3));
                     } else {
-                        const float z[4] = {z0, z1, z2, z3};
+                        const float a[4] = {a0, a1, a2, a3};
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if (nib & (1u << k)) {
-                                flush_mean(p.agg, p.ld_agg, cur, cur_inv, o, 0.5f * (run_s + run_a));
+                                flush_mean(p.agg, p.ld_agg, cur, cur_inv, o, run_sum());
                                 cur = lds_i32(dsts + 4 * (e0 + 4 * g + k));                   // used at the NEXT flush:
                                 cur_inv = __uint_as_float(lds_b32(dsts + FwdSmem::SLOTS * FTE * 4 + 4 * (e0 + 4 * g + k)));
-                                run_s = run_a = 0.f;                                          // latency stays hidden
+                                run_s = 0ull;                                                 // latency stays hidden
+                                run_a = 0.f;
                             }
-                            run_s += z[k];
-                            run_a += fabsf(z[k]);
+                            run_s = add2(run_s, pack2(a[k], 0.f));
+                            run_a += fabsf(a[k]);
                         }
                     }
-                    word = __funnelshift_l(__float_as_uint(0.f - z0), word, 1);
-                    word = __funnelshift_l(__float_as_uint(0.f - z1), word, 1);
-                    word = __funnelshift_l(__float_as_uint(0.f - z2), word, 1);
-                    word = __funnelshift_l(__float_as_uint(0.f - z3), word, 1);
+                    word = __funnelshift_l(vc[4 * g], word, 1);
+                    word = __funnelshift_l(vc[4 * g + 1], word, 1);
+                    word = __funnelshift_l(vc[4 * g + 2], word, 1);
+                    word = __funnelshift_l(vc[4 * g + 3], word, 1);
                 }
             };
             uint32_t va[8], vb[8];
@@ -232,7 +339,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
                 tmem_wait_ld8(vb);
                 if (pc + 2 < 4) {
                     tmem_ld8_async(d_addr + (pc + 2) * 8, va);
-                } else {                                                   // all 32 columns are in registers: release the stage
+                } else {                                                   // all 32 columns are in registers: back to -b2, release
+                    tmem_fill32(d_addr, nbias);
+                    tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tm_empty + 8 * b);
@@ -241,7 +350,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
             }
             // mask2[chunk of 32 edges][channel]: bit j = (z2 > 0) of edge 32*chunk + j
             p.mask2[((t * 4 + quarter) * 128) + o] = __brev(word);
-            flush_mean(p.agg, p.ld_agg, cur, cur_inv, o, 0.5f * (run_s + run_a));
+            flush_mean(p.agg, p.ld_agg, cur, cur_inv, o, run_sum());
             if (warp == 0) TL(3, i, 2);
         }
     } else if (warp < F_MMA_WARP) {
@@ -249,39 +358,59 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
         reg_inc<F_BLD_REGS>();
         const int w = warp - F_EPI_WARPS;
         const int row0 = w * 16;
-        Gather8 ga, gb;
+        const uint32_t ring = sbase + FwdSmem::RING + (uint32_t)w * (16 * 512);      // this warp's 16 Q' rows
+        const uint32_t qbar = q_full + 16 * w;                                       // [half] at +8*half
         const int64_t G = gridDim.x;
-        // row indices run two tiles ahead of the build, the gathers one half tile / one tile ahead
-        RowIdx idx = load_row_idx<16>(p.dst, p.src, (int64_t)blockIdx.x * FTE, row0, p.n_edges, (int64_t)blockIdx.x < n_tiles);
-        RowIdx idx_n = load_row_idx<16>(p.dst, p.src, (blockIdx.x + G) * FTE, row0, p.n_edges, blockIdx.x + G < n_tiles);
-        float inv = (idx.d >= 0) ? __ldg(p.inv_deg + idx.d) : 0.f;
-        gather8(ga, p.PQ, idx, 0, lane);
+        // Q'[src] rows of half h (8 rows = two gather4 messages, issued by lanes 2h and 2h+1 from their four indices)
+        auto issue_half = [&](int h, const int4& s4) {
+            if (lane == 2 * h) mbar_arrive_expect_tx(qbar + 8 * h, 8 * 512);
+            if ((lane >> 1) == h) tma::gather4(ring + (uint32_t)lane * 2048, &q_map, 128, s4.x, s4.y, s4.z, s4.w, qbar + 8 * h);
+        };
+        // target indices run two tiles ahead of the build, the source indices feed the TMA one tile ahead, P' rows are
+        // prefetched in registers half a tile ahead
+        int d_cur = load_row_idx<16>(p.dst, p.src, (int64_t)blockIdx.x * FTE, row0, p.n_edges, (int64_t)blockIdx.x < n_tiles).d;
+        int d_nxt = load_row_idx<16>(p.dst, p.src, (blockIdx.x + G) * FTE, row0, p.n_edges, blockIdx.x + G < n_tiles).d;
+        int4 s_cur = load_src4<16>(p.src, (int64_t)blockIdx.x * FTE, row0, p.n_edges, (int64_t)blockIdx.x < n_tiles);
+        int4 s_nxt = load_src4<16>(p.src, (blockIdx.x + G) * FTE, row0, p.n_edges, blockIdx.x + G < n_tiles);
+        float inv = (d_cur >= 0) ? __ldg(p.inv_deg + d_cur) : 0.f;
+        if ((int64_t)blockIdx.x < n_tiles) { issue_half(0, s_cur); issue_half(1, s_cur); }
+        PRows ga, gb;
+        gather_p(ga, p.PQ, d_cur, 0, lane);
         int i = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += G, ++i) {
             const int b = i & 1;
+            const uint32_t qph = (uint32_t)i & 1u;
+            const bool more = t + G < n_tiles;
             if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 0);
-            const RowIdx idx_nn = load_row_idx<16>(p.dst, p.src, (t + 2 * G) * FTE, row0, p.n_edges, t + 2 * G < n_tiles);
-            const float inv_n = (idx_n.d >= 0) ? __ldg(p.inv_deg + idx_n.d) : 0.f;
-            gather8(gb, p.PQ, idx, 8, lane);
+            const int d_nn = load_row_idx<16>(p.dst, p.src, (t + 2 * G) * FTE, row0, p.n_edges, t + 2 * G < n_tiles).d;
+            const int4 s_nn = load_src4<16>(p.src, (t + 2 * G) * FTE, row0, p.n_edges, t + 2 * G < n_tiles);
+            const float inv_n = (d_nxt >= 0) ? __ldg(p.inv_deg + d_nxt) : 0.f;
+            gather_p(gb, p.PQ, d_cur, 8, lane);
             mbar_wait(h_empty + 8 * b, ((uint32_t)(i >> 1) & 1u) ^ 1u);    // MMA of tile i-2 has consumed this stage
             if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 1);
             const uint32_t img = sbase + FwdSmem::H + b * (2 * F_IMG);
             if (lane < 16) {
                 const uint32_t slot = sbase + FwdSmem::DST + (uint32_t)((i & (FwdSmem::SLOTS - 1)) * FTE + row0 + lane) * 4;
-                sts_b32(slot, (uint32_t)idx.d);
+                sts_b32(slot, (uint32_t)d_cur);
                 sts_b32(slot + FwdSmem::SLOTS * FTE * 4, __float_as_uint(inv));
             }
-            build_h8<FTE>(img, row0, ga, idx, 0, p.PQ, lane);
-            gather8(ga, p.PQ, idx_n, 0, lane);                             // first half of the NEXT tile
-            build_h8<FTE>(img, row0 + 8, gb, idx, 8, p.PQ, lane);
+            mbar_wait(qbar, qph);                                          // rows 0..7 have landed
+            build8<FTE>(img, row0, ring, ga, d_cur, s_cur, 0, p.PQ, lane);
+            __syncwarp();                                                  // every lane has consumed its part of the rows
+            if (more) issue_half(0, s_nxt);                                // refill them for the NEXT tile
+            gather_p(ga, p.PQ, d_nxt, 0, lane);                            // first half of the next tile
+            mbar_wait(qbar + 8, qph);
+            build8<FTE>(img, row0 + 8, ring + 8 * 512, gb, d_cur, s_cur, 8, p.PQ, lane);
+            __syncwarp();
+            if (more) issue_half(1, s_nxt);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(h_full + 8 * b);
             if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 2);
-            idx = idx_n; idx_n = idx_nn; inv = inv_n;
+            d_cur = d_nxt; d_nxt = d_nn; s_cur = s_nxt; s_nxt = s_nn; inv = inv_n;
         }
     } else {
-        // ------------------------------------------------------------------ MMA issuer (one thread of warp 12)
+        // ------------------------------------------------------------------ MMA issuer (one thread of warp 24)
         reg_dec<F_MMA_REGS>();
         constexpr uint32_t idesc = idesc_bf16(128, FTE, 0, 0);
         int i = 0;
@@ -298,13 +427,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
             constexpr uint32_t b_hi = desc_hi_sw128(1024);
             const uint32_t d_tm = tmem_d + b * FTE;
 #pragma unroll
-            for (int prod = 0; prod < 3; ++prod) {                         // hi*hi + hi*lo + lo*hi
+            for (int prod = 0; prod < 3; ++prod) {                         // hi*hi + hi*lo + lo*hi, on top of -b2
                 const uint32_t a = (prod == 2) ? tmem_w_lo : tmem_w_hi;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
                     umma_bf16_ts_lh(d_tm, a + ks * 8,
-                                    b_lo + (((prod == 1 ? F_IMG : 0) + (ks >> 2) * (FTE * 128) + (ks & 3) * 32) >> 4), b_hi, idesc,
-                                    (prod | ks) ? 1u : 0u);
+                                    b_lo + (((prod == 1 ? F_IMG : 0) + (ks >> 2) * (FTE * 128) + (ks & 3) * 32) >> 4), b_hi, idesc, 1u);
             }
             umma_commit(h_empty + 8 * b);
             umma_commit(tm_full + 8 * b);
@@ -619,15 +747,18 @@ static int edge_grid(int64_t n_tiles) { return (int)imin64(n_tiles, sm_count());
 
 extern "C" int mmpde_edge_fwd(const float* PQ, const int32_t* edge_src, const int32_t* edge_dst, const float* inv_deg,
                               int64_t n_edges, const float* w2, const float* b2, float* agg, int64_t ld_agg,
-                              uint32_t* mask2, void* stream) {
-    if (n_edges < 0 || ld_agg < 128) return MMPDE_EINVAL;
+                              uint32_t* mask2, int64_t n_src, void* stream) {
+    if (n_edges < 0 || ld_agg < 128 || n_src < 0) return MMPDE_EINVAL;
     if (n_edges == 0) return MMPDE_OK;
+    if (n_src == 0 || ((reinterpret_cast<uintptr_t>(PQ) | reinterpret_cast<uintptr_t>(edge_src)) & 15)) return MMPDE_EINVAL;
     constexpr size_t smem = FwdSmem::TOTAL + 1024;
     MMPDE_ENSURE_SMEM(edge_fwd_tc_kernel, smem);
+    CUtensorMap q_map;                                     // the Q' half of PQ, one 128-float row per box (TMA row gathers)
+    if (int rc = tma::make_row_gather_map(&q_map, PQ + 128, n_src, 256, 128)) return rc;
     EdgeFwdArgs p;
     p.PQ = PQ; p.src = edge_src; p.dst = edge_dst; p.inv_deg = inv_deg; p.n_edges = n_edges; p.w2 = w2; p.b2 = b2;
     p.agg = agg; p.ld_agg = ld_agg; p.mask2 = mask2;
-    edge_fwd_tc_kernel<<<edge_grid((n_edges + FTE - 1) / FTE), F_THREADS, smem, (cudaStream_t)stream>>>(p);
+    edge_fwd_tc_kernel<<<edge_grid((n_edges + FTE - 1) / FTE), F_THREADS, smem, (cudaStream_t)stream>>>(p, q_map);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }

@@ -25,26 +25,43 @@ def _rel(a, b, atol=0.0):
     return 0.0 if err <= atol else err / float(b.norm().clamp_min(1e-30))
 
 
-def _grad_report(model, omodel, tag, floor):
-    """Relative L2 of every parameter gradient; gradients whose reference norm is below `floor` (biases in front of a
-    BatchNorm: analytically zero, pure rounding noise on both sides) are compared absolutely."""
+def _grad_report(model, omodel, tag, floor=1e-5):
+    """Relative L2 of every parameter gradient.  Gradients that are analytically ZERO (a bias in front of a BatchNorm:
+    the mean subtraction cancels it) are rounding noise on both sides -- recognised by a reference norm below `floor`
+    times the largest gradient norm of the module, and compared absolutely against that scale instead."""
     worst, rows = 0.0, []
     on = dict(omodel.named_parameters())
+    scale = max(float(q.grad.norm()) for q in on.values() if q.grad is not None)
     for k, p in model.named_parameters():
         ref = on[k].grad
         if ref is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
         nrm = float(ref.norm())
-        if nrm < floor:
-            assert float((p.grad.cpu() - ref).norm()) < 10 * floor, (tag, k, nrm)
+        if nrm < floor * scale:
+            assert float((p.grad.cpu() - ref).norm()) < 10 * floor * scale, (tag, k, nrm)
             continue
         r = _rel(p.grad, ref)
         rows.append((r, k))
         worst = max(worst, r)
     rows.sort(reverse=True)
-    print(f"[{tag}] worst gradient rel-L2 {worst:.3e}; top: " + ", ".join(f"{k}={r:.2e}" for r, k in rows[:4]))
+    print(f"[{tag}] worst gradient rel-L2 {worst:.3e}; top: " + ", ".join(f"{k}={r:.2e}" for r, k in rows[:5]))
     return worst, rows
+
+
+class HostMover(torch.nn.Module):
+    """Evaluates the wrapped mesh mover (and, through autograd, its gradient) on the HOST whatever device the inputs live
+    on, so that the CUDA path and the CPU oracle see bit-identical moved meshes.  The mover is outside the hot path (plain
+    PyTorch on both sides); evaluated in fp32 on two different devices its sin/cos/tanh differ in the last bit, which on a
+    barely moved lattice (displacement ~0.2 h) reorders nearly equidistant neighbours -- two equally valid graphs, but no
+    longer comparable edge by edge."""
+
+    def __init__(self, inner):
+        super().__init__()
+        self.inner = inner
+
+    def forward(self, u, grid, rf=False):
+        return self.inner(u.cpu(), grid.cpu()).to(grid.device)
 
 
 def _copy_bn(model):
@@ -68,7 +85,7 @@ def test_c2_burgers_mm_step_full_size_vs_oracle():
         p.grid_size = p.movingmesh_grid_size = p.ori_grid_size = res
     fields = synthetic.burgers_fields(B, seed=0)
     steps = [1 + (7 * i) % 30 for i in range(B)]
-    mover = synthetic.AnalyticMover()
+    mover = HostMover(synthetic.AnalyticMover())
     torch.manual_seed(0)
     omodel, omodel_b = oproc.MP_PDE_Solver_2D(opde), oproc.MP_PDE_Solver_2D(opde)
     onet = oitp.ItpNet(48, 48, [128, 64], [128, 64], [1, 4, 16, 4, 1])
@@ -97,13 +114,13 @@ def test_c2_burgers_mm_step_full_size_vs_oracle():
     assert moved.edge_index.shape == (2, B * 2304 * 35)
     assert torch.equal(moved.edge_index.cpu(), omoved.edge_index)
     assert torch.equal(uniform.edge_index.cpu(), ouniform.edge_index)
-    assert _rel(moved.x, omoved.x) < 1e-4 and _rel(moved.pos, omoved.pos) < 1e-6
+    assert torch.equal(moved.pos.cpu(), omoved.pos) and _rel(moved.x, omoved.x) < 1e-4
     r_pred = _rel(pred, opred)
     print(f"[C2 full] pred rel-L2 {r_pred:.3e}  loss {float(loss):.7f} vs {float(oloss):.7f}")
     assert r_pred < TOL
     assert abs(float(loss) - float(oloss)) <= 1e-4 * abs(float(oloss))
     for tag, m, om in (("model", model, omodel), ("model_b", model_b, omodel_b), ("itp", net, onet)):
-        worst, _ = _grad_report(m, om, f"C2 full / {tag}", floor=1e-9)
+        worst, _ = _grad_report(m, om, f"C2 full / {tag}")
         assert worst < TOL, (tag, worst)
     for m, om in ((model, omodel), (model_b, omodel_b)):
         ref = _copy_bn(om)
@@ -122,14 +139,14 @@ def test_c3_cylinder_mm_step_full_size_vs_oracle():
     from oracle import creator as ocreator, itp as oitp, pdes as opdes, processor as oproc
     torch.set_num_threads(os.cpu_count() or 1)
     dev = torch.device("cuda:0")
-    n, B = 2521, 4
+    n, B = 2521, 16
     cloud = synthetic.cylinder_cloud(n, seed=0)
     pde, opde = cy(ori_grid=cloud, device=dev), opdes.cy(ori_grid=cloud)
     for p in (pde, opde):
         p.grid_size = p.movingmesh_grid_size = p.ori_grid_size = [30, n]
     fields = synthetic.cylinder_fields(B, cloud, 30, seed=3)
-    steps = [2, 9, 17, 28]
-    mover = synthetic.AnalyticMover()
+    steps = [1 + (5 * i) % 28 for i in range(B)]
+    mover = HostMover(synthetic.AnalyticMover())
     torch.manual_seed(1)
     omodel, omodel_b = oproc.MP_PDE_Solver_2D(opde), oproc.MP_PDE_Solver_2D(opde)
     onet = oitp.ItpNet(n, None, [128, 64], [128, 64], [1, 4, 16, 4, 1])
@@ -160,7 +177,7 @@ def test_c3_cylinder_mm_step_full_size_vs_oracle():
     assert r_pred < TOL
     assert abs(float(loss) - float(oloss)) <= 1e-4 * abs(float(oloss))
     for tag, m, om in (("model", model, omodel), ("model_b", model_b, omodel_b), ("itp", net, onet)):
-        worst, _ = _grad_report(m, om, f"C3 full / {tag}", floor=1e-9)
+        worst, _ = _grad_report(m, om, f"C3 full / {tag}")
         assert worst < TOL, (tag, worst)
 
 
@@ -234,8 +251,12 @@ def test_c4_graph_knn_1m_tie_aware():
     d_ref, i_ref = tree.query(xy.double().numpy(), k=36, workers=-1)
     i_ref, d_ref = i_ref[:, 1:], d_ref[:, 1:]                # drop self (distance 0, jittered points are distinct)
     x64 = xy.double().numpy()
-    d_got = np.sqrt(((x64[nbr] - x64[:, None, :]) ** 2).sum(-1))
-    assert (np.diff(d_got.astype(np.float32) ** 2, axis=1) >= -1e-12).all()           # ascending in the fp32 rule
+    # ascending in the frozen fp32 rule d2 = fmaf(dy, dy, dx*dx): differences in fp32, the fma emulated in fp64
+    x32 = xy.numpy()
+    dx = x32[nbr, 0] - x32[:, None, 0]
+    dy = x32[nbr, 1] - x32[:, None, 1]
+    d2_rule = (dy.astype(np.float64) * dy.astype(np.float64) + (dx * dx).astype(np.float64)).astype(np.float32)
+    assert (np.diff(d2_rule, axis=1) >= 0).all()
     same_set = (np.sort(nbr, 1) == np.sort(i_ref, 1)).all(1)
     bad = np.nonzero(~same_set)[0]
     kth = d_ref[:, -1]
@@ -244,7 +265,7 @@ def test_c4_graph_knn_1m_tie_aware():
         missing = np.setdiff1d(i_ref[r], nbr[r])
         de = np.sqrt(((x64[extra] - x64[r]) ** 2).sum(-1))
         dm = np.sqrt(((x64[missing] - x64[r]) ** 2).sum(-1))
-        assert np.all(np.abs(de ** 2 - kth[r] ** 2) <= 4e-7 * kth[r] ** 2 + 1e-12), r
-        assert np.all(np.abs(dm ** 2 - kth[r] ** 2) <= 4e-7 * kth[r] ** 2 + 1e-12), r
+        assert np.all(np.abs(de ** 2 - kth[r] ** 2) <= 1e-6 * kth[r] ** 2 + 1e-12), r
+        assert np.all(np.abs(dm ** 2 - kth[r] ** 2) <= 1e-6 * kth[r] ** 2 + 1e-12), r
     print(f"[C4 1M] graph 35-NN sets equal to cKDTree: {same_set.mean():.6f} ({len(bad)} rows differ by fp32 near-ties)")
     assert len(bad) <= n // 1000

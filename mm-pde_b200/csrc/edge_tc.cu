@@ -19,7 +19,6 @@
 // connected by mbarrier pipelines (operand tiles and accumulators are double-buffered); registers are moved between the
 // roles with setmaxnreg (forward 896 threads: 56 / 120 / 40 per thread; backward 512 threads: 104 / 184 / 40).
 #include "tc_common.cuh"
-#include "tma_host.cuh"
 
 namespace mmpde {
 using namespace tc;
@@ -104,13 +103,17 @@ __device__ __forceinline__ int lds_i32(uint32_t saddr) { return (int)lds_b32(sad
 // ================================================================================================================
 // Forward warp roles (896 threads): 16 epilogue warps (TMEM lane quadrant = warp & 3, 32-column quarter = warp >> 2),
 // 8 builder warps, 1 MMA warp (+ 3 idle to fill the warpgroup).  Every role is an instruction-issue-bound stream, so
-// what counts is the number of instructions per edge: the Q'[src] rows are fetched by the TMA (gather4 into a
-// shared-memory ring, no address arithmetic / predicates / register prefetch in the builders), element-wise math uses
-// the packed fp32x2 forms, and the bias lives in the accumulator (tcgen05.st) instead of an add per element.
+// what counts is the number of instructions per edge: the Q'[src] rows are gathered ASYNCHRONOUSLY into a shared-memory
+// ring (cp.async, 16 bytes per lane = one row per warp instruction, half a tile ahead: no register prefetch state, no
+// scoreboard stalls in the builders), element-wise math uses the packed fp32x2 forms, and the bias lives in the
+// accumulator (tcgen05.st) instead of an add per element.
+// Why cp.async and not the TMA: measured on a B200 (profiles/r02_tma_gather4_probe.txt, r02_async_row_copy_probe.txt)
+// the TMA spends ~60 clk PER ROW on tile::gather4 (8.6 B/clk/SM for 512-byte rows; 68-100 clk per row for 1-D bulk
+// copies), cp.async sustains a row every 10-12 clk (42-51 B/clk/SM) -- the edge kernels need ~25.
 // Register budget per thread moved with setmaxnreg from the launch value 72 (the CTA's pool is what it was launched
-// with: 896*72 = 64512): 16*32*56 + 8*32*120 + 4*32*40 = 64512.
+// with: 896*72 = 64512): 16*32*64 + 8*32*104 + 4*32*40 = 64512 (the builders hold no prefetched rows any more).
 constexpr int F_EPI_WARPS = 16, F_BLD_WARPS = 8, F_MMA_WARP = F_EPI_WARPS + F_BLD_WARPS, F_THREADS = 896;
-constexpr int F_EPI_REGS = 56, F_BLD_REGS = 120, F_MMA_REGS = 40;
+constexpr int F_EPI_REGS = 64, F_BLD_REGS = 104, F_MMA_REGS = 40;
 
 // ---- packed fp32x2 (sm_100: FADD2 -- one issue slot for two fp32 additions) ---------------------------------------------
 __device__ __forceinline__ uint64_t pack2(float a, float b) {
@@ -132,7 +135,8 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
 
 // One operand row: 2*h1 = 2*relu(p + q) = z + |z| of this lane's 4 channels, split into bf16 hi / lo and written into
 // the two SWIZZLE_128B images (the lo image follows the hi image).  Same arithmetic as relu2_add + split4, 16 instead of
-// 24 instructions.
+// 24 instructions.  (Callers select p with sel4, never with a branch: a branch per row would fence the rows of a warp
+// off from each other and serialise their dependency chains.)
 template <int ROWS>
 __device__ __forceinline__ void build_row(uint32_t img, int row, int lane, const float4& p, const float4& q) {
     float z0, z1, z2, z3, l0, l1, l2, l3;
@@ -147,61 +151,51 @@ __device__ __forceinline__ void build_row(uint32_t img, int row, int lane, const
     sts_v2(a + 2 * ROWS * 128, make_uint2(cvt_bf16x2(l0, l1), cvt_bf16x2(l2, l3)));
 }
 
-// P'[dst] of 8 consecutive rows of one builder warp (lane = 4 channels): a target's rows are consecutive, so 8 rows span
-// <= 2 targets unless some in-degree is < 4; such rows are listed in `odd` and patched afterwards.
-struct PRows {
-    float4 pa, pb;
-    int da, db;
-    uint32_t odd;
-};
-__device__ __forceinline__ void gather_p(PRows& g, const float* __restrict__ PQ, int d_lane, int r0, int lane) {
-    g.da = __shfl_sync(0xffffffffu, d_lane, r0);
-    g.db = __shfl_sync(0xffffffffu, d_lane, r0 + 7);
-    g.pa = g.pb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g.da >= 0) g.pa = ldg4(PQ + (int64_t)g.da * 256 + lane * 4);
-    if (g.db >= 0) g.pb = ldg4(PQ + (int64_t)g.db * 256 + lane * 4);
-    g.odd = (__ballot_sync(0xffffffffu, d_lane >= 0 && d_lane != g.da && d_lane != g.db) >> r0) & 0xFFu;
+// cp.async: 16 bytes global -> shared without passing through registers; src_bytes = 0 zero-fills (rows past the last edge)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-// Source indices of a builder warp's rows, four per lane: lane l (< ROWS/4) holds rows 4l .. 4l+3 (-1 beyond the last edge:
-// the TMA fills such rows with zeros).  e is a multiple of 4 and the edge list is 16-byte aligned (checked on the host).
-template <int ROWS>
-__device__ __forceinline__ int4 load_src4(const int* __restrict__ src, int64_t e0, int row0, int64_t n_edges, bool valid_tile) {
-    int4 r = make_int4(-1, -1, -1, -1);
-    const int lane = threadIdx.x & 31;
-    const int64_t e = e0 + row0 + 4 * lane;
-    if (valid_tile && lane < ROWS / 4 && e < n_edges) {
-        if (e + 3 < n_edges) {
-            r = __ldg(reinterpret_cast<const int4*>(src + e));
-        } else {
-            r.x = __ldg(src + e);
-            if (e + 1 < n_edges) r.y = __ldg(src + e + 1);
-            if (e + 2 < n_edges) r.z = __ldg(src + e + 2);
-        }
-    }
-    return r;
-}
-__device__ __forceinline__ int src_of_row(const int4& s4, int r) {           // r warp-uniform
-    const int c = r & 3;
-    const int v = (c == 0) ? s4.x : (c == 1) ? s4.y : (c == 2) ? s4.z : s4.w;
-    return __shfl_sync(0xffffffffu, v, r >> 2);
-}
-// 8 gathered Q' rows (fp32, 512 bytes each, in the shared-memory ring at `rows`) + P' of their targets -> operand image
-// rows rowbase .. rowbase+7; then the rare patch loop (rows of a third target).
-template <int ROWS>
-__device__ __forceinline__ void build8(uint32_t img, int rowbase, uint32_t rows, const PRows& g, int d_lane, const int4& s4, int r0,
-                                       const float* __restrict__ PQ, int lane) {
-    float4 q[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) q[k] = lds_v4f(rows + k * 512 + lane * 16);
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// One cp.async group = the operands of 8 consecutive rows of a builder warp (lane r0+k holds target / source of row k):
+// Q'[src] of the 8 rows -> `rows` (8 x 512 B) and P'[dst] of the first and the last row -> `prow` (2 x 512 B).  A target's
+// rows are consecutive, so 8 rows span <= 2 targets unless some in-degree is < 4 (such rows are patched at build time).
+// Every lane copies -- and later reads back -- ITS 16 bytes of each row, so the copies need no cross-lane synchronisation.
+__device__ __forceinline__ void gather_half_async(uint32_t rows, uint32_t prow, const float* __restrict__ PQ, RowIdx idx, int r0, int lane) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int d = __shfl_sync(0xffffffffu, d_lane, r0 + k);
-        if (d == g.da) build_row<ROWS>(img, rowbase + k, lane, g.pa, q[k]);
-        else build_row<ROWS>(img, rowbase + k, lane, g.pb, q[k]);
+        const int s = __shfl_sync(0xffffffffu, idx.s, r0 + k);
+        cp_async16(rows + k * 512 + lane * 16, PQ + (int64_t)(s >= 0 ? s : 0) * 256 + 128 + lane * 4, s >= 0 ? 16u : 0u);
     }
-    for (uint32_t odd = g.odd; odd != 0u; odd &= odd - 1u) {
-        const int k = __ffs(odd) - 1;
-        const int d = __shfl_sync(0xffffffffu, d_lane, r0 + k), sr = src_of_row(s4, r0 + k);
+    const int da = __shfl_sync(0xffffffffu, idx.d, r0), db = __shfl_sync(0xffffffffu, idx.d, r0 + 7);
+    cp_async16(prow + lane * 16, PQ + (int64_t)(da >= 0 ? da : 0) * 256 + lane * 4, da >= 0 ? 16u : 0u);
+    cp_async16(prow + 512 + lane * 16, PQ + (int64_t)(db >= 0 ? db : 0) * 256 + lane * 4, db >= 0 ? 16u : 0u);
+    cp_async_commit();
+}
+// 8 gathered Q' rows (fp32, 512 bytes each, in the shared-memory ring at `rows`) + P' of their targets (`prow`) -> operand
+// image rows rowbase .. rowbase+7; then the rare patch loop (rows of a third target).
+template <int ROWS>
+__device__ __forceinline__ void build8(uint32_t img, int rowbase, uint32_t rows, uint32_t prow, RowIdx idx, int r0,
+                                       const float* __restrict__ PQ, int lane) {
+    const int da = __shfl_sync(0xffffffffu, idx.d, r0), db = __shfl_sync(0xffffffffu, idx.d, r0 + 7);
+    const uint32_t odd = (__ballot_sync(0xffffffffu, idx.d >= 0 && idx.d != da && idx.d != db) >> r0) & 0xFFu;
+    const float4 pa = lds_v4f(prow + lane * 16), pb = lds_v4f(prow + 512 + lane * 16);
+    // two groups of four rows: the shared-memory loads / stores are volatile asm and keep their order, so at most four
+    // rows (and their temporaries) are live at a time
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float4 q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = lds_v4f(rows + (4 * h + k) * 512 + lane * 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int d = __shfl_sync(0xffffffffu, idx.d, r0 + 4 * h + k);
+            build_row<ROWS>(img, rowbase + 4 * h + k, lane, sel4(d == da, pa, pb), q[k]);
+        }
+    }
+    for (uint32_t o = odd; o != 0u; o &= o - 1u) {
+        const int k = __ffs(o) - 1;
+        const int d = __shfl_sync(0xffffffffu, idx.d, r0 + k), sr = __shfl_sync(0xffffffffu, idx.s, r0 + k);
         build_row<ROWS>(img, rowbase + k, lane, ldg4(PQ + (int64_t)d * 256 + lane * 4), ldg4(PQ + (int64_t)sr * 256 + 128 + lane * 4));
     }
 }
@@ -225,21 +219,21 @@ struct FwdSmem {
     // slot being read and the slot being written apart by construction, not by timing.
     static constexpr int SLOTS = 8;
     static constexpr uint32_t H = 0;                       // 2 stages x (hi, lo)
-    static constexpr uint32_t RING = 2 * 2 * F_IMG;        // Q' rows of one tile: 8 builder warps x 16 rows x 512 B (TMA destination)
-    static constexpr uint32_t DST = RING + FTE * 512;      // int dst[SLOTS][128]
+    static constexpr uint32_t RING = 2 * 2 * F_IMG;        // Q' rows of one tile: 8 builder warps x 16 rows x 512 B (cp.async destination)
+    static constexpr uint32_t PROW = RING + FTE * 512;     // P' rows: 8 builder warps x 2 halves x 2 rows x 512 B
+    static constexpr uint32_t DST = PROW + 8 * 2 * 1024;   // int dst[SLOTS][128]
     static constexpr uint32_t INV = DST + SLOTS * FTE * 4; // float inv_deg[dst][SLOTS][128]
-    static constexpr uint32_t BAR = INV + SLOTS * FTE * 4; // h_full[2] h_empty[2] tm_full[2] tm_empty[2] q_full[8][2], tmem slot
-    static constexpr uint32_t TOTAL = BAR + 256;
+    static constexpr uint32_t BAR = INV + SLOTS * FTE * 4; // h_full[2] h_empty[2] tm_full[2] tm_empty[2], tmem slot
+    static constexpr uint32_t TOTAL = BAR + 128;
 };
 
-__global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p, const __grid_constant__ CUtensorMap q_map) {
+__global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(sm);
     const uint32_t bar0 = sbase + FwdSmem::BAR;
     const uint32_t h_full = bar0, h_empty = bar0 + 16, tm_full = bar0 + 32, tm_empty = bar0 + 48;   // [b] at +8*b
-    const uint32_t q_full = bar0 + 64;                                                              // [warp][half] at +16*w + 8*h
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + FwdSmem::BAR + 64 + F_BLD_WARPS * 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + FwdSmem::BAR + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -248,7 +242,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
             mbar_init(h_full + 8 * b, F_BLD_WARPS); mbar_init(h_empty + 8 * b, 1);
             mbar_init(tm_full + 8 * b, 1); mbar_init(tm_empty + 8 * b, F_EPI_WARPS);
         }
-        for (int k = 0; k < 2 * F_BLD_WARPS; ++k) mbar_init(q_full + 8 * k, 1);
         fence_mbar_init();
     }
     tc_fence_before();
@@ -345,6 +338,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tm_empty + 8 * b);
+                    if (warp == 0) TL(3, i, 1);
                 }
                 process8(vb, pc + 1);
             }
@@ -359,56 +353,45 @@ __global__ void __launch_bounds__(F_THREADS, 1) edge_fwd_tc_kernel(EdgeFwdArgs p
         const int w = warp - F_EPI_WARPS;
         const int row0 = w * 16;
         const uint32_t ring = sbase + FwdSmem::RING + (uint32_t)w * (16 * 512);      // this warp's 16 Q' rows
-        const uint32_t qbar = q_full + 16 * w;                                       // [half] at +8*half
+        const uint32_t prow = sbase + FwdSmem::PROW + (uint32_t)w * 2048;            // and the P' rows of its two halves
         const int64_t G = gridDim.x;
-        // Q'[src] rows of half h (8 rows = two gather4 messages, issued by lanes 2h and 2h+1 from their four indices)
-        auto issue_half = [&](int h, const int4& s4) {
-            if (lane == 2 * h) mbar_arrive_expect_tx(qbar + 8 * h, 8 * 512);
-            if ((lane >> 1) == h) tma::gather4(ring + (uint32_t)lane * 2048, &q_map, 128, s4.x, s4.y, s4.z, s4.w, qbar + 8 * h);
-        };
-        // target indices run two tiles ahead of the build, the source indices feed the TMA one tile ahead, P' rows are
-        // prefetched in registers half a tile ahead
-        int d_cur = load_row_idx<16>(p.dst, p.src, (int64_t)blockIdx.x * FTE, row0, p.n_edges, (int64_t)blockIdx.x < n_tiles).d;
-        int d_nxt = load_row_idx<16>(p.dst, p.src, (blockIdx.x + G) * FTE, row0, p.n_edges, blockIdx.x + G < n_tiles).d;
-        int4 s_cur = load_src4<16>(p.src, (int64_t)blockIdx.x * FTE, row0, p.n_edges, (int64_t)blockIdx.x < n_tiles);
-        int4 s_nxt = load_src4<16>(p.src, (blockIdx.x + G) * FTE, row0, p.n_edges, blockIdx.x + G < n_tiles);
-        float inv = (d_cur >= 0) ? __ldg(p.inv_deg + d_cur) : 0.f;
-        if ((int64_t)blockIdx.x < n_tiles) { issue_half(0, s_cur); issue_half(1, s_cur); }
-        PRows ga, gb;
-        gather_p(ga, p.PQ, d_cur, 0, lane);
+        // Indices run two tiles ahead of the build; the operands of a half tile (one cp.async group) are requested as soon
+        // as the same half of the previous tile has been consumed.  Nothing is prefetched into registers.
+        RowIdx idx = load_row_idx<16>(p.dst, p.src, (int64_t)blockIdx.x * FTE, row0, p.n_edges, (int64_t)blockIdx.x < n_tiles);
+        RowIdx idx_n = load_row_idx<16>(p.dst, p.src, (blockIdx.x + G) * FTE, row0, p.n_edges, blockIdx.x + G < n_tiles);
+        float inv = (idx.d >= 0) ? __ldg(p.inv_deg + idx.d) : 0.f;
+        gather_half_async(ring, prow, p.PQ, idx, 0, lane);
+        gather_half_async(ring + 8 * 512, prow + 1024, p.PQ, idx, 8, lane);
         int i = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += G, ++i) {
             const int b = i & 1;
-            const uint32_t qph = (uint32_t)i & 1u;
-            const bool more = t + G < n_tiles;
             if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 0);
-            const int d_nn = load_row_idx<16>(p.dst, p.src, (t + 2 * G) * FTE, row0, p.n_edges, t + 2 * G < n_tiles).d;
-            const int4 s_nn = load_src4<16>(p.src, (t + 2 * G) * FTE, row0, p.n_edges, t + 2 * G < n_tiles);
-            const float inv_n = (d_nxt >= 0) ? __ldg(p.inv_deg + d_nxt) : 0.f;
-            gather_p(gb, p.PQ, d_cur, 8, lane);
+            const RowIdx idx_nn = load_row_idx<16>(p.dst, p.src, (t + 2 * G) * FTE, row0, p.n_edges, t + 2 * G < n_tiles);
+            const float inv_n = (idx_n.d >= 0) ? __ldg(p.inv_deg + idx_n.d) : 0.f;
             mbar_wait(h_empty + 8 * b, ((uint32_t)(i >> 1) & 1u) ^ 1u);    // MMA of tile i-2 has consumed this stage
             if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 1);
             const uint32_t img = sbase + FwdSmem::H + b * (2 * F_IMG);
             if (lane < 16) {
                 const uint32_t slot = sbase + FwdSmem::DST + (uint32_t)((i & (FwdSmem::SLOTS - 1)) * FTE + row0 + lane) * 4;
-                sts_b32(slot, (uint32_t)d_cur);
+                sts_b32(slot, (uint32_t)idx.d);
                 sts_b32(slot + FwdSmem::SLOTS * FTE * 4, __float_as_uint(inv));
             }
-            mbar_wait(qbar, qph);                                          // rows 0..7 have landed
-            build8<FTE>(img, row0, ring, ga, d_cur, s_cur, 0, p.PQ, lane);
-            __syncwarp();                                                  // every lane has consumed its part of the rows
-            if (more) issue_half(0, s_nxt);                                // refill them for the NEXT tile
-            gather_p(ga, p.PQ, d_nxt, 0, lane);                            // first half of the next tile
-            mbar_wait(qbar + 8, qph);
-            build8<FTE>(img, row0 + 8, ring + 8 * 512, gb, d_cur, s_cur, 8, p.PQ, lane);
-            __syncwarp();
-            if (more) issue_half(1, s_nxt);
+            cp_async_wait<1>();                                            // rows 0..7 have landed (groups complete in order)
+            if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 3);
+            build8<FTE>(img, row0, ring, prow, idx, 0, p.PQ, lane);
+            if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 4);
+            gather_half_async(ring, prow, p.PQ, idx_n, 0, lane);           // the same rows of the NEXT tile (all -1 past the end)
+            cp_async_wait<1>();                                            // rows 8..15
+            if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 5);
+            build8<FTE>(img, row0 + 8, ring + 8 * 512, prow + 1024, idx, 8, p.PQ, lane);
+            gather_half_async(ring + 8 * 512, prow + 1024, p.PQ, idx_n, 8, lane);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(h_full + 8 * b);
             if (w == 0 || w == F_BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 2);
-            d_cur = d_nxt; d_nxt = d_nn; s_cur = s_nxt; s_nxt = s_nn; inv = inv_n;
+            idx = idx_n; idx_n = idx_nn; inv = inv_n;
         }
+        cp_async_wait<0>();
     } else {
         // ------------------------------------------------------------------ MMA issuer (one thread of warp 24)
         reg_dec<F_MMA_REGS>();
@@ -747,18 +730,16 @@ static int edge_grid(int64_t n_tiles) { return (int)imin64(n_tiles, sm_count());
 
 extern "C" int mmpde_edge_fwd(const float* PQ, const int32_t* edge_src, const int32_t* edge_dst, const float* inv_deg,
                               int64_t n_edges, const float* w2, const float* b2, float* agg, int64_t ld_agg,
-                              uint32_t* mask2, int64_t n_src, void* stream) {
-    if (n_edges < 0 || ld_agg < 128 || n_src < 0) return MMPDE_EINVAL;
+                              uint32_t* mask2, void* stream) {
+    if (n_edges < 0 || ld_agg < 128) return MMPDE_EINVAL;
     if (n_edges == 0) return MMPDE_OK;
-    if (n_src == 0 || ((reinterpret_cast<uintptr_t>(PQ) | reinterpret_cast<uintptr_t>(edge_src)) & 15)) return MMPDE_EINVAL;
+    if (reinterpret_cast<uintptr_t>(PQ) & 15) return MMPDE_EINVAL;
     constexpr size_t smem = FwdSmem::TOTAL + 1024;
     MMPDE_ENSURE_SMEM(edge_fwd_tc_kernel, smem);
-    CUtensorMap q_map;                                     // the Q' half of PQ, one 128-float row per box (TMA row gathers)
-    if (int rc = tma::make_row_gather_map(&q_map, PQ + 128, n_src, 256, 128)) return rc;
     EdgeFwdArgs p;
     p.PQ = PQ; p.src = edge_src; p.dst = edge_dst; p.inv_deg = inv_deg; p.n_edges = n_edges; p.w2 = w2; p.b2 = b2;
     p.agg = agg; p.ld_agg = ld_agg; p.mask2 = mask2;
-    edge_fwd_tc_kernel<<<edge_grid((n_edges + FTE - 1) / FTE), F_THREADS, smem, (cudaStream_t)stream>>>(p, q_map);
+    edge_fwd_tc_kernel<<<edge_grid((n_edges + FTE - 1) / FTE), F_THREADS, smem, (cudaStream_t)stream>>>(p);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }

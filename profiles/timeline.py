@@ -47,8 +47,8 @@ def main():
     def bwd():
         assert lib.mmpde_edge_bwd(*common, pp(mask), pp(g_agg), 128, pp(outs[0]), pp(outs[1]), pp(outs[2]), st) == 0
 
-    names = {"fwd": (fwd, {0: ["step start", "h_empty ok", "built+arrive"], 1: ["step start", "h_empty ok", "built+arrive"],
-                           2: ["h_full ok", "tm_empty ok", "issued"], 3: ["tm_full ok", "-", "done+arrive"]}),
+    bf = ["step start", "h_empty ok", "built+arrive", "rows 0-7 landed", "rows 0-7 built", "rows 8-15 landed"]
+    names = {"fwd": (fwd, {0: bf, 1: bf, 2: ["h_full ok", "tm_empty ok", "issued"], 3: ["tm_full ok", "acc released", "done"]}),
              "bwd": (bwd, {0: ["step start", "hg_empty ok", "built+arrive", "st_full ok", "rows done"],
                            1: ["step start", "hg_empty ok", "built+arrive", "st_full ok", "rows done"],
                            2: ["hg_full ok", "d1_empty ok", "MMA-A issued", "MMA-B issued"],

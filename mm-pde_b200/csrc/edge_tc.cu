@@ -11,13 +11,14 @@
 // Both kernels are persistent (one CTA per SM) and warp-specialised:
 //   epilogue warps : thread = TMEM lane = channel; tcgen05.ld, bias, ReLU / masks / per-target sums
 //                    (forward: 16 warps, lane quadrant x 32-column quarter; backward: 4 warps)
-//   builder warps  : gather P'/Q' rows with 128-bit loads (next tile prefetched into registers), ReLU, split into bf16
-//     (8)            hi/lo and write the SWIZZLE_128B operand tile -- the neighbour gather IS the operand load of the
-//                    GEMM, no [E,260] / [E,128] tensor ever exists; in the backward they also run the row phase
+//   builder warps  : the Q'[src] rows arrive through a cp.async ring in shared memory (requested half a tile / a tile
+//     (8)            ahead; no register prefetch), P'[dst] is added, ReLU, split into bf16 hi/lo, written as the
+//                    SWIZZLE_128B operand tile -- the neighbour gather IS the operand load of the GEMM, no [E,260] /
+//                    [E,128] tensor ever exists; in the backward they also run the row phase
 //   MMA warp       : one thread issues tcgen05.mma; W2 (hi, lo) lives in TENSOR MEMORY as the A operand for the whole
 //                    kernel, so only the per-tile operand is read from shared memory
 // connected by mbarrier pipelines (operand tiles and accumulators are double-buffered); registers are moved between the
-// roles with setmaxnreg (forward 896 threads: 56 / 120 / 40 per thread; backward 512 threads: 104 / 184 / 40).
+// roles with setmaxnreg (forward 896 threads: 64 / 104 / 40 per thread; backward 512 threads: 104 / 184 / 40).
 #include "tc_common.cuh"
 
 namespace mmpde {
@@ -45,55 +46,9 @@ __device__ __forceinline__ RowIdx load_row_idx(const int* __restrict__ dst, cons
     return r;
 }
 
-// gathered operands of 8 consecutive rows of one builder warp (lane = 4 channels)
-struct Gather8 {
-    float4 q[8];          // Q'[src] rows
-    float4 pa, pb;        // P'[dst] of the first / last row: a target's rows are consecutive, so 8 rows span <= 2 targets
-    int da, db;           //   unless some in-degree is < 4; such rows are listed in `odd` and patched afterwards
-    uint32_t odd;         // bit k: row k belongs to a third target
-};
-__device__ __forceinline__ void gather8(Gather8& g, const float* __restrict__ PQ, RowIdx idx, int r0, int lane) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int s = __shfl_sync(0xffffffffu, idx.s, r0 + k);
-        g.q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s >= 0) g.q[k] = ldg4(PQ + (int64_t)s * 256 + 128 + lane * 4);
-    }
-    g.da = __shfl_sync(0xffffffffu, idx.d, r0);
-    g.db = __shfl_sync(0xffffffffu, idx.d, r0 + 7);
-    g.pa = g.pb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g.da >= 0) g.pa = ldg4(PQ + (int64_t)g.da * 256 + lane * 4);
-    if (g.db >= 0) g.pb = ldg4(PQ + (int64_t)g.db * 256 + lane * 4);
-    g.odd = (__ballot_sync(0xffffffffu, idx.d >= 0 && idx.d != g.da && idx.d != g.db) >> r0) & 0xFFu;
-}
 __device__ __forceinline__ float4 sel4(bool c, const float4& a, const float4& b) {
     return make_float4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
 }
-// 2*relu(a + b) = z + |z|: two adds on the (mostly idle, full-rate) FMA pipe instead of an add plus a max on the ALU
-// pipe, which is the busiest unit of these kernels (profiles/r01_edge_bwd_ncu.json).  The factor 2 is exact; the forward
-// folds 1/2 into W2 when it loads it into tensor memory, the backward into the final dW2 reduction.
-__device__ __forceinline__ float4 relu2_add(const float4& a, const float4& b) {
-    const float4 z = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-    return make_float4(z.x + fabsf(z.x), z.y + fabsf(z.y), z.z + fabsf(z.z), z.w + fabsf(z.w));
-}
-// 2*h1 = 2*relu(P'[dst] + Q'[src]) of 8 gathered rows -> operand image rows rowbase .. rowbase+7.  Straight-line code
-// (rows beyond the last edge come out as zero: their Q' and the last row's P' are zero), then the rare patch loop.
-template <int ROWS>
-__device__ __forceinline__ void build_h8(uint32_t img, int rowbase, const Gather8& g, RowIdx idx, int r0,
-                                         const float* __restrict__ PQ, int lane) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int d = __shfl_sync(0xffffffffu, idx.d, r0 + k);
-        store_split<ROWS>(img, rowbase + k, lane, relu2_add(sel4(d == g.da, g.pa, g.pb), g.q[k]));
-    }
-    for (uint32_t odd = g.odd; odd != 0u; odd &= odd - 1u) {
-        const int k = __ffs(odd) - 1;
-        const int d = __shfl_sync(0xffffffffu, idx.d, r0 + k), sr = __shfl_sync(0xffffffffu, idx.s, r0 + k);
-        store_split<ROWS>(img, rowbase + k, lane,
-                          relu2_add(ldg4(PQ + (int64_t)d * 256 + lane * 4), ldg4(PQ + (int64_t)sr * 256 + 128 + lane * 4)));
-    }
-}
-
 // mean message of one finished target: agg[cur][o] += run / deg (partial runs of a target add up atomically)
 __device__ __noinline__ void flush_mean(float* agg, int64_t ld, int cur, float inv, int o, float run) {
     if (cur >= 0) atomicAdd(agg + (int64_t)cur * ld + o, run * inv);
@@ -134,8 +89,9 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
 }
 
 // One operand row: 2*h1 = 2*relu(p + q) = z + |z| of this lane's 4 channels, split into bf16 hi / lo and written into
-// the two SWIZZLE_128B images (the lo image follows the hi image).  Same arithmetic as relu2_add + split4, 16 instead of
-// 24 instructions.  (Callers select p with sel4, never with a branch: a branch per row would fence the rows of a warp
+// the two SWIZZLE_128B images (the lo image follows the hi image).  z + |z| is two adds on the FMA pipe instead of an add
+// plus a max on the ALU pipe, the busiest unit of these kernels; the factor 2 is exact: the forward folds 1/2 into W2 when
+// it loads it into tensor memory, the backward into the final dW2 reduction.  (Callers select p with sel4, never with a branch: a branch per row would fence the rows of a warp
 // off from each other and serialise their dependency chains.)
 template <int ROWS>
 __device__ __forceinline__ void build_row(uint32_t img, int row, int lane, const float4& p, const float4& q) {
@@ -172,14 +128,20 @@ __device__ __forceinline__ void gather_half_async(uint32_t rows, uint32_t prow, 
     cp_async16(prow + 512 + lane * 16, PQ + (int64_t)(db >= 0 ? db : 0) * 256 + lane * 4, db >= 0 ? 16u : 0u);
     cp_async_commit();
 }
-// 8 gathered Q' rows (fp32, 512 bytes each, in the shared-memory ring at `rows`) + P' of their targets (`prow`) -> operand
-// image rows rowbase .. rowbase+7; then the rare patch loop (rows of a third target).
+// only the 8 Q' rows (backward: the per-target operands P', g_agg, 1/deg, mask words are prefetched in registers)
+__device__ __forceinline__ void gather_q8_async(uint32_t rows, const float* __restrict__ PQ, int s_lane, int lane) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int s = __shfl_sync(0xffffffffu, s_lane, k);
+        cp_async16(rows + k * 512 + lane * 16, PQ + (int64_t)(s >= 0 ? s : 0) * 256 + 128 + lane * 4, s >= 0 ? 16u : 0u);
+    }
+    cp_async_commit();
+}
+// 8 gathered Q' rows (fp32, 512 bytes each, in the shared-memory ring at `rows`) + P' of their (<= 2) targets -> operand
+// image rows rowbase .. rowbase+7; then the rare patch loop (rows of a third target, listed in `odd`).
 template <int ROWS>
-__device__ __forceinline__ void build8(uint32_t img, int rowbase, uint32_t rows, uint32_t prow, RowIdx idx, int r0,
-                                       const float* __restrict__ PQ, int lane) {
-    const int da = __shfl_sync(0xffffffffu, idx.d, r0), db = __shfl_sync(0xffffffffu, idx.d, r0 + 7);
-    const uint32_t odd = (__ballot_sync(0xffffffffu, idx.d >= 0 && idx.d != da && idx.d != db) >> r0) & 0xFFu;
-    const float4 pa = lds_v4f(prow + lane * 16), pb = lds_v4f(prow + 512 + lane * 16);
+__device__ __forceinline__ void build8_core(uint32_t img, int rowbase, uint32_t rows, const float4& pa, const float4& pb, int da,
+                                            uint32_t odd, RowIdx idx, int r0, const float* __restrict__ PQ, int lane) {
     // two groups of four rows: the shared-memory loads / stores are volatile asm and keep their order, so at most four
     // rows (and their temporaries) are live at a time
 #pragma unroll
@@ -198,6 +160,15 @@ __device__ __forceinline__ void build8(uint32_t img, int rowbase, uint32_t rows,
         const int d = __shfl_sync(0xffffffffu, idx.d, r0 + k), sr = __shfl_sync(0xffffffffu, idx.s, r0 + k);
         build_row<ROWS>(img, rowbase + k, lane, ldg4(PQ + (int64_t)d * 256 + lane * 4), ldg4(PQ + (int64_t)sr * 256 + 128 + lane * 4));
     }
+}
+// the same with the P' rows taken from the shared-memory slot gather_half_async filled
+template <int ROWS>
+__device__ __forceinline__ void build8(uint32_t img, int rowbase, uint32_t rows, uint32_t prow, RowIdx idx, int r0,
+                                       const float* __restrict__ PQ, int lane) {
+    const int da = __shfl_sync(0xffffffffu, idx.d, r0), db = __shfl_sync(0xffffffffu, idx.d, r0 + 7);
+    const uint32_t odd = (__ballot_sync(0xffffffffu, idx.d >= 0 && idx.d != da && idx.d != db) >> r0) & 0xFFu;
+    const float4 pa = lds_v4f(prow + lane * 16), pb = lds_v4f(prow + 512 + lane * 16);
+    build8_core<ROWS>(img, rowbase, rows, pa, pb, da, odd, idx, r0, PQ, lane);
 }
 
 // ================================================================================================================
@@ -447,7 +418,8 @@ struct EdgeBwdArgs {
 struct BwdSmem {
     static constexpr uint32_t HG = 0;                      // 2 stages x (H hi, H lo, G hi, G lo) = 2 x 64 KB
     static constexpr uint32_t ST = 2 * 4 * B_IMG;          // 2 x fp32 [64][128] staging = 2 x 32 KB
-    static constexpr uint32_t BAR = ST + 2 * BTE * 128 * 4;
+    static constexpr uint32_t RING = ST + 2 * BTE * 128 * 4;   // Q' rows of one tile: 8 builder warps x 8 rows x 512 B (cp.async)
+    static constexpr uint32_t BAR = RING + BTE * 512;
     static constexpr uint32_t TOTAL = BAR + 128;
 };
 
@@ -543,16 +515,29 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
         // gathered operands of one tile's 8 rows; ga/gb = g_agg[dst] of the first / last row with sa/sb = inv_deg,
         // mw = z2 sign words of the rows' 32-edge chunk for channels 4*lane..4*lane+3.  Everything is kept raw:
         // nothing may depend on a load inside the prefetch, or the prefetch turns into a stall.
-        struct Tile { Gather8 g; float4 ga, gb; float sa, sb; uint4 mw; };
+        // (the 8 Q'[src] rows themselves come through the cp.async ring, not through registers)
+        struct TileG { float4 pa, pb; int da, db; uint32_t odd; };
+        struct Tile { TileG g; float4 ga, gb; float sa, sb; uint4 mw; };
         Tile cur, nxt;
         int i = 0;
+        const uint32_t ring = sbase + BwdSmem::RING + (uint32_t)w * (8 * 512);
         auto gather_tile = [&](Tile& T, RowIdx idx, int64_t t) {
-            gather8(T.g, p.PQ, idx, 0, lane);
-            T.ga = T.gb = make_float4(0.f, 0.f, 0.f, 0.f);
+            T.g.da = __shfl_sync(0xffffffffu, idx.d, 0);
+            T.g.db = __shfl_sync(0xffffffffu, idx.d, 7);
+            T.g.odd = __ballot_sync(0xffffffffu, idx.d >= 0 && idx.d != T.g.da && idx.d != T.g.db) & 0xFFu;
+            T.g.pa = T.g.pb = T.ga = T.gb = make_float4(0.f, 0.f, 0.f, 0.f);
             T.sa = T.sb = 0.f;
             T.mw = make_uint4(0u, 0u, 0u, 0u);
-            if (T.g.da >= 0) { T.sa = __ldg(p.inv_deg + T.g.da); T.ga = ldg4(p.g_agg + (int64_t)T.g.da * p.ld_gagg + lane * 4); }
-            if (T.g.db >= 0) { T.sb = __ldg(p.inv_deg + T.g.db); T.gb = ldg4(p.g_agg + (int64_t)T.g.db * p.ld_gagg + lane * 4); }
+            if (T.g.da >= 0) {
+                T.g.pa = ldg4(p.PQ + (int64_t)T.g.da * 256 + lane * 4);
+                T.sa = __ldg(p.inv_deg + T.g.da);
+                T.ga = ldg4(p.g_agg + (int64_t)T.g.da * p.ld_gagg + lane * 4);
+            }
+            if (T.g.db >= 0) {
+                T.g.pb = ldg4(p.PQ + (int64_t)T.g.db * 256 + lane * 4);
+                T.sb = __ldg(p.inv_deg + T.g.db);
+                T.gb = ldg4(p.g_agg + (int64_t)T.g.db * p.ld_gagg + lane * 4);
+            }
             if (t < n_tiles) T.mw = __ldg(reinterpret_cast<const uint4*>(p.mask2 + ((t * BTE + row0) >> 5) * 128 + lane * 4));
         };
         // row phase of a finished tile: this warp's rows of D1 from the staging tile, g_z1 = D1 * [h1 > 0] with the
@@ -577,7 +562,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
                 const int d = __shfl_sync(0xffffffffu, idx.d, k);
                 const int sr = __shfl_sync(0xffffffffu, idx.s, k);
                 const float4 g = masked_row(stage, imgH, k);               // rows beyond the last edge are exactly zero
+#ifndef MMPDE_EXPERIMENT_NO_DQ_RED
                 if (sr >= 0) red_add_v4(p.dPQ + (int64_t)sr * 256 + 128 + lane * 4, g);    // dQ'[src]
+#else
+                if (sr == -12345) red_add_v4(p.dPQ + (int64_t)sr * 256 + 128 + lane * 4, g);
+#endif
                 const float fa = (d == da) ? 1.f : 0.f, fb = (d == db && d != da) ? 1.f : 0.f;
                 acc_a.x = fmaf(fa, g.x, acc_a.x); acc_a.y = fmaf(fa, g.y, acc_a.y);
                 acc_a.z = fmaf(fa, g.z, acc_a.z); acc_a.w = fmaf(fa, g.w, acc_a.w);
@@ -603,6 +592,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
         int da_prev = -1, db_prev = -1;
         uint32_t odd_prev = 0u;
         // per tile: `cur` was gathered one step ago; gather `nxt` (tile t + G) now, build tile t, then finish tile t - G
+        gather_q8_async(ring, p.PQ, idx.s, lane);
         gather_tile(cur, idx, blockIdx.x);
         for (int64_t t = blockIdx.x; t < n_tiles; t += G) {
             const int b = i & 1;
@@ -630,7 +620,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
             if (w == 0 || w == BLD_WARPS - 1) TL(w == 0 ? 0 : 1, i, 1);
             const uint32_t imgH = sbase + BwdSmem::HG + b * (4 * B_IMG);
             const uint32_t imgG = imgH + 2 * B_IMG;
-            build_h8<BTE>(imgH, row0, cur.g, idx, 0, p.PQ, lane);
+            cp_async_wait<0>();                                            // this tile's Q' rows have landed
+            build8_core<BTE>(imgH, row0, ring, cur.g.pa, cur.g.pb, cur.g.da, cur.g.odd, idx, 0, p.PQ, lane);
+            gather_q8_async(ring, p.PQ, idx_n.s, lane);                    // the ring is free again: rows of the NEXT tile
             auto store_g = [&](int k, uint2 ghi, uint2 glo) {              // keep the halves whose z2 sign bit is set
                 const uint32_t k01 = (((mx >> k) & 1u) ? 0x0000FFFFu : 0u) | (((my >> k) & 1u) ? 0xFFFF0000u : 0u);
                 const uint32_t k23 = (((mz >> k) & 1u) ? 0x0000FFFFu : 0u) | (((mw >> k) & 1u) ? 0xFFFF0000u : 0u);
@@ -665,6 +657,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) edge_bwd_tc_kernel(EdgeBwdArg
             cur = nxt;                                                     // loads issued a whole step ago: no stall
             ++i;
         }
+        cp_async_wait<0>();
         if (i > 0) row_phase((i - 1) & 1, (uint32_t)((i - 1) >> 1) & 1u, idx_prev, da_prev, db_prev, odd_prev);
 #pragma unroll
         for (int f = 0; f < 4; ++f) atomicAdd(p.db2 + lane * 4 + f, db2_acc[f]);

@@ -38,6 +38,12 @@ BATCH = 16
 K_NEIGH = 35
 LAYERS = 6
 FLOP_PER_EDGE_FWD = 99328          # 2*260*128 + 2*128*128 (reference formulation)
+# The mesh mover of the step: a seeded, default-initialised DMM with the reference's constructor arguments
+# (/root/reference/mmpde.py:199 for Burgers, /root/reference/README.md:31 for the cylinder); trained checkpoints live on
+# Google Drive.  Default initialisation moves the nodes by about one cell.
+MOVER_SEED = 4321
+DMM_ARRAY = dict(branch_layer=7, trunk_layer=[2, 32, 512], out_layer=[1024, 512, 1])
+DMM_GRAPH = dict(branch_layer=[4, 3], trunk_layer=[2, 16, 512], out_layer=[1024, 512, 1])
 
 
 RESULT_OUT = sys.stdout
@@ -119,7 +125,9 @@ def _oracle_setup(batch, seed=0):
     opt = torch.optim.AdamW([{"params": model.parameters()}, {"params": model_b.parameters()},
                              {"params": net.parameters()}], lr=2e-3)
     fields = synthetic.burgers_fields(batch, RES[0], RES[1], RES[2], seed=seed)
-    mover = synthetic.AnalyticMover()
+    from oracle import dmm as odmm
+    torch.manual_seed(MOVER_SEED)                 # the same seeded default-initialised DMM as the CUDA arm (mmpde.py:199)
+    mover = odmm.DMM(s=RES[1], mode="array", **DMM_ARRAY).eval()
     return gc, model, model_b, net, opt, fields, mover, loops
 
 
@@ -145,8 +153,8 @@ def cpu_reference_step_time(sample_batch, steps, warmup, budget_s=1200.0):
     return edge_updates / mean, mean, torch.get_num_threads(), len(times)
 
 
-WORKLOAD_BURGERS = ("Burgers 2D MM-PDE training step (moved mesh + interpolation + 2x 6-layer processor), "
-                    "31x48x48, k=35")
+WORKLOAD_BURGERS = ("Burgers 2D MM-PDE training step (DMM-moved mesh [default-initialised DMM, array mode] + interpolation "
+                    "+ 2x 6-layer processor), 31x48x48, k=35")
 
 
 def run_reference(args):
@@ -402,6 +410,7 @@ def run_ours(args):
     from mmpde_b200.data_creator_2d import GraphCreator_FS_2D
     from mmpde_b200.gnn_2d import MP_PDE_Solver_2D
     from mmpde_b200.interpolate import ItpNet
+    from mmpde_b200.mesh.dmm_model import DMM
     from mmpde_b200.mmpde import criterion
     from mmpde_b200.train_helper_2d import StepGraph, _forward_gnn, test_timestep_losses, training_loop_branch
     import torch.distributed as dist
@@ -441,18 +450,21 @@ def run_ours(args):
             pde.grid_size = pde.movingmesh_grid_size = pde.ori_grid_size = CY_RES
             w = {"gc": GraphCreator_FS_2D(pde, K_NEIGH, "knn", 1, CY_RES[0]), "nodes_per_sample": CY_RES[1],
                  "net": ItpNet(CY_RES[1], None, [128, 64], [128, 64], [1, 4, 16, 4, 1]).to(dev),
-                 "name": "Flow around a cylinder MM-PDE training step (moved nodes + interpolation + 2x 6-layer "
-                         "processor), 30x2521 unstructured nodes, k=35",
+                 "name": "Flow around a cylinder MM-PDE training step (DMM-moved nodes [default-initialised DMM, graph mode] + "
+                         "interpolation + 2x 6-layer processor), 30x2521 unstructured nodes, k=35",
+                 "mover": lambda: DMM(mode="graph", grid=cloud.to(dev), **DMM_GRAPH),
                  "fields": lambda r: synthetic.cylinder_fields(BATCH, cloud, CY_RES[0], seed=100 + r)}
         else:
             pde = burgers()
             pde.grid_size = pde.movingmesh_grid_size = pde.ori_grid_size = RES
             w = {"gc": GraphCreator_FS_2D(pde, K_NEIGH, "knn", 1, RES[0]), "nodes_per_sample": RES[1] * RES[2],
                  "net": ItpNet(RES[1], RES[2], [128, 64], [128, 64], [1, 4, 16, 4, 1]).to(dev), "name": WORKLOAD_BURGERS,
+                 "mover": lambda: DMM(s=RES[1], mode="array", **DMM_ARRAY),
                  "fields": lambda r: synthetic.burgers_fields(BATCH, RES[0], RES[1], RES[2], seed=100 + r)}
         w["pde"] = pde
         w["model"], w["model_b"] = MP_PDE_Solver_2D(pde).to(dev), MP_PDE_Solver_2D(pde).to(dev)
-        w["mover"] = synthetic.AnalyticMover().to(dev)
+        torch.manual_seed(MOVER_SEED)
+        w["mover"] = w["mover"]().to(dev).eval()
         w["params"] = [p for m in (w["model"], w["model_b"], w["net"]) for p in m.parameters()]
         w["opt"] = torch.optim.AdamW([{"params": w["model"].parameters()}, {"params": w["model_b"].parameters()},
                                       {"params": w["net"].parameters()}], lr=2e-3, capturable=not args.no_graph,

@@ -134,6 +134,14 @@ class GraphCreator_FS_2D(nn.Module):
     # ------------------------------------------------------------------ mesh movement (:88-137)
     @staticmethod
     def _displace(u, mesh_model, xi1, xi2):
+        # x = xi + grad_xi phi(u, xi)  (:98-113).  A mover that knows its own Jacobian (mesh.dmm_model.DMM.displacement:
+        # analytic forward mode, no autograd graph, recordable into the step's CUDA graph) is asked for it; any other
+        # callable goes through autograd like the reference.
+        analytic = getattr(mesh_model, "displacement", None)
+        if analytic is not None:
+            g = analytic(u.detach(), torch.cat((xi1, xi2), dim=-1).detach())
+            if g is not None:
+                return (g[0] + xi1).detach(), (g[1] + xi2).detach()
         with torch.enable_grad():
             xi1 = xi1.detach().requires_grad_(True)
             xi2 = xi2.detach().requires_grad_(True)

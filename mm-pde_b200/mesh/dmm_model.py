@@ -5,6 +5,11 @@ Adjacent to the hot path: it supplies the moved mesh and runs a
 match the reference (including DenseNet's unused ``fc0``, :29) so its checkpoints load unchanged; the
 reference's hard-coded ``device="cuda"`` tensors (:27-28) are dropped because forward never reads them.
 The graph-mode branch reuses this repo's CUDA k-NN for its static 35-NN graph (:222-234).
+
+``DMM.displacement`` gives the mesh displacement grad_xi phi(u, xi) ANALYTICALLY (forward-mode Jacobian of trunk +
+out_nn) instead of the reference's two ``autograd.grad(create_graph=True)`` calls
+(/root/reference/data_creator_2d.py:106-107): the double-backward graph those build only feeds the frozen mover
+(SURVEY.md 8f-1, appendix C.10), and an autograd call inside the step cannot be recorded into the step's CUDA graph.
 """
 import torch
 from torch import nn
@@ -126,3 +131,38 @@ class DMM(nn.Module):
         if rf:
             return out, hidden, torch.ones_like(hidden).type_as(trunk).reshape(-1, 1)
         return out
+
+    def _latent(self, u):
+        return self.branch(u.unsqueeze(1)).unsqueeze(1) if self.mode == "array" else self._branch_graph(u)
+
+    @torch.no_grad()
+    def displacement(self, u, grid):
+        """(d phi / d xi_1, d phi / d xi_2), each [N,1], for grid = xi [N,2] (N = samples * nodes per sample).
+
+        Only the two-layer tanh trunk and the two-layer tanh out_nn depend on xi:
+            a = tanh(W1 xi + b1)                          [N,32]     trunk.layers[0]
+            trunk = W2 a + b2                             [N,512]    trunk.layers[1]
+            z = Wl latent + Wt trunk + bo ,  h = tanh(z)  [N,512]    out_nn.layers[0] = [Wl | Wt]
+            phi = w h + c                                 [N,1]      out_nn.layers[1]
+        so with M = Wt W2 ([512,32], weights only):  z = (Wl latent + Wt b2 + bo)[sample] + a M^T  and
+            d phi / d xi_d = ((1 - h^2) * (((1 - a^2) * W1[:, d]) M^T)) . w
+        i.e. one [3N,32] x [32,512] product for the value and both directional derivatives.  Deeper trunk / out stacks
+        (not used by the reference's configurations, mmpde.py:199, README.md:31) fall back to autograd."""
+        if len(self.trunk.layers) != 2 or len(self.out_nn.layers) != 2:
+            return None
+        per_sample = grid.shape[0] // u.shape[0]
+        t1, t2 = self.trunk.layers
+        o1, o2 = self.out_nn.layers
+        n_lat = o1.weight.shape[1] - t2.weight.shape[0]
+        Wl, Wt = o1.weight[:, :n_lat], o1.weight[:, n_lat:]
+        latent = self._latent(u).reshape(u.shape[0], -1)                        # [B, n_lat]
+        const = latent @ Wl.t() + (Wt @ t2.bias + o1.bias)                      # [B, 512]
+        M = Wt @ t2.weight                                                      # [512, 32]
+        a = torch.tanh(grid @ t1.weight.t() + t1.bias)                          # [N, 32]
+        da = 1.0 - a * a
+        stacked = torch.cat((a, da * t1.weight[:, 0], da * t1.weight[:, 1])) @ M.t()     # [3N, 512]
+        N = grid.shape[0]
+        z = stacked[:N].reshape(u.shape[0], per_sample, -1) + const[:, None, :]
+        h = torch.tanh(z).reshape(N, -1)
+        gate = (1.0 - h * h) * o2.weight.reshape(1, -1)                         # [N, 512]
+        return (gate * stacked[N:2 * N]).sum(1, keepdim=True), (gate * stacked[2 * N:]).sum(1, keepdim=True)

@@ -113,7 +113,49 @@ def _mesh_mover(args, pde, device):
                     trunk_layer=[2] + a.trunk_layers, out_layer=a.out_layers)
         m.load_state_dict(ckpt["model_state_dict"])
         return m.to(device).eval()
+    if getattr(args, "synthetic_mover", "analytic") == "dmm":
+        # default-initialised DMM with the reference's constructor arguments (mmpde.py:199, README.md:31)
+        torch.manual_seed(args.seed + 1)
+        if args.experiment == "cy":
+            m = DMM(mode="graph", grid=pde.ori_grid.to(device), branch_layer=[4, 3], trunk_layer=[2, 16, 512],
+                    out_layer=[1024, 512, 1])
+        else:
+            m = DMM(s=pde.movingmesh_grid_size[-1], mode="array", branch_layer=7, trunk_layer=[2, 32, 512],
+                    out_layer=[1024, 512, 1])
+        return m.to(device).eval()
     return synthetic.AnalyticMover().to(device).eval()
+
+
+def save_checkpoint(path, args, epoch, model, model_b, itp_model, mesh_model, optimizer, scheduler, train_losses, itp_losses,
+                    test_losses):
+    """The reference's checkpoint dictionary (mmpde.py:292-310: model / model_b / mesh_model / itp_model state dicts, args,
+    loss histories) plus what a resumed run needs and the reference does not store: optimizer, scheduler, epoch."""
+    state = {"model_state_dict": model.state_dict(), "args": args, "train_losses": train_losses, "itp_losses": itp_losses,
+             "test_timestep_losses": test_losses, "epoch": epoch, "optimizer_state_dict": optimizer.state_dict(),
+             "scheduler_state_dict": scheduler.state_dict() if scheduler is not None else None}
+    if model_b is not None:
+        state.update(model_b_state_dict=model_b.state_dict(), itp_model_state_dict=itp_model.state_dict())
+        if mesh_model is not None:
+            state["mesh_model_state_dict"] = mesh_model.state_dict()
+    torch.save(state, path)
+    return state
+
+
+def load_checkpoint(path, model, model_b, itp_model, optimizer=None, scheduler=None, map_location="cpu"):
+    """Restores what save_checkpoint wrote (also accepts the reference's own checkpoints, which lack the optimizer /
+    scheduler / epoch entries).  Returns (next epoch, train_losses, itp_losses, test_losses)."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    model.load_state_dict(ckpt["model_state_dict"])
+    if model_b is not None and "model_b_state_dict" in ckpt:
+        model_b.load_state_dict(ckpt["model_b_state_dict"])
+    if itp_model is not None and "itp_model_state_dict" in ckpt:
+        itp_model.load_state_dict(ckpt["itp_model_state_dict"])
+    if optimizer is not None and ckpt.get("optimizer_state_dict") is not None:
+        optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+    if scheduler is not None and ckpt.get("scheduler_state_dict") is not None:
+        scheduler.load_state_dict(ckpt["scheduler_state_dict"])
+    return (int(ckpt.get("epoch", -1)) + 1, ckpt.get("train_losses", []), ckpt.get("itp_losses", []),
+            ckpt.get("test_timestep_losses", []))
 
 
 def main(args):
@@ -189,7 +231,12 @@ def main(args):
         after_backward = bucket.allreduce
 
     train_losses, itp_losses, test_losses = [], [], []
-    for epoch in range(args.num_epochs):
+    first_epoch = 0
+    if getattr(args, "resume", None):
+        first_epoch, train_losses, itp_losses, test_losses = load_checkpoint(args.resume, model, model_b, itp_model, optimizer,
+                                                                             scheduler, map_location=device)
+        print(f"Resumed from {args.resume} at epoch {first_epoch}")
+    for epoch in range(first_epoch, args.num_epochs):
         print(f"Epoch {epoch}")
         tl, il = train(args, pde, epoch, model, model_b, itp_model, mesh_model, optimizer, None, train_loader,
                        graph_creator, criterion, device=device, after_backward=after_backward, step_graph=step_graph)
@@ -198,17 +245,13 @@ def main(args):
         print("Testing:")
         test_losses.append(test(args, pde, model, model_b, itp_model, mesh_model, test_loader, graph_creator,
                                 criterion, device=device, step_graph=step_graph))
+        scheduler.step()                       # before the save: a resumed run continues with the next epoch's rate
         if rank == 0:
-            state = {"model_state_dict": model.state_dict(), "args": args, "train_losses": train_losses,
-                     "itp_losses": itp_losses, "test_timestep_losses": test_losses}
-            if args.moving_mesh:
-                state.update(model_b_state_dict=model_b.state_dict(), mesh_model_state_dict=mesh_model.state_dict(),
-                             itp_model_state_dict=itp_model.state_dict())
-            torch.save(state, save_path)
+            save_checkpoint(save_path, args, epoch, model, model_b, itp_model, mesh_model, optimizer, scheduler, train_losses,
+                            itp_losses, test_losses)
             print(f"Saved model at {save_path}\n")
         if world > 1:
             torch.distributed.barrier()        # rank-0-only work above: keep the ranks' exchange sequences aligned
-        scheduler.step()
     if step_graph is not None:
         step_graph.release()
     return train_losses, test_losses
@@ -245,6 +288,8 @@ def build_parser():
     p.add_argument("--n_traj", type=int, default=20, help="synthetic trajectories")
     p.add_argument("--step_graph", type=eval, default=True, help="replay the recorded step as a CUDA graph")
     p.add_argument("--max_passes", type=int, default=None, help="bound the passes per epoch (default t_res)")
+    p.add_argument("--synthetic_mover", type=str, default="analytic", help="[analytic, dmm] mover when no DMM checkpoint exists")
+    p.add_argument("--resume", type=str, default=None, help="checkpoint written by this script to continue from")
     return p
 
 

@@ -106,18 +106,20 @@ def main():
            "bn_exchange": "peer" if comm.peer is not None else "nccl",
            "loss_rel": abs(float(loss_glob) - float(loss_g)) / abs(float(loss_g)),
            "pred_rel": rel(pred_s, pred_g[lo * n:hi * n])}
-    worst, worst_name = 0.0, ""
+    worst, worst_name, zero_abs = 0.0, "", 0.0
+    scale = max(float(b.norm()) for b in grads_g if b is not None)
     for nm, a, b in zip(names, grads_s, grads_g):
         if b is None:
             continue
         nb = float(b.norm())
-        if nb < 1e-9:                                # biases in front of a BatchNorm: analytically zero
-            assert float((a - b).norm()) < 1e-7, nm
+        if nb < 1e-6 * scale:                        # a bias in front of a BatchNorm: analytically zero, rounding noise on both
+            zero_abs = max(zero_abs, float((a - b).norm()) / scale)                       # sides; held against the largest gradient
             continue
         r = rel(a, b)
         if r > worst:
             worst, worst_name = r, nm
-    out["grad_rel_max"], out["grad_rel_argmax"] = worst, worst_name
+    out["grad_rel_max"], out["grad_rel_argmax"], out["zero_grads_abs_over_scale"] = worst, worst_name, zero_abs
+    assert zero_abs < 1e-5, zero_abs
     bn = 0.0
     for bs, bg in zip(bufs_s, bufs_g):
         for k in bg:

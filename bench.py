@@ -252,13 +252,17 @@ def profile_kernels(train_step_eager, steps, peaks, barrier):
         ops_mod._cabi.call = real_call
     by = {}
     for name, s, e, bound, work in rec:
-        d = by.setdefault(name, {"n": 0, "ms": 0.0, "work": 0.0, "bound": bound})
+        d = by.setdefault(name, {"n": 0, "ms": 0.0, "work": 0.0, "bound": bound, "all": []})
+        t = s.elapsed_time(e)
         d["n"] += 1
-        d["ms"] += s.elapsed_time(e)
+        d["ms"] += t
+        d["all"].append(t)
         d["work"] += work
     table = []
     for name, d in sorted(by.items(), key=lambda kv: -kv[1]["ms"]):
+        srt = sorted(d["all"])
         row = {"name": name, "launches_per_step": d["n"] / steps, "avg_us": 1e3 * d["ms"] / d["n"],
+               "min_us": 1e3 * srt[0], "median_us": 1e3 * srt[len(srt) // 2], "max_us": 1e3 * srt[-1],
                "us_per_step": 1e3 * d["ms"] / steps, "bound": d["bound"]}
         if d["bound"] == "tensor" and d["ms"] > 0:
             row["achieved_tflops"] = d["work"] / (d["ms"] * 1e-3) / 1e12
@@ -412,7 +416,7 @@ def run_ours(args):
     from mmpde_b200.interpolate import ItpNet
     from mmpde_b200.mesh.dmm_model import DMM
     from mmpde_b200.mmpde import criterion
-    from mmpde_b200.train_helper_2d import StepGraph, _forward_gnn, test_timestep_losses, training_loop_branch
+    from mmpde_b200.train_helper_2d import StepGraph, _forward_gnn, _overlap_solvers, test_timestep_losses, training_loop_branch
     import torch.distributed as dist
 
     if not torch.cuda.is_available():
@@ -637,7 +641,7 @@ def run_ours(args):
                                       + ("sums exchanged over NVLink peer memory in one kernel" if getattr(mdist.ops.COMM, "peer", None) is not None
                                          else "NCCL all-reduce of the sums" if world > 1 else "single rank") + "), flat grad all-reduce",
                        "launch": "eager" if step_graph is None else "CUDA graph replay of the whole step (StepGraph)"
-                                 + (", the two solvers as parallel graph branches" if world == 1 else ""),
+                                 + (", the two solvers as parallel graph branches" if _overlap_solvers(dev) else ""),
                        "l2": "per-step working set ~1.7 GB > 126 MB L2, no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "edge-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},

@@ -210,9 +210,23 @@ int mmpde_colsum(const float* A, int64_t lda, int64_t M, int N, float* colsum, v
  * w1[4*16] b1[4] w2[8*4*12] b2[8] w3[8*8] b3[1]  (525 floats, torch Conv1d weight order). */
 int mmpde_decoder_fwd(const float* h, int64_t ldh, int64_t M, const float* params, float scale,
                       float* out, void* stream);
+/* The same forward, additionally saving the post-ReLU activations of the two hidden blocks for the backward:
+ * act1 [M,256] (column c*38+i = channel c, position i of the first block; columns 152.. zero) and act2 [M,128]
+ * (column o*9+j; columns 72.. zero), both contiguous and 16-byte aligned.  With them the backward runs as dense
+ * (Toeplitz) contractions on mmpde_node_gemm / mmpde_node_wgrad_grouped while every ReLU mask comes from this fp32
+ * evaluation (a mask taken from a split-bf16 contraction flips for pre-activations within ~1e-6 of zero). */
+int mmpde_decoder_fwd_acts(const float* h, int64_t ldh, int64_t M, const float* params, float scale, float* out,
+                           float* act1, float* act2, void* stream);
 /* g_out[M] -> g_h [M,128] (ldg, overwritten) and g_params[525] (accumulated). */
 int mmpde_decoder_bwd(const float* h, int64_t ldh, int64_t M, const float* params, float scale,
                       const float* g_out, float* g_h, int64_t ldg, float* g_params, void* stream);
+
+/* out[m][c] = g[m] * w[c] * (act[m][c] > 0), c < 128: the decoder's last convolution is a dot product with w, so this is
+ * dL/d(pre-activation) of the block in front of it.  The product path runs the decoder BACKWARD as Toeplitz contractions on
+ * mmpde_node_gemm / mmpde_node_wgrad_grouped (ops._decoder_backward); mmpde_decoder_bwd above is the direct
+ * warp-per-node form, kept as a second implementation the tests compare against. */
+int mmpde_outer_gate(const float* g, const float* w, const float* act, int64_t lda, float* out, int64_t ldo, int64_t M,
+                     void* stream);
 
 /* ---- fused k-NN interpolation (data_creator_2d.py:77-83 + interpolate.py:79-93) ----------------
  * For query q of sample s: p = (x_1,y_1,...,x_30,y_30,x_q,y_q) from idx[q,0..29];

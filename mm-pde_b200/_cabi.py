@@ -51,7 +51,9 @@ SIGNATURES = {
     "mmpde_relu_bwd": [_p, _l, _p, _l, _l, _p, _l, _p, _p],
     "mmpde_colsum": [_p, _l, _l, _i, _p, _p],
     "mmpde_decoder_fwd": [_p, _l, _l, _p, _f, _p, _p],
+    "mmpde_decoder_fwd_acts": [_p, _l, _l, _p, _f, _p, _p, _p, _p],
     "mmpde_decoder_bwd": [_p, _l, _l, _p, _f, _p, _p, _l, _p, _p],
+    "mmpde_outer_gate": [_p, _p, _p, _l, _p, _l, _l, _p],
     "mmpde_itp_fwd": [_p, _p, _p, _p, _l, _p, _p, _p],
     "mmpde_itp_bwd": [_p, _p, _p, _p, _l, _p, _p, _p, _p, _p],
     "mmpde_rows_gather": [_p, _l, _p, _l, _i, _p, _p],

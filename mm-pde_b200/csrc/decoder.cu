@@ -45,9 +45,13 @@ __device__ __forceinline__ float dec_forward(const float* sp, DecScratch& s, int
     return warp_sum(part) + sp[OFF_B3];
 }
 
+// act1 [M,256] / act2 [M,128] (optional): the post-ReLU activations of the two hidden blocks in the layout of the
+// Toeplitz form (column c*38+i / o*9+j, zero padding behind) -- saved for a backward that runs as dense contractions
+// on the tensor cores while every ReLU mask still comes from THIS fp32 evaluation.
 __global__ void __launch_bounds__(WARPS * 32) decoder_fwd_kernel(const float* __restrict__ h, int64_t ldh, int64_t M,
                                                                  const float* __restrict__ params, float scale,
-                                                                 float* __restrict__ out) {
+                                                                 float* __restrict__ out, float* __restrict__ act1,
+                                                                 float* __restrict__ act2) {
     __shared__ float sp[DEC_NP];
     __shared__ __align__(16) DecScratch scr[WARPS];
     for (int i = threadIdx.x; i < DEC_NP; i += blockDim.x) sp[i] = __ldg(params + i);
@@ -60,6 +64,19 @@ __global__ void __launch_bounds__(WARPS * 32) decoder_fwd_kernel(const float* __
         __syncwarp();
         float v = dec_forward(sp, s, lane);
         if (lane == 0) out[n] = scale * v;
+        if (act1 != nullptr) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c0 = (j * 32 + lane) * 4;                   // 152 = 38 float4
+                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 < 152) v4 = *reinterpret_cast<const float4*>(&s.a1[c0]);
+                *reinterpret_cast<float4*>(act1 + n * 256 + c0) = v4;
+            }
+            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < 18) v4 = *reinterpret_cast<const float4*>(&s.a2[lane * 4]);     // 72 = 18 float4
+            *reinterpret_cast<float4*>(act2 + n * 128 + lane * 4) = v4;
+        }
     }
 }
 
@@ -202,12 +219,53 @@ __global__ void __launch_bounds__(WARPS * 32) decoder_bwd_kernel(const float* __
 
 using namespace mmpde;
 
+// out[m][c] = g[m] * w[c] * (act[m][c] > 0): dL/d(pre-activation) of the decoder's second block from dL/d(out) (the last
+// convolution is a dot product with w) -- the first step of the Toeplitz-GEMM decoder backward (ops._decoder_backward)
+namespace mmpde {
+__global__ void outer_gate_kernel(const float* __restrict__ g, const float* __restrict__ w, const float* __restrict__ act, int64_t lda,
+                                  float* __restrict__ out, int64_t ldo, int64_t M) {
+    const int lane = threadIdx.x & 31;
+    const float4 wv = ldg4(w + lane * 4);
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t m = warp; m < M; m += n_warps) {
+        const float gm = __ldg(g + m);
+        const float4 a = ldg4(act + m * lda + lane * 4);
+        float4 o;
+        o.x = a.x > 0.f ? gm * wv.x : 0.f; o.y = a.y > 0.f ? gm * wv.y : 0.f;
+        o.z = a.z > 0.f ? gm * wv.z : 0.f; o.w = a.w > 0.f ? gm * wv.w : 0.f;
+        *reinterpret_cast<float4*>(out + m * ldo + lane * 4) = o;
+    }
+}
+}  // namespace mmpde
+
+extern "C" int mmpde_outer_gate(const float* g, const float* w, const float* act, int64_t lda, float* out, int64_t ldo, int64_t M,
+                                void* stream) {
+    if (M < 0 || (lda & 3) || (ldo & 3)) return MMPDE_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(act) | reinterpret_cast<uintptr_t>(out)) & 15) return MMPDE_EINVAL;
+    if (M == 0) return MMPDE_OK;
+    const int grid = (int)imin64((M + 7) / 8, (int64_t)sm_count() * 8);
+    outer_gate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, w, act, lda, out, ldo, M);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
 extern "C" int mmpde_decoder_fwd(const float* h, int64_t ldh, int64_t M, const float* params, float scale, float* out,
                                  void* stream) {
     if (M < 0 || ldh % 4) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
     int grid = (int)imin64((M + WARPS - 1) / WARPS, (int64_t)sm_count() * 8);
-    decoder_fwd_kernel<<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(h, ldh, M, params, scale, out);
+    decoder_fwd_kernel<<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(h, ldh, M, params, scale, out, nullptr, nullptr);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_decoder_fwd_acts(const float* h, int64_t ldh, int64_t M, const float* params, float scale, float* out,
+                                      float* act1, float* act2, void* stream) {
+    if (M < 0 || ldh % 4 || act1 == nullptr || act2 == nullptr) return MMPDE_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(act1) | reinterpret_cast<uintptr_t>(act2)) & 15) return MMPDE_EINVAL;
+    if (M == 0) return MMPDE_OK;
+    int grid = (int)imin64((M + WARPS - 1) / WARPS, (int64_t)sm_count() * 8);
+    decoder_fwd_kernel<<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(h, ldh, M, params, scale, out, act1, act2);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }

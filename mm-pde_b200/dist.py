@@ -46,22 +46,34 @@ class PeerExchange:
 
 
 class DistComm(ops._Comm):
+    """Cross-rank sums of the BatchNorm statistics.  With peer memory every solver BRANCH of the step (the two solvers run
+    concurrently on two streams, train_helper_2d._forward_gnn) gets its own exchange buffer and sequence: within a
+    branch all ranks issue the same exchanges in the same order, while the two branches interleave differently on
+    different GPUs -- one shared sequence would pair up the wrong exchanges.  (A spin-waiting exchange kernel is one
+    small CTA; the persistent kernels of the other branch are ordinary grids without inter-CTA dependencies, so they make
+    progress around it.)  Without peer memory the sums go through NCCL, whose collectives must be issued in one global
+    order: then the branches are not overlapped (n_branches = 1)."""
+
     def __init__(self, group=None):
         self.group = group
         self.world = dist.get_world_size(group)
         self.peer = None
+        self.peers = []
         if self.world > 1 and torch.cuda.is_available() and os.environ.get("MMPDE_PEER_BN", "1") != "0":
             try:
-                self.peer = PeerExchange(group)
+                self.peers = [PeerExchange(group), PeerExchange(group)]
+                self.peer = self.peers[0]
             except Exception as e:                    # no peer access / no symmetric memory: NCCL all-reduce instead
+                self.peers, self.peer = [], None
                 if dist.get_rank(group) == 0:
                     print(f"[mmpde_b200.dist] peer-memory BatchNorm exchange unavailable ({type(e).__name__}: {e}); "
                           "using NCCL all-reduce", flush=True)
+        self.n_branches = len(self.peers) if (self.peers and os.environ.get("MMPDE_BRANCH_EXCHANGE", "1") != "0") else 1
 
-    def reduce_bn_sums(self, spread):
+    def reduce_bn_sums(self, spread, branch=0):
         """[n_rep, 256] local accumulator copies -> [256] sums over all ranks."""
-        if self.peer is not None and spread.is_cuda:
-            return self.peer.sum(spread)
+        if self.peers and spread.is_cuda:
+            return self.peers[branch if branch < self.n_branches else 0].sum(spread)
         return self.allreduce_(spread.sum(0) if spread.dim() == 2 else spread)
 
     def allreduce_(self, t):

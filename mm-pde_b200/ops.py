@@ -58,11 +58,16 @@ class _Comm:
     identity.  mmpde_b200.dist installs the torch.distributed (NCCL) version.  ``total_rows`` (set while a
     partitioned mesh is being processed) is the node count of the whole mesh = the BatchNorm row count."""
     total_rows = None
+    # Which of the step's two concurrent solver branches is being recorded (train_helper_2d._forward_gnn issues the two
+    # solvers on two streams).  Every branch owns its own cross-rank exchange sequence: the branches interleave
+    # differently on different ranks, the exchanges WITHIN a branch come in the same order everywhere.
+    branch = 0
+    n_branches = 1
 
     def allreduce_(self, t):
         return t
 
-    def reduce_bn_sums(self, spread):
+    def reduce_bn_sums(self, spread, branch=0):
         """[n_rep, 256] local accumulator copies -> [256] sums over all ranks (here: one rank)."""
         return spread.sum(0) if spread.dim() == 2 else spread
 
@@ -250,7 +255,7 @@ def _split_for(rows):
 
 class _BNState:
     """mean/rstd [2,128] of one BatchNorm application (saved for the backward)."""
-    __slots__ = ("mean_rstd", "count", "rows", "training")
+    __slots__ = ("mean_rstd", "count", "rows", "training", "branch")
 
 
 def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st, sums=None):
@@ -260,6 +265,7 @@ def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st, sums=N
     dev = gamma.device
     state.rows = sum(it[4] for it in items)
     state.training = bool(training)
+    state.branch = COMM.branch                         # the backward of this BatchNorm exchanges on the same sequence
     if training:
         if sums is None:                               # else: a zeroed [BN_REPLICAS, 256] slice handed in by the solver
             sums = torch.zeros(BN_REPLICAS, 2 * H, dtype=torch.float64, device=dev)
@@ -268,7 +274,7 @@ def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st, sums=N
         state.count = COMM.global_rows(state.rows)
         n_rep = BN_REPLICAS
         if state.count != float(state.rows):          # other ranks hold rows too: fold + sum over the ranks -> [2,128]
-            sums, n_rep = COMM.reduce_bn_sums(sums), 1
+            sums, n_rep = COMM.reduce_bn_sums(sums, state.branch), 1
         state.mean_rstd = torch.empty(2 * H, dtype=torch.float32, device=dev)
         _cabi.call("mmpde_bn_finalize", _ptr(sums), n_rep, state.count, BN_EPS, BN_MOMENTUM, _ptr(state.mean_rstd),
                    _ptr(rmean), _ptr(rvar), st)
@@ -299,7 +305,7 @@ def _bn_backward(items, relu, state, gamma, st, spread=None):
         # terms vanish and dL/dy = g * gamma * rstd (what nn.BatchNorm1d.eval() gives); dgamma / dbeta stay the sums.
         glob = torch.zeros_like(local)
     elif COMM.global_rows(state.rows) != float(state.rows):
-        glob = COMM.reduce_bn_sums(spread)
+        glob = COMM.reduce_bn_sums(spread, state.branch)
     for g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy, *gated in items:
         gyg, ldgg = gated if gated else (None, 0)
         _cabi.call("mmpde_bn_bwd_apply", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(gamma),
@@ -313,6 +319,122 @@ def _bn_backward(items, relu, state, gamma, st, spread=None):
 # ordinary case; several parts = a partitioned mesh whose halo rows are exchanged once per layer
 # (partition.py).  Parts of other ranks are reached through the exchange object.
 # ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# Conv1d decoder (gnn_2d.py:108-114,136-139) as three dense contractions on the tcgen05 node-GEMM kernels.
+# A Conv1d over the 128-wide feature axis is a banded (Toeplitz) matrix: Conv1d(1,4,16,s3) = T1 [152,128] with
+# T1[c*38+i, 3i+k] = w1[c,0,k];  Conv1d(4,8,12,s3) = T2 [72,152] with T2[o*9+j, c*38+3j+k] = w2[o,c,k];  Conv1d(8,1,8,s2)
+# reads positions 0..7 of the 9 = a dot product with w3row[o*9+j] = w3[0,o,j].  Padded to the kernels' 128-wide blocks
+# (T1 -> [256,128], T2 -> [128,256]) the BACKWARD of the stack is three data-gradient GEMMs (ReLU gates fused into the
+# epilogues), ONE grouped weight-gradient launch, and an index_add that folds the dense matrix gradients back onto the
+# 525 convolution parameters.  The forward stays the direct fp32 kernel (see _decoder_forward).
+# ------------------------------------------------------------------------------------------------
+_DEC = {}
+DEC_OFF = dict(w1=0, b1=64, w2=68, b2=452, w3=460, b3=524)
+
+
+def _decoder_maps(device):
+    """Static maps: (gather) element of (T1 | b1e | T2 | b2e | w3row) -> index into the flat parameter vector padded with
+    a zero at position 525; (fold) parameter -> the dense elements holding it."""
+    key = str(device)
+    if key not in _DEC:
+        Z = DEC_NPARAM
+        t1 = torch.full((2 * H, H), Z, dtype=torch.int64)
+        b1 = torch.full((2 * H,), Z, dtype=torch.int64)
+        for c in range(4):
+            for i in range(38):
+                b1[c * 38 + i] = DEC_OFF["b1"] + c
+                for k in range(16):
+                    t1[c * 38 + i, 3 * i + k] = DEC_OFF["w1"] + c * 16 + k
+        t2 = torch.full((H, 2 * H), Z, dtype=torch.int64)
+        b2 = torch.full((H,), Z, dtype=torch.int64)
+        w3 = torch.full((H,), Z, dtype=torch.int64)
+        for o in range(8):
+            for j in range(9):
+                b2[o * 9 + j] = DEC_OFF["b2"] + o
+                if j < 8:
+                    w3[o * 9 + j] = DEC_OFF["w3"] + o * 8 + j
+                for c in range(4):
+                    for k in range(12):
+                        t2[o * 9 + j, c * 38 + 3 * j + k] = DEC_OFF["w2"] + (o * 4 + c) * 12 + k
+        gather = torch.cat((t1.reshape(-1), b1, t2.reshape(-1), b2, w3))
+        # inverse map for the gradient fold: parameter p <- the (<= 38) dense elements that hold it, padded with the index
+        # of an appended zero; a gather + row sum is deterministic, an index_add_ with duplicates is not
+        n_dense = gather.numel()
+        order = torch.argsort(gather, stable=True)
+        counts = torch.bincount(gather, minlength=Z + 1)[:Z]
+        fold = torch.full((Z, int(counts.max())), n_dense, dtype=torch.int64)
+        start = torch.cumsum(counts, 0) - counts
+        for p_ in range(Z):
+            fold[p_, :int(counts[p_])] = order[int(start[p_]):int(start[p_]) + int(counts[p_])]
+        _DEC[key] = (gather.to(device), fold.to(device))
+    return _DEC[key]
+
+
+_DEC_SPLIT = [2 * H * H, 2 * H, H * 2 * H, H, H]          # T1 b1e T2 b2e w3row
+
+
+def _decoder_forward(parts, hs, dec, scale, st):
+    """hs[p] [n_own,128] -> out[p] [n_own]; returns (outs, saved).  The forward is the direct fp32 kernel (every ReLU mask
+    must come from an fp32 evaluation: a mask taken from a split-bf16 contraction flips for pre-activations within ~1e-6
+    of zero, ~1e-3 of the rows, and each flip moves that row's upstream gradient by several percent); it also writes the
+    activations in the Toeplitz layout for the backward."""
+    f32 = dict(dtype=torch.float32, device=dec.device)
+    outs, saved = [], []
+    for part, h in zip(parts, hs):
+        N = part.n_own
+        out = torch.empty(N, **f32)
+        A1, C2 = torch.empty(N, 2 * H, **f32), torch.empty(N, H, **f32)
+        _cabi.call("mmpde_decoder_fwd_acts", _ptr(h), H, N, _ptr(dec), float(scale), _ptr(out), _ptr(A1), _ptr(C2), st)
+        outs.append(out)
+        saved.append((A1, C2))
+    return outs, saved
+
+
+def _decoder_backward(parts, hs, dec, scale, dec_saved, g_outs, st):
+    """-> ([dL/dh per part], dL/d(flat decoder parameters) [525])."""
+    saved = dec_saved
+    dev = dec.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    gather_map, fold_map = _decoder_maps(dev)
+    padded = torch.cat((dec, dec.new_zeros(1)))
+    T1, _, T2, _, w3row = torch.split(padded[gather_map], _DEC_SPLIT)
+    w3s = w3row * scale
+    # dense gradients of (T1 | b1e | T2 | b2e | w3row), one zeroed buffer, folded onto the parameters at the end
+    flat = torch.zeros(sum(_DEC_SPLIT) + 1, **f32)         # + one slot that stays zero (padding target of the fold)
+    dT1, db1e, dT2, db2e, dw3, _ = torch.split(flat, _DEC_SPLIT + [1])
+    dw3x = torch.zeros(H, 4, **f32)                   # column 0 = C2^T g_out (the extension slot of the weight-gradient kernel)
+    g_b3 = torch.zeros((), **f32)
+    g_hs, tasks, keep = [], [], []
+    for part, h, (A1, C2), g_out in zip(parts, hs, saved, g_outs):
+        N = part.n_own
+        g = g_out.contiguous().view(-1)
+        g_b3 = g_b3 + g.sum()
+        g4 = torch.zeros(N, 4, **f32)
+        g4[:, 0] = g
+        # dL/dC2 = g_out (x) (scale * w3row), gated by the ReLU of C2
+        g_C2 = torch.empty(N, H, **f32)
+        _cabi.call("mmpde_outer_gate", _ptr(g), _ptr(w3s), _ptr(C2), H, _ptr(g_C2), H, N, st)
+        g_A1 = torch.empty(N, 2 * H, **f32)
+        node_gemm(_ptr(g_C2), H, _ptr(T2), 1, 2 * H, _ptr(g_A1), 2 * H, N, relu=2, R1=_ptr(A1), ldr1=2 * H, st=st)
+        node_gemm(_ptr(g_C2), H, _ptr(T2, H), 1, 2 * H, _ptr(g_A1, H), 2 * H, N, relu=2, R1=_ptr(A1, H), ldr1=2 * H, st=st)
+        g_h = torch.empty(N, H, **f32)
+        node_gemm(_ptr(g_A1), 2 * H, _ptr(T1), 1, H, _ptr(g_h), H, N, A1=_ptr(g_A1, H), lda1=2 * H, W1=_ptr(T1, H * H), w1_ns=1,
+                  w1_ks=H, st=st)
+        g_hs.append(g_h)
+        tasks += [wgrad_task(_ptr(g_C2), H, N, B=_ptr(A1), ldb=2 * H, dW=_ptr(dT2), ldw=2 * H, dbias=_ptr(db2e)),
+                  wgrad_task(_ptr(g_C2), H, N, B=_ptr(A1, H), ldb=2 * H, dW=_ptr(dT2, H), ldw=2 * H),
+                  wgrad_task(_ptr(g_A1), 2 * H, N, B=_ptr(h), ldb=H, dW=_ptr(dT1), ldw=H, dbias=_ptr(db1e)),
+                  wgrad_task(_ptr(g_A1, H), 2 * H, N, B=_ptr(h), ldb=H, dW=_ptr(dT1, H * H), ldw=H, dbias=_ptr(db1e, H)),
+                  wgrad_task(_ptr(C2), H, N, Bext=_ptr(g4), dWext=_ptr(dw3x))]
+        keep.append((g4, g_C2, g_A1))
+    node_wgrad_grouped(tasks, st)
+    del keep
+    dw3.copy_(dw3x[:, 0] * scale)
+    g_dec = flat[fold_map].sum(1)
+    g_dec[DEC_OFF["b3"]] = g_b3 * scale
+    return g_hs, g_dec
+
+
 N_ENC = 8          # We1 be1 g1 bt1 We2 be2 g2 bt2
 N_LAYER = 10       # W1 b1 W2 b2 W3 b3 W4 b4 gamma beta
 
@@ -536,13 +658,9 @@ def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st):
         lp = params[N_ENC + N_LAYER * l: N_ENC + N_LAYER * (l + 1)]
         layers.append(_layer_forward(parts, X[l], lp, bn_buffers[2 + l], training, dest(l + 1), exch, st,
                                      prep=preps[l], bn_sums=bn_sums[2 + l]))
-    outs = []
-    for part, h in zip(parts, hL):
-        out = torch.empty(part.n_own, **f32)
-        _cabi.call("mmpde_decoder_fwd", _ptr(h), H, part.n_own, _ptr(dec), float(scale), _ptr(out), st)
-        outs.append(out)
+    outs, dec_saved = _decoder_forward(parts, hL, dec, float(scale), st)
     return outs, dict(parts=parts, L=L, scale=float(scale), params=params, enc=(e1s, e1ns, e2s, bn1, bn2), X=X, hL=hL,
-                      layers=layers, exch=exch, preps=preps)
+                      layers=layers, exch=exch, preps=preps, dec=dec_saved)
 
 
 def _solver_backward(sv, g_outs, need_u, st):
@@ -555,13 +673,7 @@ def _solver_backward(sv, g_outs, need_u, st):
     e1s, e1ns, e2s, bn1, bn2 = sv["enc"]
     grads = [None] * len(params)
     g_node4s = [torch.zeros(part.n_own, 4, **f32) for part in parts] if need_u else None
-    g_dec = torch.zeros(DEC_NPARAM, **f32)
-    g_hs = []
-    for part, h, g_out in zip(parts, sv["hL"], g_outs):
-        g_h = torch.empty(part.n_own, H, **f32)
-        _cabi.call("mmpde_decoder_bwd", _ptr(h), H, part.n_own, _ptr(dec), sv["scale"], _ptr(g_out.contiguous().view(-1)),
-                   _ptr(g_h), H, _ptr(g_dec), st)
-        g_hs.append(g_h)
+    g_hs, g_dec = _decoder_backward(parts, sv["hL"], dec, sv["scale"], sv["dec"], g_outs, st)
     grads[N_ENC + N_LAYER * L] = g_dec
     flat_all = torch.zeros(max(L, 1), sum(LAYER_GRAD_SIZES), **f32)   # every layer's gradient accumulators, zeroed at once
     spread_all = torch.zeros(2 + L, BN_REPLICAS, 2 * H, dtype=torch.float64, device=dev)

@@ -118,12 +118,14 @@ def _overlap_solvers(device):
     """The two solvers of a step (uniform grid, moved mesh) are independent until their outputs are added.  Their big
     kernels are persistent one-CTA-per-SM kernels, so they cannot share an SM -- but issued on two streams (two parallel
     branches of the step's CUDA graph) the launch ramp and the tail of every kernel of one branch are filled by the
-    other branch.  Off with several ranks: the cross-GPU exchanges need the same order on every rank."""
+    other branch.  With several ranks each branch needs its own cross-GPU exchange sequence (dist.DistComm gives every
+    branch its own peer-memory buffer); a COMM that cannot (NCCL fallback: collectives need ONE global order) keeps the
+    solvers on one stream."""
     import os
     from . import ops
     if os.environ.get("MMPDE_OVERLAP_SOLVERS", "1") == "0" or not torch.cuda.is_available():
         return False
-    return torch.device(device).type == "cuda" and type(ops.COMM) is ops._Comm
+    return torch.device(device).type == "cuda" and (type(ops.COMM) is ops._Comm or ops.COMM.n_branches >= 2)
 
 
 def _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, steps, device):
@@ -136,7 +138,11 @@ def _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, lab
         cur, side = torch.cuda.current_stream(), _side_stream(device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            on_uniform = model(uniform)
+            ops.COMM.branch = 1              # this solver's BatchNorm exchanges (forward AND backward) use sequence 1
+            try:
+                on_uniform = model(uniform)
+            finally:
+                ops.COMM.branch = 0
         moved = graph_creator.create_graph(itp_model, data, labels, steps, device, mesh_model)
         on_moved = graph_creator.interpolate_pred(itp_model, model_b(moved), moved, data, device)
         cur.wait_stream(side)

@@ -34,7 +34,9 @@ def main():
     gc = GraphCreator_FS_2D(pde, bench.K_NEIGH, "knn", 1, bench.RES[0])
     model, model_b = MP_PDE_Solver_2D(pde).to(dev), MP_PDE_Solver_2D(pde).to(dev)
     net = ItpNet(bench.RES[1], bench.RES[2], [128, 64], [128, 64], [1, 4, 16, 4, 1]).to(dev)
-    mover = synthetic.AnalyticMover().to(dev)
+    from mmpde_b200.mesh.dmm_model import DMM
+    torch.manual_seed(bench.MOVER_SEED)
+    mover = (synthetic.AnalyticMover() if "--analytic-mover" in sys.argv else DMM(s=bench.RES[1], mode="array", **bench.DMM_ARRAY)).to(dev).eval()
     opt = torch.optim.AdamW([{"params": model.parameters()}, {"params": model_b.parameters()}, {"params": net.parameters()}],
                             lr=2e-3, capturable=True, fused=True)
     fields = synthetic.burgers_fields(bench.BATCH, *bench.RES, seed=100).to(dev)
@@ -65,7 +67,7 @@ def main():
             cnt[name] += 1
     busy = sum(tot.values()) / steps / 1e3
     print(f"{'eager' if eager else 'graph replay'}: step {wall:.2f} ms under the profiler; kernels+copies busy {busy:.2f} ms/step")
-    for name, v in tot.most_common(45):
+    for name, v in tot.most_common(60):
         print(f"  {v / steps / 1e3:8.3f} ms {100 * v / steps / 1e3 / wall:5.1f}%  x{cnt[name] / steps:6.1f}  avg {v / cnt[name]:8.1f} us  {name[:90]}")
 
 

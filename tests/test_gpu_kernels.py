@@ -244,6 +244,33 @@ def test_decoder_forward_backward():
     assert _rel(gp, torch.cat([p.grad.reshape(-1) for p in dec.parameters()])) < 1e-5
 
 
+@pytest.mark.parametrize("M", [1, 130, 777, 5000])
+def test_decoder_toeplitz_contractions_equal_conv1d(M):
+    """The product path of the decoder (ops._decoder_forward: direct fp32 kernel that saves the activations;
+    ops._decoder_backward: Toeplitz contractions on the tcgen05 node-GEMM kernels) against nn.Conv1d and its autograd:
+    outputs, dL/dh and all 525 parameter gradients."""
+    from mmpde_b200 import ops
+    dev = _dev()
+    torch.manual_seed(2)
+    dec = torch.nn.Sequential(torch.nn.Conv1d(1, 4, 16, stride=3), torch.nn.ReLU(), torch.nn.Conv1d(4, 8, 12, stride=3),
+                              torch.nn.ReLU(), torch.nn.Conv1d(8, 1, 8, stride=2))
+    h = torch.randn(M, 128, requires_grad=True)
+    ref = 0.1 * dec(h[:, None]).squeeze(1)
+    g = torch.randn(M, 1)
+    ref.backward(g)
+    flat = torch.cat([p.detach().reshape(-1) for p in dec.parameters()]).to(dev)
+    hd = h.detach().to(dev).contiguous()
+
+    class P:
+        n_own = M
+    st = ops._stream()
+    outs, saved = ops._decoder_forward([P], [hd], flat, 0.1, st)
+    assert _rel(outs[0], ref.view(-1)) < 2e-6
+    g_hs, g_dec = ops._decoder_backward([P], [hd], flat, 0.1, saved, [g.view(-1).to(dev)], st)
+    assert _rel(g_hs[0], h.grad) < 3e-5
+    assert _rel(g_dec, torch.cat([p.grad.reshape(-1) for p in dec.parameters()])) < 3e-5
+
+
 # ------------------------------------------------------------------------------------------- edge kernels
 def _grad_tol(n_nodes):
     """Gradient tolerance of the LAYER-level tests on tiny graphs.  Forward outputs agree with the fp32 reference to

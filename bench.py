@@ -199,11 +199,11 @@ def _kernel_work(name, a, ctx):
         return "tensor", 2 * a[20] * H * k
     if name == "mmpde_node_wgrad_grouped":
         return "tensor", ctx.get("wgrad_flops", 0)
-    if name in ("mmpde_bn_stats",):                     # one pass over [M,128] (+ the residual operand)
+    if name in ("mmpde_bn_stats", "mmpde_bn_stats_fused"):   # one pass over [M,128] (+ the residual operand)
         return "hbm", a[4] * H * 4 * (2 if a[2] else 1)
     if name == "mmpde_bn_apply":
         return "hbm", a[4] * H * 4 * ((2 if a[2] else 1) + 1)
-    if name == "mmpde_bn_bwd_reduce":
+    if name in ("mmpde_bn_bwd_reduce", "mmpde_bn_bwd_reduce_fused"):
         return "hbm", a[9] * H * 4 * (2 + (1 if a[7] else 0))
     if name == "mmpde_bn_bwd_apply":
         return "hbm", a[9] * H * 4 * (2 + (1 if a[7] else 0) + 1 + (1 if a[17] else 0))
@@ -215,6 +215,10 @@ def _kernel_work(name, a, ctx):
         return "hbm", a[4] * 144
     if name == "mmpde_itp_bwd":
         return "hbm", a[4] * (144 + 30 * 4)
+    if name == "mmpde_itp_fwd_tc":                      # tcgen05: 2*(62*128 + 128*64 + 64*30) = 36 096 FLOP / query (x3 executed)
+        return "tensor", a[4] * 36096
+    if name == "mmpde_itp_bwd_tc":                      # forward again + the two data-gradient contractions (weight gradients
+        return "tensor", a[4] * (36096 + 2 * (30 * 64 + 64 * 128))      # go out as a grouped node_wgrad launch)
     return None, 0
 
 

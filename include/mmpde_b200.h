@@ -198,6 +198,22 @@ int mmpde_bn_exchange(const double* sums, int n_rep, const int64_t* peer_base, i
                       void* stream);
 int mmpde_bn_exchange_set_timeout(double seconds);
 
+/* The reducing BatchNorm kernels with the rest of the pass done by their LAST CTA (a ticket counter, zeroed together
+ * with the sums, tells a CTA that all partial sums have been delivered): fold of the accumulator copies, the cross-GPU
+ * exchange of mmpde_bn_exchange (peer_base == NULL or world == 1: this rank only) and, forward, the finalisation of
+ * mmpde_bn_finalize -- one launch instead of three or four per BatchNorm pass.
+ * stats_fused: `count` = rows of the whole batch over all ranks; writes mean_rstd and updates the running statistics.
+ * bwd_reduce_fused: local_out[256] = this rank's (sum g | sum g*yhat) (= dbeta | dgamma), glob_out[256] = the sums over
+ * all ranks for mmpde_bn_bwd_apply; either may be NULL (glob_out NULL also skips the exchange: eval mode). */
+int mmpde_bn_stats_fused(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, double* sums,
+                         uint32_t* ticket, double count, float eps, float momentum, float* mean_rstd,
+                         float* running_mean, float* running_var, const int64_t* peer_base, int rank, int world,
+                         void* stream);
+int mmpde_bn_bwd_reduce_fused(const float* g, int64_t ldg, const float* out, int64_t ldo, int relu,
+                              const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
+                              const float* mean_rstd, double* bsums, uint32_t* ticket, double* local_out,
+                              double* glob_out, const int64_t* peer_base, int rank, int world, void* stream);
+
 /* ---- small elementwise helpers of the node path -------------------------------------------------
  * relu_bwd: out = g * (act > 0); colsum[128] += column sums of out (NULL to skip).  [M,128] */
 int mmpde_relu_bwd(const float* g, int64_t ldg, const float* act, int64_t lda, int64_t M,
@@ -238,6 +254,21 @@ int mmpde_itp_fwd(const float* src_xy, const float* src_val, const float* qry_xy
 int mmpde_itp_bwd(const float* src_xy, const float* src_val, const float* qry_xy, const int32_t* idx,
                   int64_t n_queries, const float* params, const float* g_out,
                   float* g_params, float* g_src_val, void* stream);
+
+/* The same interpolation on the tensor cores (tcgen05, split-bf16 products, 128 queries per tile; csrc/itp_tc.cu) -- the
+ * form the product path uses (ops.InterpolateFn); mmpde_itp_fwd / mmpde_itp_bwd above are the direct fp32 form, kept as a
+ * second implementation the tests compare against.  src_xy / qry_xy 8-byte aligned; idx and qry_xy 16-byte aligned
+ * lets the neighbour lists come in through the TMA (otherwise they are loaded by the threads).
+ * Backward: g_src_val[P] is accumulated atomically (NULL to skip); the weight gradients are left as the operands of
+ * three contractions over the query axis, all [Q,128] fp32, 16-byte aligned, fully overwritten:
+ *   G1 = dL/dza   G2 = [dL/dzb (64) | dL/dw (30) 0 0 | 0 (32)]   X1 = [p (62) 0 0 | hb (64)]   X2 = ha
+ * dWa = (G1^T X1)[:, :62], ba = colsum G1;  dWb = (G2^T X2)[:64], bb = colsum G2[:, :64];
+ * dWc = (G2^T X1)[64:94, 64:], bc = colsum G2[:, 64:94]  -- one mmpde_node_wgrad_grouped launch with three tasks. */
+int mmpde_itp_fwd_tc(const float* src_xy, const float* src_val, const float* qry_xy, const int32_t* idx,
+                     int64_t n_queries, const float* params, float* out, void* stream);
+int mmpde_itp_bwd_tc(const float* src_xy, const float* src_val, const float* qry_xy, const int32_t* idx,
+                     int64_t n_queries, const float* params, const float* g_out, float* g_src_val,
+                     float* G1, float* G2, float* X1, float* X2, void* stream);
 
 /* ---- halo exchange of the graph-partitioned processor (no reference counterpart) ----
  * Rows of a strided fp32 matrix <-> a contiguous buffer; ncols and the leading dimension are multiples of 4,

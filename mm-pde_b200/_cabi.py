@@ -45,6 +45,8 @@ SIGNATURES = {
     "mmpde_bn_finalize": [_p, _i, _d, _f, _f, _p, _p, _p, _p],
     "mmpde_bn_exchange": [_p, _i, _p, _i, _i, _p, _p],
     "mmpde_bn_exchange_set_timeout": [_d],
+    "mmpde_bn_stats_fused": [_p, _l, _p, _l, _l, _p, _p, _d, _f, _f, _p, _p, _p, _p, _i, _i, _p],
+    "mmpde_bn_bwd_reduce_fused": [_p, _l, _p, _l, _i, _p, _l, _p, _l, _l, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "mmpde_bn_apply": [_p, _l, _p, _l, _l, _p, _p, _p, _i, _p, _l, _p],
     "mmpde_bn_bwd_reduce": [_p, _l, _p, _l, _i, _p, _l, _p, _l, _l, _p, _p, _p],
     "mmpde_bn_bwd_apply": [_p, _l, _p, _l, _i, _p, _l, _p, _l, _l, _p, _p, _p, _d, _p, _l, _i, _p, _l, _p],
@@ -56,6 +58,8 @@ SIGNATURES = {
     "mmpde_outer_gate": [_p, _p, _p, _l, _p, _l, _l, _p],
     "mmpde_itp_fwd": [_p, _p, _p, _p, _l, _p, _p, _p],
     "mmpde_itp_bwd": [_p, _p, _p, _p, _l, _p, _p, _p, _p, _p],
+    "mmpde_itp_fwd_tc": [_p, _p, _p, _p, _l, _p, _p, _p],
+    "mmpde_itp_bwd_tc": [_p, _p, _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _p],
     "mmpde_rows_gather": [_p, _l, _p, _l, _i, _p, _p],
     "mmpde_rows_scatter_add": [_p, _p, _l, _i, _p, _l, _p],
     "mmpde_rows_dot": [_p, _l, _i, _p, _p, _l, _l, _i, _p],

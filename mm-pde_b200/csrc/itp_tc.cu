@@ -1,0 +1,499 @@
+// Fused k-NN interpolation between the moved mesh and the reference mesh on the 5th-gen tensor cores (tcgen05 + TMEM).
+// Replaces the gather points[indices] / labels[indices] + ItpNet modes '1'/'2' + weighted sum
+// (/root/reference/data_creator_2d.py:77-83, /root/reference/interpolate.py:79-93) and their autograd.
+//
+//   p = (x_1,y_1,...,x_30,y_30,x_q,y_q);  w = Wc tanh(Wb tanh(Wa p + ba) + bb) + bc;  out[q] = sum_k w_k val[idx[q,k]]
+//
+// Tile = 128 queries, one persistent CTA per SM, 512 threads.  Thread (r, g): r = TMEM lane = query of the tile, g = one
+// of four column groups (warp = 4 g + r / 32: a warp may only touch the TMEM lanes 32 (warp % 4) ..).  Per tile the three
+// layers run as dense contractions D[query][channel] = A[query][k] B[channel][k]: the activation tile is the A operand
+// (M = 128 queries), the weights sit in shared memory for the whole kernel as B operands (N = 128 / 64 / 32), every
+// product as three bf16 MMAs (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM).  Between two layers the thread that
+// owns (query, 32 / 16 channels) pulls its accumulator columns out of TMEM, adds the bias, applies tanh, splits to
+// bf16 hi / lo and writes its 64 / 32 contiguous bytes of the next layer's K-major operand row (16-byte stores, the
+// SWIZZLE_128B pattern spreads the 32 rows of a warp over all banks).  The last layer leaves the 30 weights of a query in
+// ITS thread group's registers next to the neighbour values the same threads gathered, so the weighted sum needs no
+// shuffle: four partial sums per query meet in shared memory.
+//
+// Input precision: the coordinates enter CENTRED, p'' = (x_k - x_q, y_k - y_q | x_q, y_q | r(x_q), r(y_q)) against
+// Wa'' = [Wa[:, :60] | sx sy | sx sy] with sx = sum of the x columns of Wa (sy alike): algebraically Wa p, but the
+// hi/lo split (2^-17 relative) now acts on neighbour OFFSETS, and the two absolute coordinates carry a third bf16 term
+// (r = what hi + lo leaves over) in the two spare columns of K = 64.
+//
+// Data movement: the tile's neighbour lists (128 x 30 int32 = 15 360 contiguous bytes) and query coordinates (1 KB) are
+// fetched by the TMA (cp.async.bulk, completion on an mbarrier) one tile ahead; the gathers of neighbour coordinates
+// and values for tile i+1 are issued right after tile i's operand is built and land while tile i runs.
+//
+// Backward (mmpde_itp_bwd_tc): the same forward, then dL/dw = g_out * val, two data-gradient contractions
+// (g_zb = (g_w Wc) (1 - hb^2), g_za = (g_zb Wb) (1 - ha^2); the weight images are simply read MN-major) and
+// dL/dval scattered atomically.  The kernel writes the operands of the three weight-gradient contractions
+//   G1 = g_za [Q,128]   G2 = [g_zb | g_w | 0] [Q,128]   X1 = [p | 0 0 | hb] [Q,128]   X2 = ha [Q,128]
+// and the caller runs them as ONE grouped mmpde_node_wgrad_grouped launch (dWa = G1^T X1[:, :62], dWb = (G2^T X2)[:64],
+// dWc = (G2^T X1)[64:94, 64:], biases = column sums of G1 / G2).
+#include "tc_common.cuh"
+
+namespace mmpde {
+namespace itp {
+using namespace tc;
+
+constexpr int KN = 30, IN0 = 62, H1 = 128, H2 = 64;
+constexpr int P_WA = 0, P_BA = 7936, P_WB = 8064, P_BB = 16256, P_WC = 16320, P_BC = 18240;
+constexpr int THREADS = 512, TQ = 128;
+constexpr uint32_t IDX_BYTES = TQ * KN * 4, QXY_BYTES = TQ * 8;
+
+struct Args {
+    const float2* src_xy; const float* src_val; const float2* qry_xy; const int* idx; int64_t nq; const float* params;
+    float* out; int use_tma;
+    const float* g_out; float* g_src_val; float* G1; float* G2; float* X1; float* X2;          // backward only
+};
+
+template <bool BWD>
+struct Smem {
+    static constexpr uint32_t WA = 0;                          // Wa'' [128 out][64 k]  hi | lo   2 x 16 KB
+    static constexpr uint32_t WB = WA + 32768;                 // Wb   [64 out][128 k]  hi | lo   2 x 16 KB (two 64-column blocks of 8 KB)
+    static constexpr uint32_t WC = WB + 32768;                 // Wc   [32 out][64 k]   hi | lo   2 x 4 KB
+    static constexpr uint32_t AA = WC + 8192;                  // p'' tile, later hb tile [128 q][64]  hi | lo   2 x 16 KB
+    static constexpr uint32_t AB = AA + 32768;                 // ha tile [128 q][128]  hi | lo   2 x 32 KB
+    static constexpr uint32_t GW = AB + 65536;                 // backward: g_w tile, later g_zb tile [128 q][64]  hi | lo
+    static constexpr uint32_t IDX = GW + (BWD ? 32768 : 0);    // neighbour lists of the NEXT tile (TMA destination)
+    static constexpr uint32_t QXY = IDX + IDX_BYTES;           // its query coordinates
+    static constexpr uint32_t BIAS = QXY + QXY_BYTES;          // ba[128] bb[64] bc[32]
+    static constexpr uint32_t PART = BIAS + 1024;              // partial weighted sums [2][4][128]
+    static constexpr uint32_t SXY = PART + 4096;               // sx[128] sy[128] (prologue)
+    static constexpr uint32_t BAR = SXY + 1024;                // mma_bar, idx_bar, tmem slot
+    static constexpr uint32_t TOTAL = BAR + 64;
+};
+
+__device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo) {
+    uint2 h0, l0, h1, l1;
+    split4(make_float4(f[0], f[1], f[2], f[3]), h0, l0);
+    split4(make_float4(f[4], f[5], f[6], f[7]), h1, l1);
+    hi = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
+}
+// byte offset of the 16-byte chunk c (8 bf16) of row r inside one 64-column block (rows of 128 bytes, SWIZZLE_128B)
+__device__ __forceinline__ uint32_t chunk_off(int r, int c) { return (uint32_t)r * 128u + (((uint32_t)c ^ ((uint32_t)r & 7u)) << 4); }
+// hi + lo of the 8 bf16 pairs of a chunk pair back to fp32
+__device__ __forceinline__ void join8(uint4 hi, uint4 lo, float (&f)[8]) {
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        f[2 * m] = __uint_as_float(h[m] << 16) + __uint_as_float(l[m] << 16);
+        f[2 * m + 1] = __uint_as_float(h[m] & 0xFFFF0000u) + __uint_as_float(l[m] & 0xFFFF0000u);
+    }
+}
+// tanh(x) = 1 - 2 / (1 + 2^(2 log2(e) |x|)) with the sign copied back: two MUFU operations (ex2, rcp) and four FP
+// instructions, no branch (tanhf() switches between a polynomial and this form per lane: ~20 issue slots once a warp
+// holds both kinds).  Absolute error ~1e-7 (ex2.approx 2^-22 relative, rcp.approx 1 ulp): the 1e-5 bar of the tile is set
+// by the bf16 hi/lo split, not by this.  Large |x|: ex2 -> +inf, rcp -> 0, result +-1.
+__device__ __forceinline__ float tanh_fast(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return copysignf(fmaf(-2.f, r, 1.f), x);
+}
+__device__ __forceinline__ void stg4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+
+template <bool BWD>
+__global__ void __launch_bounds__(THREADS, 1) itp_tc_kernel(const __grid_constant__ Args p) {
+    using S = Smem<BWD>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(sm);
+    const uint32_t mma_bar = sbase + S::BAR, idx_bar = sbase + S::BAR + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + S::BAR + 16);
+    float* s_bias = reinterpret_cast<float*>(sm + S::BIAS);
+    float* s_part = reinterpret_cast<float*>(sm + S::PART);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = (warp & 3) * 32 + lane, g = warp >> 2;
+    constexpr uint32_t TCOLS = BWD ? 512 : 256;
+
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TCOLS);
+    if (tid == 32) { mbar_init(mma_bar, 1); mbar_init(idx_bar, 1); fence_mbar_init(); }
+    // ---- weights -> bf16 hi / lo operand images (once per CTA)
+    {
+        float* s_sxy = reinterpret_cast<float*>(sm + S::SXY);
+        if (tid < 256) {                                                 // sx / sy: sums of the x / y columns of Wa
+            const int o = tid & 127, par = tid >> 7;
+            float s = 0.f;
+            for (int k = par; k < IN0; k += 2) s += __ldg(p.params + P_WA + o * IN0 + k);
+            s_sxy[par * 128 + o] = s;
+        }
+        __syncthreads();
+        // one 16-byte chunk (8 consecutive k of one output row) per step: 8 values -> hi / lo -> two 128-bit stores
+        auto put8 = [&](uint32_t img_hi, uint32_t img_lo, uint32_t off, const float (&v)[8]) {
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            sts_v4(sbase + img_hi + off, hi);
+            sts_v4(sbase + img_lo + off, lo);
+        };
+        for (int i = tid; i < H1 * 8; i += THREADS) {                    // Wa'': rows of 62 floats (8-byte aligned)
+            const int o = i >> 3, c = i & 7;
+            const float* row = p.params + P_WA + o * IN0;
+            float v[8];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int k = 8 * c + 2 * m;
+                float2 w = make_float2(0.f, 0.f);
+                if (k < 60) w = __ldg(reinterpret_cast<const float2*>(row + k));
+                else w = make_float2(s_sxy[o], s_sxy[128 + o]);          // k = 60, 62: (sx, sy)
+                v[2 * m] = w.x; v[2 * m + 1] = w.y;
+            }
+            put8(S::WA, S::WA + 16384, chunk_off(o, c), v);
+        }
+        for (int i = tid; i < H2 * 16; i += THREADS) {
+            const int o = i >> 4, c = i & 15;
+            const float4 a = ldg4(p.params + P_WB + o * H1 + 8 * c), b = ldg4(p.params + P_WB + o * H1 + 8 * c + 4);
+            const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            put8(S::WB, S::WB + 16384, (uint32_t)(c >> 3) * 8192u + chunk_off(o, c & 7), v);
+        }
+        for (int i = tid; i < 32 * 8; i += THREADS) {
+            const int o = i >> 3, c = i & 7;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (o < KN) {
+                const float4 a = ldg4(p.params + P_WC + o * H2 + 8 * c), b = ldg4(p.params + P_WC + o * H2 + 8 * c + 4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            }
+            put8(S::WC, S::WC + 4096, chunk_off(o, c), v);
+        }
+        if (tid < H1) s_bias[tid] = __ldg(p.params + P_BA + tid);
+        else if (tid < H1 + H2) s_bias[tid] = __ldg(p.params + P_BB + tid - H1);
+        else if (tid < H1 + H2 + 32) s_bias[tid] = (tid - H1 - H2 < KN) ? __ldg(p.params + P_BC + tid - H1 - H2) : 0.f;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t d_a = tmem_base + lane_addr, d_b = d_a + 128, d_c = d_a + 192, d_gzb = d_a + 256, d_gza = d_a;
+    const int64_t n_tiles = (p.nq + TQ - 1) / TQ;
+    const int64_t G = gridDim.x;
+    uint32_t mma_ph = 0, idx_ph = 0;
+
+    auto sync_all = [&]() { fence_proxy_async(); tc_fence_before(); __syncthreads(); tc_fence_after(); };
+    auto wait_mma = [&]() { mbar_wait(mma_bar, mma_ph); mma_ph ^= 1u; tc_fence_after(); };
+    // three bf16 products of one layer, issued by one thread: A tile (K-major rows of 128 B; `a_blk` between its 64-column
+    // blocks), B image either K-major (rows = outputs) or MN-major (rows = K: the same image used for the data gradient)
+    auto mma3 = [&](uint32_t d_col, uint32_t a_img, uint32_t a_lo_off, uint32_t a_blk, uint32_t b_img, uint32_t b_lo_off,
+                    uint32_t b_blk, int ksteps, uint32_t idesc, bool b_mn) {
+        constexpr uint32_t d_hi = desc_hi_sw128(1024);
+#pragma unroll 1
+        for (int prod = 0; prod < 3; ++prod) {
+            const uint32_t a0 = desc_lo_sw128(sbase + a_img + (prod == 2 ? a_lo_off : 0u), 16);
+            const uint32_t b0 = desc_lo_sw128(sbase + b_img + (prod == 1 ? b_lo_off : 0u), b_mn ? b_blk : 16u);
+#pragma unroll 1
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t a_off = (uint32_t)(ks >> 2) * a_blk + (uint32_t)(ks & 3) * 32u;
+                const uint32_t b_off = b_mn ? (uint32_t)ks * 2048u : (uint32_t)(ks >> 2) * b_blk + (uint32_t)(ks & 3) * 32u;
+                umma_bf16_lh(tmem_base + d_col, a0 + (a_off >> 4), d_hi, b0 + (b_off >> 4), d_hi, idesc, (prod | ks) ? 1u : 0u);
+            }
+        }
+        umma_commit(mma_bar);
+    };
+    // neighbour lists + query coordinates of tile t -> the shared-memory slot (TMA for full tiles; partial / unaligned: by hand)
+    auto fill_slot = [&](int64_t t) {
+        if (t >= n_tiles) return;
+        if (p.use_tma && (t + 1) * TQ <= p.nq) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(idx_bar, IDX_BYTES + QXY_BYTES);
+                tma_bulk_g2s(sbase + S::IDX, p.idx + t * (TQ * KN), IDX_BYTES, idx_bar);
+                tma_bulk_g2s(sbase + S::QXY, p.qry_xy + t * TQ, QXY_BYTES, idx_bar);
+            }
+        } else {
+            int* s_idx = reinterpret_cast<int*>(sm + S::IDX);
+            float2* s_q = reinterpret_cast<float2*>(sm + S::QXY);
+            for (int e = tid; e < TQ * KN; e += THREADS) {
+                const int64_t q = t * TQ + e / KN;
+                s_idx[e] = (q < p.nq) ? __ldg(p.idx + t * (TQ * KN) + e) : -1;
+            }
+            if (tid < TQ) s_q[tid] = (t * TQ + tid < p.nq) ? __ldg(p.qry_xy + t * TQ + tid) : make_float2(0.f, 0.f);
+            if (tid == 0) mbar_arrive(idx_bar);           // the data itself becomes visible through the next __syncthreads
+        }
+    };
+    // this thread's 8 neighbours (k = 8g .. 8g+7; k >= 30 does not exist) of tile t: indices from the slot, then the gathers
+    float2 xy[8], qc;
+    float val[8];
+    auto gather = [&](int64_t t) {
+        int ix[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ix[j] = -1;
+        qc = make_float2(0.f, 0.f);
+        if (t < n_tiles) {
+            mbar_wait(idx_bar, idx_ph);
+            idx_ph ^= 1u;
+            const uint2 q2 = lds_v2(sbase + S::QXY + r * 8);
+            qc = make_float2(__uint_as_float(q2.x), __uint_as_float(q2.y));
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                if (8 * g + 2 * jj < KN) {
+                    const uint2 v = lds_v2(sbase + S::IDX + (uint32_t)(r * KN + 8 * g + 2 * jj) * 4u);
+                    ix[2 * jj] = (int)v.x; ix[2 * jj + 1] = (int)v.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            xy[j] = make_float2(0.f, 0.f);
+            val[j] = 0.f;
+            if (ix[j] >= 0) { xy[j] = __ldg(p.src_xy + ix[j]); val[j] = __ldg(p.src_val + ix[j]); }
+        }
+    };
+
+    fill_slot(blockIdx.x);
+    __syncthreads();
+    gather(blockIdx.x);
+    __syncthreads();
+    fill_slot(blockIdx.x + G);
+
+    int i = 0;
+    int64_t t_prev = -1;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += G, ++i) {
+        const int64_t q = t * TQ + r;
+        const bool q_ok = q < p.nq;
+        // ---- layer a operand: this thread's 16 columns (8 neighbours; for g = 3: 6 neighbours, the query, its residual)
+        float vcur[8];
+        {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { f[2 * j] = xy[j].x - qc.x; f[2 * j + 1] = xy[j].y - qc.y; vcur[j] = val[j]; }
+            if (g == 3) {
+                const __nv_bfloat16 hx = __float2bfloat16_rn(qc.x), hy = __float2bfloat16_rn(qc.y);
+                const float r1x = qc.x - __bfloat162float(hx), r1y = qc.y - __bfloat162float(hy);
+                f[12] = qc.x; f[13] = qc.y;
+                f[14] = r1x - __bfloat162float(__float2bfloat16_rn(r1x));
+                f[15] = r1y - __bfloat162float(__float2bfloat16_rn(r1y));
+            }
+            if (BWD && q_ok) {                                           // X1[:, 0:64] = p in the reference's own (absolute) form
+                float* x1 = p.X1 + q * 128 + 16 * g;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    float a[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = 2 * m + (e >> 1);
+                        a[e] = (e & 1) ? xy[j].y : xy[j].x;
+                        if (g == 3 && j == 6) a[e] = (e & 1) ? qc.y : qc.x;
+                        if (g == 3 && j == 7) a[e] = 0.f;
+                    }
+                    stg4(x1 + 4 * m, a[0], a[1], a[2], a[3]);
+                }
+            }
+            uint4 hi, lo;
+            const float (&f0)[8] = *reinterpret_cast<const float (*)[8]>(&f[0]);
+            const float (&f1)[8] = *reinterpret_cast<const float (*)[8]>(&f[8]);
+            split8(f0, hi, lo);
+            sts_v4(sbase + S::AA + chunk_off(r, 2 * g), hi);
+            sts_v4(sbase + S::AA + 16384 + chunk_off(r, 2 * g), lo);
+            split8(f1, hi, lo);
+            sts_v4(sbase + S::AA + chunk_off(r, 2 * g + 1), hi);
+            sts_v4(sbase + S::AA + 16384 + chunk_off(r, 2 * g + 1), lo);
+        }
+        sync_all();                                                      // S1
+        if (tid == 0) mma3(0, S::AA, 16384, 0, S::WA, 16384, 0, 4, idesc_bf16(128, 128, 0, 0), false);
+        if (t_prev >= 0 && g == 0 && p.out != nullptr) {                 // previous tile: the four partial sums of a query
+            const float* pp = s_part + ((i - 1) & 1) * 512 + r;
+            const int64_t qp = t_prev * TQ + r;
+            if (qp < p.nq) p.out[qp] = (pp[0] + pp[128]) + (pp[256] + pp[384]);
+        }
+        gather(t + G);                                                   // next tile's coordinates / values: in flight from here on
+        wait_mma();
+        // ---- ha = tanh(za + ba): 32 channels per thread in two halves
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+            uint32_t v[16];
+            tmem_ld16_async(d_a + 32 * g + 16 * hf, v);
+            tmem_wait_ld16(v);
+            float h[16];
+            const float* b = s_bias + 32 * g + 16 * hf;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] = tanh_fast(__uint_as_float(v[j]) + b[j]);
+            if (BWD && q_ok) {
+                float* x2 = p.X2 + q * 128 + 32 * g + 16 * hf;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) stg4(x2 + 4 * m, h[4 * m], h[4 * m + 1], h[4 * m + 2], h[4 * m + 3]);
+            }
+            const uint32_t blk = sbase + S::AB + (uint32_t)(g >> 1) * 16384u;
+            const int c = 4 * (g & 1) + 2 * hf;
+            uint4 hi, lo;
+            split8(*reinterpret_cast<const float (*)[8]>(&h[0]), hi, lo);
+            sts_v4(blk + chunk_off(r, c), hi);
+            sts_v4(blk + 32768 + chunk_off(r, c), lo);
+            split8(*reinterpret_cast<const float (*)[8]>(&h[8]), hi, lo);
+            sts_v4(blk + chunk_off(r, c + 1), hi);
+            sts_v4(blk + 32768 + chunk_off(r, c + 1), lo);
+        }
+        sync_all();                                                      // S2
+        if (tid == 0) mma3(128, S::AB, 32768, 16384, S::WB, 16384, 8192, 8, idesc_bf16(128, 64, 0, 0), false);
+        fill_slot(t + 2 * G);                                            // every thread has read the slot (tile t + G) before S2
+        wait_mma();
+        // ---- hb = tanh(zb + bb): 16 channels per thread, written over the p'' tile
+        {
+            uint32_t v[16];
+            tmem_ld16_async(d_b + 16 * g, v);
+            tmem_wait_ld16(v);
+            float h[16];
+            const float* b = s_bias + H1 + 16 * g;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] = tanh_fast(__uint_as_float(v[j]) + b[j]);
+            if (BWD && q_ok) {
+                float* x1 = p.X1 + q * 128 + 64 + 16 * g;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) stg4(x1 + 4 * m, h[4 * m], h[4 * m + 1], h[4 * m + 2], h[4 * m + 3]);
+            }
+            uint4 hi, lo;
+            split8(*reinterpret_cast<const float (*)[8]>(&h[0]), hi, lo);
+            sts_v4(sbase + S::AA + chunk_off(r, 2 * g), hi);
+            sts_v4(sbase + S::AA + 16384 + chunk_off(r, 2 * g), lo);
+            split8(*reinterpret_cast<const float (*)[8]>(&h[8]), hi, lo);
+            sts_v4(sbase + S::AA + chunk_off(r, 2 * g + 1), hi);
+            sts_v4(sbase + S::AA + 16384 + chunk_off(r, 2 * g + 1), lo);
+        }
+        sync_all();                                                      // S3
+        if (tid == 0) mma3(192, S::AA, 16384, 0, S::WC, 4096, 0, 4, idesc_bf16(128, 32, 0, 0), false);
+        wait_mma();
+        // ---- interpolation weights of this thread's 8 neighbours and their share of the weighted sum
+        {
+            uint32_t v[8];
+            tmem_ld8_async(d_c + 8 * g, v);
+            tmem_wait_ld8(v);
+            float w[8], part = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { w[j] = __uint_as_float(v[j]) + s_bias[H1 + H2 + 8 * g + j]; part = fmaf(w[j], vcur[j], part); }
+            s_part[(i & 1) * 512 + g * 128 + r] = part;
+            if (BWD) {
+                const float go = q_ok ? __ldg(p.g_out + q) : 0.f;
+                float gw[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    gw[j] = go * vcur[j];                                // 0 where the neighbour does not exist
+                    if (p.g_src_val != nullptr && q_ok && 8 * g + j < KN) {
+                        const int ik = __ldg(p.idx + q * KN + 8 * g + j);
+                        if (ik >= 0) atomicAdd(p.g_src_val + ik, go * w[j]);
+                    }
+                }
+                if (q_ok) {
+                    float* g2 = p.G2 + q * 128;
+                    stg4(g2 + 64 + 8 * g, gw[0], gw[1], gw[2], gw[3]);
+                    stg4(g2 + 68 + 8 * g, gw[4], gw[5], gw[6], gw[7]);
+                    stg4(g2 + 96 + 8 * g, 0.f, 0.f, 0.f, 0.f);
+                    stg4(g2 + 100 + 8 * g, 0.f, 0.f, 0.f, 0.f);
+                }
+                uint4 hi, lo;
+                split8(gw, hi, lo);
+                sts_v4(sbase + S::GW + chunk_off(r, g), hi);
+                sts_v4(sbase + S::GW + 16384 + chunk_off(r, g), lo);
+            }
+        }
+        if (BWD) {
+            sync_all();
+            // g_zb_raw[q][k] = sum_o g_w[q][o] Wc[o][k]: the Wc image read MN-major (rows = o = K, 16 rows per step)
+            if (tid == 0) mma3(256, S::GW, 16384, 0, S::WC, 4096, 4096, 2, idesc_bf16(128, 64, 0, 1), true);
+            wait_mma();
+            {
+                uint32_t v[16];
+                tmem_ld16_async(d_gzb + 16 * g, v);
+                tmem_wait_ld16(v);
+                float hb[16], gz[16];
+                join8(lds_v4(sbase + S::AA + chunk_off(r, 2 * g)), lds_v4(sbase + S::AA + 16384 + chunk_off(r, 2 * g)),
+                      *reinterpret_cast<float (*)[8]>(&hb[0]));
+                join8(lds_v4(sbase + S::AA + chunk_off(r, 2 * g + 1)), lds_v4(sbase + S::AA + 16384 + chunk_off(r, 2 * g + 1)),
+                      *reinterpret_cast<float (*)[8]>(&hb[8]));
+#pragma unroll
+                for (int j = 0; j < 16; ++j) gz[j] = __uint_as_float(v[j]) * (1.f - hb[j] * hb[j]);
+                if (q_ok) {
+                    float* g2 = p.G2 + q * 128 + 16 * g;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) stg4(g2 + 4 * m, gz[4 * m], gz[4 * m + 1], gz[4 * m + 2], gz[4 * m + 3]);
+                }
+                uint4 hi, lo;                                            // the g_w tile has been consumed: g_zb takes its place
+                split8(*reinterpret_cast<const float (*)[8]>(&gz[0]), hi, lo);
+                sts_v4(sbase + S::GW + chunk_off(r, 2 * g), hi);
+                sts_v4(sbase + S::GW + 16384 + chunk_off(r, 2 * g), lo);
+                split8(*reinterpret_cast<const float (*)[8]>(&gz[8]), hi, lo);
+                sts_v4(sbase + S::GW + chunk_off(r, 2 * g + 1), hi);
+                sts_v4(sbase + S::GW + 16384 + chunk_off(r, 2 * g + 1), lo);
+            }
+            sync_all();
+            // g_za_raw[q][k] = sum_o g_zb[q][o] Wb[o][k]: the Wb image read MN-major (two 64-column blocks = N 128)
+            if (tid == 0) mma3(0, S::GW, 16384, 0, S::WB, 16384, 8192, 4, idesc_bf16(128, 128, 0, 1), true);
+            wait_mma();
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[16];
+                tmem_ld16_async(d_gza + 32 * g + 16 * hf, v);
+                tmem_wait_ld16(v);
+                const uint32_t blk = sbase + S::AB + (uint32_t)(g >> 1) * 16384u;
+                const int c = 4 * (g & 1) + 2 * hf;
+                float ha[16];
+                join8(lds_v4(blk + chunk_off(r, c)), lds_v4(blk + 32768 + chunk_off(r, c)), *reinterpret_cast<float (*)[8]>(&ha[0]));
+                join8(lds_v4(blk + chunk_off(r, c + 1)), lds_v4(blk + 32768 + chunk_off(r, c + 1)), *reinterpret_cast<float (*)[8]>(&ha[8]));
+                if (q_ok) {
+                    float* g1 = p.G1 + q * 128 + 32 * g + 16 * hf;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        stg4(g1 + 4 * m, __uint_as_float(v[4 * m]) * (1.f - ha[4 * m] * ha[4 * m]),
+                             __uint_as_float(v[4 * m + 1]) * (1.f - ha[4 * m + 1] * ha[4 * m + 1]),
+                             __uint_as_float(v[4 * m + 2]) * (1.f - ha[4 * m + 2] * ha[4 * m + 2]),
+                             __uint_as_float(v[4 * m + 3]) * (1.f - ha[4 * m + 3] * ha[4 * m + 3]));
+                }
+            }
+        }
+        t_prev = t;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (t_prev >= 0 && g == 0 && p.out != nullptr) {
+        const float* pp = s_part + ((i - 1) & 1) * 512 + r;
+        const int64_t qp = t_prev * TQ + r;
+        if (qp < p.nq) p.out[qp] = (pp[0] + pp[128]) + (pp[256] + pp[384]);
+    }
+    if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
+}
+
+}  // namespace itp
+}  // namespace mmpde
+
+using namespace mmpde;
+
+static bool itp_aligned(const void* a, const void* b) {
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
+extern "C" int mmpde_itp_fwd_tc(const float* src_xy, const float* src_val, const float* qry_xy, const int32_t* idx,
+                                int64_t n_queries, const float* params, float* out, void* stream) {
+    if (n_queries < 0) return MMPDE_EINVAL;
+    if (n_queries == 0) return MMPDE_OK;
+    if (((reinterpret_cast<uintptr_t>(src_xy) | reinterpret_cast<uintptr_t>(qry_xy)) & 7) || (reinterpret_cast<uintptr_t>(params) & 15))
+        return MMPDE_EINVAL;
+    constexpr size_t smem = itp::Smem<false>::TOTAL + 1024;
+    MMPDE_ENSURE_SMEM(itp::itp_tc_kernel<false>, smem);
+    itp::Args a{};
+    a.src_xy = (const float2*)src_xy; a.src_val = src_val; a.qry_xy = (const float2*)qry_xy; a.idx = idx; a.nq = n_queries;
+    a.params = params; a.out = out; a.use_tma = itp_aligned(idx, qry_xy) ? 1 : 0;
+    const int64_t n_tiles = (n_queries + itp::TQ - 1) / itp::TQ;
+    itp::itp_tc_kernel<false><<<(int)imin64(n_tiles, sm_count()), itp::THREADS, smem, (cudaStream_t)stream>>>(a);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_itp_bwd_tc(const float* src_xy, const float* src_val, const float* qry_xy, const int32_t* idx,
+                                int64_t n_queries, const float* params, const float* g_out, float* g_src_val,
+                                float* G1, float* G2, float* X1, float* X2, void* stream) {
+    if (n_queries < 0 || g_out == nullptr || G1 == nullptr || G2 == nullptr || X1 == nullptr || X2 == nullptr) return MMPDE_EINVAL;
+    if (n_queries == 0) return MMPDE_OK;
+    if (((reinterpret_cast<uintptr_t>(src_xy) | reinterpret_cast<uintptr_t>(qry_xy)) & 7) || (reinterpret_cast<uintptr_t>(params) & 15))
+        return MMPDE_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(G1) | reinterpret_cast<uintptr_t>(G2) | reinterpret_cast<uintptr_t>(X1) |
+         reinterpret_cast<uintptr_t>(X2)) & 15) return MMPDE_EINVAL;
+    constexpr size_t smem = itp::Smem<true>::TOTAL + 1024;
+    MMPDE_ENSURE_SMEM(itp::itp_tc_kernel<true>, smem);
+    itp::Args a{};
+    a.src_xy = (const float2*)src_xy; a.src_val = src_val; a.qry_xy = (const float2*)qry_xy; a.idx = idx; a.nq = n_queries;
+    a.params = params; a.out = nullptr; a.use_tma = itp_aligned(idx, qry_xy) ? 1 : 0;
+    a.g_out = g_out; a.g_src_val = g_src_val; a.G1 = G1; a.G2 = G2; a.X1 = X1; a.X2 = X2;
+    const int64_t n_tiles = (n_queries + itp::TQ - 1) / itp::TQ;
+    itp::itp_tc_kernel<true><<<(int)imin64(n_tiles, sm_count()), itp::THREADS, smem, (cudaStream_t)stream>>>(a);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}

@@ -1,7 +1,7 @@
 // BatchNorm over all nodes of the batch + the elementwise helpers of the node path (all HBM-bound).
 // Replaces PyG BatchNorm / nn.BatchNorm1d (/root/reference/gnn_2d.py:51,56,101,104) and autograd's ReLU masks.
 // Row-major [M,128] fp32; every thread moves one float4 (4 channels), a warp one 512-byte row.
-#include "common.cuh"
+#include "peer.cuh"
 #include <cstdlib>
 
 namespace mmpde {
@@ -35,9 +35,61 @@ __device__ __forceinline__ void block_reduce_to_double(float4 v, double* dst) {
     }
 }
 
+// What the LAST CTA of a column-reducing kernel does once the sums are complete (ticket == nullptr: nothing -- the caller
+// folds / exchanges / finalises with separate launches).  Saves a launch for the fold (+ one for the cross-GPU exchange
+// + one for the finalisation) per BatchNorm pass: a step runs 32 passes, each on its critical path.
+struct BnTail {
+    unsigned int* ticket;                  // zeroed with the sums; counts the CTAs that have delivered their partials
+    const int64_t* peer_base;              // cross-rank exchange buffers (mmpde_bn_exchange) or nullptr = this rank only
+    int rank, world;
+    unsigned long long timeout_ns;
+    double* local_out;                     // [256] this rank's folded sums (backward: dbeta | dgamma), or nullptr
+    double* glob_out;                      // [256] sums over all ranks, or nullptr
+    double count;                          // forward: rows of the whole batch; <= 0: no finalisation
+    float eps, momentum;
+    float* mean_rstd; float* rmean; float* rvar;
+};
+
+__device__ __forceinline__ void bn_tail(const BnTail& t, const double* __restrict__ sums_all) {
+    if (t.ticket == nullptr) return;
+    __shared__ bool s_last;
+    __shared__ double s_fold[256];
+    __threadfence();                       // this CTA's atomics before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(t.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int c = threadIdx.x;
+    double v = 0.0;
+#pragma unroll
+    for (int r = 0; r < MMPDE_BN_REPLICAS; ++r) v += __ldcg(sums_all + r * 256 + c);
+    if (t.local_out) t.local_out[c] = v;
+    if (t.peer_base != nullptr && t.world > 1) v = peer_exchange_256(v, t.peer_base, t.rank, t.world, t.timeout_ns);
+    if (t.glob_out) t.glob_out[c] = v;
+    if (t.count > 0) {
+        s_fold[c] = v;
+        __syncthreads();
+        if (c < 128) {
+            const double mean = s_fold[c] / t.count;
+            double var = s_fold[128 + c] / t.count - mean * mean;
+            if (var < 0) var = 0;
+            t.mean_rstd[c] = (float)mean;
+            t.mean_rstd[128 + c] = (float)(1.0 / sqrt(var + (double)t.eps));
+            if (t.rmean) {
+                const double unbiased = t.count > 1 ? var * t.count / (t.count - 1) : var;
+                t.rmean[c] = (float)((1.0 - t.momentum) * t.rmean[c] + t.momentum * mean);
+                t.rvar[c] = (float)((1.0 - t.momentum) * t.rvar[c] + t.momentum * unbiased);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
-                                                       int64_t ldb, int64_t M, double* __restrict__ sums) {
+                                                       int64_t ldb, int64_t M, double* __restrict__ sums,
+                                                       const __grid_constant__ BnTail tail) {
     const int c4 = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const double* sums_all = sums;
     // fp32 partials over the CTA's row blocks (a thread sees M / (8 * grid) rows), ONE fp64 reduction per CTA into
     // replica blockIdx % MMPDE_BN_REPLICAS: same-address atomics serialise in L2 (~30-50 ns each when every CTA
     // arrives at once), so the time of the tail is the number of CTAs per replica (profiles/r01_norm_bench.txt)
@@ -60,6 +112,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
     }
     block_reduce_to_double(s, sums);
     block_reduce_to_double(q, sums + 128);
+    bn_tail(tail, sums_all);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int n_rep, double count, float eps, float momentum,
@@ -122,8 +175,10 @@ __device__ __forceinline__ float4 gated_grad(const float* g, int64_t ldg, const 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ out,
                                                             int64_t ldo, int relu, const float* __restrict__ A, int64_t lda,
                                                             const float* __restrict__ B, int64_t ldb, int64_t M,
-                                                            const float* __restrict__ mean_rstd, double* __restrict__ bsums) {
+                                                            const float* __restrict__ mean_rstd, double* __restrict__ bsums,
+                                                            const __grid_constant__ BnTail tail) {
     const int c4 = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const double* sums_all = bsums;
     float4 mu = ldg4(mean_rstd + c4 * 4), rs = ldg4(mean_rstd + 128 + c4 * 4);
     float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
     bsums += (blockIdx.x % MMPDE_BN_REPLICAS) * 256;
@@ -152,6 +207,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     }
     block_reduce_to_double(s, bsums);
     block_reduce_to_double(q, bsums + 128);
+    bn_tail(tail, sums_all);
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ out,
@@ -277,7 +333,28 @@ using namespace mmpde;
 extern "C" int mmpde_bn_stats(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, double* sums, void* stream) {
     if (M < 0 || lda % 4 || (B && ldb % 4)) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
-    bn_stats_kernel<<<reduce_grid(M), 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, M, sums);
+    bn_stats_kernel<<<reduce_grid(M), 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, M, sums, BnTail{});
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+static int check_peer(const int64_t* peer_base, int rank, int world) {
+    if (world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world || (world > 1 && peer_base == nullptr)) return MMPDE_EINVAL;
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_bn_stats_fused(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, double* sums,
+                                    uint32_t* ticket, double count, float eps, float momentum, float* mean_rstd,
+                                    float* running_mean, float* running_var, const int64_t* peer_base, int rank, int world,
+                                    void* stream) {
+    if (M <= 0 || lda % 4 || (B && ldb % 4) || !sums || !ticket || !mean_rstd || count <= 0) return MMPDE_EINVAL;
+    if ((running_mean == nullptr) != (running_var == nullptr)) return MMPDE_EINVAL;
+    if (int rc = check_peer(peer_base, rank, world)) return rc;
+    BnTail t{};
+    t.ticket = ticket; t.peer_base = world > 1 ? peer_base : nullptr; t.rank = rank; t.world = world;
+    t.timeout_ns = peer_timeout_ns(); t.count = count; t.eps = eps; t.momentum = momentum;
+    t.mean_rstd = mean_rstd; t.rmean = running_mean; t.rvar = running_var;
+    bn_stats_kernel<<<reduce_grid(M), 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, M, sums, t);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }
@@ -304,7 +381,21 @@ extern "C" int mmpde_bn_bwd_reduce(const float* g, int64_t ldg, const float* out
                                    double* bsums, void* stream) {
     if (M < 0 || ldg % 4 || lda % 4 || (B && ldb % 4) || (relu && (!out || ldo % 4))) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
-    bn_bwd_reduce_kernel<<<reduce_grid(M), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, bsums);
+    bn_bwd_reduce_kernel<<<reduce_grid(M), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, bsums, BnTail{});
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_bn_bwd_reduce_fused(const float* g, int64_t ldg, const float* out, int64_t ldo, int relu, const float* A,
+                                         int64_t lda, const float* B, int64_t ldb, int64_t M, const float* mean_rstd,
+                                         double* bsums, uint32_t* ticket, double* local_out, double* glob_out,
+                                         const int64_t* peer_base, int rank, int world, void* stream) {
+    if (M <= 0 || ldg % 4 || lda % 4 || (B && ldb % 4) || (relu && (!out || ldo % 4)) || !bsums || !ticket) return MMPDE_EINVAL;
+    if (int rc = check_peer(peer_base, rank, world)) return rc;
+    BnTail t{};
+    t.ticket = ticket; t.peer_base = (world > 1 && glob_out) ? peer_base : nullptr; t.rank = rank; t.world = world;
+    t.timeout_ns = peer_timeout_ns(); t.local_out = local_out; t.glob_out = glob_out; t.count = 0.0;
+    bn_bwd_reduce_kernel<<<reduce_grid(M), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, bsums, t);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }

@@ -76,6 +76,12 @@ class DistComm(ops._Comm):
             return self.peers[branch if branch < self.n_branches else 0].sum(spread)
         return self.allreduce_(spread.sum(0) if spread.dim() == 2 else spread)
 
+    def peer_args(self, branch=0):
+        if not self.peers:
+            return None                         # NCCL: fold / all-reduce / finalise as separate launches
+        p = self.peers[branch if branch < self.n_branches else 0]
+        return (ops._ptr(p.peer_base), p.rank, p.world)
+
     def allreduce_(self, t):
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)

@@ -71,6 +71,11 @@ class _Comm:
         """[n_rep, 256] local accumulator copies -> [256] sums over all ranks (here: one rank)."""
         return spread.sum(0) if spread.dim() == 2 else spread
 
+    def peer_args(self, branch=0):
+        """(peer_base pointer, rank, world) for the reducing BatchNorm kernels that exchange in their last CTA
+        (mmpde_bn_stats_fused / mmpde_bn_bwd_reduce_fused), or None when the sums have to go through reduce_bn_sums."""
+        return (None, 0, 1)
+
     def global_rows(self, n):
         return float(n) if self.total_rows is None else float(self.total_rows)
 
@@ -258,26 +263,45 @@ class _BNState:
     __slots__ = ("mean_rstd", "count", "rows", "training", "branch")
 
 
+BN_ACC = BN_REPLICAS * 2 * H + 1       # fp64 accumulator copies of one BatchNorm pass + the ticket of its last-CTA tail
+
+
+def bn_accumulators(n, device):
+    """n zeroed accumulator blocks [n, BN_ACC] (one fill for all BatchNorm passes of a solver pass)."""
+    return torch.zeros(n, BN_ACC, dtype=torch.float64, device=device)
+
+
 def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st, sums=None):
     """BatchNorm over the rows of ALL local parts (and all ranks, through COMM).
-    items: one (A, lda, B, ldb, M, out, ldo) per local part, y = A (+ B)."""
+    items: one (A, lda, B, ldb, M, out, ldo) per local part, y = A (+ B).  Training: the column sums of the last part's
+    launch are folded, summed over the ranks and turned into mean / rstd / running statistics by that launch's last CTA
+    (mmpde_bn_stats_fused); only without peer memory (NCCL) the three steps are separate launches."""
     state = _BNState()
     dev = gamma.device
     state.rows = sum(it[4] for it in items)
     state.training = bool(training)
     state.branch = COMM.branch                         # the backward of this BatchNorm exchanges on the same sequence
     if training:
-        if sums is None:                               # else: a zeroed [BN_REPLICAS, 256] slice handed in by the solver
-            sums = torch.zeros(BN_REPLICAS, 2 * H, dtype=torch.float64, device=dev)
-        for A, lda, B, ldb, M, _, _ in items:
-            _cabi.call("mmpde_bn_stats", A, lda, B, ldb, M, _ptr(sums), st)
+        if sums is None:                               # else: a zeroed [BN_ACC] block handed in by the solver
+            sums = bn_accumulators(1, dev)[0]
         state.count = COMM.global_rows(state.rows)
-        n_rep = BN_REPLICAS
-        if state.count != float(state.rows):          # other ranks hold rows too: fold + sum over the ranks -> [2,128]
-            sums, n_rep = COMM.reduce_bn_sums(sums, state.branch), 1
         state.mean_rstd = torch.empty(2 * H, dtype=torch.float32, device=dev)
-        _cabi.call("mmpde_bn_finalize", _ptr(sums), n_rep, state.count, BN_EPS, BN_MOMENTUM, _ptr(state.mean_rstd),
-                   _ptr(rmean), _ptr(rvar), st)
+        peer = COMM.peer_args(state.branch)
+        live = [it for it in items if it[4] > 0]
+        if peer is not None and live:
+            for A, lda, B, ldb, M, _, _ in live[:-1]:
+                _cabi.call("mmpde_bn_stats", A, lda, B, ldb, M, _ptr(sums), st)
+            A, lda, B, ldb, M, _, _ = live[-1]
+            _cabi.call("mmpde_bn_stats_fused", A, lda, B, ldb, M, _ptr(sums), _ptr(sums, BN_ACC - 1), state.count, BN_EPS,
+                       BN_MOMENTUM, _ptr(state.mean_rstd), _ptr(rmean), _ptr(rvar), peer[0], peer[1], peer[2], st)
+        else:
+            for A, lda, B, ldb, M, _, _ in items:
+                _cabi.call("mmpde_bn_stats", A, lda, B, ldb, M, _ptr(sums), st)
+            red, n_rep = sums[:BN_ACC - 1].view(BN_REPLICAS, 2 * H), BN_REPLICAS
+            if state.count != float(state.rows):      # other ranks hold rows too: fold + sum over the ranks -> [2,128]
+                red, n_rep = COMM.reduce_bn_sums(red, state.branch), 1
+            _cabi.call("mmpde_bn_finalize", _ptr(red), n_rep, state.count, BN_EPS, BN_MOMENTUM, _ptr(state.mean_rstd),
+                       _ptr(rmean), _ptr(rvar), st)
         if nbt is not None:
             nbt += 1
     else:
@@ -291,21 +315,39 @@ def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st, sums=N
 def _bn_backward(items, relu, state, gamma, st, spread=None):
     """items: one (g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy[, gy_gated, ldgg]) per local part (gy_gated =
     gy * (B > 0), the ReLU backward of a residual branch B fused into this pass).  Returns this rank's
-    (dgamma, dbeta) as fp64 views; writes dL/dy into gy.  With several ranks the two column sums are all-reduced for the
-    normalisation term (sync-BN), while the parameter grads stay per-rank sums (the gradient all-reduce adds
-    them up afterwards)."""
+    (dgamma, dbeta) as fp64 views; writes dL/dy into gy.  With several ranks the two column sums are summed over the
+    ranks for the normalisation term (sync-BN), while the parameter grads stay per-rank sums (the gradient all-reduce adds
+    them up afterwards).  Fold and cross-rank sum happen in the last CTA of the last part's reducing launch."""
+    dev = gamma.device
     if spread is None:
-        spread = torch.zeros(BN_REPLICAS, 2 * H, dtype=torch.float64, device=gamma.device)
-    for g, ldg, out, ldo, A, lda, B, ldb, M, *_ in items:
-        _cabi.call("mmpde_bn_bwd_reduce", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(spread), st)
-    local = spread.sum(0)
-    glob = local
-    if not state.training:
-        # eval mode normalised with the running statistics: they do not depend on the batch, so the two batch-mean
-        # terms vanish and dL/dy = g * gamma * rstd (what nn.BatchNorm1d.eval() gives); dgamma / dbeta stay the sums.
-        glob = torch.zeros_like(local)
-    elif COMM.global_rows(state.rows) != float(state.rows):
-        glob = COMM.reduce_bn_sums(spread, state.branch)
+        spread = bn_accumulators(1, dev)[0]
+    peer = COMM.peer_args(state.branch)
+    live = [it for it in items if it[8] > 0]
+    multi = COMM.global_rows(state.rows) != float(state.rows)
+    if peer is not None and live:
+        both = torch.empty(2, 2 * H, dtype=torch.float64, device=dev)
+        local, glob = both[0], both[1]
+        for g, ldg, out, ldo, A, lda, B, ldb, M, *_ in live[:-1]:
+            _cabi.call("mmpde_bn_bwd_reduce", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(spread), st)
+        g, ldg, out, ldo, A, lda, B, ldb, M, *_ = live[-1]
+        want_glob = state.training
+        _cabi.call("mmpde_bn_bwd_reduce_fused", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd),
+                   _ptr(spread), _ptr(spread, BN_ACC - 1), _ptr(local), _ptr(glob) if want_glob else None,
+                   peer[0] if multi else None, peer[1] if multi else 0, peer[2] if multi else 1, st)
+        if not want_glob:
+            glob = torch.zeros_like(local)
+    else:
+        for g, ldg, out, ldo, A, lda, B, ldb, M, *_ in items:
+            _cabi.call("mmpde_bn_bwd_reduce", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(spread), st)
+        red = spread[:BN_ACC - 1].view(BN_REPLICAS, 2 * H)
+        local = red.sum(0)
+        glob = local
+        if state.training and multi:
+            glob = COMM.reduce_bn_sums(red, state.branch)
+        if not state.training:
+            glob = torch.zeros_like(local)
+    # eval mode normalised with the running statistics: they do not depend on the batch, so the two batch-mean terms
+    # vanish (glob = 0) and dL/dy = g * gamma * rstd (what nn.BatchNorm1d.eval() gives); dgamma / dbeta stay the sums.
     for g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy, *gated in items:
         gyg, ldgg = gated if gated else (None, 0)
         _cabi.call("mmpde_bn_bwd_apply", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(gamma),
@@ -631,7 +673,7 @@ def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st):
     dec = params[N_ENC + N_LAYER * L]
     # ---- encoder: Linear(4,128) BN ReLU Linear(128,128) BN        (gnn_2d.py:99-106,130-131)
     preps = _layer_prep([params[N_ENC + N_LAYER * l] for l in range(L)], [params[N_ENC + N_LAYER * l + 4] for l in range(L)]) if L else []
-    bn_sums = torch.zeros(2 + L, BN_REPLICAS, 2 * H, dtype=torch.float64, device=dev) if training else [None] * (2 + L)
+    bn_sums = bn_accumulators(2 + L, dev) if training else [None] * (2 + L)
     e1s, e1ns, e2s = [], [], []
     for part in parts:
         e1 = torch.empty(part.n_own, H, **f32)
@@ -676,7 +718,7 @@ def _solver_backward(sv, g_outs, need_u, st):
     g_hs, g_dec = _decoder_backward(parts, sv["hL"], dec, sv["scale"], sv["dec"], g_outs, st)
     grads[N_ENC + N_LAYER * L] = g_dec
     flat_all = torch.zeros(max(L, 1), sum(LAYER_GRAD_SIZES), **f32)   # every layer's gradient accumulators, zeroed at once
-    spread_all = torch.zeros(2 + L, BN_REPLICAS, 2 * H, dtype=torch.float64, device=dev)
+    spread_all = bn_accumulators(2 + L, dev)
     for l in reversed(range(L)):
         base = N_ENC + N_LAYER * l
         saved, bn = sv["layers"][l]
@@ -774,9 +816,11 @@ class PartitionedSolverFn(torch.autograd.Function):
 # fused interpolation
 # ------------------------------------------------------------------------------------------------
 class InterpolateFn(torch.autograd.Function):
-    """out[Q] = sum_k ItpNet(p_q)_k * src_val[idx[q,k]]   (data_creator_2d.py:77-83, interpolate.py:79-93).
-    Gradients: flat ItpNet parameters and src_val; coordinates are treated as constants (they only lead to
-    the frozen mesh mover)."""
+    """out[Q] = sum_k ItpNet(p_q)_k * src_val[idx[q,k]]   (data_creator_2d.py:77-83, interpolate.py:79-93) on the tensor
+    cores (csrc/itp_tc.cu).  Gradients: flat ItpNet parameters and src_val; coordinates are treated as constants (they
+    only lead to the frozen mesh mover).  The backward kernel redoes the forward, runs the
+    two data-gradient contractions and leaves the operands of the three weight-gradient contractions over the query axis,
+    which go out as ONE grouped tcgen05 weight-gradient launch."""
 
     @staticmethod
     def forward(ctx, src_val, src_xy, qry_xy, idx, flat_params):
@@ -786,7 +830,7 @@ class InterpolateFn(torch.autograd.Function):
             _chk(src_val, name="src_val"); _chk(src_xy, name="src_xy"); _chk(qry_xy, name="qry_xy")
             _chk(idx, torch.int32, "idx"); _chk(flat_params, name="flat_params")
             out = torch.empty(Q, dtype=torch.float32, device=src_val.device)
-            _cabi.call("mmpde_itp_fwd", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), Q, _ptr(flat_params),
+            _cabi.call("mmpde_itp_fwd_tc", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), Q, _ptr(flat_params),
                        _ptr(out), _stream())
         ctx.save_for_backward(src_val, src_xy, qry_xy, idx, flat_params)
         return out
@@ -795,9 +839,36 @@ class InterpolateFn(torch.autograd.Function):
     def backward(ctx, g_out):
         src_val, src_xy, qry_xy, idx, flat_params = ctx.saved_tensors
         g_out = g_out.contiguous()
-        g_params = torch.zeros_like(flat_params)
+        Q = qry_xy.shape[0]
+        dev = src_val.device
         g_val = torch.zeros_like(src_val) if ctx.needs_input_grad[0] else None
         with _on(src_val):
-            _cabi.call("mmpde_itp_bwd", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), qry_xy.shape[0],
-                       _ptr(flat_params), _ptr(g_out), _ptr(g_params), _ptr(g_val), _stream())
+            st = _stream()
+            ws = torch.empty(4, max(Q, 1), H, dtype=torch.float32, device=dev)      # G1 G2 X1 X2
+            G1, G2, X1, X2 = (_ptr(ws[k]) for k in range(4))
+            _cabi.call("mmpde_itp_bwd_tc", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), Q, _ptr(flat_params),
+                       _ptr(g_out), _ptr(g_val), G1, G2, X1, X2, st)
+            acc = torch.zeros(3 * H * H + 2 * H, dtype=torch.float32, device=dev)
+            T, db = acc[:3 * H * H].view(3, H, H), acc[3 * H * H:].view(2, H)
+            node_wgrad_grouped([wgrad_task(G1, H, Q, B=X1, ldb=H, dW=_ptr(T[0]), ldw=H, dbias=_ptr(db[0])),
+                                wgrad_task(G2, H, Q, B=X2, ldb=H, dW=_ptr(T[1]), ldw=H, dbias=_ptr(db[1])),
+                                wgrad_task(G2, H, Q, B=X1, ldb=H, dW=_ptr(T[2]), ldw=H)], st)
+            g_params = torch.cat((T[0][:, :62].reshape(-1), db[0], T[1][:64].reshape(-1), db[1][:64],
+                                  T[2][64:64 + KN, 64:].reshape(-1), db[1][64:64 + KN]))
         return g_val, None, None, None, g_params
+
+
+def interpolate_direct(src_val, src_xy, qry_xy, idx, flat_params, g_out=None, want_g_val=True):
+    """The direct fp32 form of the same operator (mmpde_itp_fwd / mmpde_itp_bwd, csrc/itp.cu): a second implementation
+    the tests hold the tensor-core path against.  Returns out, or (out, g_params, g_val) when g_out is given."""
+    Q = qry_xy.shape[0]
+    with _on(src_val):
+        out = torch.empty(Q, dtype=torch.float32, device=src_val.device)
+        _cabi.call("mmpde_itp_fwd", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), Q, _ptr(flat_params), _ptr(out), _stream())
+        if g_out is None:
+            return out
+        g_params = torch.zeros_like(flat_params)
+        g_val = torch.zeros_like(src_val) if want_g_val else None
+        _cabi.call("mmpde_itp_bwd", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), Q, _ptr(flat_params),
+                   _ptr(g_out.contiguous()), _ptr(g_params), _ptr(g_val), _stream())
+    return out, g_params, g_val

@@ -383,6 +383,45 @@ def test_fused_interpolation_matches_oracle(nu, P, Q):
             assert n1 == n2 and _rel(p1.grad, p2.grad) < 1e-4, (mode, n1)
 
 
+@pytest.mark.parametrize("P,Q,unaligned", [(5000, 40000, False), (700, 129, False), (64, 7, False), (3000, 19001, True)])
+def test_tensor_core_interpolation_equals_direct_form(P, Q, unaligned):
+    """The tcgen05 interpolation (csrc/itp_tc.cu: 128-query tiles, split-bf16 products, neighbour lists through the TMA)
+    against the direct fp32 kernel (csrc/itp.cu) on identical inputs: several tiles per CTA, a partial last tile, fewer
+    queries than one tile, and neighbour lists / query coordinates that are only 8-byte aligned (no TMA: loaded by the
+    threads).  Forward 1e-5, gradients 1e-4 relative L2."""
+    from mmpde_b200 import ops
+    from mmpde_b200.interpolate import ItpNet
+    dev = _dev()
+    g = torch.Generator().manual_seed(P + Q)
+    net = ItpNet(12, 12, [128, 64], [128, 64], [1, 4, 16, 4, 1]).to(dev)
+    flat = net.flat_params("2").detach()
+    pts = torch.rand(P, 2, generator=g).to(dev)
+    qry_src = torch.rand(Q + 1, 2, generator=g).to(dev)
+    qry = qry_src[1:] if unaligned else qry_src[:Q].contiguous()
+    off = torch.tensor([0, P], dtype=torch.int32, device=dev)
+    qoff = torch.tensor([0, Q], dtype=torch.int32, device=dev)
+    idx0 = ops.knn_indices(pts, off, qry.contiguous(), qoff, 30, 1, False)
+    if unaligned:
+        big = torch.empty(Q * 30 + 2, dtype=torch.int32, device=dev)
+        big[2:] = idx0.reshape(-1)
+        idx = big[2:].view(Q, 30)
+        assert idx.data_ptr() % 16 == 8 and qry.data_ptr() % 16 == 8 and idx.is_contiguous() and qry.is_contiguous()
+    else:
+        idx = idx0
+    vals = torch.randn(P, generator=g).to(dev)
+    r = torch.randn(Q, generator=g).to(dev)
+    ref, gp_ref, gv_ref = ops.interpolate_direct(vals, pts, qry, idx, flat, g_out=r)
+    v = vals.clone().requires_grad_(True)
+    fl = flat.clone().requires_grad_(True)
+    out = ops.InterpolateFn.apply(v, pts, qry, idx, fl)
+    (out * r).sum().backward()
+    assert _rel(out, ref) < 1e-5
+    assert _rel(v.grad, gv_ref) < 1e-4
+    bounds = [0, 7936, 8064, 16256, 16320, 18240, 18270]             # Wa ba Wb bb Wc bc
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        assert _rel(fl.grad[a:b], gp_ref[a:b]) < 1e-4, (a, b)
+
+
 # ------------------------------------------------------------------------------------------- tcgen05 edge kernels
 def _edge_inputs(sizes, seed, dev, k=35):
     c = _layer_case(sizes, seed, k)

@@ -122,6 +122,25 @@ int mmpde_node_gemm(const float* A0, int64_t lda0, const float* A1, int64_t lda1
                     const float* Aext, const float* Wext, const float* bias, int relu,
                     const float* R1, int64_t ldr1, const float* R2, int64_t ldr2,
                     float* C, int64_t ldc, int64_t M, void* stream);
+/* Pre-split weight operands ("weight images").  The node contractions need W as two bf16 matrices (hi, lo) in the
+ * tensor cores' SWIZZLE_128B K-major tile format.  mmpde_node_gemm builds them in registers in every CTA of every launch;
+ * a training step launches ~100 contractions on ~60 distinct 128 x 128 weight blocks that only change in the optimizer.
+ * mmpde_weight_images converts any number of blocks in one launch (image = MMPDE_WIMG_BYTES bytes, 128-byte aligned:
+ * scale * W(n,k) for n, k < 128, element (n,k) read at W[n*w_ns + k*w_ks]); mmpde_node_gemm_img is mmpde_node_gemm
+ * with the blocks given as images: the kernel fetches them with TMA bulk copies and moves them into tensor memory with
+ * tcgen05.cp.  Same arithmetic, bit-identical results. */
+#define MMPDE_WIMG_BYTES 65536
+typedef struct mmpde_wimg_task {
+    const float* W; int64_t w_ns, w_ks;
+    float scale;
+    void* image;
+} mmpde_wimg_task;
+int mmpde_weight_images(const mmpde_wimg_task* tasks, int n_tasks, void* stream);
+int mmpde_node_gemm_img(const float* A0, int64_t lda0, const float* A1, int64_t lda1,
+                        const void* image0, const void* image1,
+                        const float* Aext, const float* Wext, const float* bias, int relu,
+                        const float* R1, int64_t ldr1, const float* R2, int64_t ldr2,
+                        float* C, int64_t ldc, int64_t M, void* stream);
 int mmpde_node_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, const float* Bext,
                      float* dW, int64_t ldw, float* dWext, int64_t ldwext, float* dbias, int64_t M, void* stream);
 int mmpde_node_wgrad_grouped(const mmpde_wgrad_task* tasks, int n_tasks, void* stream);
@@ -243,6 +262,31 @@ int mmpde_decoder_bwd(const float* h, int64_t ldh, int64_t M, const float* param
  * warp-per-node form, kept as a second implementation the tests compare against. */
 int mmpde_outer_gate(const float* g, const float* w, const float* act, int64_t lda, float* out, int64_t ldo, int64_t M,
                      void* stream);
+
+/* ---- ItpNet 'res_cut' residual network on a regular grid (interpolate.py:54-63,95-97) -------------
+ * out = tanh(conv4(tanh(conv3(tanh(conv2(tanh(conv1(x)))))))), Conv2d 5x5 / padding 2 with channels 1 -> 4 -> 16 -> 4 -> 1
+ * (the reference's configuration, mmpde.py:343), x / out [B,1,H,W] fp32, one launch per direction (tile-resident stack).
+ * params: w1[4*1*25] b1[4] w2[16*4*25] b2[16] w3[4*16*25] b3[4] w4[1*4*25] b4[1] (torch Conv2d layouts),
+ * MMPDE_RESCUT_NPARAM floats.  acts [B, MMPDE_RESCUT_ACT_CHANNELS, H, W]: the three hidden activations, written by the
+ * forward when non-NULL and read by the backward.  The backward OVERWRITES g_params[MMPDE_RESCUT_NPARAM] (x carries no
+ * gradient); workspace = mmpde_rescut_bwd_workspace_floats(...) floats.  Deterministic (no atomics). */
+#define MMPDE_RESCUT_NPARAM 3425
+#define MMPDE_RESCUT_ACT_CHANNELS 24
+int mmpde_rescut_fwd(const float* x, int64_t batch, int height, int width, const float* params, float* out,
+                     float* acts, void* stream);
+int64_t mmpde_rescut_bwd_workspace_floats(int64_t batch, int height, int width);
+int mmpde_rescut_bwd(const float* x, int64_t batch, int height, int width, const float* params, const float* out,
+                     const float* acts, const float* g_out, float* workspace, float* g_params, void* stream);
+
+/* ---- DMM mesh mover, graph branch (mesh/dmm_model.py:94-142), forward only (the mover is frozen) --------
+ * One tanh message-passing layer of hidden width 4 over a target-sorted edge list in CSR form:
+ *   m_ij = tanh(W2 tanh(W1 [x_i | x_j | u_i-u_j | px_i-px_j | py_i-py_j] + b1) + b2),
+ *   out[i] = x[i] + tanh(W4 tanh(W3 [x[i] | mean_j m_ij] + b3) + b4)      (the BatchNorm that follows stays in the caller).
+ * x, out [N,4]; upos [N,4] = (u, px, py, unused); row_ptr int32 [N+1]; edge_src int32 [E]; weights = DEVICE pointer to
+ * W1[4*11] b1[4] W2[4*4] b2[4] W3[4*8] b3[4] W4[4*4] b4[4] (nn.Linear layouts), MMPDE_DMM_GNN_NPARAM floats. */
+#define MMPDE_DMM_GNN_NPARAM 124
+int mmpde_dmm_gnn_layer(const float* x, const float* upos, const int32_t* row_ptr, const int32_t* edge_src,
+                        int64_t n_nodes, const float* weights, float* out, void* stream);
 
 /* ---- fused k-NN interpolation (data_creator_2d.py:77-83 + interpolate.py:79-93) ----------------
  * For query q of sample s: p = (x_1,y_1,...,x_30,y_30,x_q,y_q) from idx[q,0..29];

@@ -19,6 +19,11 @@ class WgradTask(ctypes.Structure):
                 ("dWext", _p), ("ldwext", _l), ("dbias", _p), ("M", _l)]
 
 
+class WimgTask(ctypes.Structure):
+    """include/mmpde_b200.h: mmpde_wimg_task."""
+    _fields_ = [("W", _p), ("w_ns", _l), ("w_ks", _l), ("scale", _f), ("image", _p)]
+
+
 class KnnTask(ctypes.Structure):
     """include/mmpde_b200.h: mmpde_knn_task."""
     _fields_ = [("pts", _p), ("pts_off", _p), ("qry", _p), ("qry_off", _p), ("n_samples", ctypes.c_int32), ("k", ctypes.c_int32),
@@ -37,6 +42,8 @@ SIGNATURES = {
     "mmpde_radius": [_p, _p, _i, _l, _f, _i, _p, _p],
     "mmpde_gemm": [_p, _l, _i, _p, _l, _i, _p, _l, _l, _i, _l, _p, _p, _l, _p, _i, _i, _i, _p],
     "mmpde_node_gemm": [_p, _l, _p, _l, _p, _l, _l, _p, _l, _l, _p, _p, _p, _i, _p, _l, _p, _l, _p, _l, _l, _p],
+    "mmpde_weight_images": [_p, _i, _p],
+    "mmpde_node_gemm_img": [_p, _l, _p, _l, _p, _p, _p, _p, _p, _i, _p, _l, _p, _l, _p, _l, _l, _p],
     "mmpde_node_wgrad": [_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _l, _p],
     "mmpde_node_wgrad_grouped": [_p, _i, _p],
     "mmpde_edge_fwd": [_p, _p, _p, _p, _l, _p, _p, _p, _l, _p, _p],
@@ -60,6 +67,9 @@ SIGNATURES = {
     "mmpde_itp_bwd": [_p, _p, _p, _p, _l, _p, _p, _p, _p, _p],
     "mmpde_itp_fwd_tc": [_p, _p, _p, _p, _l, _p, _p, _p],
     "mmpde_itp_bwd_tc": [_p, _p, _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _p],
+    "mmpde_rescut_fwd": [_p, _l, _i, _i, _p, _p, _p, _p],
+    "mmpde_rescut_bwd": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "mmpde_dmm_gnn_layer": [_p, _p, _p, _p, _l, _p, _p, _p],
     "mmpde_rows_gather": [_p, _l, _p, _l, _i, _p, _p],
     "mmpde_rows_scatter_add": [_p, _p, _l, _i, _p, _l, _p],
     "mmpde_rows_dot": [_p, _l, _i, _p, _p, _l, _l, _i, _p],

@@ -32,6 +32,7 @@ constexpr uint32_t G_XIMG = GT * 128;                                      // ex
 struct NodeGemmArgs {
     const float* A[2]; int64_t lda[2]; int nseg;
     const float* W[2]; int64_t w_ns[2], w_ks[2];
+    const unsigned char* Wimg[2];                                          // pre-split operand images (mmpde_weight_images) or NULL
     const float* Aext; const float* Wext;
     const float* bias; int relu;
     const float* R1; int64_t ldr1; const float* R2; int64_t ldr2;
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
     const uint32_t sbase = smem_u32(sm);
     const uint32_t bar0 = sbase + GemmSmem::BAR;
     const uint32_t h_full = bar0, h_empty = bar0 + 16, tm_full = bar0 + 32, tm_empty = bar0 + 48;   // [b] at +8*b
+    const uint32_t w_full = bar0 + 72, w_cp = bar0 + 80;                   // weight image landed | copied to TMEM ([seg] at +8*seg)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + GemmSmem::BAR + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -58,7 +60,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
         for (int b = 0; b < 2; ++b) {
             mbar_init(h_full + 8 * b, G_BLD_WARPS); mbar_init(h_empty + 8 * b, 1);
             mbar_init(tm_full + 8 * b, 1); mbar_init(tm_empty + 8 * b, G_EPI_WARPS);
+            mbar_init(w_cp + 8 * b, 1);
         }
+        mbar_init(w_full, 1);
         fence_mbar_init();
     }
     tc_fence_before();
@@ -67,6 +71,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
     const uint32_t tmem_base = *tmem_slot;
     const int nseg = p.nseg;
     const bool has_ext = p.Aext != nullptr;
+    const bool use_img = p.Wimg[0] != nullptr;
     const int d_stages = (nseg == 1) ? 2 : 1;                              // TMEM: D stages | W0 hi lo | ext hi lo | W1 hi lo
     const uint32_t tmem_d = tmem_base, tmem_w = tmem_base + d_stages * GT;
     const uint32_t tmem_x_hi = tmem_w + 128, tmem_x_lo = tmem_w + 136;
@@ -85,8 +90,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
         const bool gate = p.relu == 2;                                     // ReLU backward: C = acc where R1 > 0, else 0
         const int nres = gate ? 1 : (p.R1 != nullptr) + (p.R1 != nullptr && p.R2 != nullptr);
         // W -> tensor memory, shared by the two warps of a lane quadrant (32-column groups 2*half, 2*half+1)
-        weight_to_tmem(p.W[0], p.w_ns[0], p.w_ks[0], n, tmem_w + lane_addr, tmem_w + 64 + lane_addr, 2 * half, 2 * half + 2);
-        if (nseg == 2)
+        // (with pre-split images the MMA thread brings W in: TMA bulk copy -> shared memory -> tcgen05.cp, see below)
+        if (!use_img) weight_to_tmem(p.W[0], p.w_ns[0], p.w_ks[0], n, tmem_w + lane_addr, tmem_w + 64 + lane_addr, 2 * half, 2 * half + 2);
+        if (!use_img && nseg == 2)
             weight_to_tmem(p.W[1], p.w_ns[1], p.w_ks[1], n, tmem_w + 144 + lane_addr, tmem_w + 208 + lane_addr, 2 * half, 2 * half + 2);
         if (has_ext && half == 1) {
             // extension weights: K step of 16 = (w0 w1)(w2 w3) then zeros; hi in columns +0..7, lo in +8..15
@@ -204,6 +210,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
             if (has_ext && seg == nseg - 1) {
                 // extension K step: columns 0..3 = node4[m], 4..15 = 0.  16 rows x 4 pieces of 8 bytes (hi image; lo follows)
                 const int64_t t = (int64_t)blockIdx.x + (int64_t)ti * gridDim.x;
+                if (use_img && ti == 0) mbar_wait(w_cp + 8 * (nseg - 1), 0);   // the weight images were staged in this region
                 const uint32_t ximg = sbase + GemmSmem::EXT + (uint32_t)(ti & 1) * (2 * G_XIMG);
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
@@ -226,6 +233,28 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
         reg_dec<G_MMA_REGS>();
         constexpr uint32_t idesc = idesc_bf16(128, GT, 0, 0);
         if (warp == G_MMA_WARP && lane == 0) {
+            if (use_img) {
+                // W (hi | lo operand images, 64 KB per 128 x 128 block, already in the SWIZZLE_128B K-major tile format)
+                // -> shared memory with TMA bulk copies, -> tensor memory with tcgen05.cp (32 bytes = 16 k of every row
+                // per copy, the same start-address stepping the MMA uses).  Copies and MMAs execute in issue order.
+                const uint32_t stage = sbase + GemmSmem::EXT;
+                for (int seg = 0; seg < nseg; ++seg) {
+                    if (seg > 0) mbar_wait(w_cp, 0);                       // staging area drained by the copies of segment 0
+                    mbar_arrive_expect_tx(w_full, 2 * G_IMG);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tma_bulk_g2s(stage + c * (G_IMG / 2), p.Wimg[seg] + c * (G_IMG / 2), G_IMG / 2, w_full);
+                    mbar_wait(w_full, (uint32_t)seg & 1u);
+                    tc_fence_after();
+                    const uint32_t t_hi = tmem_w + (seg == 0 ? 0 : 144);
+                    const uint32_t s_lo = desc_lo_sw128(stage, 16);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        utccp_128x256b(t_hi + (q >> 3) * 64 + (q & 7) * 8,
+                                       s_lo + (((q >> 3) * G_IMG + ((q & 7) >> 2) * (GT * 128) + (q & 3) * 32) >> 4), desc_hi_sw128(1024));
+                    umma_commit(w_cp + 8 * seg);
+                }
+                TL(2, 0, 4);
+            }
             int i = 0;
             int64_t j = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
@@ -265,6 +294,35 @@ __global__ void __launch_bounds__(G_THREADS, 1) node_gemm_tc_kernel(NodeGemmArgs
     tc_fence_before();
     __syncthreads();
     if (warp == 0) { TL(3, 0, 7); tmem_dealloc(tmem_base, N_TMEM_COLS); }
+}
+
+// ================================================================================================================
+// weight images: W (fp32, element (n, k) at W[n*ns + k*ks], 128 x 128) * scale -> bf16 hi | lo operand images in the
+// SWIZZLE_128B K-major tile format (tile_off<128>(n, k); 32 KB each), ONCE per optimizer step for every weight block
+// the node contractions of a solver pass use.  The GEMM kernels then fetch an image with TMA bulk copies and move it
+// to tensor memory with tcgen05.cp instead of 148 CTAs x 100 launches re-splitting the same fp32 matrix in registers.
+// ================================================================================================================
+constexpr int IMG_MAX_TASKS = 64;
+struct WImgTask { const float* W; int64_t ns, ks; unsigned char* img; float scale; };
+struct WImgGroup { WImgTask t[IMG_MAX_TASKS]; };
+
+__global__ void __launch_bounds__(256) weight_images_kernel(const __grid_constant__ WImgGroup grp) {
+    const WImgTask& T = grp.t[blockIdx.x];
+    const int n0 = blockIdx.y * 32;
+    const bool k_fast = T.ks == 1;                                         // lanes along the contiguous axis of W
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int g = it * 256 + (int)threadIdx.x;                        // 32 rows x 32 groups of 4 consecutive k
+        const int n = n0 + (k_fast ? (g >> 5) : (g & 31));
+        const int k = 4 * (k_fast ? (g & 31) : (g >> 5));
+        const float* q = T.W + (int64_t)n * T.ns + (int64_t)k * T.ks;
+        const float4 v = make_float4(__ldg(q) * T.scale, __ldg(q + T.ks) * T.scale, __ldg(q + 2 * T.ks) * T.scale, __ldg(q + 3 * T.ks) * T.scale);
+        uint2 hi, lo;
+        split4(v, hi, lo);
+        unsigned char* dst = T.img + tile_off<128>(n, k);
+        *reinterpret_cast<uint2*>(dst) = hi;
+        *reinterpret_cast<uint2*>(dst + G_IMG) = lo;
+    }
 }
 
 // ================================================================================================================
@@ -491,13 +549,35 @@ using namespace mmpde;
 extern "C" int mmpde_debug_timeline_node(long long* buf) { return (int)cudaMemcpyToSymbol(g_timeline, &buf, sizeof(buf)); }
 #endif
 
-extern "C" int mmpde_node_gemm(const float* A0, int64_t lda0, const float* A1, int64_t lda1,
-                               const float* W0, int64_t w0_ns, int64_t w0_ks, const float* W1, int64_t w1_ns, int64_t w1_ks,
-                               const float* Aext, const float* Wext, const float* bias, int relu,
-                               const float* R1, int64_t ldr1, const float* R2, int64_t ldr2,
-                               float* C, int64_t ldc, int64_t M, void* stream) {
-    if (M < 0 || A0 == nullptr || W0 == nullptr || C == nullptr) return MMPDE_EINVAL;
-    if ((A1 == nullptr) != (W1 == nullptr) || (Aext == nullptr) != (Wext == nullptr)) return MMPDE_EINVAL;
+extern "C" int mmpde_weight_images(const mmpde_wimg_task* tasks, int n_tasks, void* stream) {
+    if (n_tasks < 0 || (n_tasks > 0 && tasks == nullptr)) return MMPDE_EINVAL;
+    for (int k = 0; k < n_tasks; ++k)
+        if (tasks[k].W == nullptr || tasks[k].image == nullptr || (reinterpret_cast<uintptr_t>(tasks[k].image) & 127)) return MMPDE_EINVAL;
+    for (int k0 = 0; k0 < n_tasks; k0 += IMG_MAX_TASKS) {
+        WImgGroup g;
+        const int n = (int)imin64(IMG_MAX_TASKS, n_tasks - k0);
+        for (int k = 0; k < n; ++k) {
+            const mmpde_wimg_task& t = tasks[k0 + k];
+            g.t[k].W = t.W; g.t[k].ns = t.w_ns; g.t[k].ks = t.w_ks; g.t[k].img = static_cast<unsigned char*>(t.image); g.t[k].scale = t.scale;
+        }
+        for (int k = n; k < IMG_MAX_TASKS; ++k) g.t[k] = g.t[0];
+        weight_images_kernel<<<dim3(n, 4), 256, 0, (cudaStream_t)stream>>>(g);
+        MMPDE_CHECK_LAUNCH();
+    }
+    return MMPDE_OK;
+}
+
+static int node_gemm_launch(const float* A0, int64_t lda0, const float* A1, int64_t lda1,
+                            const float* W0, int64_t w0_ns, int64_t w0_ks, const float* W1, int64_t w1_ns, int64_t w1_ks,
+                            const void* img0, const void* img1,
+                            const float* Aext, const float* Wext, const float* bias, int relu,
+                            const float* R1, int64_t ldr1, const float* R2, int64_t ldr2,
+                            float* C, int64_t ldc, int64_t M, void* stream) {
+    const bool img = img0 != nullptr;
+    if (M < 0 || A0 == nullptr || (W0 == nullptr && !img) || C == nullptr) return MMPDE_EINVAL;
+    if (img ? ((A1 == nullptr) != (img1 == nullptr)) : ((A1 == nullptr) != (W1 == nullptr))) return MMPDE_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(img0) | reinterpret_cast<uintptr_t>(img1)) & 127) return MMPDE_EINVAL;
+    if ((Aext == nullptr) != (Wext == nullptr)) return MMPDE_EINVAL;
     if ((lda0 & 3) || (A1 && (lda1 & 3))) return MMPDE_EINVAL;
     if (relu < 0 || relu > 2 || (relu == 2 && (R1 == nullptr || R2 != nullptr))) return MMPDE_EINVAL;
     if ((reinterpret_cast<uintptr_t>(A0) | reinterpret_cast<uintptr_t>(A1) | reinterpret_cast<uintptr_t>(Aext) |
@@ -508,12 +588,32 @@ extern "C" int mmpde_node_gemm(const float* A0, int64_t lda0, const float* A1, i
     NodeGemmArgs p;
     p.A[0] = A0; p.A[1] = A1; p.lda[0] = lda0; p.lda[1] = lda1; p.nseg = A1 ? 2 : 1;
     p.W[0] = W0; p.W[1] = W1; p.w_ns[0] = w0_ns; p.w_ks[0] = w0_ks; p.w_ns[1] = w1_ns; p.w_ks[1] = w1_ks;
+    p.Wimg[0] = static_cast<const unsigned char*>(img0); p.Wimg[1] = static_cast<const unsigned char*>(img1);
     p.Aext = Aext; p.Wext = Wext; p.bias = bias; p.relu = relu; p.R1 = R1; p.ldr1 = ldr1; p.R2 = R2; p.ldr2 = ldr2;
     p.C = C; p.ldc = ldc; p.M = M;
     const int64_t n_tiles = (M + GT - 1) / GT;
     node_gemm_tc_kernel<<<(int)imin64(n_tiles, sm_count()), G_THREADS, smem, (cudaStream_t)stream>>>(p);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
+}
+
+extern "C" int mmpde_node_gemm(const float* A0, int64_t lda0, const float* A1, int64_t lda1,
+                               const float* W0, int64_t w0_ns, int64_t w0_ks, const float* W1, int64_t w1_ns, int64_t w1_ks,
+                               const float* Aext, const float* Wext, const float* bias, int relu,
+                               const float* R1, int64_t ldr1, const float* R2, int64_t ldr2,
+                               float* C, int64_t ldc, int64_t M, void* stream) {
+    return node_gemm_launch(A0, lda0, A1, lda1, W0, w0_ns, w0_ks, W1, w1_ns, w1_ks, nullptr, nullptr, Aext, Wext, bias, relu,
+                            R1, ldr1, R2, ldr2, C, ldc, M, stream);
+}
+
+extern "C" int mmpde_node_gemm_img(const float* A0, int64_t lda0, const float* A1, int64_t lda1,
+                                   const void* image0, const void* image1,
+                                   const float* Aext, const float* Wext, const float* bias, int relu,
+                                   const float* R1, int64_t ldr1, const float* R2, int64_t ldr2,
+                                   float* C, int64_t ldc, int64_t M, void* stream) {
+    if (image0 == nullptr) return MMPDE_EINVAL;
+    return node_gemm_launch(A0, lda0, A1, lda1, nullptr, 0, 0, nullptr, 0, 0, image0, image1, Aext, Wext, bias, relu,
+                            R1, ldr1, R2, ldr2, C, ldc, M, stream);
 }
 
 static int check_wgrad_task(const mmpde_wgrad_task& t) {

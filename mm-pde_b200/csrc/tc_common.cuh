@@ -231,7 +231,15 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uin
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// All MMAs issued so far by this thread -> arrive (count 1) on the mbarrier when they have completed.
+// shared memory -> tensor memory, 128 lanes x 32 bytes per copy (8 TMEM columns); the source is described like an MMA operand
+__device__ __forceinline__ void utccp_128x256b(uint32_t taddr, uint32_t s_lo, uint32_t s_hi) {
+    asm volatile(
+        "{\n\t.reg .b64 ds;\n\t"
+        "mov.b64 ds, {%1, %2};\n\t"
+        "tcgen05.cp.cta_group::1.128x256b [%0], ds;\n\t}" ::"r"(taddr), "r"(s_lo), "r"(s_hi)
+        : "memory");
+}
+// All MMAs / copies issued so far by this thread -> arrive (count 1) on the mbarrier when they have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

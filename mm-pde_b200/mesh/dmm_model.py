@@ -72,6 +72,22 @@ class GNN_Layer_FS_2D(nn.Module):
         self.update_net_2 = nn.Sequential(nn.Linear(hidden_features, out_features), nn.Tanh())
         self.norm = _Norm(hidden_features)
 
+    def packed(self):
+        """W1 b1 W2 b2 W3 b3 W4 b4 flattened in the order mmpde_dmm_gnn_layer expects."""
+        return torch.cat([t.reshape(-1) for seq in (self.message_net_1, self.message_net_2, self.update_net_1, self.update_net_2)
+                          for t in (seq[0].weight, seq[0].bias)])
+
+    def forward_fused(self, x, upos, row_ptr, src32):
+        """The same layer as ONE pass over the edge list (csrc/dmm_gnn.cu); forward only -- the mover is frozen."""
+        from .. import _cabi
+        w = self.packed()
+        assert w.numel() == 124, "the fused layer is built for hidden width 4"
+        out = torch.empty_like(x)
+        with ops._on(x):
+            _cabi.call("mmpde_dmm_gnn_layer", ops._ptr(x), ops._ptr(upos), ops._ptr(row_ptr), ops._ptr(src32), x.shape[0],
+                       ops._ptr(w), ops._ptr(out), ops._stream())
+        return self.norm(out)
+
     def forward(self, x, u, pos_x, pos_y, src, dst, inv_deg):
         feats = torch.cat((x[dst], x[src], u[dst] - u[src], pos_x[dst] - pos_x[src], pos_y[dst] - pos_y[src]), -1)
         msg = self.message_net_2(self.message_net_1(feats))
@@ -100,6 +116,7 @@ class DMM(nn.Module):
         self.trunk = DenseNet(trunk_layer)
         self.out_nn = DenseNet(out_layer)
         self._graph_cache = {}
+        self.fused = True            # graph branch through csrc/dmm_gnn.cu when no autograd graph is being built
 
     def _static_graph(self, n_samples, device):
         key = (n_samples, str(device))
@@ -109,16 +126,22 @@ class DMM(nn.Module):
             off = torch.arange(n_samples + 1, dtype=torch.int32, device=device) * n
             nbr = ops.knn_indices(pts, off, pts, off, 35, rule=0, exclude_self=True)
             e = ops.EdgeList.from_knn(nbr, has_pad=n - 1 < 35)
-            self._graph_cache[key] = (pts, e.src.long(), e.dst.long(), e.inv_deg)
+            deg = torch.bincount(e.dst.long(), minlength=n_samples * n)
+            row_ptr = torch.cat((deg.new_zeros(1), deg.cumsum(0))).to(torch.int32)
+            self._graph_cache[key] = (pts, e.src.long(), e.dst.long(), e.inv_deg, row_ptr, e.src.contiguous())
         return self._graph_cache[key]
 
     def _branch_graph(self, u):
-        pts, src, dst, inv_deg = self._static_graph(u.shape[0], u.device)
+        pts, src, dst, inv_deg, row_ptr, src32 = self._static_graph(u.shape[0], u.device)
         x = u.reshape(-1, 1)
         px, py = pts[:, 0:1], pts[:, 1:2]
         h = self.embedding_mlp(torch.cat((x, px, py), -1))
+        # frozen mover (no autograd graph wanted), hidden width 4, on the GPU: each layer is one fused pass over the edges
+        fused = self.fused and u.is_cuda and self.hidden_features == 4 and not torch.is_grad_enabled()
+        if fused:
+            upos = torch.cat((x, pts, torch.zeros_like(x)), -1).to(torch.float32).contiguous()
         for layer in self.gnn_layers:
-            h = layer(h, x, px, py, src, dst, inv_deg)
+            h = layer.forward_fused(h.contiguous(), upos, row_ptr, src32) if fused else layer(h, x, px, py, src, dst, inv_deg)
         h, _ = self.decoding_mlp(h)
         return self.output_mlp(h.reshape(u.shape[0], 1, -1))
 

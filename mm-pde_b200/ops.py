@@ -226,10 +226,34 @@ def gemm(A, lda, a_k, B, ldb, b_k, C, ldc, M, N, K, bias=None, r1_row=None, r1_s
                relu, acc, split_k, st if st is not None else _stream())
 
 
+WIMG_BYTES = 65536         # include/mmpde_b200.h: MMPDE_WIMG_BYTES
+USE_WEIGHT_IMAGES = __import__("os").environ.get("MMPDE_WEIGHT_IMAGES", "1") != "0"     # 0: every CTA splits the fp32 weights itself
+
+
+def weight_images(blocks, device, st=None):
+    """blocks: [(W pointer, w_ns, w_ks)] or [(W pointer, w_ns, w_ks, scale)] -> ([image pointer per block], the uint8
+    buffer holding them).  One launch pre-splits all 128 x 128 weight blocks into the bf16 hi | lo operand images the
+    tensor-core kernels fetch by TMA (mmpde_weight_images)."""
+    import ctypes
+    buf = torch.empty(max(len(blocks), 1), WIMG_BYTES, dtype=torch.uint8, device=device)
+    base = buf.data_ptr()
+    tasks = [_cabi.WimgTask(b[0], b[1], b[2], b[3] if len(b) > 3 else 1.0, base + i * WIMG_BYTES) for i, b in enumerate(blocks)]
+    if tasks:
+        arr = (_cabi.WimgTask * len(tasks))(*tasks)
+        _cabi.call("mmpde_weight_images", ctypes.addressof(arr), len(tasks), st if st is not None else _stream())
+    return [base + i * WIMG_BYTES for i in range(len(blocks))], buf
+
+
 def node_gemm(A0, lda0, W0, w0_ns, w0_ks, C, ldc, M, A1=None, lda1=0, W1=None, w1_ns=0, w1_ks=0, ext=None, bias=None, relu=0,
-              R1=None, ldr1=0, R2=None, ldr2=0, st=None):
-    """tcgen05 node contraction (include/mmpde_b200.h: mmpde_node_gemm); ext = (node4 pointer, Wext pointer)."""
+              R1=None, ldr1=0, R2=None, ldr2=0, st=None, img0=None, img1=None):
+    """tcgen05 node contraction (include/mmpde_b200.h: mmpde_node_gemm); ext = (node4 pointer, Wext pointer).  With
+    ``img0`` (and ``img1`` for the second K segment) the weight blocks are taken from pre-split images
+    (mmpde_node_gemm_img) and the W pointers / strides are ignored."""
     aext, wext = ext if ext is not None else (None, None)
+    if img0 is not None:
+        _cabi.call("mmpde_node_gemm_img", A0, lda0, A1, lda1, img0, img1, aext, wext, bias, relu, R1, ldr1, R2, ldr2, C, ldc, M,
+                   st if st is not None else _stream())
+        return
     _cabi.call("mmpde_node_gemm", A0, lda0, A1, lda1, W0, w0_ns, w0_ks, W1, w1_ns, w1_ks, aext, wext, bias, relu,
                R1, ldr1, R2, ldr2, C, ldc, M, st if st is not None else _stream())
 
@@ -302,7 +326,7 @@ def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st, sums=N
                 red, n_rep = COMM.reduce_bn_sums(red, state.branch), 1
             _cabi.call("mmpde_bn_finalize", _ptr(red), n_rep, state.count, BN_EPS, BN_MOMENTUM, _ptr(state.mean_rstd),
                        _ptr(rmean), _ptr(rvar), st)
-        if nbt is not None:
+        if nbt is not None:        # (the solver passes None and bumps all of its counters with one launch)
             nbt += 1
     else:
         state.count = float(state.rows)
@@ -511,10 +535,32 @@ def _layer_prep(W1s, W3s):
     return [(w1c[l], w1cq[l], w3x[l], wu[l]) for l in range(L)]
 
 
+def _layer_image_blocks(lp, backward):
+    """The 128 x 128 weight blocks one layer's node contractions read: forward p q u1a u1b u2, backward (transposed
+    reads) u2T u1aT u1bT pT qT."""
+    W1, W3, W4 = lp[0], lp[4], lp[6]
+    blocks = [(_ptr(W1), 260, 1), (_ptr(W1, H), 260, 1), (_ptr(W3), 257, 1), (_ptr(W3, H), 257, 1), (_ptr(W4), H, 1)]
+    if backward:
+        blocks += [(_ptr(W4), 1, H), (_ptr(W3), 1, 257), (_ptr(W3, H), 1, 257), (_ptr(W1), 1, 260), (_ptr(W1, H), 1, 260)]
+    return blocks
+
+
+class _LayerImages:
+    """Image pointers of one layer (None = let the kernel split the fp32 weights itself)."""
+    __slots__ = ("p", "q", "u1a", "u1b", "u2", "u2T", "u1aT", "u1bT", "pT", "qT")
+
+    def __init__(self, ptrs=None):
+        for k, name in enumerate(self.__slots__):
+            setattr(self, name, ptrs[k] if ptrs is not None and k < len(ptrs) else None)
+
+
+_NO_IMAGES = _LayerImages()
+
+
 LAYER_GRAD_SIZES = [H * 260, H, H * H, H, H * 257, H, H * H, H, 2 * H * 4, H * 4]    # dW1 db1 dW2 db2 dW3 db3 dW4 db4 dW1c dW3x
 
 
-def _layer_forward(parts, Xs, lp, bnbuf, training, nxts, exch, st, prep=None, bn_sums=None):
+def _layer_forward(parts, Xs, lp, bnbuf, training, nxts, exch, st, prep=None, bn_sums=None, im=_NO_IMAGES):
     """One GNN_Layer_FS_2D (gnn_2d.py:53-69) on every part.  Xs[p] [n_own,256]: cols 0..127 hold the layer input
     h, cols 128..255 must be ZERO on entry and receive the mean message.  Output BN(h + update) -> nxts[p] =
     (pointer, leading dimension)."""
@@ -528,8 +574,8 @@ def _layer_forward(parts, Xs, lp, bnbuf, training, nxts, exch, st, prep=None, bn
         f32 = dict(dtype=torch.float32, device=Xl.device)
         x, n4 = _ptr(Xl), _ptr(part.node4)
         PQ = torch.empty(part.n_src, 2 * H, **f32)
-        node_gemm(x, 2 * H, _ptr(W1), 260, 1, _ptr(PQ), 2 * H, N, ext=(n4, _ptr(w1c)), bias=_ptr(b1), st=st)
-        node_gemm(x, 2 * H, _ptr(W1, H), 260, 1, _ptr(PQ, H), 2 * H, N, ext=(n4, _ptr(w1cq)), st=st)
+        node_gemm(x, 2 * H, _ptr(W1), 260, 1, _ptr(PQ), 2 * H, N, ext=(n4, _ptr(w1c)), bias=_ptr(b1), st=st, img0=im.p)
+        node_gemm(x, 2 * H, _ptr(W1, H), 260, 1, _ptr(PQ, H), 2 * H, N, ext=(n4, _ptr(w1cq)), st=st, img0=im.q)
         PQs.append(PQ)
     if exch is not None:
         exch.forward(PQs)                                         # Q' rows of the halo nodes
@@ -544,16 +590,16 @@ def _layer_forward(parts, Xs, lp, bnbuf, training, nxts, exch, st, prep=None, bn
         # update_net_1/2 + residual                                 (gnn_2d.py:65-69)
         h3 = torch.empty(N, H, **f32)
         node_gemm(x, 2 * H, _ptr(W3), 257, 1, _ptr(h3), H, N, A1=_ptr(Xl, H), lda1=2 * H, W1=_ptr(W3, H), w1_ns=257, w1_ks=1,
-                  ext=(_ptr(part.node4), _ptr(w3x)), bias=_ptr(b3), relu=1, st=st)
+                  ext=(_ptr(part.node4), _ptr(w3x)), bias=_ptr(b3), relu=1, st=st, img0=im.u1a, img1=im.u1b)
         r4 = torch.empty(N, H, **f32)
-        node_gemm(_ptr(h3), H, _ptr(W4), H, 1, _ptr(r4), H, N, bias=_ptr(b4), relu=1, st=st)
+        node_gemm(_ptr(h3), H, _ptr(W4), H, 1, _ptr(r4), H, N, bias=_ptr(b4), relu=1, st=st, img0=im.u2)
         saved.append((PQ, mask2, h3, r4))
         bn_items.append((x, 2 * H, _ptr(r4), H, N, nxt[0], nxt[1]))
     bn = _bn_forward(bn_items, gam, bet, 0, training, *bnbuf, st, sums=bn_sums)
     return saved, bn
 
 
-def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st, prep=None, flat=None, bn_spread=None):
+def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st, prep=None, flat=None, bn_spread=None, im=_NO_IMAGES):
     """Backward of _layer_forward.  g_hs[p] [n_own,128] = dL/d(output).  Returns ([dL/dh_in per part], 10 param
     grads summed over the local parts); adds the layer's dL/du into g_node4s[p][:,0] when given."""
     W1, b1, W2, b2, W3, b3, W4, b4, gam, bet = lp
@@ -586,13 +632,13 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st, prep=Non
         # at the end (nothing but the optimizer waits for them), so their operands stay alive until then.
         wtasks.append(wgrad_task(_ptr(g_z4), H, N, B=_ptr(h3), ldb=H, dW=_ptr(dW4), ldw=H, dbias=_ptr(db4)))
         g_z3 = torch.empty(N, H, **f32)
-        node_gemm(_ptr(g_z4), H, _ptr(W4), 1, H, _ptr(g_z3), H, N, relu=2, R1=_ptr(h3), ldr1=H, st=st)
+        node_gemm(_ptr(g_z4), H, _ptr(W4), 1, H, _ptr(g_z3), H, N, relu=2, R1=_ptr(h3), ldr1=H, st=st, img0=im.u2T)
         wtasks.append(wgrad_task(_ptr(g_z3), H, N, B=x, ldb=2 * H, dW=_ptr(dW3), ldw=257, Bext=n4, dWext=_ptr(dW3x), dbias=_ptr(db3)))
         wtasks.append(wgrad_task(_ptr(g_z3), H, N, B=_ptr(Xl, H), ldb=2 * H, dW=_ptr(dW3, H), ldw=257))
         # dL/dh_in so far: g_y (residual) + g_z3 W3[:, :128];  dL/d(mean message) = g_z3 W3[:, 128:256]
-        node_gemm(_ptr(g_z3), H, _ptr(W3), 1, 257, _ptr(g_y), H, N, R1=_ptr(g_y), ldr1=H, st=st)
+        node_gemm(_ptr(g_z3), H, _ptr(W3), 1, 257, _ptr(g_y), H, N, R1=_ptr(g_y), ldr1=H, st=st, img0=im.u1aT)
         g_agg = torch.empty(N, H, **f32)
-        node_gemm(_ptr(g_z3), H, _ptr(W3, H), 1, 257, _ptr(g_agg), H, N, st=st)
+        node_gemm(_ptr(g_z3), H, _ptr(W3, H), 1, 257, _ptr(g_agg), H, N, st=st, img0=im.u1bT)
         keep.append((g_z3, g_z4))
         # message passing backward
         dPQ = torch.zeros(part.n_src, 2 * H, **f32)
@@ -612,7 +658,7 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st, prep=Non
             _cabi.call("mmpde_rows_dot", _ptr(dPQ), 2 * H, 2 * H, _ptr(wu), _ptr(g_node4), 4, N, 1, st)
         # dL/dh_in += dP' W1a + dQ' W1b
         node_gemm(_ptr(dPQ), 2 * H, _ptr(W1), 1, 260, _ptr(g_y), H, N, A1=_ptr(dPQ, H), lda1=2 * H, W1=_ptr(W1, H), w1_ns=1,
-                  w1_ks=260, R1=_ptr(g_y), ldr1=H, st=st)
+                  w1_ks=260, R1=_ptr(g_y), ldr1=H, st=st, img0=im.pT, img1=im.qT)
     node_wgrad_grouped(wtasks, st)
     del keep
     if fold_here:
@@ -665,7 +711,7 @@ class LayerFn(torch.autograd.Function):
         return (g_xs[0], g_node4, None, None, None, *grads)
 
 
-def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st):
+def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st, want_backward=True):
     """Encoder, L layers and decoder on every part.  Returns ([out [n_own] per part], saved state)."""
     dev = parts[0].node4.device
     f32 = dict(dtype=torch.float32, device=dev)
@@ -674,6 +720,23 @@ def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st):
     # ---- encoder: Linear(4,128) BN ReLU Linear(128,128) BN        (gnn_2d.py:99-106,130-131)
     preps = _layer_prep([params[N_ENC + N_LAYER * l] for l in range(L)], [params[N_ENC + N_LAYER * l + 4] for l in range(L)]) if L else []
     bn_sums = bn_accumulators(2 + L, dev) if training else [None] * (2 + L)
+    if training:                # num_batches_tracked of all 2 + L BatchNorms: one launch instead of one per BatchNorm pass
+        counters = [b[2] for b in bn_buffers if b[2] is not None]
+        if counters:
+            torch._foreach_add_(counters, 1)
+        bn_buffers = [(b[0], b[1], None) for b in bn_buffers]
+    # every weight block of the pass as bf16 hi | lo operand images, one launch (the weights only change in the optimizer)
+    per = 10 if want_backward else 5
+    blocks = [(_ptr(We2), H, 1)] + ([(_ptr(We2), 1, H)] if want_backward else [])
+    n_enc_img = len(blocks)
+    for l in range(L):
+        blocks += _layer_image_blocks(params[N_ENC + N_LAYER * l: N_ENC + N_LAYER * (l + 1)], want_backward)
+    if USE_WEIGHT_IMAGES:
+        img_ptrs, img_buf = weight_images(blocks, dev, st)
+        images = [_LayerImages(img_ptrs[n_enc_img + per * l: n_enc_img + per * (l + 1)]) for l in range(L)]
+        enc_images = (img_ptrs[0], img_ptrs[1] if want_backward else None)
+    else:
+        img_buf, images, enc_images = None, [_NO_IMAGES] * L, (None, None)
     e1s, e1ns, e2s = [], [], []
     for part in parts:
         e1 = torch.empty(part.n_own, H, **f32)
@@ -684,7 +747,7 @@ def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st):
                       g1, bt1, 1, training, *bn_buffers[0], st, sums=bn_sums[0])
     for part, e1n in zip(parts, e1ns):
         e2 = torch.empty(part.n_own, H, **f32)
-        node_gemm(_ptr(e1n), H, _ptr(We2), H, 1, _ptr(e2), H, part.n_own, bias=_ptr(be2), st=st)
+        node_gemm(_ptr(e1n), H, _ptr(We2), H, 1, _ptr(e2), H, part.n_own, bias=_ptr(be2), st=st, img0=enc_images[0])
         e2s.append(e2)
     # X[l][p] = [h_l | agg_l]  ([n_own,256]); the last hidden state lives alone in hL
     X = [[torch.zeros(part.n_own, 2 * H, **f32) for part in parts] for _ in range(L)]
@@ -699,10 +762,10 @@ def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st):
     for l in range(L):
         lp = params[N_ENC + N_LAYER * l: N_ENC + N_LAYER * (l + 1)]
         layers.append(_layer_forward(parts, X[l], lp, bn_buffers[2 + l], training, dest(l + 1), exch, st,
-                                     prep=preps[l], bn_sums=bn_sums[2 + l]))
+                                     prep=preps[l], bn_sums=bn_sums[2 + l], im=images[l]))
     outs, dec_saved = _decoder_forward(parts, hL, dec, float(scale), st)
     return outs, dict(parts=parts, L=L, scale=float(scale), params=params, enc=(e1s, e1ns, e2s, bn1, bn2), X=X, hL=hL,
-                      layers=layers, exch=exch, preps=preps, dec=dec_saved)
+                      layers=layers, exch=exch, preps=preps, dec=dec_saved, images=images, enc_images=enc_images, img_buf=img_buf)
 
 
 def _solver_backward(sv, g_outs, need_u, st):
@@ -723,7 +786,7 @@ def _solver_backward(sv, g_outs, need_u, st):
         base = N_ENC + N_LAYER * l
         saved, bn = sv["layers"][l]
         g_hs, lg = _layer_backward(parts, sv["X"][l], params[base:base + N_LAYER], saved, bn, g_hs, g_node4s, exch, st,
-                                   prep=sv["preps"][l], flat=flat_all[l], bn_spread=spread_all[2 + l])
+                                   prep=sv["preps"][l], flat=flat_all[l], bn_spread=spread_all[2 + l], im=sv["images"][l])
         grads[base:base + N_LAYER] = lg
     if L:
         _fold_extension_grads(flat_all)
@@ -737,7 +800,7 @@ def _solver_backward(sv, g_outs, need_u, st):
     for part, g_e2, e1n in zip(parts, g_e2s, e1ns):
         node_wgrad(_ptr(g_e2), H, part.n_own, B=_ptr(e1n), ldb=H, dW=_ptr(dWe2), ldw=H, dbias=_ptr(dbe2), st=st)
         g_e1n = torch.empty(part.n_own, H, **f32)
-        node_gemm(_ptr(g_e2), H, _ptr(We2), 1, H, _ptr(g_e1n), H, part.n_own, st=st)
+        node_gemm(_ptr(g_e2), H, _ptr(We2), 1, H, _ptr(g_e1n), H, part.n_own, st=st, img0=sv["enc_images"][1])
         g_e1ns.append(g_e1n)
     g_e1s = g_e2s                                                     # reuse
     dg1, db1_ = _bn_backward([(_ptr(g_e1n), H, _ptr(e1n), H, _ptr(e1), H, None, 0, part.n_own, _ptr(g_e1), H)
@@ -767,7 +830,7 @@ class SolverFn(torch.autograd.Function):
             for i, p in enumerate(params):
                 _chk(p, name=f"param{i}")
             outs, ctx.sv = _solver_forward([GraphPart(node4, edges)], n_layers, training, scale, bn_buffers, params, None,
-                                           _stream())
+                                           _stream(), want_backward=any(ctx.needs_input_grad))
         return outs[0].view(-1, 1)
 
     @staticmethod
@@ -793,7 +856,8 @@ class PartitionedSolverFn(torch.autograd.Function):
         COMM.total_rows = float(parts[0][1].n_total)
         try:
             with _on(node4s[0]):
-                outs, ctx.sv = _solver_forward(gps, n_layers, training, scale, bn_buffers, params, exch, _stream())
+                outs, ctx.sv = _solver_forward(gps, n_layers, training, scale, bn_buffers, params, exch, _stream(),
+                                               want_backward=any(ctx.needs_input_grad))
         finally:
             COMM.total_rows = None
         ctx.n = n
@@ -815,6 +879,9 @@ class PartitionedSolverFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # fused interpolation
 # ------------------------------------------------------------------------------------------------
+ITP_TENSOR_CORES = __import__("os").environ.get("MMPDE_ITP_TC", "1") != "0"     # 0: the direct fp32 kernels (csrc/itp.cu), for A/B checks
+
+
 class InterpolateFn(torch.autograd.Function):
     """out[Q] = sum_k ItpNet(p_q)_k * src_val[idx[q,k]]   (data_creator_2d.py:77-83, interpolate.py:79-93) on the tensor
     cores (csrc/itp_tc.cu).  Gradients: flat ItpNet parameters and src_val; coordinates are treated as constants (they
@@ -830,8 +897,8 @@ class InterpolateFn(torch.autograd.Function):
             _chk(src_val, name="src_val"); _chk(src_xy, name="src_xy"); _chk(qry_xy, name="qry_xy")
             _chk(idx, torch.int32, "idx"); _chk(flat_params, name="flat_params")
             out = torch.empty(Q, dtype=torch.float32, device=src_val.device)
-            _cabi.call("mmpde_itp_fwd_tc", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), Q, _ptr(flat_params),
-                       _ptr(out), _stream())
+            _cabi.call("mmpde_itp_fwd_tc" if ITP_TENSOR_CORES else "mmpde_itp_fwd", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy),
+                       _ptr(idx), Q, _ptr(flat_params), _ptr(out), _stream())
         ctx.save_for_backward(src_val, src_xy, qry_xy, idx, flat_params)
         return out
 
@@ -842,6 +909,12 @@ class InterpolateFn(torch.autograd.Function):
         Q = qry_xy.shape[0]
         dev = src_val.device
         g_val = torch.zeros_like(src_val) if ctx.needs_input_grad[0] else None
+        if not ITP_TENSOR_CORES:
+            with _on(src_val):
+                g_params = torch.zeros_like(flat_params)
+                _cabi.call("mmpde_itp_bwd", _ptr(src_xy), _ptr(src_val), _ptr(qry_xy), _ptr(idx), Q, _ptr(flat_params),
+                           _ptr(g_out), _ptr(g_params), _ptr(g_val), _stream())
+            return g_val, None, None, None, g_params
         with _on(src_val):
             st = _stream()
             ws = torch.empty(4, max(Q, 1), H, dtype=torch.float32, device=dev)      # G1 G2 X1 X2
@@ -856,6 +929,46 @@ class InterpolateFn(torch.autograd.Function):
             g_params = torch.cat((T[0][:, :62].reshape(-1), db[0], T[1][:64].reshape(-1), db[1][:64],
                                   T[2][64:64 + KN, 64:].reshape(-1), db[1][64:64 + KN]))
         return g_val, None, None, None, g_params
+
+
+RESCUT_CHANNELS = (1, 4, 16, 4, 1)
+RESCUT_NPARAM = 3425           # include/mmpde_b200.h: MMPDE_RESCUT_NPARAM
+RESCUT_ACT_CHANNELS = 24
+_RESCUT_SHAPES = [(4, 1, 5, 5), (4,), (16, 4, 5, 5), (16,), (4, 16, 5, 5), (4,), (1, 4, 5, 5), (1,)]
+
+
+class ResCutFn(torch.autograd.Function):
+    """ItpNet 'res_cut' (interpolate.py:54-63,95-97): four 5x5 convolutions 1 -> 4 -> 16 -> 4 -> 1 with tanh, on
+    [B,1,H,W], as ONE tile-resident launch per direction (csrc/rescut.cu) instead of 12 cuDNN launches.  Gradients go to
+    the eight convolution parameters; the input field carries none (it is the step's data)."""
+
+    @staticmethod
+    def forward(ctx, data, *params):
+        assert [tuple(p.shape) for p in params] == _RESCUT_SHAPES
+        B, _, Hh, Ww = data.shape
+        with _on(data):
+            data = _chk(data.contiguous(), name="data")
+            flat = torch.cat([p.reshape(-1) for p in params])
+            out = torch.empty(B, 1, Hh, Ww, dtype=torch.float32, device=data.device)
+            need = any(ctx.needs_input_grad[1:])
+            acts = torch.empty(B, RESCUT_ACT_CHANNELS, Hh, Ww, dtype=torch.float32, device=data.device) if need else None
+            _cabi.call("mmpde_rescut_fwd", _ptr(data), B, Hh, Ww, _ptr(flat), _ptr(out), _ptr(acts), _stream())
+        ctx.save_for_backward(data, flat, out, acts)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        data, flat, out, acts = ctx.saved_tensors
+        B, _, Hh, Ww = data.shape
+        with _on(data):
+            g_out = _chk(g_out.contiguous(), name="g_out")
+            tiles = B * ((Hh + 15) // 16) * ((Ww + 15) // 16)
+            ws = torch.empty(max(tiles, 1) * RESCUT_NPARAM, dtype=torch.float32, device=data.device)
+            g_flat = torch.empty(RESCUT_NPARAM, dtype=torch.float32, device=data.device)
+            _cabi.call("mmpde_rescut_bwd", _ptr(data), B, Hh, Ww, _ptr(flat), _ptr(out), _ptr(acts), _ptr(g_out), _ptr(ws),
+                       _ptr(g_flat), _stream())
+        grads = [g.reshape(s) for g, s in zip(torch.split(g_flat, [int(torch.Size(s).numel()) for s in _RESCUT_SHAPES]), _RESCUT_SHAPES)]
+        return (None, *grads)
 
 
 def interpolate_direct(src_val, src_xy, qry_xy, idx, flat_params, g_out=None, want_g_val=True):

@@ -1,7 +1,7 @@
 """GPU-time breakdown of the bench step as it really runs (replayed from the CUDA graph): kernel durations from CUPTI
 activity records through torch.profiler, summed per kernel name.  Unlike step_breakdown.py (events around eager calls)
 this carries no per-launch event overhead and sees the torch glue kernels too.
-usage: python profiles/kineto_breakdown.py [steps] [--eager]"""
+usage: python profiles/kineto_breakdown.py [steps] [--eager] [--ops] [--cylinder] [--analytic-mover]"""
 import collections
 import os
 import random
@@ -29,17 +29,33 @@ def main():
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     random.seed(0)
-    pde = burgers()
-    pde.grid_size = pde.movingmesh_grid_size = pde.ori_grid_size = bench.RES
-    gc = GraphCreator_FS_2D(pde, bench.K_NEIGH, "knn", 1, bench.RES[0])
-    model, model_b = MP_PDE_Solver_2D(pde).to(dev), MP_PDE_Solver_2D(pde).to(dev)
-    net = ItpNet(bench.RES[1], bench.RES[2], [128, 64], [128, 64], [1, 4, 16, 4, 1]).to(dev)
     from mmpde_b200.mesh.dmm_model import DMM
+    cyl = "--cylinder" in sys.argv
+    if cyl:                                      # BASELINE.json configs[2], set up like bench.py's workload("cylinder")
+        from mmpde_b200.PDEs import cy
+        cloud = synthetic.cylinder_cloud(bench.CY_RES[1], seed=0)
+        pde = cy(ori_grid=cloud, device=dev)
+        pde.grid_size = pde.movingmesh_grid_size = pde.ori_grid_size = bench.CY_RES
+        gc = GraphCreator_FS_2D(pde, bench.K_NEIGH, "knn", 1, bench.CY_RES[0])
+        net = ItpNet(bench.CY_RES[1], None, [128, 64], [128, 64], [1, 4, 16, 4, 1]).to(dev)
+    else:
+        pde = burgers()
+        pde.grid_size = pde.movingmesh_grid_size = pde.ori_grid_size = bench.RES
+        gc = GraphCreator_FS_2D(pde, bench.K_NEIGH, "knn", 1, bench.RES[0])
+        net = ItpNet(bench.RES[1], bench.RES[2], [128, 64], [128, 64], [1, 4, 16, 4, 1]).to(dev)
+    model, model_b = MP_PDE_Solver_2D(pde).to(dev), MP_PDE_Solver_2D(pde).to(dev)
     torch.manual_seed(bench.MOVER_SEED)
-    mover = (synthetic.AnalyticMover() if "--analytic-mover" in sys.argv else DMM(s=bench.RES[1], mode="array", **bench.DMM_ARRAY)).to(dev).eval()
+    if "--analytic-mover" in sys.argv:
+        mover = synthetic.AnalyticMover()
+    elif cyl:
+        mover = DMM(mode="graph", grid=cloud.to(dev), **bench.DMM_GRAPH)
+    else:
+        mover = DMM(s=bench.RES[1], mode="array", **bench.DMM_ARRAY)
+    mover = mover.to(dev).eval()
     opt = torch.optim.AdamW([{"params": model.parameters()}, {"params": model_b.parameters()}, {"params": net.parameters()}],
                             lr=2e-3, capturable=True, fused=True)
-    fields = synthetic.burgers_fields(bench.BATCH, *bench.RES, seed=100).to(dev)
+    fields = (synthetic.cylinder_fields(bench.BATCH, cloud, bench.CY_RES[0], seed=100) if cyl
+              else synthetic.burgers_fields(bench.BATCH, *bench.RES, seed=100)).to(dev)
     sg = None if eager else StepGraph()
 
     def step():

@@ -28,6 +28,32 @@ print("kernel start -> (clks)  W in TMEM:", rel(t[3,0,0]), " end:", rel(t[3,0,7]
 for i in range(2):
     print(f" tile {i}: builder start {rel(t[0,i,0])} empty-ok {rel(t[0,i,1])} built {rel(t[0,i,2])} | mma tm_empty-ok {rel(t[2,i,0])} issued {rel(t[2,i,2])} | epi acc-ready {rel(t[3,i,1])} stored {rel(t[3,i,2])}")
 
+# ---- the same contraction with the weight block as a pre-split image (TMA bulk copy + tcgen05.cp instead of the register split)
+lib.mmpde_node_gemm_img.argtypes = _cabi.SIGNATURES["mmpde_node_gemm_img"]
+imgs, keep = ops.weight_images([(pp(W), 260, 1)], dev)
+def run_i():
+    assert lib.mmpde_node_gemm_img(pp(X), 256, None, 0, imgs[0], None, None, None, pp(b), 0, None, 0, None, 0, pp(C), 128, N, st) == 0
+for _ in range(3): run_i()
+torch.cuda.synchronize(); buf.zero_(); lib.mmpde_debug_timeline_node(pp(buf)); run_i(); torch.cuda.synchronize(); lib.mmpde_debug_timeline_node(None)
+t = buf.cpu().numpy().reshape(4, 48, 8)
+t0 = t[3, 0, 6]
+print("weight image: copies issued (MMA thread):", rel(t[2,0,4]), " end:", rel(t[3,0,7]))
+for i in range(2):
+    print(f" tile {i}: builder start {rel(t[0,i,0])} empty-ok {rel(t[0,i,1])} built {rel(t[0,i,2])} | mma tm_empty-ok {rel(t[2,i,0])} issued {rel(t[2,i,2])} | epi acc-ready {rel(t[3,i,1])} stored {rel(t[3,i,2])}")
+
+# ---- stand-alone launch time (release build, CUDA events over 200 back-to-back launches; operands L2-resident)
+def timed(fn, n=200):
+    for _ in range(10): fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / n
+for M in (36864, 18432, 4608):
+    t_reg = timed(lambda: ops.node_gemm(pp(X), 256, pp(W), 260, 1, pp(C), 128, M, bias=pp(b)))
+    t_img = timed(lambda: ops.node_gemm(pp(X), 256, None, 0, 0, pp(C), 128, M, bias=pp(b), img0=imgs[0]))
+    print(f"back-to-back launches, M = {M}: register split {t_reg:.2f} us, weight image {t_img:.2f} us")
+
 # ---- dgrad + residual in place: W^T by strides, R1 = C
 def run_d():
     assert lib.mmpde_node_gemm(pp(X), 256, None, 0, pp(W), 1, 260, None, 0, 0, None, None, None, 0, pp(C), 128, None, 0, pp(C), 128, N, st) == 0

@@ -422,6 +422,32 @@ def test_tensor_core_interpolation_equals_direct_form(P, Q, unaligned):
         assert _rel(fl.grad[a:b], gp_ref[a:b]) < 1e-4, (a, b)
 
 
+@pytest.mark.parametrize("B,Hh,Ww", [(16, 48, 48), (2, 12, 12), (3, 50, 37), (1, 16, 16), (2, 5, 70)])
+def test_fused_res_cut_equals_conv_stack(B, Hh, Ww):
+    """csrc/rescut.cu (the four 5x5 convolutions + tanh of ItpNet 'res_cut' in one tile-resident launch per direction)
+    against the same nn.Sequential evaluated in fp64 on the CPU: output 1e-6, all eight parameter gradients 1e-5 relative
+    L2 -- grids smaller than a tile, not multiples of the tile, and the benchmark size."""
+    from mmpde_b200.interpolate import ItpNet
+    dev = _dev()
+    torch.manual_seed(B * 1000 + Hh)
+    net = ItpNet(Hh, Ww, [128, 64], [128, 64], [1, 4, 16, 4, 1])
+    ref = ItpNet(Hh, Ww, [128, 64], [128, 64], [1, 4, 16, 4, 1]).double()
+    ref.load_state_dict({k: v.double() for k, v in net.state_dict().items()})
+    net = net.to(dev)
+    x = torch.randn(B, 1, Hh, Ww)
+    r = torch.randn(B, 1, Hh, Ww)
+    out_ref = ref.down(x.double())
+    (out_ref * r.double()).sum().backward()
+    assert net._fused_res_cut(x.to(dev))
+    out = net(None, None, mode="res_cut", data=x.to(dev))
+    (out * r.to(dev)).sum().backward()
+    assert _rel(out, out_ref.float()) < 1e-6, _rel(out, out_ref.float())
+    for (n1, p1), (n2, p2) in zip(net.down.named_parameters(), ref.down.named_parameters()):
+        assert n1 == n2 and _rel(p1.grad, p2.grad.float()) < 1e-5, (n1, _rel(p1.grad, p2.grad.float()))
+    with torch.no_grad():                                       # inference: no activations saved, same output
+        assert torch.equal(net(None, None, mode="res_cut", data=x.to(dev)), out)
+
+
 # ------------------------------------------------------------------------------------------- tcgen05 edge kernels
 def _edge_inputs(sizes, seed, dev, k=35):
     c = _layer_case(sizes, seed, k)
@@ -549,6 +575,47 @@ def test_node_gemm_tensor_core(M, variant):
                    None, None, None, 0, ops._ptr(C), 128, ops._ptr(R2), 256, ops._ptr(C), 128, M, st)
     torch.cuda.synchronize()
     assert _rel(C, ref) < 2e-5, _rel(C, ref)
+
+
+@pytest.mark.parametrize("M", [1, 130, 5000, 36864])
+@pytest.mark.parametrize("variant", ["linear", "k256_ext_relu", "dgrad_transposed", "scaled"])
+def test_node_gemm_weight_images_bit_identical(M, variant):
+    """mmpde_node_gemm_img (weights as pre-split operand images: TMA bulk copy -> shared memory -> tcgen05.cp -> TMEM)
+    returns the same bits as mmpde_node_gemm (weights split in registers by every CTA), for row-major and transposed
+    weight reads, one and two K segments, the node-scalar extension, and an image scale."""
+    from mmpde_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(M + 31)
+    X = torch.randn(M, 256, generator=g).to(dev)
+    n4 = torch.randn(M, 4, generator=g).to(dev)
+    W = (torch.randn(128, 260, generator=g) / 13).to(dev)
+    b = torch.randn(128, generator=g).to(dev)
+    wext = torch.randn(128, 4, generator=g).to(dev)
+    R = torch.randn(M, 128, generator=g).to(dev)
+    p = ops._ptr
+    a, c = torch.full((M, 128), float("nan"), device=dev), torch.full((M, 128), float("nan"), device=dev)
+    if variant == "linear":
+        imgs, keep = ops.weight_images([(p(W), 260, 1)], dev)
+        ops.node_gemm(p(X), 256, p(W), 260, 1, p(a), 128, M, bias=p(b), relu=1)
+        ops.node_gemm(p(X), 256, None, 0, 0, p(c), 128, M, bias=p(b), relu=1, img0=imgs[0])
+    elif variant == "k256_ext_relu":
+        imgs, keep = ops.weight_images([(p(W), 260, 1), (p(W, 128), 260, 1)], dev)
+        kw = dict(A1=p(X, 128), lda1=256, ext=(p(n4), p(wext)), bias=p(b), relu=1, R1=p(R), ldr1=128)
+        ops.node_gemm(p(X), 256, p(W), 260, 1, p(a), 128, M, W1=p(W, 128), w1_ns=260, w1_ks=1, **kw)
+        ops.node_gemm(p(X), 256, None, 0, 0, p(c), 128, M, img0=imgs[0], img1=imgs[1], **kw)
+    elif variant == "dgrad_transposed":
+        imgs, keep = ops.weight_images([(p(W), 1, 260), (p(W, 128), 1, 260)], dev)
+        kw = dict(A1=p(X, 128), lda1=256, relu=2, R1=p(R), ldr1=128)
+        ops.node_gemm(p(X), 256, p(W), 1, 260, p(a), 128, M, W1=p(W, 128), w1_ns=1, w1_ks=260, **kw)
+        ops.node_gemm(p(X), 256, None, 0, 0, p(c), 128, M, img0=imgs[0], img1=imgs[1], **kw)
+    else:
+        W2 = (2.0 * W[:, :128]).contiguous()
+        imgs, keep = ops.weight_images([(p(W), 260, 1, 2.0)], dev)
+        ops.node_gemm(p(X), 256, p(W2), 128, 1, p(a), 128, M)
+        ops.node_gemm(p(X), 256, None, 0, 0, p(c), 128, M, img0=imgs[0])
+    torch.cuda.synchronize()
+    assert not bool(torch.isnan(c).any())
+    assert torch.equal(a, c), float((a - c).abs().max())
 
 
 @pytest.mark.parametrize("M", [1, 63, 64, 1000, 36864])

@@ -247,7 +247,28 @@ def test_dmm_golden_fixture(golden_dir):
     assert sorted(d_gr.state_dict().keys()) == g["keys_graph"]
     xi = g["pts"][None].repeat(2, 1, 1).reshape(-1, 2).to(dev)
     with torch.no_grad():
-        assert _rel(d_gr(g["u_graph"].to(dev), xi), g["phi_graph"]) < 1e-4
+        assert _rel(d_gr(g["u_graph"].to(dev), xi), g["phi_graph"]) < 1e-4       # graph branch = the fused layer kernel
+        d_gr.fused = False
+        assert _rel(d_gr(g["u_graph"].to(dev), xi), g["phi_graph"]) < 1e-4       # ... and as plain tensor ops
+
+
+def test_dmm_graph_branch_fused_layer_equals_tensor_ops():
+    """mmpde_dmm_gnn_layer (one pass over the edge list per layer) against the tensor-op form of the same layers at the
+    cylinder size (16 x 2521 nodes, 35 neighbours), default-initialised mover: latent code and displacement."""
+    from mmpde_b200 import synthetic
+    from mmpde_b200.mesh.dmm_model import DMM
+    dev = _dev()
+    cloud = synthetic.cylinder_cloud(2521, seed=0)
+    torch.manual_seed(5)
+    mover = DMM(mode="graph", grid=cloud.to(dev), branch_layer=[4, 3], trunk_layer=[2, 16, 512], out_layer=[1024, 512, 1]).to(dev).eval()
+    u = synthetic.cylinder_fields(16, cloud, 30, seed=3)[:, 7].to(dev)
+    xi = cloud.to(dev)[None].expand(16, -1, -1).reshape(-1, 2).contiguous()
+    with torch.no_grad():
+        lat_f, (dx_f, dy_f) = mover._latent(u), mover.displacement(u, xi)
+        mover.fused = False
+        lat_t, (dx_t, dy_t) = mover._latent(u), mover.displacement(u, xi)
+    assert _rel(lat_f, lat_t) < 1e-5, _rel(lat_f, lat_t)
+    assert _rel(dx_f, dx_t) < 1e-5 and _rel(dy_f, dy_t) < 1e-5
 
 
 def test_config1_full_size_properties():

@@ -30,6 +30,7 @@
 //   G1 = g_za [Q,128]   G2 = [g_zb | g_w | 0] [Q,128]   X1 = [p | 0 0 | hb] [Q,128]   X2 = ha [Q,128]
 // and the caller runs them as ONE grouped mmpde_node_wgrad_grouped launch (dWa = G1^T X1[:, :62], dWb = (G2^T X2)[:64],
 // dWc = (G2^T X1)[64:94, 64:], biases = column sums of G1 / G2).
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 namespace mmpde {
@@ -64,12 +65,48 @@ struct Smem {
     static constexpr uint32_t TOTAL = BAR + 64;
 };
 
+// Operand format of the three contractions.  The BACKWARD kernel splits into bf16 hi + lo (16 mantissa bits, fp32 range:
+// gradients may be 1e-10).  The FORWARD kernel splits into fp16 hi + lo: 22 mantissa bits at the same three products, i.e.
+// fp32-grade results (~3e-7 instead of ~7e-6) -- every operand there is a coordinate difference, a weight or a tanh
+// output, all far inside the fp16 range (below 6e-5 a half is subnormal: absolute error 3e-8, nothing to lose against
+// O(0.1) weights).  The moved-mesh values the forward produces are the INPUT of a solver, whose ReLU masks amplify a 1e-5
+// perturbation into 3e-4 of gradient noise (the g5 fixture's training_itp losses sit right behind two AdamW steps of it).
+template <bool F16>
 __device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo) {
-    uint2 h0, l0, h1, l1;
-    split4(make_float4(f[0], f[1], f[2], f[3]), h0, l0);
-    split4(make_float4(f[4], f[5], f[6], f[7]), h1, l1);
-    hi = make_uint4(h0.x, h0.y, h1.x, h1.y);
-    lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
+    if constexpr (!F16) {
+        uint2 h0, l0, h1, l1;
+        split4(make_float4(f[0], f[1], f[2], f[3]), h0, l0);
+        split4(make_float4(f[4], f[5], f[6], f[7]), h1, l1);
+        hi = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
+    } else {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const __half2 hh = __floats2half2_rn(f[2 * m], f[2 * m + 1]);          // .x = low half = first element
+            const float2 back = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(f[2 * m] - back.x, f[2 * m + 1] - back.y);
+            h[m] = *reinterpret_cast<const uint32_t*>(&hh);
+            l[m] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        hi = make_uint4(h[0], h[1], h[2], h[3]);
+        lo = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+// x - hi(x) - lo(x): what the two-term split of the chosen format leaves over
+template <bool F16>
+__device__ __forceinline__ float split_rest(float x) {
+    if constexpr (F16) {
+        const float r1 = x - __half2float(__float2half_rn(x));
+        return r1 - __half2float(__float2half_rn(r1));
+    } else {
+        const float r1 = x - __bfloat162float(__float2bfloat16_rn(x));
+        return r1 - __bfloat162float(__float2bfloat16_rn(r1));
+    }
+}
+// kind::f16 instruction descriptor with A and B as fp16 (format 0) instead of bf16 (format 1)
+__host__ __device__ constexpr uint32_t idesc_ab(bool f16, int M, int N, int a_mn, int b_mn) {
+    return f16 ? (idesc_bf16(M, N, a_mn, b_mn) & ~((1u << 7) | (1u << 10))) : idesc_bf16(M, N, a_mn, b_mn);
 }
 // byte offset of the 16-byte chunk c (8 bf16) of row r inside one 64-column block (rows of 128 bytes, SWIZZLE_128B)
 __device__ __forceinline__ uint32_t chunk_off(int r, int c) { return (uint32_t)r * 128u + (((uint32_t)c ^ ((uint32_t)r & 7u)) << 4); }
@@ -107,6 +144,7 @@ __global__ void __launch_bounds__(THREADS, 1) itp_tc_kernel(const __grid_constan
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r = (warp & 3) * 32 + lane, g = warp >> 2;
     constexpr uint32_t TCOLS = BWD ? 512 : 256;
+    constexpr bool F16 = !BWD;                                           // operand format of the forward contractions, see split8
 
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TCOLS);
     if (tid == 32) { mbar_init(mma_bar, 1); mbar_init(idx_bar, 1); fence_mbar_init(); }
@@ -123,7 +161,7 @@ __global__ void __launch_bounds__(THREADS, 1) itp_tc_kernel(const __grid_constan
         // one 16-byte chunk (8 consecutive k of one output row) per step: 8 values -> hi / lo -> two 128-bit stores
         auto put8 = [&](uint32_t img_hi, uint32_t img_lo, uint32_t off, const float (&v)[8]) {
             uint4 hi, lo;
-            split8(v, hi, lo);
+            split8<F16>(v, hi, lo);
             sts_v4(sbase + img_hi + off, hi);
             sts_v4(sbase + img_lo + off, lo);
         };
@@ -258,11 +296,9 @@ __global__ void __launch_bounds__(THREADS, 1) itp_tc_kernel(const __grid_constan
 #pragma unroll
             for (int j = 0; j < 8; ++j) { f[2 * j] = xy[j].x - qc.x; f[2 * j + 1] = xy[j].y - qc.y; vcur[j] = val[j]; }
             if (g == 3) {
-                const __nv_bfloat16 hx = __float2bfloat16_rn(qc.x), hy = __float2bfloat16_rn(qc.y);
-                const float r1x = qc.x - __bfloat162float(hx), r1y = qc.y - __bfloat162float(hy);
-                f[12] = qc.x; f[13] = qc.y;
-                f[14] = r1x - __bfloat162float(__float2bfloat16_rn(r1x));
-                f[15] = r1y - __bfloat162float(__float2bfloat16_rn(r1y));
+                f[12] = qc.x; f[13] = qc.y;                              // absolute coordinates: what hi + lo leave over rides
+                f[14] = split_rest<F16>(qc.x);                           // along as two more columns (weights: the same sums)
+                f[15] = split_rest<F16>(qc.y);
             }
             if (BWD && q_ok) {                                           // X1[:, 0:64] = p in the reference's own (absolute) form
                 float* x1 = p.X1 + q * 128 + 16 * g;
@@ -282,15 +318,15 @@ __global__ void __launch_bounds__(THREADS, 1) itp_tc_kernel(const __grid_constan
             uint4 hi, lo;
             const float (&f0)[8] = *reinterpret_cast<const float (*)[8]>(&f[0]);
             const float (&f1)[8] = *reinterpret_cast<const float (*)[8]>(&f[8]);
-            split8(f0, hi, lo);
+            split8<F16>(f0, hi, lo);
             sts_v4(sbase + S::AA + chunk_off(r, 2 * g), hi);
             sts_v4(sbase + S::AA + 16384 + chunk_off(r, 2 * g), lo);
-            split8(f1, hi, lo);
+            split8<F16>(f1, hi, lo);
             sts_v4(sbase + S::AA + chunk_off(r, 2 * g + 1), hi);
             sts_v4(sbase + S::AA + 16384 + chunk_off(r, 2 * g + 1), lo);
         }
         sync_all();                                                      // S1
-        if (tid == 0) mma3(0, S::AA, 16384, 0, S::WA, 16384, 0, 4, idesc_bf16(128, 128, 0, 0), false);
+        if (tid == 0) mma3(0, S::AA, 16384, 0, S::WA, 16384, 0, 4, idesc_ab(F16, 128, 128, 0, 0), false);
         if (t_prev >= 0 && g == 0 && p.out != nullptr) {                 // previous tile: the four partial sums of a query
             const float* pp = s_part + ((i - 1) & 1) * 512 + r;
             const int64_t qp = t_prev * TQ + r;
@@ -316,15 +352,15 @@ __global__ void __launch_bounds__(THREADS, 1) itp_tc_kernel(const __grid_constan
             const uint32_t blk = sbase + S::AB + (uint32_t)(g >> 1) * 16384u;
             const int c = 4 * (g & 1) + 2 * hf;
             uint4 hi, lo;
-            split8(*reinterpret_cast<const float (*)[8]>(&h[0]), hi, lo);
+            split8<F16>(*reinterpret_cast<const float (*)[8]>(&h[0]), hi, lo);
             sts_v4(blk + chunk_off(r, c), hi);
             sts_v4(blk + 32768 + chunk_off(r, c), lo);
-            split8(*reinterpret_cast<const float (*)[8]>(&h[8]), hi, lo);
+            split8<F16>(*reinterpret_cast<const float (*)[8]>(&h[8]), hi, lo);
             sts_v4(blk + chunk_off(r, c + 1), hi);
             sts_v4(blk + 32768 + chunk_off(r, c + 1), lo);
         }
         sync_all();                                                      // S2
-        if (tid == 0) mma3(128, S::AB, 32768, 16384, S::WB, 16384, 8192, 8, idesc_bf16(128, 64, 0, 0), false);
+        if (tid == 0) mma3(128, S::AB, 32768, 16384, S::WB, 16384, 8192, 8, idesc_ab(F16, 128, 64, 0, 0), false);
         fill_slot(t + 2 * G);                                            // every thread has read the slot (tile t + G) before S2
         wait_mma();
         // ---- hb = tanh(zb + bb): 16 channels per thread, written over the p'' tile
@@ -342,15 +378,15 @@ __global__ void __launch_bounds__(THREADS, 1) itp_tc_kernel(const __grid_constan
                 for (int m = 0; m < 4; ++m) stg4(x1 + 4 * m, h[4 * m], h[4 * m + 1], h[4 * m + 2], h[4 * m + 3]);
             }
             uint4 hi, lo;
-            split8(*reinterpret_cast<const float (*)[8]>(&h[0]), hi, lo);
+            split8<F16>(*reinterpret_cast<const float (*)[8]>(&h[0]), hi, lo);
             sts_v4(sbase + S::AA + chunk_off(r, 2 * g), hi);
             sts_v4(sbase + S::AA + 16384 + chunk_off(r, 2 * g), lo);
-            split8(*reinterpret_cast<const float (*)[8]>(&h[8]), hi, lo);
+            split8<F16>(*reinterpret_cast<const float (*)[8]>(&h[8]), hi, lo);
             sts_v4(sbase + S::AA + chunk_off(r, 2 * g + 1), hi);
             sts_v4(sbase + S::AA + 16384 + chunk_off(r, 2 * g + 1), lo);
         }
         sync_all();                                                      // S3
-        if (tid == 0) mma3(192, S::AA, 16384, 0, S::WC, 4096, 0, 4, idesc_bf16(128, 32, 0, 0), false);
+        if (tid == 0) mma3(192, S::AA, 16384, 0, S::WC, 4096, 0, 4, idesc_ab(F16, 128, 32, 0, 0), false);
         wait_mma();
         // ---- interpolation weights of this thread's 8 neighbours and their share of the weighted sum
         {
@@ -380,7 +416,7 @@ __global__ void __launch_bounds__(THREADS, 1) itp_tc_kernel(const __grid_constan
                     stg4(g2 + 100 + 8 * g, 0.f, 0.f, 0.f, 0.f);
                 }
                 uint4 hi, lo;
-                split8(gw, hi, lo);
+                split8<false>(gw, hi, lo);
                 sts_v4(sbase + S::GW + chunk_off(r, g), hi);
                 sts_v4(sbase + S::GW + 16384 + chunk_off(r, g), lo);
             }
@@ -407,10 +443,10 @@ __global__ void __launch_bounds__(THREADS, 1) itp_tc_kernel(const __grid_constan
                     for (int m = 0; m < 4; ++m) stg4(g2 + 4 * m, gz[4 * m], gz[4 * m + 1], gz[4 * m + 2], gz[4 * m + 3]);
                 }
                 uint4 hi, lo;                                            // the g_w tile has been consumed: g_zb takes its place
-                split8(*reinterpret_cast<const float (*)[8]>(&gz[0]), hi, lo);
+                split8<false>(*reinterpret_cast<const float (*)[8]>(&gz[0]), hi, lo);
                 sts_v4(sbase + S::GW + chunk_off(r, 2 * g), hi);
                 sts_v4(sbase + S::GW + 16384 + chunk_off(r, 2 * g), lo);
-                split8(*reinterpret_cast<const float (*)[8]>(&gz[8]), hi, lo);
+                split8<false>(*reinterpret_cast<const float (*)[8]>(&gz[8]), hi, lo);
                 sts_v4(sbase + S::GW + chunk_off(r, 2 * g + 1), hi);
                 sts_v4(sbase + S::GW + 16384 + chunk_off(r, 2 * g + 1), lo);
             }

@@ -324,6 +324,10 @@ int mmpde_rows_gather(const float* src, int64_t ld_src, const int32_t* idx, int6
 int mmpde_rows_scatter_add(const float* in, const int32_t* idx, int64_t n_rows, int ncols,
                            float* dst, int64_t ld_dst, void* stream);
 
+/* out[m][n] = bias[n] + sum_f node4[m][f] W[n][f], n < 128, f < 4: the encoder's input layer nn.Linear(4,128)
+ * (gnn_2d.py:100) as an elementwise pass.  node4 [M,4], W [128,4], bias [128] or NULL, out [M, ldo >= 128]; 16-byte aligned. */
+int mmpde_node4_linear(const float* node4, const float* W, const float* bias, float* out, int64_t ldo, int64_t n_rows,
+                       void* stream);
 /* out[m*out_stride] (+)= sum_c A[m][c] * w[c]  (c < ncols, multiple of 4): the N = 1 contractions of the backward,
  * e.g. dL/du = dP'.W1c[:,0] - dQ'.W1c[:,0] of gnn_2d.py:61 (autograd) as ONE pass over dPQ [M,256]. */
 int mmpde_rows_dot(const float* A, int64_t lda, int ncols, const float* w, float* out, int64_t out_stride,

@@ -308,21 +308,18 @@ struct WImgGroup { WImgTask t[IMG_MAX_TASKS]; };
 
 __global__ void __launch_bounds__(256) weight_images_kernel(const __grid_constant__ WImgGroup grp) {
     const WImgTask& T = grp.t[blockIdx.x];
-    const int n0 = blockIdx.y * 32;
+    const int n0 = blockIdx.y * 8;                                         // 8 rows x 32 groups of 4 consecutive k per CTA
     const bool k_fast = T.ks == 1;                                         // lanes along the contiguous axis of W
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int g = it * 256 + (int)threadIdx.x;                        // 32 rows x 32 groups of 4 consecutive k
-        const int n = n0 + (k_fast ? (g >> 5) : (g & 31));
-        const int k = 4 * (k_fast ? (g & 31) : (g >> 5));
-        const float* q = T.W + (int64_t)n * T.ns + (int64_t)k * T.ks;
-        const float4 v = make_float4(__ldg(q) * T.scale, __ldg(q + T.ks) * T.scale, __ldg(q + 2 * T.ks) * T.scale, __ldg(q + 3 * T.ks) * T.scale);
-        uint2 hi, lo;
-        split4(v, hi, lo);
-        unsigned char* dst = T.img + tile_off<128>(n, k);
-        *reinterpret_cast<uint2*>(dst) = hi;
-        *reinterpret_cast<uint2*>(dst + G_IMG) = lo;
-    }
+    const int g = (int)threadIdx.x;
+    const int n = k_fast ? n0 + (g >> 5) : (n0 & ~31) + (g & 31);
+    const int k = 4 * (k_fast ? (g & 31) : ((n0 & 31) + (g >> 5)));
+    const float* q = T.W + (int64_t)n * T.ns + (int64_t)k * T.ks;
+    const float4 v = make_float4(__ldg(q) * T.scale, __ldg(q + T.ks) * T.scale, __ldg(q + 2 * T.ks) * T.scale, __ldg(q + 3 * T.ks) * T.scale);
+    uint2 hi, lo;
+    split4(v, hi, lo);
+    unsigned char* dst = T.img + tile_off<128>(n, k);
+    *reinterpret_cast<uint2*>(dst) = hi;
+    *reinterpret_cast<uint2*>(dst + G_IMG) = lo;
 }
 
 // ================================================================================================================
@@ -561,7 +558,7 @@ extern "C" int mmpde_weight_images(const mmpde_wimg_task* tasks, int n_tasks, vo
             g.t[k].W = t.W; g.t[k].ns = t.w_ns; g.t[k].ks = t.w_ks; g.t[k].img = static_cast<unsigned char*>(t.image); g.t[k].scale = t.scale;
         }
         for (int k = n; k < IMG_MAX_TASKS; ++k) g.t[k] = g.t[0];
-        weight_images_kernel<<<dim3(n, 4), 256, 0, (cudaStream_t)stream>>>(g);
+        weight_images_kernel<<<dim3(n, 16), 256, 0, (cudaStream_t)stream>>>(g);
         MMPDE_CHECK_LAUNCH();
     }
     return MMPDE_OK;

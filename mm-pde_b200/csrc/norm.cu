@@ -19,19 +19,27 @@ __device__ __forceinline__ float4 load_y(const float* A, int64_t lda, const floa
     return y;
 }
 
-// block-level reduction of per-thread float4 partials (8 row groups x 32 lanes) into fp64 atomics on dst[0..127]
-__device__ __forceinline__ void block_reduce_to_double(float4 v, double* dst) {
-    __shared__ float4 red[8][32];
+// Column sums are accumulated in fp64 FROM THE FIRST ADD (per thread, then per CTA, then atomically): the value of a sum of
+// a few 10^4 fp32 terms then carries an error of ~1e-19 of its scale, far below half an ulp of the fp32 mean / rstd derived
+// from it -- so the statistics, and with them every activation and every ReLU mask of the forward, are the SAME BITS however
+// the rows are grouped: whole graph or partitioned, one rank or sharded over eight.  (With fp32 partial sums per CTA the
+// grouping moved mean / rstd by an ulp, and the few ReLU masks that flipped showed up as 1e-3 of gradient difference.)
+// block-level reduction of per-thread partials (8 row groups x 32 lanes x 4 channels) into fp64 atomics on dst[0..127]
+__device__ __forceinline__ void block_reduce_to_double(const double (&v)[4], double* dst) {
+    __shared__ double red[8][32][4];
     const int c4 = threadIdx.x & 31, rg = threadIdx.x >> 5;
     __syncthreads();
-    red[rg][c4] = v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[rg][c4][j] = v[j];
     __syncthreads();
     if (rg == 0) {
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        double s[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int g = 0; g < 8; ++g) { float4 t = red[g][c4]; s0 += t.x; s1 += t.y; s2 += t.z; s3 += t.w; }
-        atomicAdd(dst + c4 * 4 + 0, s0); atomicAdd(dst + c4 * 4 + 1, s1);
-        atomicAdd(dst + c4 * 4 + 2, s2); atomicAdd(dst + c4 * 4 + 3, s3);
+        for (int g = 0; g < 8; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[j] += red[g][c4][j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(dst + c4 * 4 + j, s[j]);
     }
 }
 
@@ -94,11 +102,12 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
     // replica blockIdx % MMPDE_BN_REPLICAS: same-address atomics serialise in L2 (~30-50 ns each when every CTA
     // arrives at once), so the time of the tail is the number of CTAs per replica (profiles/r01_norm_bench.txt)
     sums += (blockIdx.x % MMPDE_BN_REPLICAS) * 256;
-    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
     for (int64_t base = (int64_t)blockIdx.x * ROWS_PER_CTA; base < M; base += (int64_t)gridDim.x * ROWS_PER_CTA) {
         auto acc = [&](float4 y) {
-            s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
-            q.x = fmaf(y.x, y.x, q.x); q.y = fmaf(y.y, y.y, q.y); q.z = fmaf(y.z, y.z, q.z); q.w = fmaf(y.w, y.w, q.w);
+            const double v[4] = {(double)y.x, (double)y.y, (double)y.z, (double)y.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s[j] += v[j]; q[j] = fma(v[j], v[j], q[j]); }      // y*y is exact in fp64
         };
         if (base + ROWS_PER_CTA <= M) {                 // full block: all loads of the warp's rows in flight at once
             float4 y[ROWS_PER_WARP];
@@ -180,13 +189,15 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     const int c4 = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const double* sums_all = bsums;
     float4 mu = ldg4(mean_rstd + c4 * 4), rs = ldg4(mean_rstd + 128 + c4 * 4);
-    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
     bsums += (blockIdx.x % MMPDE_BN_REPLICAS) * 256;
     for (int64_t base = (int64_t)blockIdx.x * ROWS_PER_CTA; base < M; base += (int64_t)gridDim.x * ROWS_PER_CTA) {
         auto acc = [&](float4 gv, float4 y) {
-            s.x += gv.x; s.y += gv.y; s.z += gv.z; s.w += gv.w;
-            q.x = fmaf(gv.x, (y.x - mu.x) * rs.x, q.x); q.y = fmaf(gv.y, (y.y - mu.y) * rs.y, q.y);
-            q.z = fmaf(gv.z, (y.z - mu.z) * rs.z, q.z); q.w = fmaf(gv.w, (y.w - mu.w) * rs.w, q.w);
+            const double g4[4] = {(double)gv.x, (double)gv.y, (double)gv.z, (double)gv.w};
+            const double xh[4] = {(double)((y.x - mu.x) * rs.x), (double)((y.y - mu.y) * rs.y), (double)((y.z - mu.z) * rs.z),
+                                  (double)((y.w - mu.w) * rs.w)};                      // x-hat as the apply pass computes it (fp32)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s[j] += g4[j]; q[j] = fma(g4[j], xh[j], q[j]); }
         };
         if (base + ROWS_PER_CTA <= M) {
 #pragma unroll

@@ -15,7 +15,7 @@ namespace rescut {
 
 constexpr int C0 = 1, C1 = 4, C2 = 16, C3 = 4, C4 = 1;
 constexpr int T = 16;                                       // tile edge
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;                              // 125 registers per thread: 512 x 128 = the whole register file
 constexpr int NW1 = C1 * C0 * 25, NW2 = C2 * C1 * 25, NW3 = C3 * C2 * 25, NW4 = C4 * C3 * 25;
 constexpr int NPARAM = NW1 + C1 + NW2 + C2 + NW3 + C3 + NW4 + C4;       // 3425 = MMPDE_RESCUT_NPARAM
 constexpr int O_W1 = 0, O_B1 = NW1, O_W2 = O_B1 + C1, O_B2 = O_W2 + NW2, O_W3 = O_B2 + C2, O_B3 = O_W3 + NW3,

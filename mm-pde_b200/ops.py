@@ -740,7 +740,7 @@ def _solver_forward(parts, L, training, scale, bn_buffers, params, exch, st, wan
     e1s, e1ns, e2s = [], [], []
     for part in parts:
         e1 = torch.empty(part.n_own, H, **f32)
-        gemm(_ptr(part.node4), 4, 1, _ptr(We1), 4, 1, _ptr(e1), H, part.n_own, H, 4, bias=_ptr(be1), st=st)
+        _cabi.call("mmpde_node4_linear", _ptr(part.node4), _ptr(We1), _ptr(be1), _ptr(e1), H, part.n_own, st)
         e1s.append(e1)
         e1ns.append(torch.empty(part.n_own, H, **f32))
     bn1 = _bn_forward([(_ptr(e1), H, None, 0, part.n_own, _ptr(e1n), H) for part, e1, e1n in zip(parts, e1s, e1ns)],
@@ -806,10 +806,11 @@ def _solver_backward(sv, g_outs, need_u, st):
     dg1, db1_ = _bn_backward([(_ptr(g_e1n), H, _ptr(e1n), H, _ptr(e1), H, None, 0, part.n_own, _ptr(g_e1), H)
                               for part, g_e1n, e1n, e1, g_e1 in zip(parts, g_e1ns, e1ns, e1s, g_e1s)], 1, bn1, g1, st,
                              spread=spread_all[0])
+    we1_u = We1[:, 0].contiguous() if need_u else None
     for idx, (part, g_e1) in enumerate(zip(parts, g_e1s)):
         node_wgrad(_ptr(g_e1), H, part.n_own, Bext=_ptr(part.node4), dWext=_ptr(dWe1), dbias=_ptr(dbe1), st=st)
         if need_u:      # only the u column: positions/time feed the frozen mesh mover only
-            gemm(_ptr(g_e1), H, 1, _ptr(We1), 4, 0, _ptr(g_node4s[idx]), 4, part.n_own, 1, H, acc=1, st=st)
+            _cabi.call("mmpde_rows_dot", _ptr(g_e1), H, H, _ptr(we1_u), _ptr(g_node4s[idx]), 4, part.n_own, 1, st)
     grads[:N_ENC] = [dWe1, dbe1, dg1, db1_, dWe2, dbe2, dg2, db2_]
     # BatchNorm parameter gradients come back as fp64 views: convert all of them with two launches
     bn_idx = [2, 3, 6, 7] + [N_ENC + N_LAYER * l + k for l in range(L) for k in (8, 9)]

@@ -135,8 +135,11 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MAX)
     out["max_over_ranks"] = {"loss_rel": float(flag[0]), "pred_rel": float(flag[1]), "grad_rel": float(flag[2]),
                              "bn_rel": float(flag[3]), "grad_rel_all": float(flag[4])}
-    ok = (float(flag[0]) < 1e-5 and float(flag[1]) < 1e-5 and float(flag[2]) < 5e-4 and float(flag[3]) < 1e-5
-          and float(flag[4]) < 1e-4)
+    # With the BatchNorm sums accumulated in fp64 from the first add the sharded forward is bit-identical to the global batch
+    # (measured at 2 ranks: loss 0, predictions 8e-8, whole gradient 2.5e-7, worst single tensor -- a bias -- 5e-5): what is
+    # left is the order of the fp32 atomics in the backward.
+    ok = (float(flag[0]) < 2e-6 and float(flag[1]) < 2e-6 and float(flag[2]) < 2e-4 and float(flag[3]) < 1e-6
+          and float(flag[4]) < 1e-5)
     dist.barrier()
     if rank == 0:
         print(("SHARDED_STEP_OK " if ok else "SHARDED_STEP_FAIL ") + json.dumps(out), flush=True)

@@ -27,7 +27,7 @@ class Guarded:
         n = int(np.prod(shape))
         self.dtype = dtype
         self.buf = torch.empty(n + 2 * GUARD, dtype=dtype, device=dev or _dev())
-        self.pattern = PATTERN if dtype.is_floating_point else -1234567
+        self.pattern = PATTERN if dtype.is_floating_point else (0xA5 if dtype == torch.uint8 else -1234567)
         self.buf.fill_(self.pattern)
         self.t = self.buf[GUARD:GUARD + n].view(*shape)
         if fill is not None:

@@ -422,6 +422,26 @@ def test_tensor_core_interpolation_equals_direct_form(P, Q, unaligned):
         assert _rel(fl.grad[a:b], gp_ref[a:b]) < 1e-4, (a, b)
 
 
+@pytest.mark.parametrize("M", [1, 5, 1000, 36864])
+def test_node4_linear_and_rows_dot(M):
+    """mmpde_node4_linear (the encoder's K = 4 input layer as an elementwise pass) and mmpde_rows_dot (N = 1 contractions,
+    four rows per warp pass: row counts that are no multiple of four) against fp64."""
+    from mmpde_b200 import ops, _cabi
+    dev = _dev()
+    g = torch.Generator().manual_seed(M)
+    n4, W, b = torch.randn(M, 4, generator=g).to(dev), torch.randn(128, 4, generator=g).to(dev), torch.randn(128, generator=g).to(dev)
+    out = torch.full((M, 136), float("nan"), device=dev)
+    _cabi.call("mmpde_node4_linear", ops._ptr(n4), ops._ptr(W), ops._ptr(b), ops._ptr(out, 4), 136, M, ops._stream())
+    assert _rel(out[:, 4:132], n4.double() @ W.double().t() + b.double()) < 1e-6
+    assert bool(torch.isnan(out[:, :4]).all()) and bool(torch.isnan(out[:, 132:]).all())
+    A, w = torch.randn(M, 256, generator=g).to(dev), torch.randn(256, generator=g).to(dev)
+    acc = torch.randn(M, 4, generator=g).to(dev)
+    want = acc.clone()
+    want[:, 0] += (A.double() @ w.double()).float()
+    _cabi.call("mmpde_rows_dot", ops._ptr(A), 256, 256, ops._ptr(w), ops._ptr(acc), 4, M, 1, ops._stream())
+    assert _rel(acc[:, 0], want[:, 0]) < 1e-5 and torch.equal(acc[:, 1:], want[:, 1:])
+
+
 @pytest.mark.parametrize("B,Hh,Ww", [(16, 48, 48), (2, 12, 12), (3, 50, 37), (1, 16, 16), (2, 5, 70)])
 def test_fused_res_cut_equals_conv_stack(B, Hh, Ww):
     """csrc/rescut.cu (the four 5x5 convolutions + tanh of ItpNet 'res_cut' in one tile-resident launch per direction)

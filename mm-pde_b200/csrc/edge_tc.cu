@@ -742,11 +742,11 @@ extern "C" int mmpde_edge_bwd(const float* PQ, const int32_t* edge_src, const in
                               int64_t ld_gagg, float* dPQ, float* dW2, float* db2, void* stream) {
     if (n_edges < 0 || ld_gagg < 128) return MMPDE_EINVAL;
     if (n_edges == 0) return MMPDE_OK;
-    constexpr size_t smem = BwdSmem::TOTAL + 1024;
-    MMPDE_ENSURE_SMEM(edge_bwd_tc_kernel, smem);
     EdgeBwdArgs p;
     p.PQ = PQ; p.src = edge_src; p.dst = edge_dst; p.inv_deg = inv_deg; p.n_edges = n_edges; p.w2 = w2; p.mask2 = mask2;
     p.g_agg = g_agg; p.ld_gagg = ld_gagg; p.dPQ = dPQ; p.dW2 = dW2; p.db2 = db2;
+    constexpr size_t smem = BwdSmem::TOTAL + 1024;
+    MMPDE_ENSURE_SMEM(edge_bwd_tc_kernel, smem);
     edge_bwd_tc_kernel<<<edge_grid((n_edges + BTE - 1) / BTE), EDGE_THREADS, smem, (cudaStream_t)stream>>>(p);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;

@@ -72,6 +72,23 @@ int main() {
                             (double)G * W * per_warp * 512 / (ms * 1e-4) / 1e9);
         }
     }
+    // SM-side issue rate: 16 CTAs only (the L2 is then far from its limit), 4 / 8 warps per CTA, same rows per warp
+    printf("SM-side rate, 16 CTAs: clocks per warp instruction per SM (1.9 GHz assumed)\n");
+    for (int warps = 4; warps <= 8; warps *= 2)
+        for (int mode = 0; mode < 2; ++mode) {
+            const int rpw = 2048;
+            float ms = 0.f;
+            for (int rep = 0; rep < 2; ++rep) {
+                cudaEventRecord(e0);
+                if (mode == 0) k_red<0><<<16, warps * 32>>>(d_out, d_rows, rpw);
+                else k_red<1><<<16, warps * 32>>>(d_out, d_rows, rpw);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                cudaEventElapsedTime(&ms, e0, e1);
+            }
+            const double instr = (double)warps * rpw * (mode == 0 ? 1 : 4);
+            printf("  %2d warps  %-8s %8.1f us   %6.1f clk / warp-RED / SM   %6.1f clk per 512-byte row / SM\n", warps, mode == 0 ? "red.v4" : "red.f32",
+                   ms * 1e3, ms * 1e-3 * 1.9e9 / instr, ms * 1e-3 * 1.9e9 / ((double)warps * rpw));
+        }
     cudaError_t err = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(err));
     return err != cudaSuccess;

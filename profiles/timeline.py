@@ -15,7 +15,7 @@ TL_ITERS = 48
 
 
 def main():
-    lib = ctypes.CDLL(os.path.join(ROOT, "mm-pde_b200", "libmmpde_b200_tl.so"))
+    lib = ctypes.CDLL(os.environ.get("MMPDE_TL_LIB", os.path.join(ROOT, "mm-pde_b200", "libmmpde_b200_tl.so")))
     P, L = ctypes.c_void_p, ctypes.c_int64
     lib.mmpde_edge_fwd.argtypes = [P, P, P, P, L, P, P, P, L, P, P]
     lib.mmpde_edge_bwd.argtypes = [P, P, P, P, L, P, P, P, L, P, P, P, P]
@@ -53,6 +53,10 @@ def main():
                            1: ["step start", "hg_empty ok", "built+arrive", "st_full ok", "rows done"],
                            2: ["hg_full ok", "d1_empty ok", "MMA-A issued", "MMA-B issued"],
                            3: ["d1_full ok", "st_empty ok", "ld done", "stage written"]})}
+    if os.environ.get("MMPDE_EDGE_BWD") == "2":       # scatter in the epilogue: no staging tile, no row phase
+        names["bwd"] = (bwd, {0: ["step start", "hg_empty ok", "built+arrive"], 1: ["step start", "hg_empty ok", "built+arrive"],
+                              2: ["hg_full ok", "d1_empty ok", "MMA-A issued", "MMA-B issued"],
+                              3: ["d1_full ok", "scatter done", "tile start", "d1 released"]})
     roles = ["builder w0", "builder w7", "MMA thread", "epilogue w0"]
     for kname, (fn, slots) in names.items():
         for _ in range(3):

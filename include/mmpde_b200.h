@@ -288,6 +288,16 @@ int mmpde_rescut_bwd(const float* x, int64_t batch, int height, int width, const
 int mmpde_dmm_gnn_layer(const float* x, const float* upos, const int32_t* row_ptr, const int32_t* edge_src,
                         int64_t n_nodes, const float* weights, float* out, void* stream);
 
+/* ---- DMM mesh mover: displacement grad_xi phi(u, xi) (data_creator_2d.py:98-113, two autograd.grad calls through
+ * mesh/dmm_model.py:145-219) as one forward-mode pass over the points, for the two-layer tanh trunk / out_nn:
+ *   a = tanh(W1 xi + b1);  z = cst[n / per_sample] + M a;  h = tanh(z);
+ *   out[n][d] = sum_j (1 - h_j^2) w_j sum_k (1 - a_k^2) W1[k][d] M[j][k],   d = 0, 1.
+ * xi, out [N,2]; W1 [K,2], b1 [K] (trunk.layers[0], K <= 32); M [J,K] = Wt W2 (out_nn.layers[0][:, latent:] times
+ * trunk.layers[1].weight); cst [samples,J] = Wl latent + Wt b2 + bo; w [J] = out_nn.layers[1].weight; J % 4 == 0, J <= 1024.
+ * All pointers are device pointers. */
+int mmpde_dmm_displacement(const float* xi, const float* W1, const float* b1, int K, const float* M, const float* cst,
+                           const float* w, int J, int64_t n_points, int64_t per_sample, float* out, void* stream);
+
 /* ---- fused k-NN interpolation (data_creator_2d.py:77-83 + interpolate.py:79-93) ----------------
  * For query q of sample s: p = (x_1,y_1,...,x_30,y_30,x_q,y_q) from idx[q,0..29];
  * w = Wc*tanh(Wb*tanh(Wa*p+ba)+bb)+bc;  out[q] = sum_k w_k * src_val[idx[q,k]].

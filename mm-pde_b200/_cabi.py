@@ -70,6 +70,7 @@ SIGNATURES = {
     "mmpde_rescut_fwd": [_p, _l, _i, _i, _p, _p, _p, _p],
     "mmpde_rescut_bwd": [_p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "mmpde_dmm_gnn_layer": [_p, _p, _p, _p, _l, _p, _p, _p],
+    "mmpde_dmm_displacement": [_p, _p, _p, _i, _p, _p, _p, _i, _l, _l, _p, _p],
     "mmpde_rows_gather": [_p, _l, _p, _l, _i, _p, _p],
     "mmpde_rows_scatter_add": [_p, _p, _l, _i, _p, _l, _p],
     "mmpde_node4_linear": [_p, _p, _p, _p, _l, _l, _p],

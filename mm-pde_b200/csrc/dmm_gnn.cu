@@ -63,6 +63,74 @@ __global__ void __launch_bounds__(256) dmm_gnn_layer_kernel(const float4* __rest
     out[i] = make_float4(xi.x + r[0], xi.y + r[1], xi.z + r[2], xi.w + r[3]);
 }
 
+
+// ================================================================================================================
+// Mesh displacement grad_xi phi(u, xi) of the DMM mover (the reference: two autograd.grad(create_graph=True) calls,
+// /root/reference/data_creator_2d.py:106-107) as ONE pass -- forward-mode Jacobian of the two-layer tanh trunk and the
+// two-layer tanh out_nn (mesh/dmm_model.py:145-219 of the reference; formulas in DMM.displacement):
+//     a   = tanh(W1 xi + b1)                       [K <= 32]
+//     z_j = cst[sample][j] + sum_k a_k M[j][k]     [J],   h = tanh(z),  gate_j = (1 - h_j^2) w_j
+//     out[n][d] = sum_j gate_j * sum_k (1 - a_k^2) W1[k][d] M[j][k]
+// In tensor ops this is a [3N,32] x [32,512] fp32 product on the CUDA cores plus eight [N,512] elementwise / reduction
+// passes (~430 us of the moved-mesh branch's critical path at N = 36 864); here the [N,512] intermediates never exist.
+// Eight points per warp, four lanes per point (lane = quarter * 8 + point): every 8-lane phase of a 128-bit shared-memory
+// load reads ONE row of M (broadcast, conflict-free); the four quarters of j are summed with two shuffles.
+// ================================================================================================================
+constexpr int DISP_K = 32;                                               // trunk width, zero-padded
+__global__ void __launch_bounds__(256) dmm_displacement_kernel(const float2* __restrict__ xi, const float* __restrict__ W1,
+                                                                const float* __restrict__ b1, int K, const float* __restrict__ M,
+                                                                const float* __restrict__ cst, const float* __restrict__ w, int J,
+                                                                int64_t N, int64_t per_sample, float2* __restrict__ out) {
+    extern __shared__ float s_m[];                                       // M [J][32] (zero-padded rows) | w [J]
+    float* s_w = s_m + (size_t)J * DISP_K;
+    for (int i = threadIdx.x; i < J * DISP_K; i += blockDim.x) {
+        const int j = i / DISP_K, k = i % DISP_K;
+        s_m[i] = (k < K) ? __ldg(M + (size_t)j * K + k) : 0.f;
+    }
+    for (int j = threadIdx.x; j < J; j += blockDim.x) s_w[j] = __ldg(w + j);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, pt = lane & 7, quarter = lane >> 3;
+    const int jq = J / 4;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t base = warp0 * 8; base < N; base += n_warps * 8) {
+        const int64_t n = base + pt;
+        const bool live = n < N;
+        const float2 x = live ? __ldg(xi + n) : make_float2(0.f, 0.f);
+        const float* c_row = cst + (live ? n / per_sample : 0) * J;
+        float a[DISP_K], u[DISP_K], v[DISP_K];
+#pragma unroll
+        for (int k = 0; k < DISP_K; ++k) {
+            float wx = 0.f, wy = 0.f, bb = 0.f;
+            if (k < K) { wx = __ldg(W1 + 2 * k); wy = __ldg(W1 + 2 * k + 1); bb = __ldg(b1 + k); }
+            a[k] = tanhf(fmaf(wx, x.x, fmaf(wy, x.y, bb)));
+            const float da = 1.f - a[k] * a[k];
+            u[k] = da * wx; v[k] = da * wy;
+        }
+        float acc1 = 0.f, acc2 = 0.f;
+#pragma unroll 2
+        for (int jj = 0; jj < jq; ++jj) {
+            const int j = quarter * jq + jj;
+            const float4* row = reinterpret_cast<const float4*>(s_m + (size_t)j * DISP_K);
+            float z = __ldg(c_row + j), s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < DISP_K / 4; ++q) {
+                const float4 m = row[q];
+                z = fmaf(a[4 * q], m.x, z); z = fmaf(a[4 * q + 1], m.y, z); z = fmaf(a[4 * q + 2], m.z, z); z = fmaf(a[4 * q + 3], m.w, z);
+                s1 = fmaf(u[4 * q], m.x, s1); s1 = fmaf(u[4 * q + 1], m.y, s1); s1 = fmaf(u[4 * q + 2], m.z, s1); s1 = fmaf(u[4 * q + 3], m.w, s1);
+                s2 = fmaf(v[4 * q], m.x, s2); s2 = fmaf(v[4 * q + 1], m.y, s2); s2 = fmaf(v[4 * q + 2], m.z, s2); s2 = fmaf(v[4 * q + 3], m.w, s2);
+            }
+            const float h = tanhf(z);
+            const float gate = (1.f - h * h) * s_w[j];
+            acc1 = fmaf(gate, s1, acc1);
+            acc2 = fmaf(gate, s2, acc2);
+        }
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 8);  acc2 += __shfl_xor_sync(0xffffffffu, acc2, 8);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 16); acc2 += __shfl_xor_sync(0xffffffffu, acc2, 16);
+        if (live && quarter == 0) out[n] = make_float2(acc1, acc2);
+    }
+}
+
 }  // namespace mmpde
 
 using namespace mmpde;
@@ -77,6 +145,22 @@ extern "C" int mmpde_dmm_gnn_layer(const float* x, const float* upos, const int3
     dmm_gnn_layer_kernel<<<(unsigned)((n_nodes + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(upos), row_ptr, edge_src, n_nodes, weights,
         reinterpret_cast<float4*>(out));
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_dmm_displacement(const float* xi, const float* W1, const float* b1, int K, const float* M, const float* cst,
+                                      const float* w, int J, int64_t n_points, int64_t per_sample, float* out, void* stream) {
+    if (n_points < 0 || per_sample <= 0 || K < 1 || K > DISP_K || J < 4 || J % 4 || J > 1024 || !xi || !W1 || !b1 || !M || !cst || !w || !out)
+        return MMPDE_EINVAL;
+    if (n_points == 0) return MMPDE_OK;
+    if ((reinterpret_cast<uintptr_t>(xi) | reinterpret_cast<uintptr_t>(out)) & 7) return MMPDE_EINVAL;
+    const size_t smem = ((size_t)J * DISP_K + J) * sizeof(float);
+    MMPDE_ENSURE_SMEM(dmm_displacement_kernel, 1024 * (DISP_K + 1) * sizeof(float));
+    const int64_t warps = (n_points + 7) / 8;
+    const int grid = (int)imin64((warps + 7) / 8, sm_count());     // 158 registers x 256 threads: one CTA per SM, M staged once
+    dmm_displacement_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(xi), W1, b1, K, M, cst, w, J,
+                                                                       n_points, per_sample, reinterpret_cast<float2*>(out));
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }

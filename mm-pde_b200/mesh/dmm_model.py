@@ -181,6 +181,18 @@ class DMM(nn.Module):
         latent = self._latent(u).reshape(u.shape[0], -1)                        # [B, n_lat]
         const = latent @ Wl.t() + (Wt @ t2.bias + o1.bias)                      # [B, 512]
         M = Wt @ t2.weight                                                      # [512, 32]
+        K, J = t1.weight.shape[0], M.shape[0]
+        if self.fused and grid.is_cuda and K <= 32 and J % 4 == 0 and J <= 1024 and grid.dtype == torch.float32:
+            # one pass over the points (csrc/dmm_gnn.cu): the [3N,32] x [32,512] product and the [N,512] intermediates of
+            # the tensor-op form below never exist
+            from .. import _cabi
+            xi = grid.contiguous()
+            out = torch.empty(xi.shape[0], 2, dtype=torch.float32, device=xi.device)
+            with ops._on(xi):
+                _cabi.call("mmpde_dmm_displacement", ops._ptr(xi), ops._ptr(t1.weight.contiguous()), ops._ptr(t1.bias), K,
+                           ops._ptr(M.contiguous()), ops._ptr(const.contiguous()), ops._ptr(o2.weight.reshape(-1).contiguous()), J,
+                           xi.shape[0], per_sample, ops._ptr(out), ops._stream())
+            return out[:, 0:1], out[:, 1:2]
         a = torch.tanh(grid @ t1.weight.t() + t1.bias)                          # [N, 32]
         da = 1.0 - a * a
         stacked = torch.cat((a, da * t1.weight[:, 0], da * t1.weight[:, 1])) @ M.t()     # [3N, 512]

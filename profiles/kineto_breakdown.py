@@ -1,7 +1,7 @@
 """GPU-time breakdown of the bench step as it really runs (replayed from the CUDA graph): kernel durations from CUPTI
 activity records through torch.profiler, summed per kernel name.  Unlike step_breakdown.py (events around eager calls)
 this carries no per-launch event overhead and sees the torch glue kernels too.
-usage: python profiles/kineto_breakdown.py [steps] [--eager] [--ops] [--cylinder] [--analytic-mover]"""
+usage: python profiles/kineto_breakdown.py [steps] [--eager] [--ops] [--shapes] [--cylinder] [--analytic-mover]"""
 import collections
 import os
 import random
@@ -66,7 +66,8 @@ def main():
         step()
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes="--shapes" in sys.argv,
+                 with_stack="--shapes" in sys.argv) as prof:
         t0.record()
         for _ in range(steps):
             step()
@@ -89,6 +90,14 @@ def main():
 
     if "--ops" in sys.argv:          # eager only: which aten ops the small torch kernels come from
         print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=60))
+
+
+    if "--shapes" in sys.argv:       # eager only: torch ops by input shape and Python call site (which glue is worth fusing)
+        rows = [e for e in prof.key_averages(group_by_input_shape=True, group_by_stack_n=6) if e.key.startswith("aten::") and e.self_device_time_total > 0]
+        rows.sort(key=lambda e: -e.self_device_time_total)
+        for e in rows[:45]:
+            site = next((fr for fr in e.stack if "mm-pde_b200" in fr or "mmpde_b200" in fr), e.stack[0] if e.stack else "")
+            print(f"  {e.self_device_time_total / steps:8.1f} us/step x{e.count / steps:5.1f}  {e.key:28s} {str(e.input_shapes)[:70]:70s} {site[-70:]}")
 
 
 if __name__ == "__main__":

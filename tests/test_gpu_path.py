@@ -271,6 +271,39 @@ def test_dmm_graph_branch_fused_layer_equals_tensor_ops():
     assert _rel(dx_f, dx_t) < 1e-5 and _rel(dy_f, dy_t) < 1e-5
 
 
+def test_dmm_displacement_kernel_equals_tensor_ops():
+    """mmpde_dmm_displacement (one forward-mode pass over the points) against the tensor-op form of DMM.displacement and,
+    on the CPU, against the reference's formulation (autograd.grad of phi): array mode at the Burgers size (16 x 2304
+    points, trunk width 32), ragged point counts, one sample."""
+    from mmpde_b200 import synthetic
+    from mmpde_b200.mesh.dmm_model import DMM
+    dev = _dev()
+    torch.manual_seed(11)
+    mover = DMM(s=48, mode="array", branch_layer=7, trunk_layer=[2, 32, 512], out_layer=[1024, 512, 1]).to(dev).eval()
+    g = torch.linspace(0, 1, 48)
+    grid = torch.stack(torch.meshgrid(g, g, indexing="xy"), -1).reshape(-1, 2)
+    m64 = DMM(s=48, mode="array", branch_layer=7, trunk_layer=[2, 32, 512], out_layer=[1024, 512, 1]).double().eval()
+    m64.load_state_dict({k: v.double().cpu() for k, v in mover.state_dict().items()})
+    for B in (16, 1, 3):
+        u = synthetic.burgers_fields(B, 31, 48, 48, seed=B)[:, 9].to(dev)
+        xi = (grid[None].expand(B, -1, -1).reshape(-1, 2) + 0.003 * torch.randn(B * 2304, 2)).to(dev).contiguous()
+        with torch.no_grad():
+            mover.fused = True
+            dx_f, dy_f = mover.displacement(u, xi)
+            mover.fused = False
+            dx_t, dy_t = mover.displacement(u, xi)
+        assert dx_f.shape == dx_t.shape == (B * 2304, 1)
+        # the reference's formulation: d phi / d xi by autograd (data_creator_2d.py:106-107), in fp64 on the CPU
+        xg = xi.double().cpu().requires_grad_(True)
+        ref = torch.autograd.grad(m64(u.double().cpu(), xg).sum(), xg)[0]
+        e_f = _rel(torch.cat((dx_f, dy_f), -1), ref)
+        e_t = _rel(torch.cat((dx_t, dy_t), -1), ref)
+        print(f"[dmm displacement B={B}] fused kernel vs fp64 autograd {e_f:.2e}; tensor ops vs fp64 autograd {e_t:.2e}")
+        assert e_f < 3e-6 and e_t < 3e-6, (B, e_f, e_t)
+        assert _rel(dx_f, dx_t) < 1e-5 and _rel(dy_f, dy_t) < 1e-5, (B, _rel(dx_f, dx_t), _rel(dy_f, dy_t))
+    mover.fused = True
+
+
 def test_config1_full_size_properties():
     """Burgers 48x48, batch 16 (N=36 864, E=1 290 240), 6 layers: the oracle needs ~17 s/step on 8 cores, so
     full-size checks are size-independent properties; a B=2 slice of the same case is compared exactly."""

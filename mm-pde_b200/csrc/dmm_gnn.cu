@@ -77,15 +77,20 @@ __global__ void __launch_bounds__(256) dmm_gnn_layer_kernel(const float4* __rest
 // load reads ONE row of M (broadcast, conflict-free); the four quarters of j are summed with two shuffles.
 // ================================================================================================================
 constexpr int DISP_K = 32;                                               // trunk width, zero-padded
-__global__ void __launch_bounds__(256) dmm_displacement_kernel(const float2* __restrict__ xi, const float* __restrict__ W1,
+__global__ void __launch_bounds__(256, 1) dmm_displacement_kernel(const float2* __restrict__ xi, const float* __restrict__ W1,
                                                                 const float* __restrict__ b1, int K, const float* __restrict__ M,
                                                                 const float* __restrict__ cst, const float* __restrict__ w, int J,
                                                                 int64_t N, int64_t per_sample, float2* __restrict__ out) {
     extern __shared__ float s_m[];                                       // M [J][32] (zero-padded rows) | w [J]
     float* s_w = s_m + (size_t)J * DISP_K;
-    for (int i = threadIdx.x; i < J * DISP_K; i += blockDim.x) {
-        const int j = i / DISP_K, k = i % DISP_K;
-        s_m[i] = (k < K) ? __ldg(M + (size_t)j * K + k) : 0.f;
+    if (K == DISP_K && (reinterpret_cast<uintptr_t>(M) & 15) == 0) {     // rows already 32 wide: a straight 128-bit copy
+#pragma unroll 4
+        for (int i = threadIdx.x; i < J * (DISP_K / 4); i += blockDim.x) reinterpret_cast<float4*>(s_m)[i] = ldg4(M + 4 * (size_t)i);
+    } else {
+        for (int i = threadIdx.x; i < J * DISP_K; i += blockDim.x) {
+            const int j = i / DISP_K, k = i % DISP_K;
+            s_m[i] = (k < K) ? __ldg(M + (size_t)j * K + k) : 0.f;
+        }
     }
     for (int j = threadIdx.x; j < J; j += blockDim.x) s_w[j] = __ldg(w + j);
     __syncthreads();
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(256) dmm_displacement_kernel(const float2* __r
             u[k] = da * wx; v[k] = da * wy;
         }
         float acc1 = 0.f, acc2 = 0.f;
-#pragma unroll 2
+#pragma unroll 4
         for (int jj = 0; jj < jq; ++jj) {
             const int j = quarter * jq + jj;
             const float4* row = reinterpret_cast<const float4*>(s_m + (size_t)j * DISP_K);

@@ -211,19 +211,34 @@ __device__ __forceinline__ void knn_grid_body(const mmpde_knn_task& a, int64_t b
                 gap = gap * (1.0f - 1e-5f) - 2e-6f * (gx + gy) * cell;   // conservative (cell-assignment rounding): never stop early
                 if (gap > 0.f && (double)best.worst() < (double)gap * (double)gap) break;
             }
-            int ylo = cy - r, yhi = cy + r, xlo = cx - r, xhi = cx + r;
+            // the ring of cells at Chebyshev distance r: whole rows of cells at its top and bottom, the two end cells of the
+            // rows in between.  Cells of a row are neighbours in `order`, so a row piece is ONE contiguous candidate range,
+            // walked four candidates at a time: the index loads of a group go out together, then the coordinate gathers,
+            // then the insertions (one point at a time the kernel sat on two dependent L2 round trips per candidate:
+            // long_scoreboard was half of all stall cycles, profiles/r01_ncu_knn_summary.txt)
+            auto scan = [&](int c_lo, int c_hi) {                           // cells c_lo..c_hi of the sample (same row)
+                const int s1 = __ldg(cell_start + c_hi + 1);
+                for (int s = __ldg(cell_start + c_lo); s < s1; s += 4) {
+                    int p[4];
+                    float2 pp[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) p[j] = (s + j < s1) ? __ldg(order + s + j) : -1;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) pp[j] = (p[j] >= 0) ? __ldg(pts + p[j]) : make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (p[j] >= 0 && p[j] != self) best.push(Dist<D>::d2(qq.x, qq.y, pp[j].x, pp[j].y), p[j]);
+                }
+            };
+            const int ylo = cy - r, yhi = cy + r, xlo = cx - r, xhi = cx + r;
+            const int xa = max(xlo, 0), xb = min(xhi, gx - 1);
             for (int yy = max(ylo, 0); yy <= min(yhi, gy - 1); ++yy) {
-                bool edge_row = (yy == ylo) || (yy == yhi);
-                int step = edge_row ? 1 : max(xhi - xlo, 1);
-                for (int xx = xlo; xx <= xhi; xx += step) {
-                    if (xx < 0 || xx >= gx) continue;
-                    int c = cell0 + yy * gx + xx;
-                    for (int s = cell_start[c]; s < cell_start[c + 1]; ++s) {
-                        int p = order[s];
-                        if (p == self) continue;
-                        float2 pp = pts[p];
-                        best.push(Dist<D>::d2(qq.x, qq.y, pp.x, pp.y), p);
-                    }
+                const int row = cell0 + yy * gx;
+                if (yy == ylo || yy == yhi) {
+                    scan(row + xa, row + xb);
+                } else {
+                    if (xlo >= 0) scan(row + xlo, row + xlo);
+                    if (xhi < gx) scan(row + xhi, row + xhi);
                 }
             }
         }

@@ -172,6 +172,10 @@ __global__ void grid_fill_kernel(const int* __restrict__ cell_of_pt, int64_t n, 
 // is latency-bound with one thread per query (10 % of the warp slots at 36 k queries), so the three searches of a
 // training step (graph on the moved mesh, interpolation to it and back) run side by side in one launch.
 constexpr int KNN_MAX_TASKS = 4;
+#ifndef MMPDE_KNN_BATCH
+#define MMPDE_KNN_BATCH 4
+#endif
+constexpr int KNN_BATCH = MMPDE_KNN_BATCH;              // candidates whose loads are in flight together
 struct KnnGroup {
     mmpde_knn_task t[KNN_MAX_TASKS];
     int cta_begin[KNN_MAX_TASKS + 1];
@@ -213,20 +217,20 @@ __device__ __forceinline__ void knn_grid_body(const mmpde_knn_task& a, int64_t b
             }
             // the ring of cells at Chebyshev distance r: whole rows of cells at its top and bottom, the two end cells of the
             // rows in between.  Cells of a row are neighbours in `order`, so a row piece is ONE contiguous candidate range,
-            // walked four candidates at a time: the index loads of a group go out together, then the coordinate gathers,
+            // walked KNN_BATCH candidates at a time: the index loads of a group go out together, then the coordinate gathers,
             // then the insertions (one point at a time the kernel sat on two dependent L2 round trips per candidate:
             // long_scoreboard was half of all stall cycles, profiles/r01_ncu_knn_summary.txt)
             auto scan = [&](int c_lo, int c_hi) {                           // cells c_lo..c_hi of the sample (same row)
                 const int s1 = __ldg(cell_start + c_hi + 1);
-                for (int s = __ldg(cell_start + c_lo); s < s1; s += 4) {
-                    int p[4];
-                    float2 pp[4];
+                for (int s = __ldg(cell_start + c_lo); s < s1; s += KNN_BATCH) {
+                    int p[KNN_BATCH];
+                    float2 pp[KNN_BATCH];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) p[j] = (s + j < s1) ? __ldg(order + s + j) : -1;
+                    for (int j = 0; j < KNN_BATCH; ++j) p[j] = (s + j < s1) ? __ldg(order + s + j) : -1;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) pp[j] = (p[j] >= 0) ? __ldg(pts + p[j]) : make_float2(0.f, 0.f);
+                    for (int j = 0; j < KNN_BATCH; ++j) pp[j] = (p[j] >= 0) ? __ldg(pts + p[j]) : make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < KNN_BATCH; ++j)
                         if (p[j] >= 0 && p[j] != self) best.push(Dist<D>::d2(qq.x, qq.y, pp[j].x, pp[j].y), p[j]);
                 }
             };

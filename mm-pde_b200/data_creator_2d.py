@@ -83,6 +83,14 @@ class GraphCreator_FS_2D(nn.Module):
             hit = self._ref_cache[("ori_grid", str(device))] = (src, src.to(device))
         return hit[1]
 
+    def _static(self, key, make):
+        """Tensors that depend only on shapes and PDE constants (coordinate axes, the regular grid, the time axis, the
+        sample index of every node): built once per key instead of by a handful of tiny launches in every step."""
+        hit = self._ref_cache.get(key)
+        if hit is None:
+            hit = self._ref_cache[key] = make()
+        return hit
+
     # ------------------------------------------------------------------ neighbour searches of one moved-mesh step
     def _ref_points(self, key, make):
         """The reference points (regular grid / original cloud, repeated per sample) never move: the tensor and its
@@ -210,11 +218,15 @@ class GraphCreator_FS_2D(nn.Module):
             onx, ony = data.shape[-2], data.shape[-1]
             nt, nx, ny = pde.grid_size
             n = nx * ny
-            xs = torch.linspace(0, pde.Lx, nx, device=device)
-            ys = torch.linspace(0, pde.Ly, ny, device=device)
-            self._radius = float(self.n * torch.sqrt((xs[1] - xs[0]) ** 2 + (ys[1] - ys[0]) ** 2) + 0.0001) \
-                if self.e == "radius" else None
-            grid = torch.stack(torch.meshgrid(xs, ys, indexing="ij"), dim=2).float().reshape(1, n, 2).expand(B, n, 2)
+            if self.e == "radius":
+                xs = torch.linspace(0, pde.Lx, nx, device=device)
+                ys = torch.linspace(0, pde.Ly, ny, device=device)
+                self._radius = float(self.n * torch.sqrt((xs[1] - xs[0]) ** 2 + (ys[1] - ys[0]) ** 2) + 0.0001)
+            else:
+                self._radius = None
+            grid = self._static(("axes_grid", nx, ny, float(pde.Lx), float(pde.Ly), str(device)), lambda: torch.stack(
+                torch.meshgrid(torch.linspace(0, pde.Lx, nx, device=device), torch.linspace(0, pde.Ly, ny, device=device),
+                               indexing="ij"), dim=2).float().reshape(1, n, 2)).expand(B, n, 2)
             static_key = ("grid", B, nx, ny, str(device))
             if mesh_model is not None:
                 mm_nx, mm_ny = pde.movingmesh_grid_size[-2], pde.movingmesh_grid_size[-1]
@@ -253,7 +265,8 @@ class GraphCreator_FS_2D(nn.Module):
                 static_key = None
             else:
                 mesh = grid
-        t = torch.linspace(pde.tmin, pde.tmax, nt, device=device)
+        t = self._static(("t_axis", float(pde.tmin), float(pde.tmax), nt, str(device)),
+                         lambda: torch.linspace(pde.tmin, pde.tmax, nt, device=device))
         B = min(B, len(steps))
         u_new = data[:B].reshape(B, self.tw, n).permute(0, 2, 1).reshape(B * n, self.tw)
         y_new = labels[:B].reshape(B, self.tw, n).permute(0, 2, 1).reshape(B * n, self.tw)
@@ -261,7 +274,7 @@ class GraphCreator_FS_2D(nn.Module):
         # ``steps`` may already be a device tensor (train_helper_2d.StepGraph: the step indices are a graph input)
         step_idx = steps[:B] if torch.is_tensor(steps) else to_device(torch.as_tensor(list(steps[:B])), device)
         t_new = t[step_idx].repeat_interleave(n)
-        batch = torch.arange(B, device=device).repeat_interleave(n)
+        batch = self._static(("batch_index", B, n, str(device)), lambda: torch.arange(B, device=device).repeat_interleave(n))
         if static_key is not None:
             static_key = static_key + (B,)
         graph = Data(x=u_new, edges=self._edges(x_new, B, n, static_key, nbr=pre["graph"] if pre else None))
@@ -279,9 +292,9 @@ class GraphCreator_FS_2D(nn.Module):
             onx, ony = pde.ori_grid_size[1], pde.ori_grid_size[2]
             nx, ny = pde.grid_size[1], pde.grid_size[2]
             nu = pred.shape[0] // (nx * ny)
-            og = torch.stack(torch.meshgrid(torch.linspace(0, pde.Lx, onx, device=device),
-                                            torch.linspace(0, pde.Ly, ony, device=device), indexing="ij"), dim=2)
-            og = og.reshape(1, -1, 2).expand(nu, -1, 2).reshape(-1, 2)
+            og = self._static(("ori_axes_grid", nu, onx, ony, float(pde.Lx), float(pde.Ly), str(device)), lambda: torch.stack(
+                torch.meshgrid(torch.linspace(0, pde.Lx, onx, device=device), torch.linspace(0, pde.Ly, ony, device=device),
+                               indexing="ij"), dim=2).reshape(1, -1, 2).expand(nu, -1, 2).reshape(-1, 2))
             on_grid = self.interpolate(itp_model, pred.reshape(-1, nx, ny), graph.pos[:, 1:2], graph.pos[:, 2:3],
                                        og[:, 0:1], og[:, 1:2], mode="2",
                                        idx=getattr(graph, "_itp_back_idx", None)).reshape(-1, 1, onx, ony)

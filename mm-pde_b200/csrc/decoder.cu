@@ -45,6 +45,54 @@ __device__ __forceinline__ float dec_forward(const float* sp, DecScratch& s, int
     return warp_sum(part) + sp[OFF_B3];
 }
 
+// The same forward with the convolution weights of each lane in REGISTERS.  dec_forward reads a weight AND an activation
+// from shared memory for every multiply-add (the kernel sat at 2-3 % of its HBM roofline on the shared-memory pipe:
+// mio_throttle, profiles/r02_ncu_full_summary.txt).  Here a lane keeps ONE output channel per layer -- layer 1: channel
+// lane / 8, positions (lane % 8) + 8 j; layer 2: channel lane / 4, positions (lane % 4) + 4 j -- so its 16 + 48 weights are
+// loaded once per kernel and a multiply-add costs one shared-memory load.  Same accumulation order per output: same bits.
+struct DecRegs { float w1[16], b1, w2[48], b2, w3[2]; };
+__device__ __forceinline__ void dec_load_regs(const float* sp, int lane, DecRegs& r) {
+    const int c = lane >> 3, o = lane >> 2;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) r.w1[t] = sp[OFF_W1 + c * 16 + t];
+    r.b1 = sp[OFF_B1 + c];
+#pragma unroll
+    for (int t = 0; t < 48; ++t) r.w2[t] = sp[OFF_W2 + o * 48 + t];
+    r.b2 = sp[OFF_B2 + o];
+    r.w3[0] = sp[OFF_W3 + lane]; r.w3[1] = sp[OFF_W3 + 32 + lane];
+}
+__device__ __forceinline__ float dec_forward_regs(const float* sp, const DecRegs& r, DecScratch& s, int lane) {
+    const int c = lane >> 3, o = lane >> 2;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int p = (lane & 7) + 8 * j;
+        if (p < 38) {
+            float acc = r.b1;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) acc = fmaf(r.w1[t], s.h[3 * p + t], acc);
+            s.a1[c * 38 + p] = fmaxf(acc, 0.f);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int p = (lane & 3) + 4 * j;
+        if (p < 9) {
+            float acc = r.b2;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                for (int t = 0; t < 12; ++t) acc = fmaf(r.w2[cc * 12 + t], s.a1[cc * 38 + 3 * p + t], acc);
+            s.a2[o * 9 + p] = fmaxf(acc, 0.f);
+        }
+    }
+    __syncwarp();
+    float part = 0.f;
+    part = fmaf(r.w3[0], s.a2[(lane >> 3) * 9 + (lane & 7)], part);
+    part = fmaf(r.w3[1], s.a2[((lane + 32) >> 3) * 9 + (lane & 7)], part);
+    return warp_sum(part) + sp[OFF_B3];
+}
+
 // act1 [M,256] / act2 [M,128] (optional): the post-ReLU activations of the two hidden blocks in the layout of the
 // Toeplitz form (column c*38+i / o*9+j, zero padding behind) -- saved for a backward that runs as dense contractions
 // on the tensor cores while every ReLU mask still comes from THIS fp32 evaluation.
@@ -58,11 +106,13 @@ __global__ void __launch_bounds__(WARPS * 32) decoder_fwd_kernel(const float* __
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     DecScratch& s = scr[warp];
+    DecRegs regs;
+    dec_load_regs(sp, lane, regs);
     for (int64_t n = (int64_t)blockIdx.x * WARPS + warp; n < M; n += (int64_t)gridDim.x * WARPS) {
         __syncwarp();
         *reinterpret_cast<float4*>(&s.h[lane * 4]) = ldg4(h + n * ldh + lane * 4);
         __syncwarp();
-        float v = dec_forward(sp, s, lane);
+        float v = dec_forward_regs(sp, regs, s, lane);
         if (lane == 0) out[n] = scale * v;
         if (act1 != nullptr) {
             __syncwarp();
@@ -253,7 +303,7 @@ extern "C" int mmpde_decoder_fwd(const float* h, int64_t ldh, int64_t M, const f
                                  void* stream) {
     if (M < 0 || ldh % 4) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
-    int grid = (int)imin64((M + WARPS - 1) / WARPS, (int64_t)sm_count() * 8);
+    int grid = (int)imin64((M + WARPS - 1) / WARPS, (int64_t)sm_count() * 2);      // 108 registers: two CTAs per SM, weights loaded once
     decoder_fwd_kernel<<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(h, ldh, M, params, scale, out, nullptr, nullptr);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
@@ -264,7 +314,7 @@ extern "C" int mmpde_decoder_fwd_acts(const float* h, int64_t ldh, int64_t M, co
     if (M < 0 || ldh % 4 || act1 == nullptr || act2 == nullptr) return MMPDE_EINVAL;
     if ((reinterpret_cast<uintptr_t>(act1) | reinterpret_cast<uintptr_t>(act2)) & 15) return MMPDE_EINVAL;
     if (M == 0) return MMPDE_OK;
-    int grid = (int)imin64((M + WARPS - 1) / WARPS, (int64_t)sm_count() * 8);
+    int grid = (int)imin64((M + WARPS - 1) / WARPS, (int64_t)sm_count() * 2);      // 108 registers: two CTAs per SM, weights loaded once
     decoder_fwd_kernel<<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(h, ldh, M, params, scale, out, act1, act2);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;

@@ -278,6 +278,36 @@ def profile_kernels(train_step_eager, steps, peaks, barrier):
     return table, by
 
 
+def kineto_table(step, steps, path, barrier):
+    """Kernel durations (CUPTI, through torch.profiler) summed per kernel name over `steps` replayed steps -> text table."""
+    import collections
+    from torch.profiler import ProfilerActivity, profile
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    barrier()
+    if path is None:
+        return
+    wall = e0.elapsed_time(e1) / steps
+    tot, cnt = collections.Counter(), collections.Counter()
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            name = ev.name
+            for cut in ("<", "("):
+                name = name.split(cut)[0]
+            tot[name] += ev.device_time_total
+            cnt[name] += 1
+    with open(path, "w") as f:
+        f.write(f"step {wall:.3f} ms under the profiler; kernels+copies busy {sum(tot.values()) / steps / 1e3:.3f} ms/step\n")
+        for name, v in tot.most_common(60):
+            f.write(f"  {v / steps / 1e3:8.3f} ms  x{cnt[name] / steps:6.1f}  avg {v / cnt[name]:8.1f} us  {name[:90]}\n")
+
+
 def parity_probe(world, rank, dev, build_models, fields_of_rank, fwd_bwd, bucket_cls):
     """N > 1: one batch-sharded step (sync-BN across ranks, averaged gradient bucket) against the SAME global batch
     recomputed in one process on this rank's GPU (single-rank COMM) -- loss and every parameter gradient.  Driver-run
@@ -549,6 +579,8 @@ def run_ours(args):
     t_end = time.perf_counter()
     torch.cuda.profiler.stop()
     launches = _cabi.launches - launches0
+    if os.environ.get("MMPDE_KINETO"):   # CUPTI durations of every kernel inside the replayed step (any N; rank 0 writes the table)
+        kineto_table(lambda: train_step(fields_dev), 3, os.environ["MMPDE_KINETO"] if rank == 0 else None, barrier)
     # ---- every kernel of the step, timed with events on its launch stream in an eager pass of the SAME step ---
     # (with the step replayed from a CUDA graph the kernels inside it cannot carry events; --no-graph: same eager path)
     kern_steps = min(args.steps, 3)

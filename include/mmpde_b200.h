@@ -232,6 +232,15 @@ int mmpde_bn_bwd_reduce_fused(const float* g, int64_t ldg, const float* out, int
                               const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
                               const float* mean_rstd, double* bsums, uint32_t* ticket, double* local_out,
                               double* glob_out, const int64_t* peer_base, int rank, int world, void* stream);
+/* The same exchange in two halves, so that independent work can be queued between them: mmpde_bn_bwd_reduce_post reduces like
+ * mmpde_bn_bwd_reduce_fused but its last CTA only delivers this rank's sums to the peers (local_out as above, world >= 2);
+ * mmpde_bn_exchange_wait (one small kernel, later on the SAME stream, no other exchange of this buffer in between) waits for
+ * the peers' sums and writes the sums over all ranks [256] to out. */
+int mmpde_bn_bwd_reduce_post(const float* g, int64_t ldg, const float* out, int64_t ldo, int relu, const float* A,
+                             int64_t lda, const float* B, int64_t ldb, int64_t M, const float* mean_rstd,
+                             double* bsums, uint32_t* ticket, double* local_out, const int64_t* peer_base, int rank,
+                             int world, void* stream);
+int mmpde_bn_exchange_wait(const int64_t* peer_base, int rank, int world, double* out, void* stream);
 
 /* ---- small elementwise helpers of the node path -------------------------------------------------
  * relu_bwd: out = g * (act > 0); colsum[128] += column sums of out (NULL to skip).  [M,128] */

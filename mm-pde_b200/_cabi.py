@@ -54,6 +54,8 @@ SIGNATURES = {
     "mmpde_bn_exchange_set_timeout": [_d],
     "mmpde_bn_stats_fused": [_p, _l, _p, _l, _l, _p, _p, _d, _f, _f, _p, _p, _p, _p, _i, _i, _p],
     "mmpde_bn_bwd_reduce_fused": [_p, _l, _p, _l, _i, _p, _l, _p, _l, _l, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "mmpde_bn_bwd_reduce_post": [_p, _l, _p, _l, _i, _p, _l, _p, _l, _l, _p, _p, _p, _p, _p, _i, _i, _p],
+    "mmpde_bn_exchange_wait": [_p, _i, _i, _p, _p],
     "mmpde_bn_apply": [_p, _l, _p, _l, _l, _p, _p, _p, _i, _p, _l, _p],
     "mmpde_bn_bwd_reduce": [_p, _l, _p, _l, _i, _p, _l, _p, _l, _l, _p, _p, _p],
     "mmpde_bn_bwd_apply": [_p, _l, _p, _l, _i, _p, _l, _p, _l, _l, _p, _p, _p, _d, _p, _l, _i, _p, _l, _p],

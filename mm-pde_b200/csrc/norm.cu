@@ -50,6 +50,7 @@ struct BnTail {
     unsigned int* ticket;                  // zeroed with the sums; counts the CTAs that have delivered their partials
     const int64_t* peer_base;              // cross-rank exchange buffers (mmpde_bn_exchange) or nullptr = this rank only
     int rank, world;
+    int post_only;                         // 1: deliver this rank's sums to the peers and return (mmpde_bn_exchange_wait finishes)
     unsigned long long timeout_ns;
     double* local_out;                     // [256] this rank's folded sums (backward: dbeta | dgamma), or nullptr
     double* glob_out;                      // [256] sums over all ranks, or nullptr
@@ -73,7 +74,10 @@ __device__ __forceinline__ void bn_tail(const BnTail& t, const double* __restric
 #pragma unroll
     for (int r = 0; r < MMPDE_BN_REPLICAS; ++r) v += __ldcg(sums_all + r * 256 + c);
     if (t.local_out) t.local_out[c] = v;
-    if (t.peer_base != nullptr && t.world > 1) v = peer_exchange_256(v, t.peer_base, t.rank, t.world, t.timeout_ns);
+    if (t.peer_base != nullptr && t.world > 1) {
+        if (t.post_only) { peer_post_256(v, t.peer_base, t.rank, t.world); return; }
+        v = peer_exchange_256(v, t.peer_base, t.rank, t.world, t.timeout_ns);
+    }
     if (t.glob_out) t.glob_out[c] = v;
     if (t.count > 0) {
         s_fold[c] = v;
@@ -406,6 +410,25 @@ extern "C" int mmpde_bn_bwd_reduce_fused(const float* g, int64_t ldg, const floa
     BnTail t{};
     t.ticket = ticket; t.peer_base = (world > 1 && glob_out) ? peer_base : nullptr; t.rank = rank; t.world = world;
     t.timeout_ns = peer_timeout_ns(); t.local_out = local_out; t.glob_out = glob_out; t.count = 0.0;
+    bn_bwd_reduce_kernel<<<reduce_grid(M), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, bsums, t);
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+// The same reduction, but the last CTA only POSTS this rank's sums to the peers (first half of the exchange): the caller
+// queues independent work behind it -- the weight-gradient launch of the layer above -- and completes the exchange with
+// mmpde_bn_exchange_wait right before mmpde_bn_bwd_apply, so neither the link latency nor a peer that is a few tens of
+// microseconds behind stalls this rank's backward chain.
+extern "C" int mmpde_bn_bwd_reduce_post(const float* g, int64_t ldg, const float* out, int64_t ldo, int relu, const float* A,
+                                        int64_t lda, const float* B, int64_t ldb, int64_t M, const float* mean_rstd,
+                                        double* bsums, uint32_t* ticket, double* local_out, const int64_t* peer_base, int rank,
+                                        int world, void* stream) {
+    if (M <= 0 || ldg % 4 || lda % 4 || (B && ldb % 4) || (relu && (!out || ldo % 4)) || !bsums || !ticket || !peer_base || world < 2)
+        return MMPDE_EINVAL;
+    if (int rc = check_peer(peer_base, rank, world)) return rc;
+    BnTail t{};
+    t.ticket = ticket; t.peer_base = peer_base; t.rank = rank; t.world = world; t.post_only = 1;
+    t.timeout_ns = peer_timeout_ns(); t.local_out = local_out; t.glob_out = nullptr; t.count = 0.0;
     bn_bwd_reduce_kernel<<<reduce_grid(M), 256, 0, (cudaStream_t)stream>>>(g, ldg, out, ldo, relu, A, lda, B, ldb, M, mean_rstd, bsums, t);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;

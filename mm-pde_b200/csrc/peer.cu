@@ -28,6 +28,12 @@ __global__ void __launch_bounds__(256) bn_exchange_kernel(const double* __restri
     out[c] = peer_exchange_256(v, peer_base, rank, world, timeout_ns);
 }
 
+// second half of an exchange whose first half ran in the last CTA of an earlier kernel (mmpde_bn_bwd_reduce_post)
+__global__ void __launch_bounds__(256) bn_exchange_wait_kernel(const int64_t* __restrict__ peer_base, int rank, int world,
+                                                               double* __restrict__ out, unsigned long long timeout_ns) {
+    out[threadIdx.x] = peer_wait_256(peer_base, rank, world, timeout_ns);
+}
+
 }  // namespace mmpde
 
 using namespace mmpde;
@@ -55,6 +61,13 @@ extern "C" int mmpde_bn_exchange(const double* sums, int n_rep, const int64_t* p
     if (!sums || !peer_base || !out || n_rep < 1 || world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world)
         return MMPDE_EINVAL;
     bn_exchange_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, n_rep, peer_base, rank, world, out, peer_timeout_ns());
+    MMPDE_CHECK_LAUNCH();
+    return MMPDE_OK;
+}
+
+extern "C" int mmpde_bn_exchange_wait(const int64_t* peer_base, int rank, int world, double* out, void* stream) {
+    if (!peer_base || !out || world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world) return MMPDE_EINVAL;
+    bn_exchange_wait_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(peer_base, rank, world, out, peer_timeout_ns());
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }

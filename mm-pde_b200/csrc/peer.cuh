@@ -30,17 +30,18 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 
 
-// Exchange number counter+1 of this rank's buffer: all 256 threads of the calling CTA take part; thread c contributes v
-// (this rank's c-th sum) and returns the c-th sum over all ranks, added in rank order (identical bits everywhere).
-__device__ __forceinline__ double peer_exchange_256(double v, const int64_t* __restrict__ peer_base, int rank, int world,
-                                                    unsigned long long timeout_ns) {
-    __shared__ uint32_t s_seq;
+// Exchange number counter+1 of this rank's buffer, in two halves; all 256 threads of the calling CTA take part.
+// POST: thread c stores v (this rank's c-th sum) into the slot of every peer, then the flags are raised.  The counter is
+// not advanced: the matching WAIT (same kernel or a later one on the same stream, with no other exchange of this buffer
+// in between) derives the same sequence number from it.
+__device__ __forceinline__ void peer_post_256(double v, const int64_t* __restrict__ peer_base, int rank, int world) {
+    __shared__ uint32_t s_seq_post;
     const int c = threadIdx.x;
     unsigned char* mine = reinterpret_cast<unsigned char*>(peer_base[rank]);
     __syncthreads();
-    if (c == 0) s_seq = *reinterpret_cast<volatile uint32_t*>(mine) + 1u;
+    if (c == 0) s_seq_post = *reinterpret_cast<volatile uint32_t*>(mine) + 1u;
     __syncthreads();
-    const uint32_t seq = s_seq, slot = seq & 3u;
+    const uint32_t seq = s_seq_post, slot = seq & 3u;
     for (int r = 0; r < world; ++r) {
         double* dst = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(peer_base[r]) + PEER_SLOTS_OFF) +
                       ((size_t)slot * PEER_MAX_WORLD + rank) * 256 + c;
@@ -48,9 +49,22 @@ __device__ __forceinline__ double peer_exchange_256(double v, const int64_t* __r
     }
     __threadfence_system();
     __syncthreads();
-    if (c < world) {
+    if (c < world)
         st_release_sys(reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(peer_base[c]) + PEER_FLAGS_OFF) +
                            slot * PEER_MAX_WORLD + rank, seq);
+}
+// WAIT: until every rank's sums of this exchange have arrived; returns the c-th sum over all ranks, added in rank order
+// (identical bits everywhere), and advances the counter.
+__device__ __forceinline__ double peer_wait_256(const int64_t* __restrict__ peer_base, int rank, int world,
+                                                unsigned long long timeout_ns) {
+    __shared__ uint32_t s_seq_wait;
+    const int c = threadIdx.x;
+    unsigned char* mine = reinterpret_cast<unsigned char*>(peer_base[rank]);
+    __syncthreads();
+    if (c == 0) s_seq_wait = *reinterpret_cast<volatile uint32_t*>(mine) + 1u;
+    __syncthreads();
+    const uint32_t seq = s_seq_wait, slot = seq & 3u;
+    if (c < world) {
         const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + PEER_FLAGS_OFF) + slot * PEER_MAX_WORLD + c;
         // A peer may legitimately be late by many seconds (rank-0-only checkpoint save, a re-recorded step graph, a
         // data-loader stall), so the wait is bounded in WALL time (globaltimer, independent of the SM clock) by a
@@ -69,8 +83,14 @@ __device__ __forceinline__ double peer_exchange_256(double v, const int64_t* __r
     const double* slots = reinterpret_cast<const double*>(mine + PEER_SLOTS_OFF) + (size_t)slot * PEER_MAX_WORLD * 256 + c;
     double acc = 0.0;
     for (int r = 0; r < world; ++r) acc += ld_relaxed_sys_f64(slots + r * 256);
+    __syncthreads();                                   // every thread has read the counter-derived slot before it moves on
     if (c == 0) *reinterpret_cast<volatile uint32_t*>(mine) = seq;
     return acc;
+}
+__device__ __forceinline__ double peer_exchange_256(double v, const int64_t* __restrict__ peer_base, int rank, int world,
+                                                    unsigned long long timeout_ns) {
+    peer_post_256(v, peer_base, rank, world);
+    return peer_wait_256(peer_base, rank, world, timeout_ns);
 }
 
 // wall-clock limit of the flag wait (seconds -> ns); env MMPDE_PEER_TIMEOUT_S or mmpde_bn_exchange_set_timeout()

@@ -6,6 +6,8 @@ used for memory, streams, tiny O(parameters) reshuffles and autograd bookkeeping
 Reference behaviour being reproduced: /root/reference/gnn_2d.py:53-69,119-141 (processor),
 /root/reference/data_creator_2d.py:46-85 + /root/reference/interpolate.py:79-93 (interpolation).
 """
+import os
+
 import torch
 
 from . import _cabi
@@ -282,6 +284,10 @@ def _split_for(rows):
     return max(2, min(512, (rows + 255) // 256))
 
 
+# multi-rank backward: weight-gradient launches queued between the halves of the BatchNorm exchanges (see _bn_backward)
+SPLIT_BN_EXCHANGE = os.environ.get("MMPDE_SPLIT_BN_EXCHANGE", "1") != "0"
+
+
 class _BNState:
     """mean/rstd [2,128] of one BatchNorm application (saved for the backward)."""
     __slots__ = ("mean_rstd", "count", "rows", "training", "branch")
@@ -336,18 +342,26 @@ def _bn_forward(items, gamma, beta, relu, training, rmean, rvar, nbt, st, sums=N
     return state
 
 
-def _bn_backward(items, relu, state, gamma, st, spread=None):
+def _bn_backward(items, relu, state, gamma, st, spread=None, between=None):
     """items: one (g, ldg, out, ldo, A, lda, B, ldb, M, gy, ldgy[, gy_gated, ldgg]) per local part (gy_gated =
     gy * (B > 0), the ReLU backward of a residual branch B fused into this pass).  Returns this rank's
     (dgamma, dbeta) as fp64 views; writes dL/dy into gy.  With several ranks the two column sums are summed over the
     ranks for the normalisation term (sync-BN), while the parameter grads stay per-rank sums (the gradient all-reduce adds
-    them up afterwards).  Fold and cross-rank sum happen in the last CTA of the last part's reducing launch."""
+    them up afterwards).  Fold and cross-rank sum happen in the last CTA of the last part's reducing launch.
+    ``between``: independent work of the caller (the deferred weight-gradient launch of the layer above).  With several ranks
+    it is queued BETWEEN the two halves of the exchange -- the reducing launch only delivers this rank's sums, a one-CTA
+    kernel collects the peers' right before the apply pass -- so the link latency and a peer that is some tens of
+    microseconds behind (each rank interleaves its two solver branches in its own order) do not stall this rank's chain;
+    otherwise it simply runs first."""
     dev = gamma.device
     if spread is None:
         spread = bn_accumulators(1, dev)[0]
     peer = COMM.peer_args(state.branch)
     live = [it for it in items if it[8] > 0]
     multi = COMM.global_rows(state.rows) != float(state.rows)
+    split = between is not None and peer is not None and bool(live) and multi and state.training and SPLIT_BN_EXCHANGE
+    if between is not None and not split:
+        between()
     if peer is not None and live:
         both = torch.empty(2, 2 * H, dtype=torch.float64, device=dev)
         local, glob = both[0], both[1]
@@ -355,9 +369,15 @@ def _bn_backward(items, relu, state, gamma, st, spread=None):
             _cabi.call("mmpde_bn_bwd_reduce", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd), _ptr(spread), st)
         g, ldg, out, ldo, A, lda, B, ldb, M, *_ = live[-1]
         want_glob = state.training
-        _cabi.call("mmpde_bn_bwd_reduce_fused", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd),
-                   _ptr(spread), _ptr(spread, BN_ACC - 1), _ptr(local), _ptr(glob) if want_glob else None,
-                   peer[0] if multi else None, peer[1] if multi else 0, peer[2] if multi else 1, st)
+        if split:
+            _cabi.call("mmpde_bn_bwd_reduce_post", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd),
+                       _ptr(spread), _ptr(spread, BN_ACC - 1), _ptr(local), peer[0], peer[1], peer[2], st)
+            between()
+            _cabi.call("mmpde_bn_exchange_wait", peer[0], peer[1], peer[2], _ptr(glob), st)
+        else:
+            _cabi.call("mmpde_bn_bwd_reduce_fused", g, ldg, out, ldo, int(relu), A, lda, B, ldb, M, _ptr(state.mean_rstd),
+                       _ptr(spread), _ptr(spread, BN_ACC - 1), _ptr(local), _ptr(glob) if want_glob else None,
+                       peer[0] if multi else None, peer[1] if multi else 0, peer[2] if multi else 1, st)
         if not want_glob:
             glob = torch.zeros_like(local)
     else:
@@ -599,9 +619,12 @@ def _layer_forward(parts, Xs, lp, bnbuf, training, nxts, exch, st, prep=None, bn
     return saved, bn
 
 
-def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st, prep=None, flat=None, bn_spread=None, im=_NO_IMAGES):
+def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st, prep=None, flat=None, bn_spread=None, im=_NO_IMAGES,
+                    pending=None, defer=False):
     """Backward of _layer_forward.  g_hs[p] [n_own,128] = dL/d(output).  Returns ([dL/dh_in per part], 10 param
-    grads summed over the local parts); adds the layer's dL/du into g_node4s[p][:,0] when given."""
+    grads summed over the local parts); adds the layer's dL/du into g_node4s[p][:,0] when given.
+    ``pending``: the deferred weight-gradient launch of the layer above, handed to this layer's BatchNorm backward;
+    ``defer``: return this layer's own weight-gradient launch as a third value instead of running it at the end."""
     W1, b1, W2, b2, W3, b3, W4, b4, gam, bet = lp
     dev = W1.device
     f32 = dict(dtype=torch.float32, device=dev)
@@ -612,7 +635,7 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st, prep=Non
     g_z4s = [torch.empty(part.n_own, H, **f32) for part in parts]
     items = [(_ptr(g_h), H, None, 0, _ptr(Xl), 2 * H, _ptr(sv[3]), H, part.n_own, _ptr(g_y), H, _ptr(g_z4), H)
              for part, Xl, sv, g_h, g_y, g_z4 in zip(parts, Xs, saved, g_hs, g_ys, g_z4s)]
-    dgam, dbet = _bn_backward(items, 0, bn, gam, st, spread=bn_spread)
+    dgam, dbet = _bn_backward(items, 0, bn, gam, st, spread=bn_spread, between=pending)
     # all accumulators of this layer in ONE zeroed buffer (every block is a multiple of 4 floats: 16-byte aligned rows)
     fold_here = flat is None
     if fold_here:
@@ -659,6 +682,14 @@ def _layer_backward(parts, Xs, lp, saved, bn, g_hs, g_node4s, exch, st, prep=Non
         # dL/dh_in += dP' W1a + dQ' W1b
         node_gemm(_ptr(dPQ), 2 * H, _ptr(W1), 1, 260, _ptr(g_y), H, N, A1=_ptr(dPQ, H), lda1=2 * H, W1=_ptr(W1, H), w1_ns=1,
                   w1_ks=260, R1=_ptr(g_y), ldr1=H, st=st, img0=im.pT, img1=im.qT)
+    if defer:
+        assert not fold_here
+        alive = [keep, dPQs, g_z4s, list(Xs), list(saved)]          # operands of the queued contractions
+
+        def run_wgrads():
+            node_wgrad_grouped(wtasks, st)
+            alive.clear()
+        return g_ys, [dW1, db1, dW2, db2, dW3, db3, dW4, db4, dgam, dbet], run_wgrads
     node_wgrad_grouped(wtasks, st)
     del keep
     if fold_here:
@@ -782,18 +813,26 @@ def _solver_backward(sv, g_outs, need_u, st):
     grads[N_ENC + N_LAYER * L] = g_dec
     flat_all = torch.zeros(max(L, 1), sum(LAYER_GRAD_SIZES), **f32)   # every layer's gradient accumulators, zeroed at once
     spread_all = bn_accumulators(2 + L, dev)
+    # several ranks with the peer-memory exchange: a layer's weight-gradient launch is deferred into the BatchNorm backward
+    # of the layer below, between the two halves of its cross-GPU exchange (_bn_backward)
+    defer = SPLIT_BN_EXCHANGE and COMM.peer_args(COMM.branch) is not None and getattr(COMM, "world", 1) > 1
+    pending = None
     for l in reversed(range(L)):
         base = N_ENC + N_LAYER * l
         saved, bn = sv["layers"][l]
-        g_hs, lg = _layer_backward(parts, sv["X"][l], params[base:base + N_LAYER], saved, bn, g_hs, g_node4s, exch, st,
-                                   prep=sv["preps"][l], flat=flat_all[l], bn_spread=spread_all[2 + l], im=sv["images"][l])
+        res = _layer_backward(parts, sv["X"][l], params[base:base + N_LAYER], saved, bn, g_hs, g_node4s, exch, st,
+                              prep=sv["preps"][l], flat=flat_all[l], bn_spread=spread_all[2 + l], im=sv["images"][l],
+                              pending=pending, defer=defer)
+        g_hs, lg = res[0], res[1]
+        pending = res[2] if defer else None
         grads[base:base + N_LAYER] = lg
-    if L:
-        _fold_extension_grads(flat_all)
     # ---- encoder backward
     g_e2s = [torch.empty(part.n_own, H, **f32) for part in parts]
     dg2, db2_ = _bn_backward([(_ptr(g_h), H, None, 0, _ptr(e2), H, None, 0, part.n_own, _ptr(g_e2), H)
-                              for part, g_h, e2, g_e2 in zip(parts, g_hs, e2s, g_e2s)], 0, bn2, g2, st, spread=spread_all[1])
+                              for part, g_h, e2, g_e2 in zip(parts, g_hs, e2s, g_e2s)], 0, bn2, g2, st, spread=spread_all[1],
+                             between=pending)
+    if L:
+        _fold_extension_grads(flat_all)
     dWe2, dbe2 = torch.zeros(H, H, **f32), torch.zeros(H, **f32)
     dWe1, dbe1 = torch.zeros(H, 4, **f32), torch.zeros(H, **f32)
     g_e1ns = []

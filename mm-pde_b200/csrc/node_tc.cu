@@ -454,13 +454,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(const __gri
                 }
             }
         };
-        float4 ra[8], rb[8], na[8], nb[8];
-        load16(ra, rb, 0);
-        for (int64_t ti = 0; ti < my_tiles; ++ti) {
+        // convert + stage one tile from a register set whose loads were issued a WHOLE tile earlier
+        auto build_tile = [&](int64_t ti, const float4 (&ra)[8], const float4 (&rb)[8]) {
             const int sb = (int)(ti & 1);
             const int64_t t = (int64_t)bx + ti * gx;
             if (w == 0) TL(0, (int)ti, 0);
-            load16(na, nb, ti + 1);
             mbar_wait(s_empty + 8 * sb, ((uint32_t)(ti >> 1) & 1u) ^ 1u);
             if (w == 0) TL(0, (int)ti, 1);
             const uint32_t stage = sbase + sb * WgradSmem::STAGE;
@@ -492,8 +490,20 @@ __global__ void __launch_bounds__(W_THREADS, 1) node_wgrad_tc_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(s_full + 8 * sb);
             if (w == 0) TL(0, (int)ti, 2);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { ra[k] = na[k]; rb[k] = nb[k]; }
+        };
+        // Two register sets used ALTERNATELY (the loop is unrolled by two): while one tile is converted, the 16 rows of the
+        // next one are in flight into the other set and are first touched a whole tile later.  (Swapping the sets by copy
+        // at the end of each trip touched the fresh loads after one tile's worth of stores, ~500 clk: long_scoreboard was
+        // the top stall of this kernel, profiles/r02b_ncu_full_summary.txt.)
+        float4 ra[8], rb[8], na[8], nb[8];
+        load16(ra, rb, 0);
+        for (int64_t ti = 0; ti < my_tiles; ti += 2) {
+            load16(na, nb, ti + 1);
+            build_tile(ti, ra, rb);
+            if (ti + 1 < my_tiles) {
+                load16(ra, rb, ti + 2);
+                build_tile(ti + 1, na, nb);
+            }
         }
     } else {
         // ------------------------------------------------------------------ MMA issuer (one thread)

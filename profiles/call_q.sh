@@ -1,4 +1,6 @@
 #!/bin/bash
 o=gpurun_out
-for v in 0 1 0 1; do MMPDE_BRANCH_PRIORITY=$v timeout 600 python bench.py --steps 40 --warmup 5 > $o/r02_bench_prio$v.json 2> $o/r02_bench_prio$v.err; echo "prio=$v rc=$?"; python -c "
-import json; d=json.load(open('$o/r02_bench_prio$v.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['rollout']['ms_per_step'], d['cylinder']['ms_per_step'])"; done
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_guards.py -q -m gpu -x -k "wgrad or layer or solver or decoder or node" > $o/r02_pytest_wgrad.log 2>&1; echo "tests rc=$?"; tail -2 $o/r02_pytest_wgrad.log
+timeout 300 python profiles/edge_bench.py 30 2>&1 | grep node_
+timeout 600 python bench.py --steps 30 --warmup 5 --no-extras --no-cpu-baseline > $o/r02_bench_h.json 2> $o/r02_bench_h.err; echo "bench rc=$?"; python -c "
+import json; d=json.load(open('$o/r02_bench_h.json')); print(d['ms_per_step'], d['e2e']['ms_per_step']); print([ (k['name'], round(k['avg_us'],1)) for k in d['kernels'] if 'wgrad' in k['name']])"

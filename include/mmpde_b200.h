@@ -34,6 +34,12 @@ extern "C" {
 /* library / device facts: abi version, SM count the kernels were sized for. */
 int mmpde_abi_version(void);
 int mmpde_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Cap on the CTAs of the persistent one-CTA-per-SM kernels (mmpde_edge_fwd / _bwd, mmpde_node_gemm*, mmpde_node_wgrad*) on the
+ * current device; 0 = one per SM (default).  Host-side state read at launch time (a recorded CUDA graph keeps the grids it was
+ * recorded with).  Two independent solver passes issued on two streams run side by side at half width instead of taking
+ * turns on the whole chip -- same throughput on one GPU, and on several GPUs the ranks stop drifting apart between the
+ * cross-GPU BatchNorm exchanges. */
+int mmpde_set_persistent_ctas(int n);
 
 /* ---- graph construction --------------------------------------------------------------------
  * Replaces torch_cluster.knn_graph (data_creator_2d.py:260, mesh/dmm_model.py:228) and sklearn

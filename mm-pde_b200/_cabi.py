@@ -35,6 +35,7 @@ class KnnTask(ctypes.Structure):
 SIGNATURES = {
     "mmpde_abi_version": [],
     "mmpde_device_info": [_p, _p, _p],
+    "mmpde_set_persistent_ctas": [_i],
     "mmpde_knn": [_p, _p, _p, _p, _i, _l, _i, _i, _i, _p, _p],
     "mmpde_knn_grid_build": [_p, _p, _i, _l, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p],
     "mmpde_knn_grid": [_p, _p, _p, _p, _i, _l, _f, _f, _f, _i, _i, _p, _p, _i, _i, _i, _p, _p],

@@ -15,3 +15,9 @@ extern "C" int mmpde_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     if (cc_minor) *cc_minor = prop.minor;
     return MMPDE_OK;
 }
+
+extern "C" int mmpde_set_persistent_ctas(int n) {
+    if (n < 0) return MMPDE_EINVAL;
+    mmpde::persistent_cap() = n;
+    return MMPDE_OK;
+}

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #include "../../include/mmpde_b200.h"
 
 #define MMPDE_CHECK_LAUNCH()                                  \
@@ -29,6 +30,17 @@ inline int sm_count() {
         if (n[dev] <= 0) n[dev] = 148;
     }
     return n[dev];
+}
+// Cap on the CTAs of the persistent one-CTA-per-SM kernels (edge, node GEMM, weight gradient), per device; 0 = one per SM.
+// A training step runs its two solvers as parallel branches: at full width their persistent kernels take turns on the whole
+// chip, at half width they run side by side (mmpde_set_persistent_ctas; train_helper_2d sets it for the overlapped step).
+inline int& persistent_cap() {
+    static int cap[MAX_DEVICES] = {0};
+    return cap[cur_device()];
+}
+inline int persistent_ctas() {
+    const int c = persistent_cap(), n = sm_count();
+    return (c > 0 && c < n) ? c : n;
 }
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel AND device
 #define MMPDE_ENSURE_SMEM(kernel, bytes)                                                                              \

@@ -719,7 +719,7 @@ extern "C" int mmpde_debug_timeline(long long* buf) {
 }
 #endif
 
-static int edge_grid(int64_t n_tiles) { return (int)imin64(n_tiles, sm_count()); }
+static int edge_grid(int64_t n_tiles) { return (int)imin64(n_tiles, persistent_ctas()); }
 
 extern "C" int mmpde_edge_fwd(const float* PQ, const int32_t* edge_src, const int32_t* edge_dst, const float* inv_deg,
                               int64_t n_edges, const float* w2, const float* b2, float* agg, int64_t ld_agg,

@@ -599,7 +599,7 @@ static int node_gemm_launch(const float* A0, int64_t lda0, const float* A1, int6
     p.Aext = Aext; p.Wext = Wext; p.bias = bias; p.relu = relu; p.R1 = R1; p.ldr1 = ldr1; p.R2 = R2; p.ldr2 = ldr2;
     p.C = C; p.ldc = ldc; p.M = M;
     const int64_t n_tiles = (M + GT - 1) / GT;
-    node_gemm_tc_kernel<<<(int)imin64(n_tiles, sm_count()), G_THREADS, smem, (cudaStream_t)stream>>>(p);
+    node_gemm_tc_kernel<<<(int)imin64(n_tiles, persistent_ctas()), G_THREADS, smem, (cudaStream_t)stream>>>(p);
     MMPDE_CHECK_LAUNCH();
     return MMPDE_OK;
 }
@@ -656,7 +656,7 @@ extern "C" int mmpde_node_wgrad_grouped(const mmpde_wgrad_task* tasks, int n_tas
         }
         if (n == 0) break;
         // CTAs per task in proportion to its K tiles (every task at least one, none more than it has tiles)
-        const int64_t grid = imin64(total, imax64((int64_t)sm_count(), (int64_t)n));
+        const int64_t grid = imin64(total, imax64((int64_t)persistent_ctas(), (int64_t)n));
         int64_t given = 0;
         g.cta_begin[0] = 0;
         for (int k = 0; k < n; ++k) {

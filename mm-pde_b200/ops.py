@@ -288,6 +288,30 @@ def _split_for(rows):
 SPLIT_BN_EXCHANGE = os.environ.get("MMPDE_SPLIT_BN_EXCHANGE", "1") != "0"
 
 
+class persistent_ctas:
+    """``with persistent_ctas(n):`` -- the persistent tensor-core kernels launched inside use at most n CTAs (0 = one per SM)
+    on ``device``; see mmpde_set_persistent_ctas.  Not a launch: it only changes the grid of the launches that follow."""
+
+    def __init__(self, n, device=None):
+        self.n, self.device = int(n), device
+
+    def _set(self, n):
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().mmpde_set_persistent_ctas(n)
+        if rc != 0:
+            raise _cabi.MMPDEError(f"mmpde_set_persistent_ctas({n}) failed: {rc}")
+
+    def __enter__(self):
+        if self.n > 0:
+            self._set(self.n)
+        return self
+
+    def __exit__(self, *exc):
+        if self.n > 0:
+            self._set(0)
+        return False
+
+
 class _BNState:
     """mean/rstd [2,128] of one BatchNorm application (saved for the backward)."""
     __slots__ = ("mean_rstd", "count", "rows", "training", "branch")

@@ -128,6 +128,21 @@ def _overlap_solvers(device):
     return torch.device(device).type == "cuda" and (type(ops.COMM) is ops._Comm or ops.COMM.n_branches >= 2)
 
 
+def _branch_ctas(device, mesh_model):
+    """CTAs per persistent kernel while the two solvers of a step run as parallel branches: HALF the SMs, so that the
+    branches advance side by side instead of taking turns on the whole chip at kernel granularity.  One GPU: the same
+    step time (9.95 vs 9.98 ms).  Several GPUs: every rank then interleaves its branches the same way and the ranks
+    stop drifting apart between the cross-GPU BatchNorm exchanges (exchange-carrying kernels 83 -> 31 us at two
+    ranks, e2e 10.64 -> 10.17 ms).  MMPDE_BRANCH_SMS overrides (0 = full width)."""
+    import os
+    if mesh_model is None or not _overlap_solvers(device):
+        return 0
+    env = os.environ.get("MMPDE_BRANCH_SMS")
+    if env is not None:
+        return max(int(env), 0)
+    return torch.cuda.get_device_properties(device).multi_processor_count // 2
+
+
 def _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, steps, device):
     """Both branches of the MM-PDE prediction (train_helper_2d.py:107-118): the branch solver on the moved
     mesh, interpolated back to the grid (+ residual net), plus the solver on the uniform grid."""
@@ -194,9 +209,10 @@ def training_loop_branch(model, model_b, itp_model, mesh_model, unrolling, batch
     history = []
 
     def gnn_step(data, labels, steps):
-        pred = _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, steps, device)
-        loss = criterion(pred, to_device(labels, device).reshape(-1, 1))
-        loss.backward()
+        with ops.persistent_ctas(_branch_ctas(device, mesh_model), device):
+            pred = _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, steps, device)
+            loss = criterion(pred, to_device(labels, device).reshape(-1, 1))
+            loss.backward()
         if after_backward is not None:
             after_backward()
         _step_optimizers(optimizer, optimizer2)
@@ -232,6 +248,8 @@ def test_timestep_losses(model, model_b, itp_model, mesh_model, steps, batch_siz
     curve = []
 
     def gnn_eval(data, labels, step_idx):
+        # full width: eval-mode BatchNorm has no cross-GPU exchange to keep in step, and the forward-only pass spends a
+        # larger share of its time where only one branch has work (3.73 ms per batch at full width, 3.90 at half)
         pred = _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, step_idx, device)
         return criterion(pred, to_device(labels, device).reshape(-1, 1))
 

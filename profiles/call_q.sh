@@ -1,6 +1,6 @@
 #!/bin/bash
 o=gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_guards.py -q -m gpu -x -k "wgrad or layer or solver or decoder or node" > $o/r02_pytest_wgrad.log 2>&1; echo "tests rc=$?"; tail -2 $o/r02_pytest_wgrad.log
-timeout 300 python profiles/edge_bench.py 30 2>&1 | grep node_
-timeout 600 python bench.py --steps 30 --warmup 5 --no-extras --no-cpu-baseline > $o/r02_bench_h.json 2> $o/r02_bench_h.err; echo "bench rc=$?"; python -c "
-import json; d=json.load(open('$o/r02_bench_h.json')); print(d['ms_per_step'], d['e2e']['ms_per_step']); print([ (k['name'], round(k['avg_us'],1)) for k in d['kernels'] if 'wgrad' in k['name']])"
+timeout 1500 python -m pytest tests -q -m gpu > $o/r02_pytest_gpu_f.log 2>&1; echo "suite rc=$?"; tail -2 $o/r02_pytest_gpu_f.log
+for b in "" 0; do MMPDE_BRANCH_SMS=$b; if [ -z "$b" ]; then unset MMPDE_BRANCH_SMS; else export MMPDE_BRANCH_SMS; fi
+timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > $o/r02_bench_i$b.json 2> $o/r02_bench_i$b.err; echo "branch_sms='$b' rc=$?"; python -c "
+import json; d=json.load(open('$o/r02_bench_i$b.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['rollout']['ms_per_step'], d['cylinder']['ms_per_step'], d['roofline']['frac'])"; done

@@ -138,7 +138,11 @@ def main():
     # With the BatchNorm sums accumulated in fp64 from the first add the sharded forward is bit-identical to the global batch
     # (measured at 2 ranks: loss 0, predictions 8e-8, whole gradient 2.5e-7, worst single tensor -- a bias -- 5e-5): what is
     # left is the order of the fp32 atomics in the backward.
-    ok = (float(flag[0]) < 2e-6 and float(flag[1]) < 2e-6 and float(flag[2]) < 2e-4 and float(flag[3]) < 1e-6
+    # The single-tensor bar is the 5e-4 of the header: the worst tensor is always one of the update_net_2 biases, whose gradient
+    # is a nearly cancelling column sum of ~30 per-CTA partials added by fp32 atomics.  Repeated runs of the same build give
+    # 4.7e-5, 5.5e-5 or 2.5e-4 on it (the last whenever two large partials meet in the other order), with the whole
+    # gradient at 2e-7 ... 1.3e-6 every time.
+    ok = (float(flag[0]) < 2e-6 and float(flag[1]) < 2e-6 and float(flag[2]) < 5e-4 and float(flag[3]) < 1e-6
           and float(flag[4]) < 1e-5)
     dist.barrier()
     if rank == 0:

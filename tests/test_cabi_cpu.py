@@ -79,6 +79,33 @@ def test_argument_errors_are_reported_before_any_device_work():
     assert "#define MMPDE_BN_REPLICAS 16" in hdr and "#define MMPDE_BN_EXCHANGE_BYTES (1024 + 4 * 16 * 256 * 8)" in hdr
 
 
+def test_argument_errors_of_the_round2_entry_points():
+    """mmpde_dmm_displacement, the two halves of the BatchNorm exchange and the CTA cap reject bad arguments on the host."""
+    lib = _ensure_built().lib()
+    P = 0x1000
+    assert lib.mmpde_dmm_displacement(P, P, P, 33, P, P, P, 512, 10, 5, P, None) == -1      # trunk width > 32
+    assert lib.mmpde_dmm_displacement(P, P, P, 32, P, P, P, 510, 10, 5, P, None) == -1      # J not a multiple of 4
+    assert lib.mmpde_dmm_displacement(P, P, P, 32, P, P, P, 512, 10, 0, P, None) == -1      # per_sample <= 0
+    assert lib.mmpde_dmm_displacement(None, P, P, 32, P, P, P, 512, 10, 5, P, None) == -1   # missing points
+    assert lib.mmpde_dmm_displacement(P, P, P, 32, P, P, P, 512, 0, 5, P, None) == 0        # nothing to do
+    assert lib.mmpde_bn_exchange_wait(None, 0, 2, P, None) == -1
+    assert lib.mmpde_bn_exchange_wait(P, 2, 2, P, None) == -1                                # rank >= world
+    assert lib.mmpde_bn_bwd_reduce_post(P, 128, None, 0, 0, P, 128, None, 0, 64, P, P, P, P, None, 0, 2, None) == -1   # no peers
+    assert lib.mmpde_bn_bwd_reduce_post(P, 128, None, 0, 0, P, 128, None, 0, 64, P, P, P, P, P, 0, 1, None) == -1      # world < 2
+    assert lib.mmpde_set_persistent_ctas(-1) == -1
+    assert lib.mmpde_set_persistent_ctas(74) == 0 and lib.mmpde_set_persistent_ctas(0) == 0
+
+
+def test_branch_width_is_only_used_for_overlapped_training_steps():
+    """train_helper_2d._branch_ctas: no cap without a mesh mover, on the CPU, or when the overlap is switched off."""
+    _ensure_built()
+    from mmpde_b200 import ops, train_helper_2d as th
+    assert th._branch_ctas("cpu", object()) == 0
+    assert th._branch_ctas("cpu", None) == 0
+    with ops.persistent_ctas(0):                 # n = 0 is a no-op and needs no device
+        pass
+
+
 def test_no_cpu_fallback():
     from mmpde_b200 import ops, _cabi
     from mmpde_b200.gnn_2d import GNN_Layer_FS_2D

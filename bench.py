@@ -680,7 +680,8 @@ def run_ours(args):
                                       + ("sums exchanged over NVLink peer memory in one kernel" if getattr(mdist.ops.COMM, "peer", None) is not None
                                          else "NCCL all-reduce of the sums" if world > 1 else "single rank") + "), flat grad all-reduce",
                        "launch": "eager" if step_graph is None else "CUDA graph replay of the whole step (StepGraph)"
-                                 + (", the two solvers as parallel graph branches" if _overlap_solvers(dev) else ""),
+                                 + (", the two solvers as parallel graph branches whose persistent kernels run side by side at "
+                                    "half width (74 CTAs each, train_helper_2d._branch_ctas)" if _overlap_solvers(dev) else ""),
                        "l2": "per-step working set ~1.7 GB > 126 MB L2, no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "edge-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
@@ -693,8 +694,10 @@ def run_ours(args):
                          "algorithmic_flops_per_launch": alg_flops, "executed_flops_per_launch": exe_flops,
                          "frac_executed": exe_flops / (kern_avg_ms * 1e-3) / 1e12 / peaks["bf16"] if kern_avg_ms > 0 else None,
                          "peak_source": peaks["source"],
-                         "timed_in": "eager single-stream pass of the same step right after the timed region (nodes of a replayed "
-                                     "CUDA graph cannot carry events)" if step_graph is not None else "eager pass after the timed region",
+                         "timed_in": "eager single-stream pass of the same step right after the timed region, every kernel alone on the "
+                                     "whole chip (nodes of a replayed CUDA graph cannot carry events; in the replayed step the same kernel "
+                                     "runs on half the SMs beside the other solver's, for twice as long)"
+                                     if step_graph is not None else "eager pass after the timed region",
                          "share_of_step": kern_avg_ms * dom["n"] / kern_steps / ms_step if ms_step > 0 else None},
             "kernels": kernels,
             "rollout": {"steps_per_s": world * 1e3 / ms_roll, "ms_per_step": ms_roll,

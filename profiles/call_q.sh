@@ -1,5 +1,6 @@
 #!/bin/bash
+# last check of the committed build: smoke + the bench line with default flags (what the driver runs)
 o=gpurun_out
-for cfg in "0 0" "2 2" "0 2" "2 3"; do set -- $cfg
-MMPDE_FULL_FWD_UNIFORM=$1 MMPDE_FULL_BWD_MOVED=$2 timeout 600 python bench.py --steps 30 --warmup 5 --no-extras --no-cpu-baseline > $o/r02_bench_w$1$2.json 2> $o/r02_bench_w$1$2.err; echo "full fwd uniform < $1, full bwd moved < $2: rc=$?"; python -c "
-import json; d=json.load(open('$o/r02_bench_w$1$2.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'])"; done
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py > $o/r02_bench_final.json 2> $o/r02_bench_final.err; echo "bench rc=$?"; python -c "
+import json; d=json.load(open('$o/r02_bench_final.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['rollout']['ms_per_step'], d['cylinder']['ms_per_step'], d['c4']['ms_per_step'], d['roofline']['frac'], d['cpu_baseline']['value'], d['gpu_launches']); print(d['config']['launch'])"

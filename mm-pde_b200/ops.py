@@ -288,6 +288,11 @@ def _split_for(rows):
 SPLIT_BN_EXCHANGE = os.environ.get("MMPDE_SPLIT_BN_EXCHANGE", "1") != "0"
 
 
+# Width (CTAs per persistent kernel, 0 = one per SM) of the solver pass being built; train_helper_2d._forward_gnn sets it
+# around each of the two solver calls of an overlapped training step.  SolverFn keeps it for its backward.
+SOLVER_WIDTH = 0
+
+
 class persistent_ctas:
     """``with persistent_ctas(n):`` -- the persistent tensor-core kernels launched inside use at most n CTAs (0 = one per SM)
     on ``device``; see mmpde_set_persistent_ctas.  Not a launch: it only changes the grid of the launches that follow."""
@@ -893,13 +898,18 @@ class SolverFn(torch.autograd.Function):
             _chk(node4, name="node4")
             for i, p in enumerate(params):
                 _chk(p, name=f"param{i}")
-            outs, ctx.sv = _solver_forward([GraphPart(node4, edges)], n_layers, training, scale, bn_buffers, params, None,
-                                           _stream(), want_backward=any(ctx.needs_input_grad))
+            # (grad mode is always off inside Function.forward: "a backward will follow" = some input requires grad)
+            width = int(SOLVER_WIDTH) if any(ctx.needs_input_grad) else 0
+            with persistent_ctas(width, node4.device):
+                outs, ctx.sv = _solver_forward([GraphPart(node4, edges)], n_layers, training, scale, bn_buffers, params, None,
+                                               _stream(), want_backward=any(ctx.needs_input_grad))
+            if ctx.sv is not None:
+                ctx.sv["width"] = width
         return outs[0].view(-1, 1)
 
     @staticmethod
     def backward(ctx, g_out):
-        with _on(g_out):
+        with _on(g_out), persistent_ctas(ctx.sv.get("width", 0), g_out.device):
             g_node4s, grads = _solver_backward(ctx.sv, [g_out], ctx.needs_input_grad[0], _stream())
         return (g_node4s[0] if g_node4s is not None else None, None, None, None, None, None, *grads)
 

@@ -129,18 +129,23 @@ def _overlap_solvers(device):
 
 
 def _branch_ctas(device, mesh_model):
-    """CTAs per persistent kernel while the two solvers of a step run as parallel branches: HALF the SMs, so that the
-    branches advance side by side instead of taking turns on the whole chip at kernel granularity.  One GPU: the same
-    step time (9.95 vs 9.98 ms).  Several GPUs: every rank then interleaves its branches the same way and the ranks
-    stop drifting apart between the cross-GPU BatchNorm exchanges (exchange-carrying kernels 83 -> 31 us at two
-    ranks, e2e 10.64 -> 10.17 ms).  MMPDE_BRANCH_SMS overrides (0 = full width)."""
+    """(uniform, moved): CTAs per persistent kernel of the two solvers of an overlapped TRAINING step, or (0, 0) = one per
+    SM.  At full width the persistent kernels of the two branches take turns on the whole chip at kernel granularity; with
+    the SMs divided between them the branches advance side by side.  One GPU: the same step time at 74 / 74 (10.02 vs
+    10.01 ms).  Several GPUs: every rank then interleaves its branches the same way and the ranks stop drifting apart
+    between the cross-GPU BatchNorm exchanges (exchange-carrying kernels 83 -> 31 us at two ranks, e2e 10.64 -> 9.99 ms).
+    The moved-mesh branch also runs the mesh mover, the neighbour searches and the interpolation (about 1 ms with no
+    counterpart on the uniform branch), so it gets the larger share and the two finish together.
+    MMPDE_BRANCH_SMS = "u,m" or one number overrides (0 = full width)."""
     import os
     if mesh_model is None or not _overlap_solvers(device):
-        return 0
+        return 0, 0
     env = os.environ.get("MMPDE_BRANCH_SMS")
     if env is not None:
-        return max(int(env), 0)
-    return torch.cuda.get_device_properties(device).multi_processor_count // 2
+        parts = [max(int(v), 0) for v in env.split(",")]
+        return (parts[0], parts[-1])
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    return sms // 2, sms - sms // 2
 
 
 def _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, steps, device):
@@ -152,15 +157,22 @@ def _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, lab
     if _overlap_solvers(device):
         cur, side = torch.cuda.current_stream(), _side_stream(device)
         side.wait_stream(cur)
+        w_uniform, w_moved = _branch_ctas(device, mesh_model)
         with torch.cuda.stream(side):
             ops.COMM.branch = 1              # this solver's BatchNorm exchanges (forward AND backward) use sequence 1
+            ops.SOLVER_WIDTH = w_uniform
             try:
                 on_uniform = model(uniform)
             finally:
                 ops.COMM.branch = 0
+                ops.SOLVER_WIDTH = 0
         # (the longer moved-mesh branch on a high-priority stream was measured: 10.20 vs 10.13 ms per step -- not kept)
         moved = graph_creator.create_graph(itp_model, data, labels, steps, device, mesh_model)
-        on_moved = graph_creator.interpolate_pred(itp_model, model_b(moved), moved, data, device)
+        ops.SOLVER_WIDTH = w_moved
+        try:
+            on_moved = graph_creator.interpolate_pred(itp_model, model_b(moved), moved, data, device)
+        finally:
+            ops.SOLVER_WIDTH = 0
         cur.wait_stream(side)
         on_uniform.record_stream(cur)
         return on_moved + on_uniform
@@ -209,10 +221,9 @@ def training_loop_branch(model, model_b, itp_model, mesh_model, unrolling, batch
     history = []
 
     def gnn_step(data, labels, steps):
-        with ops.persistent_ctas(_branch_ctas(device, mesh_model), device):
-            pred = _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, steps, device)
-            loss = criterion(pred, to_device(labels, device).reshape(-1, 1))
-            loss.backward()
+        pred = _forward_gnn(model, model_b, itp_model, mesh_model, graph_creator, data, labels, steps, device)
+        loss = criterion(pred, to_device(labels, device).reshape(-1, 1))
+        loss.backward()
         if after_backward is not None:
             after_backward()
         _step_optimizers(optimizer, optimizer2)

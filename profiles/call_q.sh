@@ -1,6 +1,5 @@
 #!/bin/bash
-# last check of the committed build: smoke + the bench line with default flags (what the driver runs)
 o=gpurun_out
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 900 python bench.py > $o/r02_bench_final.json 2> $o/r02_bench_final.err; echo "bench rc=$?"; python -c "
-import json; d=json.load(open('$o/r02_bench_final.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['rollout']['ms_per_step'], d['cylinder']['ms_per_step'], d['c4']['ms_per_step'], d['roofline']['frac'], d['cpu_baseline']['value'], d['gpu_launches']); print(d['config']['launch'])"
+for cfg in 74,74 66,82; do
+MMPDE_BRANCH_SMS=$cfg MMPDE_KINETO=$o/r02_kineto_w_$cfg.txt timeout 600 python bench.py --steps 40 --warmup 5 --no-extras --no-cpu-baseline > $o/r02_bench_w_$cfg.json 2> $o/r02_bench_w_$cfg.err; echo "uniform,moved = $cfg: rc=$?"; python -c "
+import json; d=json.load(open('$o/r02_bench_w_$cfg.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['rollout']['ms_per_step'])"; sed -n 2,3p $o/r02_kineto_w_$cfg.txt; done

@@ -100,8 +100,8 @@ def test_branch_width_is_only_used_for_overlapped_training_steps():
     """train_helper_2d._branch_ctas: no cap without a mesh mover, on the CPU, or when the overlap is switched off."""
     _ensure_built()
     from mmpde_b200 import ops, train_helper_2d as th
-    assert th._branch_ctas("cpu", object()) == 0
-    assert th._branch_ctas("cpu", None) == 0
+    assert th._branch_ctas("cpu", object()) == (0, 0)
+    assert th._branch_ctas("cpu", None) == (0, 0)
     with ops.persistent_ctas(0):                 # n = 0 is a no-op and needs no device
         pass
 
